@@ -1,0 +1,199 @@
+/*
+ * mscl_b200.h -- C ABI of the B200-native MSCL contrastive hot path.
+ *
+ * One shared library (libmscl_b200.so, sm_100a only) exports the entry points below.
+ * Plain pointers and sizes; no torch types.  Every pointer named d_* is a DEVICE
+ * pointer owned by the caller; nothing is allocated or freed inside.  Every call
+ * enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ * immediately: 0 on success, a negative MSCL_E* code otherwise, with the text
+ * available from mscl_last_error() (thread-local).
+ *
+ * The reference (megvii-research/MSCL, an MMAction2 fork) has no native code on
+ * this path: each entry point replaces a sequence of PyTorch/NumPy calls, cited
+ * as `file:line` relative to the reference root.
+ *
+ * Device data layout:
+ *   queue   float32 [K_local, C]   one key per ROW ("key-major"); the reference
+ *                                  keeps the transpose (C, K) (moco.py:390).
+ *   birth   int32   [K_local]      enqueue number at which the row was written;
+ *                                  reference count[j] == n_enq - birth[j]
+ *                                  (moco.py:427,437).
+ *   qstate  int64   [4]            {ptr, n_enq, block-done counter, reserved}.
+ *   qpack   float32 [M, 132]       per query row: q[0:128] | pos2 | shift2 | 0 | 0
+ *   acc     float32 [M, 132]       per query row: O[0:128] | sum-exp | #neg>pos | 0 | 0
+ */
+#ifndef MSCL_B200_H_
+#define MSCL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSCL_ABI_VERSION 1
+#define MSCL_DIM 128          /* feature dimension of the contrastive space (cfg ft_dim) */
+#define MSCL_PACK_LD 132      /* row pitch (floats) of qpack / acc */
+
+#define MSCL_OK 0
+#define MSCL_EINVAL (-1)      /* bad argument (shape, alignment, null pointer) */
+#define MSCL_ECUDA (-2)       /* CUDA runtime / driver error */
+#define MSCL_EUNSUPPORTED (-3)/* not an sm_100 device, or driver too old for TMA */
+
+typedef void *mscl_stream_t;
+
+int mscl_abi_version(void);
+const char *mscl_last_error(void);
+/* 0 if device `dev` can run this library (compute capability 10.x). */
+int mscl_device_check(int dev);
+
+/* ---------------------------------------------------------------------------
+ * K5  ring-buffer enqueue.   replaces MoCoV2._dequeue_and_enqueue
+ *     (mmaction/models/recognizers/moco.py:423-440) minus the all_gather.
+ * keys [B_all, C] are the rank-major gathered keys.  Rows whose global slot
+ * ptr+i falls in [shard_begin, shard_begin+K_local) are written; the age of the
+ * written rows becomes 1 and every other age grows by one (kept implicitly as
+ * n_enq - birth).  ptr <- (ptr + B_all) % K_total; n_enq <- n_enq + 1.
+ * If d_saved != NULL the overwritten rows (those in this shard) are first copied
+ * to d_saved[B_all, C] and their birth to d_saved_birth[B_all] (snapshot support,
+ * moco.py:484-488).
+ */
+int mscl_enqueue(float *d_queue, int32_t *d_birth, int64_t *d_qstate,
+                 const float *d_keys, int32_t B_all, int32_t C,
+                 int64_t K_total, int64_t shard_begin, int64_t K_local,
+                 float *d_saved, int32_t *d_saved_birth, mscl_stream_t stream);
+
+/* Materialise the reference's buffers for state_dict(): queue_ck [C, K_local]
+ * (transposed) and count int64 [K_local] = n_enq - birth.  (moco.py:390-396) */
+int mscl_queue_export(const float *d_queue, const int32_t *d_birth,
+                      const int64_t *d_qstate, float *d_queue_ck,
+                      int64_t *d_count, int32_t C, int64_t K_local,
+                      mscl_stream_t stream);
+/* Inverse: load reference-layout buffers. birth = n_enq - count with
+ * n_enq taken from d_qstate[1] (caller sets it to max(count) beforehand). */
+int mscl_queue_import(float *d_queue, int32_t *d_birth, const int64_t *d_qstate,
+                      const float *d_queue_ck, const int64_t *d_count, int32_t C,
+                      int64_t K_local, mscl_stream_t stream);
+/* The decayed snapshot the reference calls `weight` (moco.py:484-486):
+ * weight_ck[c, j] = queue[j, c] * 0.99999^(n_enq - birth[j]), float32 [C, K_local]. */
+int mscl_queue_weight(const float *d_queue, const int32_t *d_birth,
+                      const int64_t *d_qstate, float *d_weight_ck, int32_t C,
+                      int64_t K_local, mscl_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * K4  multi-tensor momentum EMA.   replaces MoCoV2._momentum_update_key_encoder
+ *     (moco.py:408-421): k <- fl(fl(k*m) + fl(q*(1-m))) element-wise, bit-exact
+ *     with the reference's two multiplies and one add (no FMA contraction).
+ * d_k_ptrs/d_q_ptrs/d_sizes: device tables of n_tensors entries.
+ * d_blk_tensor/d_blk_start: device tables of n_blocks entries mapping a CTA to
+ * (tensor index, first element); each CTA handles up to chunk_elems elements.
+ */
+int mscl_ema_multi(float *const *d_k_ptrs, const float *const *d_q_ptrs,
+                   const int64_t *d_sizes, const int32_t *d_blk_tensor,
+                   const int64_t *d_blk_start, int32_t n_blocks,
+                   int32_t chunk_elems, float m, float one_minus_m,
+                   mscl_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * K3  FRA: flow rotation augmentation.   replaces NormFlowWithStidedAug.__call__
+ *     + norm_flow (mmaction/datasets/pipelines/transforms_motion.py:103-142,7-29).
+ * layout 0: planar      flow [N, 2, T, H*W]   (u plane then v plane per clip)
+ * layout 1: interleaved flow [N, T, H*W, 2]   (the reference's per-frame H,W,2)
+ * d_cid int32 [N] chunk id per clip; d_cs float [2*num_chunks] = cos,sin pairs of
+ * beta = (start + stride*cid)*pi.  Output planar [N, 2, 2T, H*W]: frames [0,T) =
+ * base / (max|base| + 1e-5), frames [T,2T) = rotated / (max|rotated| + 1e-5),
+ * maxima per frame.  d_maxrad float [N, T, 2] is scratch (base, rotated).
+ * mscl_fra_maxrad must run before mscl_fra_apply on the same stream.
+ */
+int mscl_fra_maxrad(const float *d_flow, const int32_t *d_cid, const float *d_cs,
+                    float *d_maxrad, int32_t N, int32_t T, int32_t HW,
+                    int32_t layout, mscl_stream_t stream);
+int mscl_fra_apply(const float *d_flow, const int32_t *d_cid, const float *d_cs,
+                   const float *d_maxrad, float *d_out, int32_t N, int32_t T,
+                   int32_t HW, int32_t layout, mscl_stream_t stream);
+/* Rotation only on an already normalised planar clip [N,2,T,HW] -> [N,2,T,HW]
+ * (Appendix A.10 of SURVEY.md: rotation preserves the per-frame maximum). */
+int mscl_fra_rotate(const float *d_flow, const int32_t *d_cid, const float *d_cs,
+                    float *d_out, int32_t N, int32_t T, int32_t HW,
+                    mscl_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * K2  LMCL frame-level contrast.   replaces MSCLWithAugPosHeadV2.forward/.loss
+ *     (mmaction/models/heads/local_cl_head.py:57-73,41-55).
+ * (a) spatial mean over H*W of R = N*C*T rows (AdaptiveAvgPool3d((None,1,1)),
+ *     local_cl_head.py:61-62) and its backward (broadcast of g/HW).
+ * (b) the loss on pooled features xq [N, C, t], xf [N, C, t2] (t2 = 2t):
+ *     L2-normalise over C (eps 1e-12), sim = xq^T xf / T, cross-entropy of row i
+ *     against column i, top-1/top-5; forward and backward in one launch.
+ *     d_out float [4] = {loss (mean over N*t rows), top1, top5, 0};
+ *     d_gxq/d_gxf = d loss / d xq, d xf for unit upstream gradient.
+ *     d_part float [N*4 + 4] is scratch; its last 4 floats must be ZERO before
+ *     the first call (the kernel re-zeroes them for the next call).
+ */
+int mscl_hw_mean_fwd(const float *d_x, float *d_out, int64_t R, int32_t HW,
+                     mscl_stream_t stream);
+int mscl_hw_mean_bwd(const float *d_gout, float *d_gx, int64_t R, int32_t HW,
+                     mscl_stream_t stream);
+int mscl_lmcl(const float *d_xq, const float *d_xf, int32_t N, int32_t C,
+              int32_t t, int32_t t2, float inv_T, float *d_out, float *d_gxq,
+              float *d_gxf, float *d_part, mscl_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * K1  fused InfoNCE: q.[k; queue] logits, temperature, age decay, log-sum-exp,
+ *     cross-entropy, top-1/5 and d loss/d q in ONE pass over the queue.
+ *     replaces MoCoV2.forward_train logits block (moco.py:481-498),
+ *     MoCoHead.loss (heads/moco_head.py:38-77), CrossEntropyLoss_torch.forward
+ *     (losses/cross_entropy_loss.py:134-138), top_k_accuracy
+ *     (core/evaluation/accuracy.py:130-149) and
+ *     MSCLWithAugMxHead._forward_moco_mx/.loss (heads/moco_head_v2.py:38-100).
+ *
+ * Three launches per pass (a collective may sit between 2 and 3 when the queue
+ * is sharded):
+ *  1 prep      qpack[i] = q_i | pos2 | shift2 ; dscale[j] ; acc <- 0
+ *              pos2_i   = (q_i . kpos_i) / T * log2(e)
+ *              shift2_i = |q_i| * key_norm_bound / T * log2(e)   (>= every logit)
+ *              dscale_j = 0.99999^(n_enq - birth_j) / T * log2(e);  d_dscale holds
+ *              ceil(K_local/64)*64 floats, the pad is written as 0
+ *  2 partial   acc[i] += ( sum_j p_ij dscale_j queue_j | sum_j p_ij | #{j: s_ij > pos2_i} )
+ *              with s_ij = (q_i . queue_j) dscale_j and p_ij = 2^(s_ij - shift2_i);
+ *              tcgen05 (tf32 operands, fp32 accumulate in TMEM), queue tiles by TMA.
+ *  3 finalize  per row: Z, lse, loss_i, p0, dq_unit_i; per group of rows_per_group
+ *              consecutive rows: mean loss, top-1, top-5.
+ * Row i belongs to group i / rows_per_group.  d_group_out float [n_groups, 4] =
+ * {loss, top1, top5, 0}.  d_dq_unit [M, C] = d(group loss)/d q_i.
+ * d_row_loss float [2*M]: loss_i for i<M, then #{j: s_ij > pos_i} (as float).
+ * finalize uses acc[130] as a CTA-done counter and leaves it zero.
+ * mscl_infonce_bwd scales: d_dq[i] = d_dq_unit[i] * d_gout[group(i)].
+ */
+int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
+                      const int32_t *d_birth, const int64_t *d_qstate,
+                      int64_t K_local, float inv_T, float key_norm_bound,
+                      float *d_qpack, float *d_dscale, float *d_acc,
+                      int32_t M_acc, mscl_stream_t stream);
+int mscl_infonce_partial(const float *d_qpack, int32_t M, const float *d_queue,
+                         const float *d_dscale, int64_t K_local, float *d_acc,
+                         int32_t with_grad, int32_t num_sms, mscl_stream_t stream);
+/* Same contract as mscl_infonce_partial on CUDA cores in fp32: validation twin. */
+int mscl_infonce_partial_simt(const float *d_qpack, int32_t M, const float *d_queue,
+                              const float *d_dscale, int64_t K_local, float *d_acc,
+                              int32_t with_grad, mscl_stream_t stream);
+int mscl_infonce_finalize(const float *d_qpack, const float *d_kpos,
+                          float *d_acc, int32_t M, int32_t rows_per_group,
+                          float inv_T, float *d_row_loss, float *d_dq_unit,
+                          float *d_group_out, mscl_stream_t stream);
+int mscl_infonce_bwd(const float *d_dq_unit, const float *d_gout, int32_t M,
+                     int32_t rows_per_group, float *d_dq, mscl_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * K6  shuffle-BN row gather.   replaces x_gather[idx_this] in
+ *     MoCo._batch_shuffle_ddp / _batch_unshuffle_ddp (moco.py:172,191).
+ * out[r, :] = x[idx[r], :] for r < n_rows, rows of row_elems floats
+ * (row_elems % 4 == 0), 128-bit copies.
+ */
+int mscl_gather_rows(const float *d_x, const int64_t *d_idx, float *d_out,
+                     int32_t n_rows, int64_t row_elems, mscl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSCL_B200_H_ */

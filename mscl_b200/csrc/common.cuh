@@ -1,0 +1,70 @@
+// Shared helpers for the mscl_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mscl_b200.h"
+
+namespace mscl {
+
+// thread-local last-error text, returned by mscl_last_error()
+char *err_buf();
+int set_err(int code, const char *fmt, ...);
+
+#define MSCL_CHECK_ARG(cond, ...)                           \
+  do {                                                      \
+    if (!(cond)) return ::mscl::set_err(MSCL_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+#define MSCL_CUDA(call)                                                      \
+  do {                                                                       \
+    cudaError_t e__ = (call);                                                \
+    if (e__ != cudaSuccess)                                                  \
+      return ::mscl::set_err(MSCL_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, \
+                             #call, cudaGetErrorString(e__));                \
+  } while (0)
+
+#define MSCL_LAUNCH_CHECK()                                                   \
+  do {                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                     \
+    if (e__ != cudaSuccess)                                                   \
+      return ::mscl::set_err(MSCL_ECUDA, "%s:%d launch: %s", __FILE__,        \
+                             __LINE__, cudaGetErrorString(e__));              \
+  } while (0)
+
+static inline cudaStream_t as_stream(mscl_stream_t s) { return (cudaStream_t)s; }
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+// The reference hard-codes the decay base 0.99999 (moco.py:484) and evaluates
+// `0.99999 ** float32_tensor` in float32, i.e. with the base rounded to
+// float32(0.99999) = 0.9999899864196777.  log2 of THAT number:
+constexpr float kLog2Decay = -1.4446615003766504e-05f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming 128-bit accesses (read-once / write-once data)
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(float4 *p, const float4 &v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+}  // namespace mscl

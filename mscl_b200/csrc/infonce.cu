@@ -1,0 +1,248 @@
+// K1 (support kernels): prep, CUDA-core validation twin of the tcgen05 pass,
+// finalize and backward scaling for the fused InfoNCE objective.
+// Contract and formulas: include/mscl_b200.h (K1 block) and DESIGN.md section 4.
+#include "common.cuh"
+
+namespace mscl {
+
+constexpr int kC = MSCL_DIM;
+constexpr int kLd = MSCL_PACK_LD;
+
+__device__ __forceinline__ float to_tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---- 1. prep --------------------------------------------------------------
+// part A (one warp per query row): qpack row = tf32-rounded q | pos2 | shift2 | 0 | 0
+// part B (one thread per key)     : dscale[j]
+// part C                          : acc <- 0
+__global__ void __launch_bounds__(256)
+infonce_prep_kernel(const float *__restrict__ q, const float *__restrict__ kpos, int M,
+                    const int32_t *__restrict__ birth, const int64_t *__restrict__ qstate,
+                    int64_t K_local, float inv_T, float key_norm_bound,
+                    float *__restrict__ qpack, float *__restrict__ dscale,
+                    float *__restrict__ acc, int M_acc) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * 8;
+  const float sc = inv_T * kLog2e;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < M; row += warps_total) {
+    const float4 a = reinterpret_cast<const float4 *>(q + (int64_t)row * kC)[lane];
+    const float4 b = reinterpret_cast<const float4 *>(kpos + (int64_t)row * kC)[lane];
+    float d = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    float ss = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    d = warp_sum(d);
+    ss = warp_sum(ss);
+    float4 r = make_float4(to_tf32_rn(a.x), to_tf32_rn(a.y), to_tf32_rn(a.z), to_tf32_rn(a.w));
+    float *dst = qpack + (int64_t)row * kLd;
+    reinterpret_cast<float4 *>(dst)[lane] = r;
+    if (lane == 0)
+      reinterpret_cast<float4 *>(dst)[32] =
+          make_float4(d * sc, sqrtf(ss) * key_norm_bound * sc, 0.f, 0.f);
+  }
+  const int64_t n_enq = qstate[1];
+  const int64_t tid = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * 256;
+  // dscale is padded to a multiple of 64 floats (the tcgen05 pass bulk-copies whole
+  // 64-key slices); the pad must be finite because P' = p * dscale feeds the second GEMM.
+  const int64_t K_pad = (K_local + 63) / 64 * 64;
+  for (int64_t j = tid; j < K_pad; j += nthreads) {
+    float v = 0.f;
+    if (j < K_local) {
+      const float age = (float)(n_enq - (int64_t)birth[j]);
+      v = exp2f(age * kLog2Decay) * sc;
+    }
+    dscale[j] = v;
+  }
+  float4 *acc4 = reinterpret_cast<float4 *>(acc);
+  const int64_t nacc = (int64_t)M_acc * (kLd / 4);
+  for (int64_t v = tid; v < nacc; v += nthreads) acc4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ---- 2'. CUDA-core twin of the tcgen05 pass (validation only) ---------------
+// One CTA per 128-key tile, 128 threads.  Phase 1: thread <-> key.  Phase 2:
+// thread <-> channel.  fp32 FMA everywhere.
+constexpr int kSimtKeys = 128;
+__global__ void __launch_bounds__(128)
+infonce_partial_simt_kernel(const float *__restrict__ qpack, int M,
+                            const float *__restrict__ queue,
+                            const float *__restrict__ dscale, int64_t K_local,
+                            float *__restrict__ acc, int with_grad) {
+  extern __shared__ float sm[];
+  float *tile = sm;                       // [128][129]
+  float *qrow = tile + kSimtKeys * 129;   // [128]
+  float *pbuf = qrow + kC;                // [128]
+  float *red = pbuf + kSimtKeys;          // [8]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t k0 = (int64_t)blockIdx.x * kSimtKeys;
+  for (int i = tid; i < kSimtKeys * (kC / 4); i += 128) {
+    const int r = i / (kC / 4), c4 = i - r * (kC / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k0 + r < K_local) v = __ldg(reinterpret_cast<const float4 *>(queue + (k0 + r) * kC) + c4);
+    float *d = tile + r * 129 + c4 * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  const bool valid = (k0 + tid) < K_local;
+  const float ds = valid ? dscale[k0 + tid] : 0.f;
+  __syncthreads();
+  for (int i = 0; i < M; ++i) {
+    const float *qp = qpack + (int64_t)i * kLd;
+    qrow[tid] = qp[tid];
+    const float pos2 = qp[kC], shift2 = qp[kC + 1];
+    __syncthreads();
+    float s = 0.f;
+    const float *kr = tile + tid * 129;
+#pragma unroll 8
+    for (int c = 0; c < kC; ++c) s = fmaf(qrow[c], kr[c], s);
+    s *= ds;
+    float p = valid ? exp2f(s - shift2) : 0.f;
+    float cnt = (valid && s > pos2) ? 1.f : 0.f;
+    pbuf[tid] = p * ds;
+    float ps = warp_sum(p), cs = warp_sum(cnt);
+    if (lane == 0) { red[warp] = ps; red[4 + warp] = cs; }
+    __syncthreads();
+    if (tid == 0) {
+      atomicAdd(acc + (int64_t)i * kLd + kC, red[0] + red[1] + red[2] + red[3]);
+      atomicAdd(acc + (int64_t)i * kLd + kC + 1, red[4] + red[5] + red[6] + red[7]);
+    }
+    if (with_grad) {
+      float o = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < kSimtKeys; ++j) o = fmaf(pbuf[j], tile[j * 129 + tid], o);
+      atomicAdd(acc + (int64_t)i * kLd + tid, o);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- 3. finalize -----------------------------------------------------------
+// One CTA (128 threads, thread <-> channel) per query row; the last CTA to finish
+// reduces the per-row losses / hit flags into per-group means in row order.
+__global__ void __launch_bounds__(128)
+infonce_finalize_kernel(const float *__restrict__ qpack, const float *__restrict__ kpos,
+                        float *__restrict__ acc, int M, int rows_per_group, float inv_T,
+                        float *__restrict__ row_loss, float *__restrict__ dq_unit,
+                        float *__restrict__ group_out) {
+  const int i = blockIdx.x, c = threadIdx.x;
+  const float *qp = qpack + (int64_t)i * kLd;
+  const float *ap = acc + (int64_t)i * kLd;
+  const float pos2 = qp[kC], shift2 = qp[kC + 1];
+  const float sum = ap[kC], cnt = ap[kC + 1];
+  const float e0 = exp2f(pos2 - shift2);
+  const float Z = e0 + sum;
+  const float inv_Z = 1.0f / Z;
+  const float p0 = e0 * inv_Z;
+  // d loss_i / d q = (1/T) [ (p0 - 1) kpos + sum_j p_j decay_j queue_j ];  the
+  // accumulated O carries decay_j * log2e / T, hence the ln2 factor.
+  const float g = (p0 - 1.0f) * kpos[(int64_t)i * kC + c] * inv_T + ap[c] * inv_Z * kLn2;
+  dq_unit[(int64_t)i * kC + c] = g / (float)rows_per_group;
+  __shared__ int is_last;
+  if (c == 0) {
+    const float loss = (shift2 + log2f(Z) - pos2) * kLn2;
+    // row_loss[i] = loss, row_loss[M + i] = #negatives above the positive
+    row_loss[i] = loss;
+    row_loss[M + i] = cnt;
+    __threadfence();
+    unsigned *counter = reinterpret_cast<unsigned *>(acc + kC + 2);
+    const unsigned done = atomicAdd(counter, 1u);
+    is_last = (done == (unsigned)M - 1u);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int n_groups = M / rows_per_group;
+  volatile const float *rl = row_loss;
+  for (int gidx = c; gidx < n_groups; gidx += 128) {
+    float sl = 0.f, s1 = 0.f, s5 = 0.f;
+    for (int r = 0; r < rows_per_group; ++r) {
+      const int row = gidx * rows_per_group + r;
+      sl += rl[row];
+      const float k = rl[M + row];
+      s1 += (k < 1.f) ? 1.f : 0.f;
+      s5 += (k < 5.f) ? 1.f : 0.f;
+    }
+    const float inv = 1.0f / (float)rows_per_group;
+    group_out[gidx * 4 + 0] = sl * inv;
+    group_out[gidx * 4 + 1] = s1 * inv;
+    group_out[gidx * 4 + 2] = s5 * inv;
+    group_out[gidx * 4 + 3] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+infonce_bwd_kernel(const float *__restrict__ dq_unit, const float *__restrict__ gout, int M,
+                   int rows_per_group, float *__restrict__ dq) {
+  const int i = blockIdx.x, c = threadIdx.x;
+  dq[(int64_t)i * kC + c] = dq_unit[(int64_t)i * kC + c] * __ldg(gout + i / rows_per_group);
+}
+
+}  // namespace mscl
+
+extern "C" {
+
+int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
+                      const int32_t *d_birth, const int64_t *d_qstate, int64_t K_local,
+                      float inv_T, float key_norm_bound, float *d_qpack, float *d_dscale,
+                      float *d_acc, int32_t M_acc, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_q && d_kpos && d_birth && d_qstate && d_qpack && d_dscale && d_acc,
+                 "null pointer");
+  MSCL_CHECK_ARG(M > 0 && M_acc >= M && K_local > 0, "bad M=%d M_acc=%d K_local=%lld", M, M_acc,
+                 (long long)K_local);
+  MSCL_CHECK_ARG(inv_T > 0.f && key_norm_bound > 0.f, "bad inv_T / key_norm_bound");
+  MSCL_CHECK_ARG((((uintptr_t)d_q | (uintptr_t)d_kpos | (uintptr_t)d_qpack | (uintptr_t)d_acc) & 15) == 0,
+                 "q/kpos/qpack/acc must be 16-byte aligned");
+  int64_t want = (K_local + 255) / 256;
+  const int64_t want_acc = ((int64_t)M_acc * (MSCL_PACK_LD / 4) + 255) / 256;
+  if (want_acc > want) want = want_acc;
+  if ((M + 7) / 8 > want) want = (M + 7) / 8;
+  if (want > 1184) want = 1184;
+  mscl::infonce_prep_kernel<<<(unsigned)want, 256, 0, mscl::as_stream(stream)>>>(
+      d_q, d_kpos, M, d_birth, d_qstate, K_local, inv_T, key_norm_bound, d_qpack, d_dscale,
+      d_acc, M_acc);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+int mscl_infonce_partial_simt(const float *d_qpack, int32_t M, const float *d_queue,
+                              const float *d_dscale, int64_t K_local, float *d_acc,
+                              int32_t with_grad, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_qpack && d_queue && d_dscale && d_acc, "null pointer");
+  MSCL_CHECK_ARG(M > 0 && K_local > 0, "bad M=%d K_local=%lld", M, (long long)K_local);
+  const size_t smem = sizeof(float) * (mscl::kSimtKeys * 129 + mscl::kC + mscl::kSimtKeys + 8);
+  MSCL_CUDA(cudaFuncSetAttribute(mscl::infonce_partial_simt_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = (K_local + mscl::kSimtKeys - 1) / mscl::kSimtKeys;
+  mscl::infonce_partial_simt_kernel<<<(unsigned)blocks, 128, smem, mscl::as_stream(stream)>>>(
+      d_qpack, M, d_queue, d_dscale, K_local, d_acc, with_grad);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+int mscl_infonce_finalize(const float *d_qpack, const float *d_kpos, float *d_acc,
+                          int32_t M, int32_t rows_per_group, float inv_T, float *d_row_loss,
+                          float *d_dq_unit, float *d_group_out, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_qpack && d_kpos && d_acc && d_row_loss && d_dq_unit && d_group_out,
+                 "null pointer");
+  MSCL_CHECK_ARG(M > 0 && rows_per_group > 0 && M % rows_per_group == 0,
+                 "M=%d must be a multiple of rows_per_group=%d", M, rows_per_group);
+  mscl::infonce_finalize_kernel<<<M, 128, 0, mscl::as_stream(stream)>>>(
+      d_qpack, d_kpos, d_acc, M, rows_per_group, inv_T, d_row_loss,
+      d_dq_unit, d_group_out);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+int mscl_infonce_bwd(const float *d_dq_unit, const float *d_gout, int32_t M,
+                     int32_t rows_per_group, float *d_dq, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_dq_unit && d_gout && d_dq, "null pointer");
+  MSCL_CHECK_ARG(M > 0 && rows_per_group > 0 && M % rows_per_group == 0,
+                 "M=%d must be a multiple of rows_per_group=%d", M, rows_per_group);
+  mscl::infonce_bwd_kernel<<<M, 128, 0, mscl::as_stream(stream)>>>(d_dq_unit, d_gout, M,
+                                                                  rows_per_group, d_dq);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+}  // extern "C"

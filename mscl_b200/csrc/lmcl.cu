@@ -1,0 +1,263 @@
+// K2: LMCL frame-level RGB-vs-flow contrast
+// (mmaction/models/heads/local_cl_head.py:57-73 forward, :41-55 loss).
+//
+//  hw_mean_fwd/bwd : the AdaptiveAvgPool3d((None,1,1)) over H*W.  This is where the
+//                    bytes are (51 MB for the r18 config's q_mlvl[0]); one warp per
+//                    (n,c,t) row, 128-bit streaming loads, HBM-bound.
+//  lmcl            : per clip, on the pooled (C,t) / (C,2t) matrices: L2-normalise
+//                    over C, t x 2t similarities / T, cross-entropy against the
+//                    diagonal, top-1/5, and the full backward to the pooled
+//                    features -- all in one launch, one CTA per clip, everything in
+//                    shared memory.  Launch-latency bound (KFLOPs of work).
+#include "common.cuh"
+
+namespace mscl {
+
+__global__ void __launch_bounds__(256)
+hw_mean_fwd_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t R, int HW,
+                   float inv_hw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const float *p = x + row * HW;
+  float acc = 0.f;
+  if ((HW & 3) == 0 && (((uintptr_t)p) & 15) == 0) {
+    const float4 *p4 = reinterpret_cast<const float4 *>(p);
+    const int nv = HW >> 2;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int v = lane;
+    for (; v + 96 < nv; v += 128) {
+      const float4 f0 = ldg_stream(p4 + v), f1 = ldg_stream(p4 + v + 32),
+                   f2 = ldg_stream(p4 + v + 64), f3 = ldg_stream(p4 + v + 96);
+      a0 += (f0.x + f0.y) + (f0.z + f0.w);
+      a1 += (f1.x + f1.y) + (f1.z + f1.w);
+      a2 += (f2.x + f2.y) + (f2.z + f2.w);
+      a3 += (f3.x + f3.y) + (f3.z + f3.w);
+    }
+    for (; v < nv; v += 32) {
+      const float4 f0 = ldg_stream(p4 + v);
+      a0 += (f0.x + f0.y) + (f0.z + f0.w);
+    }
+    acc = (a0 + a1) + (a2 + a3);
+  } else {
+    for (int i = lane; i < HW; i += 32) acc += __ldg(p + i);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc * inv_hw;
+}
+
+__global__ void __launch_bounds__(256)
+hw_mean_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gx, int64_t R, int HW,
+                   float inv_hw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const float g = __ldg(gout + row) * inv_hw;
+  float *p = gx + row * HW;
+  if ((HW & 3) == 0 && (((uintptr_t)p) & 15) == 0) {
+    const float4 g4 = make_float4(g, g, g, g);
+    float4 *p4 = reinterpret_cast<float4 *>(p);
+    for (int v = lane; v < (HW >> 2); v += 32) stg_stream(p4 + v, g4);
+  } else {
+    for (int i = lane; i < HW; i += 32) p[i] = g;
+  }
+}
+
+// One CTA (256 threads) per clip.
+// smem floats: y[C*tt] | dy[C*tt] | sim[t*t2] | nrm[tt] | dot[tt] | red[8*3]   with tt = t + t2
+// Columns 0..t-1 of y are the RGB frames, t..tt-1 the flow frames (base then FRA).
+__global__ void __launch_bounds__(256)
+lmcl_kernel(const float *__restrict__ xq, const float *__restrict__ xf, int N, int C, int t,
+            int t2, float inv_T, float *__restrict__ out, float *__restrict__ gxq,
+            float *__restrict__ gxf, float *__restrict__ part) {
+  extern __shared__ float sm[];
+  const int tt = t + t2;
+  float *y = sm;
+  float *dy = y + C * tt;
+  float *sim = dy + C * tt;
+  float *nrm = sim + t * t2;
+  float *dot = nrm + tt;
+  float *red = dot + tt;
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *xq_n = xq + (int64_t)n * C * t;
+  const float *xf_n = xf + (int64_t)n * C * t2;
+
+  // 1. stage: y[c*tt + col]
+  for (int i = tid; i < C * t; i += 256) {
+    const int c = i / t, col = i - c * t;
+    y[c * tt + col] = __ldg(xq_n + i);
+  }
+  for (int i = tid; i < C * t2; i += 256) {
+    const int c = i / t2, col = i - c * t2;
+    y[c * tt + t + col] = __ldg(xf_n + i);
+  }
+  __syncthreads();
+  // 2. column norms (F.normalize: x / max(||x||_2, 1e-12))
+  for (int col = warp; col < tt; col += 8) {
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = y[c * tt + col];
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) nrm[col] = fmaxf(sqrtf(ss), 1e-12f);
+  }
+  __syncthreads();
+  for (int i = tid; i < C * tt; i += 256) y[i] = __fdiv_rn(y[i], nrm[i % tt]);
+  __syncthreads();
+  // 3. similarities / T
+  for (int ij = tid; ij < t * t2; ij += 256) {
+    const int i = ij / t2, j = ij - i * t2;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(y[c * tt + i], y[c * tt + t + j], acc);
+    sim[ij] = acc * inv_T;
+  }
+  __syncthreads();
+  // 4. per-row cross-entropy against column i; sim <- d loss / d sim (unit upstream)
+  float l_loss = 0.f, l_t1 = 0.f, l_t5 = 0.f;
+  const float gscale = inv_T / (float)(N * t);
+  for (int i = warp; i < t; i += 8) {
+    const float spos = sim[i * t2 + i];
+    float mx = -INFINITY;
+    for (int j = lane; j < t2; j += 32) mx = fmaxf(mx, sim[i * t2 + j]);
+    mx = warp_max(mx);
+    float se = 0.f, cnt = 0.f;
+    for (int j = lane; j < t2; j += 32) {
+      const float s = sim[i * t2 + j];
+      se += __expf(s - mx);
+      cnt += (j != i && s > spos) ? 1.f : 0.f;
+    }
+    se = warp_sum(se);
+    cnt = warp_sum(cnt);
+    const float lse = mx + __logf(se);
+    for (int j = lane; j < t2; j += 32) {
+      const float p = __expf(sim[i * t2 + j] - lse);
+      sim[i * t2 + j] = (p - (j == i ? 1.f : 0.f)) * gscale;
+    }
+    if (lane == 0) {
+      l_loss += lse - spos;
+      l_t1 += (cnt < 1.f) ? 1.f : 0.f;
+      l_t5 += (cnt < 5.f) ? 1.f : 0.f;
+    }
+  }
+  if (lane == 0) {
+    red[warp * 3 + 0] = l_loss;
+    red[warp * 3 + 1] = l_t1;
+    red[warp * 3 + 2] = l_t5;
+  }
+  __syncthreads();
+  // 5. dy = d loss / d y
+  for (int i = tid; i < C * tt; i += 256) {
+    const int c = i / tt, col = i - c * tt;
+    float acc = 0.f;
+    if (col < t) {
+      for (int j = 0; j < t2; ++j) acc = fmaf(sim[col * t2 + j], y[c * tt + t + j], acc);
+    } else {
+      const int j = col - t;
+      for (int r = 0; r < t; ++r) acc = fmaf(sim[r * t2 + j], y[c * tt + r], acc);
+    }
+    dy[i] = acc;
+  }
+  __syncthreads();
+  // 6. back through the normalisation: dx = (dy - y (y . dy)) / ||x||
+  for (int col = warp; col < tt; col += 8) {
+    float d = 0.f;
+    for (int c = lane; c < C; c += 32) d = fmaf(y[c * tt + col], dy[c * tt + col], d);
+    d = warp_sum(d);
+    if (lane == 0) dot[col] = d;
+  }
+  __syncthreads();
+  float *gq_n = gxq + (int64_t)n * C * t;
+  float *gf_n = gxf + (int64_t)n * C * t2;
+  for (int i = tid; i < C * tt; i += 256) {
+    const int c = i / tt, col = i - c * tt;
+    const float g = (dy[i] - y[i] * dot[col]) / nrm[col];
+    if (col < t)
+      gq_n[c * t + col] = g;
+    else
+      gf_n[c * t2 + (col - t)] = g;
+  }
+  // 7. per-clip partials, last CTA reduces in clip order (deterministic)
+  if (tid == 0) {
+    float a = 0.f, b = 0.f, c5 = 0.f;
+    for (int w = 0; w < 8; ++w) {
+      a += red[w * 3 + 0];
+      b += red[w * 3 + 1];
+      c5 += red[w * 3 + 2];
+    }
+    part[n * 4 + 0] = a;
+    part[n * 4 + 1] = b;
+    part[n * 4 + 2] = c5;
+    __threadfence();
+    unsigned *counter = reinterpret_cast<unsigned *>(part + (int64_t)N * 4);
+    const unsigned done = atomicAdd(counter, 1u);
+    if (done == (unsigned)N - 1u) {
+      __threadfence();
+      float sl = 0.f, s1 = 0.f, s5 = 0.f;
+      volatile float *vp = part;
+      for (int k = 0; k < N; ++k) {
+        sl += vp[k * 4 + 0];
+        s1 += vp[k * 4 + 1];
+        s5 += vp[k * 4 + 2];
+      }
+      const float inv = 1.f / (float)(N * t);
+      out[0] = sl * inv;
+      out[1] = s1 * inv;
+      out[2] = s5 * inv;
+      out[3] = 0.f;
+      *counter = 0u;
+    }
+  }
+}
+
+}  // namespace mscl
+
+extern "C" {
+
+int mscl_hw_mean_fwd(const float *d_x, float *d_out, int64_t R, int32_t HW,
+                     mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_x && d_out, "null pointer");
+  MSCL_CHECK_ARG(R > 0 && HW > 0, "bad R=%lld HW=%d", (long long)R, HW);
+  const int64_t blocks = (R + 7) / 8;
+  MSCL_CHECK_ARG(blocks < (1ll << 31), "too many rows");
+  mscl::hw_mean_fwd_kernel<<<(unsigned)blocks, 256, 0, mscl::as_stream(stream)>>>(
+      d_x, d_out, R, HW, 1.0f / (float)HW);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+int mscl_hw_mean_bwd(const float *d_gout, float *d_gx, int64_t R, int32_t HW,
+                     mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_gout && d_gx, "null pointer");
+  MSCL_CHECK_ARG(R > 0 && HW > 0, "bad R=%lld HW=%d", (long long)R, HW);
+  const int64_t blocks = (R + 7) / 8;
+  MSCL_CHECK_ARG(blocks < (1ll << 31), "too many rows");
+  mscl::hw_mean_bwd_kernel<<<(unsigned)blocks, 256, 0, mscl::as_stream(stream)>>>(
+      d_gout, d_gx, R, HW, 1.0f / (float)HW);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+int mscl_lmcl(const float *d_xq, const float *d_xf, int32_t N, int32_t C, int32_t t,
+              int32_t t2, float inv_T, float *d_out, float *d_gxq, float *d_gxf,
+              float *d_part, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_xq && d_xf && d_out && d_gxq && d_gxf && d_part, "null pointer");
+  MSCL_CHECK_ARG(N > 0 && C > 0 && t > 0 && t2 >= t, "bad N=%d C=%d t=%d t2=%d", N, C, t, t2);
+  const int tt = t + t2;
+  const size_t smem = sizeof(float) * ((size_t)2 * C * tt + (size_t)t * t2 + 2 * tt + 24);
+  MSCL_CHECK_ARG(smem <= 200 * 1024, "C*(t+t2) too large for one CTA (%zu B of shared memory)",
+                 smem);
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    MSCL_CUDA(cudaFuncSetAttribute(mscl::lmcl_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  mscl::lmcl_kernel<<<N, 256, smem, mscl::as_stream(stream)>>>(d_xq, d_xf, N, C, t, t2, inv_T,
+                                                              d_out, d_gxq, d_gxf, d_part);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+}  // extern "C"
