@@ -1,0 +1,138 @@
+"""The oracle (oracle/mscl_oracle.py) against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py through oracle/ref_shim.py) and against the reference's own
+known-answer test for top_k_accuracy.  CPU only."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import inputs, mscl_oracle as O
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _run_oracle_head(inp, t):
+    leaves = {n: inp[n].clone().requires_grad_(True) for n in ("q", "q_f", "q_af", "q_map", "qf_map", "qaf_map")}
+    feats = dict(k=inp["k"], k_f=inp["k_f"], k_af=inp["k_af"], **leaves)
+    rgb = O.QueueState(inp["queue_rgb"], inp["count"], inp["ptr"])
+    flow = O.QueueState(inp["queue_flow"], inp["count"], inp["ptr"])
+    losses = O.mscl_objective(feats, rgb, flow, T=0.07, t=t)
+    loss, log_vars = O.parse_losses(losses)
+    loss.backward()
+    return log_vars, leaves, rgb, flow
+
+
+def _check_head(g, inp, t, full_queue):
+    log_vars, leaves, rgb, flow = _run_oracle_head(inp, t)
+    assert list(log_vars.keys()) == [str(k) for k in g["logvar_order"]]
+    for k, v in log_vars.items():
+        ref = float(g[f"logvar/{k}"])
+        assert abs(v - ref) <= 1e-6 * max(1.0, abs(ref)), (k, v, ref)
+    for n in ("q", "q_f", "q_af"):
+        np.testing.assert_allclose(leaves[n].grad.numpy(), g[f"grad/{n}"], rtol=1e-5, atol=1e-7)
+    for n in ("q_map", "qf_map", "qaf_map"):
+        np.testing.assert_allclose(leaves[n].grad.sum(dim=(-2, -1)).numpy(), g[f"gradsum/{n}"], rtol=1e-4, atol=1e-7)
+    for tag, st in (("rgb", rgb), ("flow", flow)):
+        assert st.ptr == int(g[f"after/{tag}/ptr"][0])
+        np.testing.assert_array_equal(st.count.numpy(), g[f"after/{tag}/count"])
+        assert st.iters == int(g[f"after/{tag}/iters"])
+        assert st.batch_size == int(g[f"after/{tag}/batch_size"])
+        if full_queue:
+            np.testing.assert_array_equal(st.queue.numpy(), g[f"after/{tag}/queue"])
+        else:
+            assert inputs.digest(st.queue) == str(g[f"after/{tag}/queue_digest"])
+
+
+def test_head_small_matches_reference(golden_dir):
+    g = _load(golden_dir, "head_small.npz")
+    inp = {k[3:]: (torch.from_numpy(g[k]) if g[k].ndim else int(g[k])) for k in g.files if k.startswith("in/")}
+    _check_head(g, inp, 4, True)
+
+
+def test_head_cfg1_matches_reference(golden_dir):
+    """BASELINE config 1: N=8, C=128, K=4096, t=8 -- inputs regenerated from the seed."""
+    g = _load(golden_dir, "head_cfg1.npz")
+    kw = eval(str(g["kwargs"]))
+    inp = inputs.head_inputs(**kw)
+    assert inputs.digest(*[inp[k] for k in sorted(inp) if isinstance(inp[k], torch.Tensor)]) == str(g["input_digest"]), \
+        "torch CPU RNG stream differs from the build that generated the fixture"
+    _check_head(g, inp, kw["t"], False)
+
+
+def test_flow_iters_advance_twice(golden_dir):
+    """the flow recognizer sees two forward_train calls per step."""
+    g = _load(golden_dir, "head_small.npz")
+    assert int(g["after/flow/iters"]) == 2 * int(g["after/rgb/iters"]) == 8
+
+
+def test_enqueue_sequence(golden_dir):
+    g = _load(golden_dir, "enqueue_seq.npz")
+    queue = torch.from_numpy(g["queue0"]).clone()
+    count = torch.zeros(queue.shape[1], dtype=torch.long)
+    ptr = 0
+    for s in range(g["keys"].shape[0]):
+        ptr = O.enqueue(queue, count, ptr, torch.from_numpy(g["keys"][s]))
+        assert ptr == int(g["ptrs"][s])
+    np.testing.assert_array_equal(queue.numpy(), g["queue"])
+    np.testing.assert_array_equal(count.numpy(), g["count"])
+    np.testing.assert_array_equal(O.decayed_weight(queue, count).numpy(), g["weight"])
+
+
+def test_ema(golden_dir):
+    g = _load(golden_dir, "ema.npz")
+    names = [str(n) for n in g["names"]]
+    ks = [torch.from_numpy(g[f"k0/{n}"]) for n in names]
+    qs = [torch.from_numpy(g[f"q/{n}"]) for n in names]
+    for step, it in enumerate(g["iters"]):
+        m = O.momentum(int(it), 1000, 0.994)
+        assert m == float(g["m"][step])
+        ks = O.ema_update(ks, qs, m)
+        for n, k in zip(names, ks):
+            np.testing.assert_array_equal(k.numpy(), g[f"k{step + 1}/{n}"])
+
+
+def test_fra(golden_dir):
+    g = _load(golden_dir, "fra.npz")
+    for i in range(2):
+        flows = [f for f in g[f"in{i}"]]
+        out = np.stack(O.fra(flows, int(g[f"cid{i}"])))
+        assert out.dtype == np.float32
+        # the fixture ran under NumPy 2 (float64 rotation); the oracle restates the float32 path
+        np.testing.assert_allclose(out, g[f"out{i}"], rtol=2e-6, atol=2e-7)
+        T = len(flows)
+        np.testing.assert_array_equal(out[:T], g[f"out{i}"][:T].astype(np.float32))   # base frames: exact
+
+
+def test_shuffle(golden_dir):
+    g = _load(golden_dir, "shuffle.npz")
+    for seed, b in ((0, 32), (0, 128), (1234, 256)):
+        torch.manual_seed(seed)
+        np.testing.assert_array_equal(torch.randperm(b).numpy(), g[f"perm_seed{seed}_b{b}"])
+        np.testing.assert_array_equal(torch.randperm(b).numpy(), g[f"perm2_seed{seed}_b{b}"])
+    torch.manual_seed(5)
+    x = torch.from_numpy(g["x"])
+    idx = torch.randperm(x.shape[0])
+    xs, unshuf = O.batch_shuffle(x, idx, 0, 1)
+    np.testing.assert_array_equal(xs.numpy(), g["x_shuffled"])
+    np.testing.assert_array_equal(unshuf.numpy(), g["idx_unshuffle"])
+    np.testing.assert_array_equal(O.batch_unshuffle(xs, unshuf, 0, 1).numpy(), g["x_restored"])
+
+
+def test_topk_known_answers():
+    """Vectors of the reference's tests/test_metrics/test_accuracy.py:118-163."""
+    scores = [np.array([-0.2203, -0.7538, 1.8789, 0.4451, -0.2526]),
+              np.array([-0.0413, 0.6366, 1.1155, 0.3484, 0.0395]),
+              np.array([0.0365, 0.5158, 1.1067, -0.9276, -0.2124]),
+              np.array([0.6232, 0.9912, -0.8562, 0.0148, 1.6413])]
+    assert O.top_k_accuracy(scores, [3, 1, 1, 1], (1,)) == [0]
+    assert O.top_k_accuracy(scores, [2, 0, 4, 3], (1,)) == [0.25]
+    assert O.top_k_accuracy(scores, [2, 2, 3, 1], (1,)) == [0.5]
+    assert O.top_k_accuracy(scores, [2, 2, 2, 3], (1,)) == [0.75]
+    assert O.top_k_accuracy(scores, [2, 2, 2, 4], (1,)) == [1.0]
+    assert O.top_k_accuracy(scores, [3, 1, 1, 1], (1, 2)) == [0, 1.0]
+    assert O.top_k_accuracy(scores, [3, 1, 2, 3], (1, 2)) == [0.25, 0.75]
+    assert O.top_k_accuracy(scores, [1, 0, 3, 2], (1, 3, 5)) == [0, 0, 1.0]
+    assert O.top_k_accuracy(scores, [1, 3, 4, 0], (1, 3, 5)) == [0, 0.5, 1.0]
+    assert O.top_k_accuracy(scores, [2, 3, 0, 2], (1, 3, 5)) == [0.25, 0.75, 1.0]
