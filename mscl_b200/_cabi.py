@@ -1,0 +1,100 @@
+"""ctypes binding of libmscl_b200.so -- the C-ABI declared in include/mscl_b200.h.
+
+There is NO fallback: if the library is missing, fails to load, or the device is not
+sm_100, every op raises.  Build it with `python -m mscl_b200.build` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmscl_b200.so")
+
+c_int = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_f32 = ctypes.c_float
+c_ptr = ctypes.c_void_p
+
+# name -> argtypes; every entry point returns int (0 = ok).  Mirrors include/mscl_b200.h.
+PROTOTYPES = {
+    "mscl_device_check": [c_int],
+    "mscl_enqueue": [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
+    "mscl_queue_export": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr],
+    "mscl_queue_import": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr],
+    "mscl_queue_weight": [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr],
+    "mscl_ema_multi": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_f32, c_f32, c_ptr],
+    "mscl_fra_maxrad": [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
+    "mscl_fra_apply": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
+    "mscl_fra_rotate": [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr],
+    "mscl_hw_mean_fwd": [c_ptr, c_ptr, c_i64, c_int, c_ptr],
+    "mscl_hw_mean_bwd": [c_ptr, c_ptr, c_i64, c_int, c_ptr],
+    "mscl_lmcl": [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "mscl_infonce_prep": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_int, c_ptr],
+    "mscl_infonce_partial": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_int, c_int, c_ptr],
+    "mscl_infonce_partial_simt": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_int, c_ptr],
+    "mscl_infonce_finalize": [c_ptr, c_ptr, c_ptr, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr],
+    "mscl_infonce_bwd": [c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr],
+    "mscl_gather_rows": [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr],
+}
+EXPORTS = ["mscl_abi_version", "mscl_last_error"] + list(PROTOTYPES)
+
+_lock = threading.Lock()
+_lib = None
+_launches = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+# how many device kernels one successful call enqueues
+_LAUNCHES_PER_CALL = {"mscl_device_check": 0}
+
+
+class MsclError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once). Raises MsclError with a build hint when absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise MsclError(
+                f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+                "Build it with `python -m mscl_b200.build`.")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.mscl_abi_version.restype = c_int
+        lib.mscl_last_error.restype = ctypes.c_char_p
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = c_int
+        if lib.mscl_abi_version() != 1:
+            raise MsclError(f"ABI version mismatch: library reports {lib.mscl_abi_version()}")
+        _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    """Invoke an entry point; raise MsclError carrying mscl_last_error() on failure."""
+    global _launches
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.mscl_last_error()
+        raise MsclError(f"{name} failed ({rc}): {msg.decode() if msg else ''}")
+    _launches += _LAUNCHES_PER_CALL.get(name, 1)
+
+
+def launches():
+    return _launches
+
+
+_checked_devices = set()
+
+
+def require_device(index):
+    """Fail loudly unless CUDA device `index` is sm_100 (B200)."""
+    if index in _checked_devices:
+        return
+    call("mscl_device_check", int(index))
+    _checked_devices.add(index)

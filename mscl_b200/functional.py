@@ -1,0 +1,370 @@
+"""PyTorch-facing ops of the MSCL contrastive hot path.
+
+Each op takes CUDA fp32 tensors, hands raw pointers + the current stream to the C-ABI
+(include/mscl_b200.h) and returns tensors; the differentiable ones are
+torch.autograd.Functions.  PyTorch is plumbing here (memory, streams, autograd graph,
+torch.distributed); all arithmetic on the path runs in the sm_100a kernels.  There is
+no CPU path: a non-CUDA tensor or a missing library raises.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+
+DIM = 128          # MSCL_DIM
+PACK_LD = 132      # MSCL_PACK_LD
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype=torch.float32, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _cabi.MsclError(f"{name} must be a CUDA tensor (the MSCL hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _cabi.MsclError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _cabi.MsclError(f"{name} must be contiguous")
+    _cabi.require_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    return t
+
+
+_SM_COUNT = {}
+
+
+def sm_count(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
+# ----------------------------------------------------------------------------------------
+# K5: the negative queue
+# ----------------------------------------------------------------------------------------
+class NegativeQueue:
+    """Device-resident ring buffer of negatives with implicit ages.
+
+    Replaces the reference's `queue` (C,K) fp32 / `queue_ptr` / `count` buffers
+    (mmaction/models/recognizers/moco.py:390-396) on the hot path.  Layout: key-major
+    fp32 [K_local, C]; ages as int32 `birth` with count = n_enq - birth; `qstate`
+    int64[4] = {ptr, n_enq, counter, 0} lives on the device so no call ever syncs.
+    With world_size G > 1 and shard=True each rank owns K/G consecutive slots.
+    """
+
+    def __init__(self, K, C=DIM, device="cuda", rank=0, world=1, shard=False):
+        if C != DIM:
+            raise _cabi.MsclError(f"feature dim must be {DIM}")
+        self.K, self.C = int(K), int(C)
+        self.world = world if shard else 1
+        self.rank = rank if shard else 0
+        if self.K % self.world:
+            raise _cabi.MsclError(f"K={K} is not divisible by the number of shards {self.world}")
+        self.K_local = self.K // self.world
+        self.shard_begin = self.rank * self.K_local
+        self.device = torch.device(device)
+        self.queue = torch.zeros(self.K_local, C, device=self.device)
+        self.birth = torch.zeros(self.K_local, dtype=torch.int32, device=self.device)
+        self.qstate = torch.zeros(4, dtype=torch.int64, device=self.device)
+        self.ptr = 0          # host mirrors (deterministic, never read back from the device)
+        self.n_enq = 0
+        self.max_key_norm = 1.0
+
+    # -- reference-layout import / export (state_dict compatibility) --
+    def load(self, queue_ck, count, ptr):
+        """queue_ck: (C, K) fp32 full queue, count: (K,) int64, ptr: int (moco.py:390-396)."""
+        queue_ck = queue_ck.to(self.device, torch.float32)
+        count = count.to(self.device, torch.int64)
+        sl = slice(self.shard_begin, self.shard_begin + self.K_local)
+        q_loc = queue_ck[:, sl].contiguous()
+        c_loc = count[sl].contiguous()
+        self.n_enq = int(count.max().item()) if count.numel() else 0
+        self.ptr = int(ptr)
+        self.qstate.copy_(torch.tensor([self.ptr, self.n_enq, 0, 0], dtype=torch.int64))
+        self.max_key_norm = max(1.0, float(queue_ck.norm(dim=0).max().item()))
+        _cabi.call("mscl_queue_import", self.queue.data_ptr(), self.birth.data_ptr(), self.qstate.data_ptr(),
+                   q_loc.data_ptr(), c_loc.data_ptr(), self.C, self.K_local, _stream())
+        # keep the staging tensors alive until the kernel has consumed them
+        torch.cuda.current_stream().synchronize()
+
+    def export(self):
+        """Return (queue_ck (C,K_local), count (K_local,) int64) of this shard."""
+        q = torch.empty(self.C, self.K_local, device=self.device)
+        c = torch.empty(self.K_local, dtype=torch.int64, device=self.device)
+        _cabi.call("mscl_queue_export", self.queue.data_ptr(), self.birth.data_ptr(), self.qstate.data_ptr(),
+                   q.data_ptr(), c.data_ptr(), self.C, self.K_local, _stream())
+        return q, c
+
+    def weight(self):
+        """Decayed snapshot (C, K_local) = queue * 0.99999**count (moco.py:484-486)."""
+        w = torch.empty(self.C, self.K_local, device=self.device)
+        _cabi.call("mscl_queue_weight", self.queue.data_ptr(), self.birth.data_ptr(), self.qstate.data_ptr(),
+                   w.data_ptr(), self.C, self.K_local, _stream())
+        return w
+
+    @torch.no_grad()
+    def enqueue(self, keys_all):
+        """keys_all: (B_all, C) rank-major gathered keys (moco.py:423-440)."""
+        _chk(keys_all, name="keys")
+        b = keys_all.shape[0]
+        if self.K % b != 0:
+            raise AssertionError(f"K={self.K} must be a multiple of the gathered batch size {b}")  # moco.py:432
+        if self.ptr + b > self.K:
+            raise _cabi.MsclError("queue pointer is not aligned to the batch size (batch size changed mid-cycle)")
+        _cabi.call("mscl_enqueue", self.queue.data_ptr(), self.birth.data_ptr(), self.qstate.data_ptr(),
+                   keys_all.data_ptr(), b, self.C, self.K, self.shard_begin, self.K_local, None, None, _stream())
+        self.ptr = (self.ptr + b) % self.K
+        self.n_enq += 1
+
+
+# ----------------------------------------------------------------------------------------
+# K1: fused InfoNCE
+# ----------------------------------------------------------------------------------------
+class _InfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, kpos, nq, rows_per_group, inv_T, impl, group):
+        M = q.shape[0]
+        dev = q.device
+        st = _stream()
+        world = dist.get_world_size(group) if (group is not None and nq.world > 1) else 1
+        M_all = M * world
+        qpack = torch.empty(M, PACK_LD, device=dev)
+        k_pad = (nq.K_local + 63) // 64 * 64
+        dscale = torch.empty(k_pad, device=dev)
+        acc = torch.empty(M_all, PACK_LD, device=dev)
+        need_grad = bool(ctx.needs_input_grad[0])
+        _cabi.call("mscl_infonce_prep", q.data_ptr(), kpos.data_ptr(), M, nq.birth.data_ptr(), nq.qstate.data_ptr(),
+                   nq.K_local, inv_T, nq.max_key_norm, qpack.data_ptr(), dscale.data_ptr(), acc.data_ptr(), M_all, st)
+        if world > 1:
+            qpack_all = torch.empty(M_all, PACK_LD, device=dev)
+            dist.all_gather_into_tensor(qpack_all, qpack, group=group)
+        else:
+            qpack_all = qpack
+        if impl == "simt":
+            _cabi.call("mscl_infonce_partial_simt", qpack_all.data_ptr(), M_all, nq.queue.data_ptr(), dscale.data_ptr(),
+                       nq.K_local, acc.data_ptr(), int(need_grad), st)
+        else:
+            _cabi.call("mscl_infonce_partial", qpack_all.data_ptr(), M_all, nq.queue.data_ptr(), dscale.data_ptr(),
+                       nq.K_local, acc.data_ptr(), int(need_grad), sm_count(dev), st)
+        if world > 1:
+            acc_local = torch.empty(M, PACK_LD, device=dev)
+            dist.reduce_scatter_tensor(acc_local, acc, op=dist.ReduceOp.SUM, group=group)
+        else:
+            acc_local = acc
+        n_groups = M // rows_per_group
+        row_loss = torch.empty(2 * M, device=dev)
+        dq_unit = torch.empty(M, DIM, device=dev)
+        group_out = torch.empty(n_groups, 4, device=dev)
+        _cabi.call("mscl_infonce_finalize", qpack.data_ptr(), kpos.data_ptr(), acc_local.data_ptr(), M, rows_per_group,
+                   inv_T, row_loss.data_ptr(), dq_unit.data_ptr(), group_out.data_ptr(), st)
+        ctx.save_for_backward(dq_unit)
+        ctx.rows_per_group = rows_per_group
+        ctx.mark_non_differentiable(row_loss)
+        return group_out, row_loss
+
+    @staticmethod
+    def backward(ctx, g_group, _g_rows):
+        (dq_unit,) = ctx.saved_tensors
+        M = dq_unit.shape[0]
+        gout = g_group[:, 0].contiguous()
+        dq = torch.empty_like(dq_unit)
+        _cabi.call("mscl_infonce_bwd", dq_unit.data_ptr(), gout.data_ptr(), M, ctx.rows_per_group, dq.data_ptr(), _stream())
+        return dq, None, None, None, None, None, None
+
+
+def infonce(q, kpos, nq, rows_per_group, T, impl="tc", group=None):
+    """Fused InfoNCE over the queue `nq`.
+
+    q, kpos: (M, 128) stacked query rows and the positive key of each row; consecutive
+    blocks of rows_per_group rows form one loss term (one "head call" of the reference).
+    Returns (group_out (M/rows_per_group, 4) = [loss, top1, top5, 0], row_stats (2M,)).
+    Gradient flows to q only (keys and queue are detached in the reference, moco.py:486,532).
+    """
+    _chk(q, name="q"), _chk(kpos, name="kpos")
+    if q.dim() != 2 or q.shape[1] != DIM or kpos.shape != q.shape:
+        raise _cabi.MsclError(f"q and kpos must both be (M, {DIM}); got {tuple(q.shape)} and {tuple(kpos.shape)}")
+    if q.shape[0] % rows_per_group:
+        raise _cabi.MsclError("number of rows must be a multiple of rows_per_group")
+    return _InfoNCE.apply(q, kpos.detach(), nq, int(rows_per_group), float(1.0 / T), impl, group)
+
+
+# ----------------------------------------------------------------------------------------
+# K2: LMCL
+# ----------------------------------------------------------------------------------------
+class _HWMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        shape = x.shape
+        HW = shape[-1] * shape[-2]
+        R = x.numel() // HW
+        out = torch.empty(shape[:-2], device=x.device)
+        _cabi.call("mscl_hw_mean_fwd", x.data_ptr(), out.data_ptr(), R, HW, _stream())
+        ctx.shape = shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        shape = ctx.shape
+        HW = shape[-1] * shape[-2]
+        gx = torch.empty(shape, device=g.device)
+        _cabi.call("mscl_hw_mean_bwd", g.data_ptr(), gx.data_ptr(), g.numel(), HW, _stream())
+        return gx
+
+
+def hw_mean(x):
+    """Mean over the last two dims: AdaptiveAvgPool3d((None,1,1)).view(b,c,t) (local_cl_head.py:61-62)."""
+    _chk(x, name="feature map")
+    return _HWMean.apply(x)
+
+
+_LMCL_PART = {}
+
+
+class _LMCL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xq, xf, inv_T):
+        N, C, t = xq.shape
+        t2 = xf.shape[2]
+        dev = xq.device
+        key = (dev.index, N)
+        if key not in _LMCL_PART:
+            _LMCL_PART[key] = torch.zeros(N * 4 + 4, device=dev)
+        part = _LMCL_PART[key]
+        out = torch.empty(4, device=dev)
+        gxq = torch.empty_like(xq)
+        gxf = torch.empty_like(xf)
+        _cabi.call("mscl_lmcl", xq.data_ptr(), xf.data_ptr(), N, C, t, t2, inv_T, out.data_ptr(), gxq.data_ptr(),
+                   gxf.data_ptr(), part.data_ptr(), _stream())
+        ctx.save_for_backward(gxq, gxf)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gxq, gxf = ctx.saved_tensors
+        s = g[0]
+        return gxq * s, gxf * s, None
+
+
+def lmcl(xq, xf, T):
+    """LMCL loss on pooled features xq (N,C,t), xf (N,C,2t) -> tensor [loss, top1, top5, 0]
+    (local_cl_head.py:63-73 + :41-51)."""
+    _chk(xq, name="xq"), _chk(xf, name="xf")
+    if xq.dim() != 3 or xf.dim() != 3 or xq.shape[:2] != xf.shape[:2] or xf.shape[2] < xq.shape[2]:
+        raise _cabi.MsclError(f"bad LMCL shapes {tuple(xq.shape)} {tuple(xf.shape)}")
+    return _LMCL.apply(xq, xf, float(1.0 / T))
+
+
+# ----------------------------------------------------------------------------------------
+# K4: multi-tensor EMA
+# ----------------------------------------------------------------------------------------
+class EmaTable:
+    """Pointer tables for one launch over every (param_k, param_q) pair (moco.py:416-421)."""
+
+    CHUNK = 16384
+
+    def __init__(self, params_k, params_q):
+        self.params_k = [p for p in params_k]
+        self.params_q = [p for p in params_q]
+        if len(self.params_k) != len(self.params_q):
+            raise _cabi.MsclError("key/query parameter lists differ in length")
+        self._sig = None
+        self._build()
+
+    def _signature(self):
+        return tuple(p.data_ptr() for p in self.params_k) + tuple(p.data_ptr() for p in self.params_q)
+
+    def _build(self):
+        dev = self.params_k[0].device
+        for pk, pq in zip(self.params_k, self.params_q):
+            _chk(pk.data, name="param_k"), _chk(pq.data, name="param_q")
+            if pk.shape != pq.shape:
+                raise _cabi.MsclError("key/query parameter shapes differ")
+        sizes = [p.numel() for p in self.params_k]
+        blk_t, blk_s = [], []
+        for i, n in enumerate(sizes):
+            for s in range(0, n, self.CHUNK):
+                blk_t.append(i)
+                blk_s.append(s)
+        self.n_blocks = len(blk_t)
+        self.numel = sum(sizes)
+        self.k_ptrs = torch.tensor([p.data_ptr() for p in self.params_k], dtype=torch.int64, device=dev)
+        self.q_ptrs = torch.tensor([p.data_ptr() for p in self.params_q], dtype=torch.int64, device=dev)
+        self.sizes = torch.tensor(sizes, dtype=torch.int64, device=dev)
+        self.blk_tensor = torch.tensor(blk_t, dtype=torch.int32, device=dev)
+        self.blk_start = torch.tensor(blk_s, dtype=torch.int64, device=dev)
+        self._sig = self._signature()
+
+    @torch.no_grad()
+    def update(self, m):
+        """k <- k*m + q*(1-m) with m a python float, rounded like the reference's scalar multiply."""
+        if self._signature() != self._sig:
+            self._build()      # parameters were re-allocated (.cuda(), load_state_dict with assign, ...)
+        m32 = float(np.float32(m))
+        om32 = float(np.float32(1.0 - m))
+        _cabi.call("mscl_ema_multi", self.k_ptrs.data_ptr(), self.q_ptrs.data_ptr(), self.sizes.data_ptr(),
+                   self.blk_tensor.data_ptr(), self.blk_start.data_ptr(), self.n_blocks, self.CHUNK, m32, om32, _stream())
+
+
+# ----------------------------------------------------------------------------------------
+# K3: FRA
+# ----------------------------------------------------------------------------------------
+def fra_table(ratios=(0.2, 1.8), num_chunks=8, device="cuda"):
+    """(cos, sin) float32 pairs of beta = (start + stride*cid)*pi (transforms_motion.py:106-124)."""
+    start = ratios[0]
+    stride = (ratios[1] - ratios[0]) / num_chunks
+    tab = [[math.cos((start + stride * c) * math.pi), math.sin((start + stride * c) * math.pi)]
+           for c in range(num_chunks)]
+    return torch.tensor(np.array(tab, dtype=np.float64).astype(np.float32), device=device).contiguous()
+
+
+@torch.no_grad()
+def fra(flow, cid, table, layout="planar"):
+    """Normalised base + rotated flow.  flow: planar (N,2,T,H,W) or interleaved (N,T,H,W,2);
+    cid int32 (N,).  Returns (N,2,2T,H,W): base frames then FRA frames (transforms_motion.py:111-142)."""
+    _chk(flow, name="flow"), _chk(cid, torch.int32, "cid"), _chk(table, name="table")
+    if layout == "planar":
+        N, two, T, H, W = flow.shape
+        lay = 0
+    else:
+        N, T, H, W, two = flow.shape
+        lay = 1
+    if two != 2:
+        raise _cabi.MsclError("flow must have exactly two components (u, v)")
+    out = torch.empty(N, 2, 2 * T, H, W, device=flow.device)
+    maxrad = torch.empty(N, T, 2, device=flow.device)
+    st = _stream()
+    _cabi.call("mscl_fra_maxrad", flow.data_ptr(), cid.data_ptr(), table.data_ptr(), maxrad.data_ptr(), N, T, H * W, lay, st)
+    _cabi.call("mscl_fra_apply", flow.data_ptr(), cid.data_ptr(), table.data_ptr(), maxrad.data_ptr(), out.data_ptr(),
+               N, T, H * W, lay, st)
+    return out
+
+
+_cabi._LAUNCHES_PER_CALL["mscl_fra_maxrad"] = 2  # memset + kernel
+
+
+@torch.no_grad()
+def fra_rotate(flow, cid, table):
+    """Rotation only of an already normalised planar clip (N,2,T,H,W)."""
+    _chk(flow, name="flow"), _chk(cid, torch.int32, "cid"), _chk(table, name="table")
+    N, two, T, H, W = flow.shape
+    out = torch.empty_like(flow)
+    _cabi.call("mscl_fra_rotate", flow.data_ptr(), cid.data_ptr(), table.data_ptr(), out.data_ptr(), N, T, H * W, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# K6: row gather for shuffle-BN
+# ----------------------------------------------------------------------------------------
+@torch.no_grad()
+def gather_rows(x, idx):
+    """out[r] = x[idx[r]] along dim 0 (moco.py:172,191)."""
+    _chk(x, name="x"), _chk(idx, torch.int64, "idx")
+    row = x[0].numel()
+    out = torch.empty((idx.numel(),) + tuple(x.shape[1:]), device=x.device)
+    _cabi.call("mscl_gather_rows", x.data_ptr(), idx.data_ptr(), out.data_ptr(), idx.numel(), row, _stream())
+    return out

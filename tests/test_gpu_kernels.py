@@ -1,0 +1,262 @@
+"""Parity of every CUDA kernel, called through the C-ABI, against the oracle and the golden
+fixtures produced by the unmodified reference.  Needs a B200: `pytest -m gpu`."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fx():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mscl_b200 import functional
+    return functional
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------ K5 enqueue (bit-exact)
+def test_enqueue_golden(fx, golden_dir):
+    g = _load(golden_dir, "enqueue_seq.npz")
+    K = g["queue0"].shape[1]
+    nq = fx.NegativeQueue(K)
+    nq.load(torch.from_numpy(g["queue0"]), torch.zeros(K, dtype=torch.long), 0)
+    keys = torch.from_numpy(g["keys"]).cuda()
+    for s in range(keys.shape[0]):
+        nq.enqueue(keys[s].contiguous())
+        assert nq.ptr == int(g["ptrs"][s])
+    q, c = nq.export()
+    torch.cuda.synchronize()
+    assert int(nq.qstate[0]) == int(g["ptrs"][-1]) and int(nq.qstate[1]) == keys.shape[0]
+    np.testing.assert_array_equal(q.cpu().numpy(), g["queue"])
+    np.testing.assert_array_equal(c.cpu().numpy(), g["count"])
+    np.testing.assert_allclose(nq.weight().cpu().numpy(), g["weight"], rtol=2e-6, atol=0)
+
+
+def test_enqueue_sharded_and_roundtrip(fx):
+    from oracle import mscl_oracle as O
+    K, B, G = 512, 32, 4
+    gen = torch.Generator().manual_seed(3)
+    q0 = F.normalize(torch.randn(128, K, generator=gen), dim=0)
+    count0 = torch.randint(0, 50, (K,), generator=gen)
+    shards = [fx.NegativeQueue(K, rank=r, world=G, shard=True) for r in range(G)]
+    for s in shards:
+        s.load(q0, count0, 7 * B)
+    q_ref, c_ref, ptr = q0.clone(), count0.clone(), 7 * B
+    for step in range(20):   # wraps past K
+        keys = torch.randn(B, 128, generator=gen)
+        ptr = O.enqueue(q_ref, c_ref, ptr, keys)
+        kd = keys.cuda()
+        for s in shards:
+            s.enqueue(kd)
+    qs, cs = zip(*[s.export() for s in shards])
+    np.testing.assert_array_equal(torch.cat(qs, 1).cpu().numpy(), q_ref.numpy())
+    np.testing.assert_array_equal(torch.cat(cs).cpu().numpy(), c_ref.numpy())
+    assert all(s.ptr == ptr for s in shards)
+
+
+def test_enqueue_rejects_bad_batch(fx):
+    nq = fx.NegativeQueue(256)
+    with pytest.raises(AssertionError):
+        nq.enqueue(torch.zeros(48, 128, device="cuda"))
+
+
+# ------------------------------------------------------------------ K4 EMA (bit-exact)
+def test_ema_golden(fx, golden_dir):
+    g = _load(golden_dir, "ema.npz")
+    names = [str(n) for n in g["names"]]
+    ks = [torch.from_numpy(g[f"k0/{n}"]).cuda() for n in names]
+    qs = [torch.from_numpy(g[f"q/{n}"]).cuda() for n in names]
+    tab = fx.EmaTable(ks, qs)
+    for step in range(3):
+        tab.update(float(g["m"][step]))
+        for n, k in zip(names, ks):
+            np.testing.assert_array_equal(k.cpu().numpy(), g[f"k{step + 1}/{n}"])
+
+
+def test_ema_large_and_ragged(fx):
+    from oracle import mscl_oracle as O
+    gen = torch.Generator().manual_seed(0)
+    sizes = [1, 3, 64, 1000, 16384, 16385, 3 * 16384 + 7, 2_000_003]
+    ks = [torch.randn(n, generator=gen) for n in sizes]
+    qs = [torch.randn(n, generator=gen) for n in sizes]
+    m = O.momentum(12345, 100000, 0.994)
+    ref = O.ema_update(ks, qs, m)
+    kd = [k.cuda() for k in ks]
+    # an unaligned view exercises the scalar path
+    big = torch.randn(4099, generator=gen)
+    kd.append(big.cuda()[3:])
+    qs.append(torch.randn(4096, generator=gen))
+    ref.append(O.ema_update([big[3:]], [qs[-1]], m)[0])
+    tab = fx.EmaTable(kd, [q.cuda() for q in qs])
+    tab.update(m)
+    for a, b in zip(kd, ref):
+        np.testing.assert_array_equal(a.cpu().numpy(), b.numpy())
+
+
+# ------------------------------------------------------------------ K3 FRA
+def test_fra_golden(fx, golden_dir):
+    g = _load(golden_dir, "fra.npz")
+    tab = fx.fra_table()
+    for i in range(2):
+        x = torch.from_numpy(g[f"in{i}"]).cuda()           # (T,H,W,2)
+        cid = torch.tensor([int(g[f"cid{i}"])], dtype=torch.int32, device="cuda")
+        ref = g[f"out{i}"]                                  # (2T,H,W,2)
+        for layout in ("interleaved", "planar"):
+            inp = x[None].contiguous() if layout == "interleaved" else x.permute(3, 0, 1, 2)[None].contiguous()
+            out = fx.fra(inp, cid, tab, layout)             # (1,2,2T,H,W)
+            got = out[0].permute(1, 2, 3, 0).cpu().numpy()
+            np.testing.assert_allclose(got, ref, rtol=3e-6, atol=3e-7)
+
+
+def test_fra_oracle_bit_exact_full_size(fx):
+    from oracle import inputs, mscl_oracle as O
+    N, T, H, W = 3, 8, 112, 112
+    rs = np.random.RandomState(0)
+    cids = rs.randint(0, 8, size=N)
+    clips = [inputs.flow_clip(seed=10 + n, T=T, H=H, W=W) for n in range(N)]
+    ref = np.stack([np.stack(O.fra(c, int(k))) for c, k in zip(clips, cids)])      # (N,2T,H,W,2)
+    x = torch.from_numpy(np.stack([np.stack(c) for c in clips])).cuda()            # (N,T,H,W,2)
+    out = fx.fra(x, torch.from_numpy(cids.astype(np.int32)).cuda(), fx.fra_table(), "interleaved")
+    got = out.permute(0, 2, 3, 4, 1).cpu().numpy()
+    np.testing.assert_array_equal(got, ref)   # same float32 operation sequence -> same bits
+    rot = fx.fra_rotate(out[:, :, :T].contiguous(), torch.from_numpy(cids.astype(np.int32)).cuda(), fx.fra_table())
+    np.testing.assert_allclose(rot.permute(0, 2, 3, 4, 1).cpu().numpy(), ref[:, T:], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ K2 LMCL
+def _oracle_lmcl(q_map, qf_map, qaf_map, T, t):
+    from oracle import mscl_oracle as O
+    leaves = [x.clone().requires_grad_(True) for x in (q_map, qf_map, qaf_map)]
+    out = O.lmcl(*leaves, T, t)
+    out["loss_pos"].backward()
+    return out, [l.grad for l in leaves]
+
+
+@pytest.mark.parametrize("N,t,hw_rgb,hw_flow", [(4, 4, 6, 3), (8, 8, 28, 7), (16, 16, 14, 7)])
+def test_lmcl_vs_oracle(fx, N, t, hw_rgb, hw_flow):
+    from oracle import inputs
+    inp = inputs.head_inputs(seed=2, N=N, K=64, t=t, hw_rgb=hw_rgb, hw_flow=hw_flow)
+    ref, gref = _oracle_lmcl(inp["q_map"], inp["qf_map"], inp["qaf_map"], 0.07, t)
+    maps = [inp[k].cuda().requires_grad_(True) for k in ("q_map", "qf_map", "qaf_map")]
+    xq = fx.hw_mean(maps[0])
+    xf = fx.hw_mean(torch.cat((maps[1], maps[2]), dim=2))
+    out = fx.lmcl(xq, xf, 0.07)
+    out[0].backward()
+    o = out.detach().cpu()
+    assert abs(float(o[0]) - float(ref["loss_pos"])) <= 1e-4 * abs(float(ref["loss_pos"]))   # 1e-3 contract, fp32 path
+    assert float(o[1]) == pytest.approx(float(ref["top1_acc_pos"]), abs=1e-6)
+    assert float(o[2]) == pytest.approx(float(ref["top5_acc_pos"]), abs=1e-6)
+    for m, g in zip(maps, gref):
+        assert _rel(m.grad.cpu(), g) < 1e-4
+
+
+# ------------------------------------------------------------------ K1 InfoNCE
+def _oracle_infonce(q, kpos, queue_ck, count, T, rpg):
+    from oracle import mscl_oracle as O
+    ql = q.clone().requires_grad_(True)
+    w = O.decayed_weight(queue_ck, count)
+    logits = O.infonce_logits(ql, kpos, w, T)
+    labels = torch.zeros(rpg, dtype=torch.long)
+    res = []
+    for g0 in range(0, q.shape[0], rpg):
+        lg = logits[g0:g0 + rpg]
+        acc = O.top_k_accuracy(lg.detach().numpy(), labels.numpy(), (1, 5))
+        res.append((O.cross_entropy_torch(lg, labels), acc[0], acc[1]))
+    sum(r[0] for r in res).backward()
+    return res, ql.grad, logits.detach()
+
+
+def _make_case(seed, M, K, b_all):
+    from oracle import inputs
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(M, 128, generator=g)
+    noise = torch.linspace(0.15, 1.6, M).unsqueeze(1)
+    q = F.normalize(z + noise * torch.randn(M, 128, generator=g), dim=1)
+    kpos = F.normalize(z + noise * torch.randn(M, 128, generator=g), dim=1)
+    queue = F.normalize(torch.randn(128, K, generator=g), dim=0)
+    count = inputs.steady_state_count(K, b_all, (5 * b_all) % K)
+    return q, kpos, queue, count
+
+
+CASES = [  # M, K, rows_per_group, b_all
+    (4, 256, 4, 4), (8, 4096, 8, 8), (24, 1000, 8, 8), (96, 65536, 32, 128), (192, 16384, 64, 64), (130, 8192, 65, 64),
+]
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("M,K,rpg,b_all", CASES)
+def test_infonce_vs_oracle(fx, impl, M, K, rpg, b_all):
+    q, kpos, queue, count = _make_case(M + K, M, K, b_all)
+    ref, gref, logits = _oracle_infonce(q, kpos, queue, count, 0.07, rpg)
+    nq = fx.NegativeQueue(K)
+    nq.load(queue, count, (5 * b_all) % K)
+    qd = q.cuda().requires_grad_(True)
+    out, rows = fx.infonce(qd, kpos.cuda(), nq, rpg, 0.07, impl=impl)
+    out[:, 0].sum().backward()
+    o = out.detach().cpu()
+    # margin between the positive and its nearest-ranked negative decides whether a top-k flag may flip
+    neg = logits[:, 1:]
+    pos = logits[:, :1]
+    tol = 2e-5 if impl == "simt" else 1e-3    # contract: 1e-3 relative (tf32 operands, fp32 accumulate)
+    for gi, (loss, t1, t5) in enumerate(ref):
+        assert abs(float(o[gi, 0]) - float(loss)) <= tol * abs(float(loss)), (gi, float(o[gi, 0]), float(loss))
+    cnt_ref = (neg > pos).sum(1).float()
+    cnt = rows[M:].cpu()
+    close_call = ((neg - pos).abs() < 0.02).sum(1)       # negatives within tf32 noise of the positive
+    assert bool(((cnt - cnt_ref).abs() <= close_call).all()), (cnt, cnt_ref)
+    for gi, (loss, t1, t5) in enumerate(ref):
+        sl = slice(gi * rpg, (gi + 1) * rpg)
+        if int(close_call[sl].sum()) == 0:
+            assert float(o[gi, 1]) == pytest.approx(t1, abs=1e-6) and float(o[gi, 2]) == pytest.approx(t5, abs=1e-6)
+    assert _rel(qd.grad.cpu(), gref) < tol, _rel(qd.grad.cpu(), gref)
+
+
+def test_infonce_tc_matches_simt_no_grad(fx):
+    M, K = 64, 32768
+    q, kpos, queue, count = _make_case(9, M, K, 64)
+    nq = fx.NegativeQueue(K)
+    nq.load(queue, count, 0)
+    with torch.no_grad():
+        a, _ = fx.infonce(q.cuda(), kpos.cuda(), nq, 32, 0.07, impl="tc")
+        b, _ = fx.infonce(q.cuda(), kpos.cuda(), nq, 32, 0.07, impl="simt")
+    assert _rel(a[:, 0].cpu(), b[:, 0].cpu()) < 1e-3
+
+
+def test_infonce_fresh_queue_and_after_enqueue(fx):
+    """count == 0 everywhere (moco.py:396) and the snapshot-after-enqueue case (App. A.2)."""
+    from oracle import mscl_oracle as O
+    M, K = 16, 1024
+    q, kpos, queue, _ = _make_case(4, M, K, 16)
+    count = torch.zeros(K, dtype=torch.long)
+    nq = fx.NegativeQueue(K)
+    nq.load(queue, count, 0)
+    keys = F.normalize(torch.randn(16, 128, generator=torch.Generator().manual_seed(1)), dim=1)
+    for step in range(3):
+        ref, gref, _ = _oracle_infonce(q, kpos, queue, count, 0.07, M)
+        qd = q.cuda().requires_grad_(True)
+        out, _ = fx.infonce(qd, kpos.cuda(), nq, M, 0.07)
+        out[0, 0].backward()
+        assert abs(float(out[0, 0]) - float(ref[0][0])) <= 1e-3 * abs(float(ref[0][0]))
+        assert _rel(qd.grad.cpu(), gref) < 1e-3
+        O.enqueue(queue, count, nq.ptr, keys)
+        nq.enqueue(keys.cuda())
+
+
+# ------------------------------------------------------------------ K6 gather
+def test_gather_rows(fx):
+    x = torch.randn(64, 3, 8, 28, 28, device="cuda")
+    idx = torch.randperm(64)[:16].cuda()
+    np.testing.assert_array_equal(fx.gather_rows(x, idx).cpu().numpy(), x[idx].cpu().numpy())
