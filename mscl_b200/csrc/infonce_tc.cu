@@ -9,15 +9,18 @@
 // makes 3 passes for the decayed snapshot plus a GEMM, and autograd a second GEMM).
 //
 // CTA = 192 threads, one CTA per SM, 128 query rows x a contiguous range of 64-key tiles:
-//   warp 0      TMA producer   queue tile [64 keys x 128 ch] fp32 -> smem (128B swizzle,
-//                              4 channel blocks of 32) + the tile's 64 dscale floats
-//   warp 1      MMA issuer     MMA1: S[128 x 64]  = Q[128 x 128] . Wt      (SS, both K-major)
-//                              MMA2: O[128 x 128] += P[128 x 64] . W       (TS, A = P in TMEM,
-//                                                   B = the SAME smem tile read MN-major)
-//   warps 2..5  softmax        thread <-> query row (TMEM lane): tcgen05.ld S, exp2, row sum,
-//                              count(s > pos), P' = p * dscale -> tcgen05.st over S
-// TMEM (512 columns): O = [0,128), S/P double buffer = [128,192) and [192,256).
-// Pipelines: full/empty (TMA <-> MMA, 4 stages), s_full (MMA1 -> softmax),
+//   warp 0      TMA producer   queue tile [64 keys x 128 ch] fp32 -> smem as 4 channel blocks of
+//                              [64][32 ch = 128 B], TWICE: once 128B-swizzled (K-major operand of
+//                              MMA1) and once with the 32-byte-atom 128B swizzle, the only layout
+//                              tcgen05 accepts for an MN-major tf32 operand (MMA2); the second
+//                              read hits L2.  Plus the tile's 64 dscale floats (bulk copy).
+//   warp 1      MMA issuer     MMA1: S[128 x 64]  = Q[128 x 128] . Wt     (TS: A = Q in TMEM, B K-major)
+//                              MMA2: O[128 x 128] += P[128 x 64] . W      (TS: A = P in TMEM, B MN-major)
+//   warps 2..5  softmax        thread <-> query row (TMEM lane): stage q into TMEM once, then per
+//                              tile tcgen05.ld S, exp2, row sum, count(s > pos), P' = p * dscale
+//                              -> tcgen05.st over S
+// TMEM (512 columns): O = [0,128), S/P double buffer = [128,192) [192,256), Q = [256,384).
+// Pipelines: full/empty (TMA <-> MMA, 3 stages), q_full, s_full (MMA1 -> softmax),
 // p_full (softmax -> MMA2), o_full (last MMA2 -> epilogue).
 #include <cuda.h>
 
@@ -30,20 +33,18 @@ constexpr int kC = MSCL_DIM;          // 128 channels
 constexpr int kLd = MSCL_PACK_LD;     // 132
 constexpr int kRows = 128;            // query rows per CTA (UMMA M)
 constexpr int kTile = 64;             // keys per stage
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kCb = 4;                // channel blocks of 32 fp32 (one 128-byte swizzle row)
 constexpr int kThreads = 192;
 
-constexpr uint32_t kQBytes = kRows * kC * 4;          // 65536
-constexpr uint32_t kWBytes = kTile * kC * 4;          // 32768
-constexpr uint32_t kQSlab = kRows * 128;              // bytes per channel block of Q
+constexpr uint32_t kWBytes = kTile * kC * 4;          // 32768: one copy of a tile
 constexpr uint32_t kWSlab = kTile * 128;              // bytes per channel block of a W tile
+constexpr uint32_t kStageBytes = 2 * kWBytes;         // K-major copy + MN-major copy
 constexpr uint32_t kDsBytes = kTile * 4;              // 256
 
 // shared memory map (offsets from the 1024-aligned base)
-constexpr uint32_t kOffQ = 0;
-constexpr uint32_t kOffW = kOffQ + kQBytes;
-constexpr uint32_t kOffDs = kOffW + kStages * kWBytes;
+constexpr uint32_t kOffW = 0;
+constexpr uint32_t kOffDs = kOffW + kStages * kStageBytes;
 constexpr uint32_t kOffBar = kOffDs + kStages * kDsBytes;
 constexpr uint32_t kNumBars = 2 * kStages + 1 + 2 + 2 + 1;  // full, empty, q, s_full[2], p_full[2], o_full
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
@@ -53,6 +54,7 @@ constexpr uint32_t kSmemBytes = kSmemUsed + 1024;     // slack for manual 1024-b
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColO = 0;
 constexpr uint32_t kColS = 128;
+constexpr uint32_t kColQ = 256;
 
 // instruction descriptors (cute::UMMA::InstrDescriptor bit layout):
 //  [4,6) c_format=1 (f32) | [7,10) a_format=2 (tf32) | [10,13) b_format=2 (tf32)
@@ -149,10 +151,11 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
 }
 
 // smem matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
-// version=1 <<46 | layout_type (2 = SWIZZLE_128B) <<61
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// version=1 <<46 | layout_type <<61  (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
-         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 
 #define TC_LD32(taddr, r)                                                                       \
@@ -227,13 +230,12 @@ __device__ __forceinline__ void softmax_tile(uint32_t taddr0, const float *ds, f
 
 template <bool GRAD>
 __global__ void __launch_bounds__(kThreads, 1)
-infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_w,
+infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_w2,
                   const float *__restrict__ qpack, int M, const float *__restrict__ dscale,
                   int64_t K_local, float *__restrict__ acc) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *gbase = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sQ = base + kOffQ;
   const uint32_t sW = base + kOffW;
   const uint32_t sDs = base + kOffDs;
   const uint32_t bar0 = base + kOffBar;
@@ -257,13 +259,13 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   const int row0 = blockIdx.y * kRows;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 1);
     }
-    mbar_init(bar_q, 1);
+    mbar_init(bar_q, 128);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_sfull(b), 1);
       mbar_init(bar_pfull(b), 128);
@@ -286,15 +288,14 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_q, kQBytes);
-      tma_load_3d(sQ, &tmap_q, bar_q, 0, row0, 0);
       for (int t = 0; t < nt; ++t) {
         const int s = t % kStages;
         const uint32_t use = (uint32_t)(t / kStages);
         mbar_wait(bar_empty(s), (use & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar_full(s), kWBytes + kDsBytes);
+        mbar_arrive_expect_tx(bar_full(s), (GRAD ? 2 * kWBytes : kWBytes) + kDsBytes);
         const int64_t key0 = (t_begin + t) * kTile;
-        tma_load_3d(sW + s * kWBytes, &tmap_w, bar_full(s), 0, (int)key0, 0);
+        tma_load_3d(sW + s * kStageBytes, &tmap_w, bar_full(s), 0, (int)key0, 0);
+        if (GRAD) tma_load_3d(sW + s * kStageBytes + kWBytes, &tmap_w2, bar_full(s), 0, (int)key0, 0);
         bulk_load_1d(sDs + s * kDsBytes, dscale + key0, kDsBytes, bar_full(s));
       }
     }
@@ -310,14 +311,14 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int cb = 0; cb < kCb; ++cb) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = make_desc(sQ + cb * kQSlab + ks * 32, 16, 1024);
-            const uint64_t bd = make_desc(sW + s * kWBytes + cb * kWSlab + ks * 32, 16, 1024);
-            mma_ss(d, ad, bd, kIdesc1, (cb | ks) ? 1u : 0u);
+            const uint64_t bd = make_desc(sW + s * kStageBytes + cb * kWSlab + ks * 32, 16, 1024);
+            mma_ts(d, tmem + kColQ + cb * 32 + ks * 8, bd, kIdesc1, (cb | ks) ? 1u : 0u);
           }
         }
         tc_commit(bar_sfull(t & 1));
       };
       mbar_wait(bar_q, 0);
+      tc_fence_after();
       if (nt > 0) issue_mma1(0);
       for (int t = 0; t < nt; ++t) {
         if (t + 1 < nt) issue_mma1(t + 1);
@@ -328,9 +329,9 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           const uint32_t a = tmem + kColS + (uint32_t)(t & 1) * kTile;
 #pragma unroll
           for (int j = 0; j < kTile / 8; ++j) {
-            // B = the stage's tile read MN-major: 8 keys per step (one swizzle atom of rows),
-            // channel blocks kWSlab bytes apart (LBO), next key atom 1024 bytes on (SBO)
-            const uint64_t bd = make_desc(sW + s * kWBytes + j * 1024, kWSlab, 1024);
+            // B = the stage's second copy read MN-major (SWIZZLE_128B_BASE32B): 8 keys per step =
+            // two 4-row atoms 512 bytes apart (SBO); channel blocks kWSlab bytes apart (LBO)
+            const uint64_t bd = make_desc(sW + s * kStageBytes + kWBytes + j * 1024, kWSlab, 512, 1);
             mma_ts(tmem + kColO, a + j * 8, bd, kIdesc2, (t | j) ? 1u : 0u);
           }
           tc_commit(bar_empty(s));
@@ -357,6 +358,26 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       thr = pos2 - shift2;
     }
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    {   // this row of Q -> TMEM columns [kColQ, kColQ+128): the A operand of every MMA1
+      const float4 *qsrc = reinterpret_cast<const float4 *>(qpack + (int64_t)row * kLd);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t v[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok) f = __ldg(qsrc + h * 8 + j4);
+          v[j4 * 4 + 0] = __float_as_uint(f.x);
+          v[j4 * 4 + 1] = __float_as_uint(f.y);
+          v[j4 * 4 + 2] = __float_as_uint(f.z);
+          v[j4 * 4 + 3] = __float_as_uint(f.w);
+        }
+        TC_ST32(lane_base + kColQ + h * 32, v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(bar_q);
+    }
     float sum = 0.f;
     int cnt = 0;
     for (int t = 0; t < nt; ++t) {
@@ -430,7 +451,8 @@ static EncodeTiledFn get_encode_fn() {
 
 // rows x 128 fp32 matrix with row pitch ld floats, viewed as {32, rows, 4} so that one box lands
 // in shared memory as 4 channel-block slabs of [box_rows][128 B], 128-byte swizzled.
-static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int ld, int box_rows) {
+static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int ld, int box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_err(MSCL_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {32, (cuuint64_t)rows, 4};
@@ -438,7 +460,7 @@ static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int ld, in
   cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 4};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(ptr), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_err(MSCL_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld ld=%d)",
@@ -459,10 +481,10 @@ extern "C" int mscl_infonce_partial(const float *d_qpack, int32_t M, const float
   MSCL_CHECK_ARG((((uintptr_t)d_qpack | (uintptr_t)d_queue | (uintptr_t)d_dscale | (uintptr_t)d_acc) & 15) == 0,
                  "qpack/queue/dscale/acc must be 16-byte aligned");
   MSCL_CHECK_ARG(num_sms > 0, "num_sms=%d", num_sms);
-  CUtensorMap tq, tw;
-  int rc = make_map(&tq, d_qpack, M, kLd, kRows);
+  CUtensorMap tw, tw2;
+  int rc = make_map(&tw, d_queue, K_local, kC, kTile);
   if (rc) return rc;
-  rc = make_map(&tw, d_queue, K_local, kC, kTile);
+  rc = make_map(&tw2, d_queue, K_local, kC, kTile, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
   const int64_t n_tiles = (K_local + kTile - 1) / kTile;
   const int row_blocks = (M + kRows - 1) / kRows;
@@ -474,11 +496,11 @@ extern "C" int mscl_infonce_partial(const float *d_qpack, int32_t M, const float
   if (with_grad) {
     MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    infonce_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(tq, tw, d_qpack, M, d_dscale, K_local, d_acc);
+    infonce_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(tw, tw2, d_qpack, M, d_dscale, K_local, d_acc);
   } else {
     MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    infonce_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(tq, tw, d_qpack, M, d_dscale, K_local, d_acc);
+    infonce_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(tw, tw2, d_qpack, M, d_dscale, K_local, d_acc);
   }
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;

@@ -126,7 +126,7 @@ class NegativeQueue:
 # ----------------------------------------------------------------------------------------
 class _InfoNCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, kpos, nq, rows_per_group, inv_T, impl, group):
+    def forward(ctx, q, kpos, nq, rows_per_group, inv_T, impl, group, need_grad):
         M = q.shape[0]
         dev = q.device
         st = _stream()
@@ -136,7 +136,6 @@ class _InfoNCE(torch.autograd.Function):
         k_pad = (nq.K_local + 63) // 64 * 64
         dscale = torch.empty(k_pad, device=dev)
         acc = torch.empty(M_all, PACK_LD, device=dev)
-        need_grad = bool(ctx.needs_input_grad[0])
         _cabi.call("mscl_infonce_prep", q.data_ptr(), kpos.data_ptr(), M, nq.birth.data_ptr(), nq.qstate.data_ptr(),
                    nq.K_local, inv_T, nq.max_key_norm, qpack.data_ptr(), dscale.data_ptr(), acc.data_ptr(), M_all, st)
         if world > 1:
@@ -173,7 +172,7 @@ class _InfoNCE(torch.autograd.Function):
         gout = g_group[:, 0].contiguous()
         dq = torch.empty_like(dq_unit)
         _cabi.call("mscl_infonce_bwd", dq_unit.data_ptr(), gout.data_ptr(), M, ctx.rows_per_group, dq.data_ptr(), _stream())
-        return dq, None, None, None, None, None, None
+        return dq, None, None, None, None, None, None, None
 
 
 def infonce(q, kpos, nq, rows_per_group, T, impl="tc", group=None):
@@ -189,7 +188,8 @@ def infonce(q, kpos, nq, rows_per_group, T, impl="tc", group=None):
         raise _cabi.MsclError(f"q and kpos must both be (M, {DIM}); got {tuple(q.shape)} and {tuple(kpos.shape)}")
     if q.shape[0] % rows_per_group:
         raise _cabi.MsclError("number of rows must be a multiple of rows_per_group")
-    return _InfoNCE.apply(q, kpos.detach(), nq, int(rows_per_group), float(1.0 / T), impl, group)
+    need_grad = bool(q.requires_grad and torch.is_grad_enabled())
+    return _InfoNCE.apply(q, kpos.detach(), nq, int(rows_per_group), float(1.0 / T), impl, group, need_grad)
 
 
 # ----------------------------------------------------------------------------------------

@@ -210,7 +210,8 @@ def test_infonce_vs_oracle(fx, impl, M, K, rpg, b_all):
     # margin between the positive and its nearest-ranked negative decides whether a top-k flag may flip
     neg = logits[:, 1:]
     pos = logits[:, :1]
-    tol = 2e-5 if impl == "simt" else 1e-3    # contract: 1e-3 relative (tf32 operands, fp32 accumulate)
+    # contract: 1e-3 relative (tf32 operands, fp32 accumulate); the CUDA-core twin only sees tf32-rounded q
+    tol = 3e-4 if impl == "simt" else 1e-3
     for gi, (loss, t1, t5) in enumerate(ref):
         assert abs(float(o[gi, 0]) - float(loss)) <= tol * abs(float(loss)), (gi, float(o[gi, 0]), float(loss))
     cnt_ref = (neg > pos).sum(1).float()
