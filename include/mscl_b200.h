@@ -15,6 +15,9 @@
  * Device data layout:
  *   queue   float32 [K_local, C]   one key per ROW ("key-major"); the reference
  *                                  keeps the transpose (C, K) (moco.py:390).
+ *   queue_tf32  same shape         the same keys rounded to nearest tf32: what the
+ *                                  tensor-core pass reads; `queue` stays the bit-exact
+ *                                  fp32 master for state_dict().
  *   birth   int32   [K_local]      enqueue number at which the row was written;
  *                                  reference count[j] == n_enq - birth[j]
  *                                  (moco.py:427,437).
@@ -56,10 +59,12 @@ int mscl_device_check(int dev);
  * n_enq - birth).  ptr <- (ptr + B_all) % K_total; n_enq <- n_enq + 1.
  * If d_saved != NULL the overwritten rows (those in this shard) are first copied
  * to d_saved[B_all, C] and their birth to d_saved_birth[B_all] (snapshot support,
- * moco.py:484-488).
+ * moco.py:484-488).  If d_queue_tf32 != NULL the same rows are also written there
+ * rounded to nearest tf32: the operand copy the tensor-core pass reads (the tensor
+ * core itself would truncate fp32, a systematic -3.5e-4 relative bias per operand).
  */
-int mscl_enqueue(float *d_queue, int32_t *d_birth, int64_t *d_qstate,
-                 const float *d_keys, int32_t B_all, int32_t C,
+int mscl_enqueue(float *d_queue, float *d_queue_tf32, int32_t *d_birth,
+                 int64_t *d_qstate, const float *d_keys, int32_t B_all, int32_t C,
                  int64_t K_total, int64_t shard_begin, int64_t K_local,
                  float *d_saved, int32_t *d_saved_birth, mscl_stream_t stream);
 
@@ -71,7 +76,8 @@ int mscl_queue_export(const float *d_queue, const int32_t *d_birth,
                       mscl_stream_t stream);
 /* Inverse: load reference-layout buffers. birth = n_enq - count with
  * n_enq taken from d_qstate[1] (caller sets it to max(count) beforehand). */
-int mscl_queue_import(float *d_queue, int32_t *d_birth, const int64_t *d_qstate,
+int mscl_queue_import(float *d_queue, float *d_queue_tf32, int32_t *d_birth,
+                      const int64_t *d_qstate,
                       const float *d_queue_ck, const int64_t *d_count, int32_t C,
                       int64_t K_local, mscl_stream_t stream);
 /* The decayed snapshot the reference calls `weight` (moco.py:484-486):

@@ -53,6 +53,16 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// round-to-nearest fp32 -> tf32 (10-bit mantissa); the tensor core itself truncates
+__device__ __forceinline__ float to_tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 to_tf32_rn(float4 v) {
+  return make_float4(to_tf32_rn(v.x), to_tf32_rn(v.y), to_tf32_rn(v.z), to_tf32_rn(v.w));
+}
+
 // streaming 128-bit accesses (read-once / write-once data)
 __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
   float4 r;

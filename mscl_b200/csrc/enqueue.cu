@@ -12,7 +12,7 @@ namespace mscl {
 
 // One thread per float4 of the key block.
 __global__ void __launch_bounds__(256)
-enqueue_kernel(float *__restrict__ queue, int32_t *__restrict__ birth,
+enqueue_kernel(float *__restrict__ queue, float *__restrict__ queue_tf32, int32_t *__restrict__ birth,
                int64_t *__restrict__ qstate, const float *__restrict__ keys,
                int B_all, int C4, int64_t K_total, int64_t shard_begin,
                int64_t K_local, float *__restrict__ saved,
@@ -33,7 +33,10 @@ enqueue_kernel(float *__restrict__ queue, int32_t *__restrict__ birth,
       reinterpret_cast<float4 *>(saved)[v] = *dst;
       if (c4 == 0) saved_birth[i] = birth[local];
     }
-    *dst = __ldg(reinterpret_cast<const float4 *>(keys) + v);
+    const float4 kv = __ldg(reinterpret_cast<const float4 *>(keys) + v);
+    *dst = kv;
+    if (queue_tf32 != nullptr)
+      reinterpret_cast<float4 *>(queue_tf32 + local * (int64_t)C4 * 4)[c4] = to_tf32_rn(kv);
     if (c4 == 0) birth[local] = (int32_t)n_enq;  // age becomes 1 after n_enq+1
   }
   __syncthreads();
@@ -54,7 +57,8 @@ enqueue_kernel(float *__restrict__ queue, int32_t *__restrict__ birth,
 // mode 0: export raw; mode 1: export decayed weight; mode 2: import.
 template <int MODE>
 __global__ void __launch_bounds__(256)
-queue_transpose_kernel(float *__restrict__ queue_kc, int32_t *__restrict__ birth,
+queue_transpose_kernel(float *__restrict__ queue_kc, float *__restrict__ queue_tf32,
+                       int32_t *__restrict__ birth,
                        const int64_t *__restrict__ qstate, float *__restrict__ ck,
                        int64_t *__restrict__ count, int C, int64_t K_local) {
   __shared__ float tile[32][33];
@@ -73,7 +77,10 @@ queue_transpose_kernel(float *__restrict__ queue_kc, int32_t *__restrict__ birth
     for (int r = ty; r < 32; r += 8) {
       const int64_t k = k0 + r;
       const int c = c0 + tx;
-      if (k < K_local && c < C) queue_kc[k * C + c] = tile[tx][r];
+      if (k < K_local && c < C) {
+        queue_kc[k * C + c] = tile[tx][r];
+        if (queue_tf32 != nullptr) queue_tf32[k * C + c] = to_tf32_rn(tile[tx][r]);
+      }
     }
     if (blockIdx.y == 0 && threadIdx.x < 32) {
       const int64_t k = k0 + threadIdx.x;
@@ -130,7 +137,7 @@ gather_rows_kernel(const float4 *__restrict__ x, const int64_t *__restrict__ idx
 
 extern "C" {
 
-int mscl_enqueue(float *d_queue, int32_t *d_birth, int64_t *d_qstate,
+int mscl_enqueue(float *d_queue, float *d_queue_tf32, int32_t *d_birth, int64_t *d_qstate,
                  const float *d_keys, int32_t B_all, int32_t C, int64_t K_total,
                  int64_t shard_begin, int64_t K_local, float *d_saved,
                  int32_t *d_saved_birth, mscl_stream_t stream) {
@@ -148,13 +155,13 @@ int mscl_enqueue(float *d_queue, int32_t *d_birth, int64_t *d_qstate,
   int blocks = (int)((total + 255) / 256);
   if (blocks > 1184) blocks = 1184;  // 8 CTAs x 148 SMs
   mscl::enqueue_kernel<<<blocks, 256, 0, mscl::as_stream(stream)>>>(
-      d_queue, d_birth, d_qstate, d_keys, B_all, C / 4, K_total, shard_begin,
+      d_queue, d_queue_tf32, d_birth, d_qstate, d_keys, B_all, C / 4, K_total, shard_begin,
       K_local, d_saved, d_saved_birth);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }
 
-static int transpose_launch(int mode, float *q, int32_t *birth, const int64_t *qstate,
+static int transpose_launch(int mode, float *q, float *q_tf32, int32_t *birth, const int64_t *qstate,
                             float *ck, int64_t *count, int32_t C, int64_t K_local,
                             mscl_stream_t stream) {
   MSCL_CHECK_ARG(q && birth && qstate && ck, "null pointer");
@@ -162,11 +169,11 @@ static int transpose_launch(int mode, float *q, int32_t *birth, const int64_t *q
   dim3 grid((unsigned)((K_local + 31) / 32), (unsigned)((C + 31) / 32));
   cudaStream_t s = mscl::as_stream(stream);
   if (mode == 0)
-    mscl::queue_transpose_kernel<0><<<grid, 256, 0, s>>>(q, birth, qstate, ck, count, C, K_local);
+    mscl::queue_transpose_kernel<0><<<grid, 256, 0, s>>>(q, q_tf32, birth, qstate, ck, count, C, K_local);
   else if (mode == 1)
-    mscl::queue_transpose_kernel<1><<<grid, 256, 0, s>>>(q, birth, qstate, ck, count, C, K_local);
+    mscl::queue_transpose_kernel<1><<<grid, 256, 0, s>>>(q, q_tf32, birth, qstate, ck, count, C, K_local);
   else
-    mscl::queue_transpose_kernel<2><<<grid, 256, 0, s>>>(q, birth, qstate, ck, count, C, K_local);
+    mscl::queue_transpose_kernel<2><<<grid, 256, 0, s>>>(q, q_tf32, birth, qstate, ck, count, C, K_local);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }
@@ -175,22 +182,22 @@ int mscl_queue_export(const float *d_queue, const int32_t *d_birth,
                       const int64_t *d_qstate, float *d_queue_ck, int64_t *d_count,
                       int32_t C, int64_t K_local, mscl_stream_t stream) {
   MSCL_CHECK_ARG(d_count != nullptr, "null count");
-  return transpose_launch(0, const_cast<float *>(d_queue), const_cast<int32_t *>(d_birth),
+  return transpose_launch(0, const_cast<float *>(d_queue), nullptr, const_cast<int32_t *>(d_birth),
                           d_qstate, d_queue_ck, d_count, C, K_local, stream);
 }
 
-int mscl_queue_import(float *d_queue, int32_t *d_birth, const int64_t *d_qstate,
+int mscl_queue_import(float *d_queue, float *d_queue_tf32, int32_t *d_birth, const int64_t *d_qstate,
                       const float *d_queue_ck, const int64_t *d_count, int32_t C,
                       int64_t K_local, mscl_stream_t stream) {
   MSCL_CHECK_ARG(d_count != nullptr, "null count");
-  return transpose_launch(2, d_queue, d_birth, d_qstate, const_cast<float *>(d_queue_ck),
+  return transpose_launch(2, d_queue, d_queue_tf32, d_birth, d_qstate, const_cast<float *>(d_queue_ck),
                           const_cast<int64_t *>(d_count), C, K_local, stream);
 }
 
 int mscl_queue_weight(const float *d_queue, const int32_t *d_birth,
                       const int64_t *d_qstate, float *d_weight_ck, int32_t C,
                       int64_t K_local, mscl_stream_t stream) {
-  return transpose_launch(1, const_cast<float *>(d_queue), const_cast<int32_t *>(d_birth),
+  return transpose_launch(1, const_cast<float *>(d_queue), nullptr, const_cast<int32_t *>(d_birth),
                           d_qstate, d_weight_ck, nullptr, C, K_local, stream);
 }
 

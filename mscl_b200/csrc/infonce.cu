@@ -8,12 +8,6 @@ namespace mscl {
 constexpr int kC = MSCL_DIM;
 constexpr int kLd = MSCL_PACK_LD;
 
-__device__ __forceinline__ float to_tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
 // ---- 1. prep --------------------------------------------------------------
 // part A (one warp per query row): qpack row = tf32-rounded q | pos2 | shift2 | 0 | 0
 // part B (one thread per key)     : dscale[j]

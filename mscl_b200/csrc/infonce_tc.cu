@@ -221,7 +221,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t taddr0, const float *ds, f
         }
         sum += p;
         cnt += hit ? 1 : 0;
-        v[j] = __float_as_uint(p * dd[e]);
+        v[j] = __float_as_uint(GRAD ? to_tf32_rn(p * dd[e]) : 0.f);
       }
     }
     if (GRAD) TC_ST32(taddr, v);

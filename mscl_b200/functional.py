@@ -67,7 +67,8 @@ class NegativeQueue:
         self.K_local = self.K // self.world
         self.shard_begin = self.rank * self.K_local
         self.device = torch.device(device)
-        self.queue = torch.zeros(self.K_local, C, device=self.device)
+        self.queue = torch.zeros(self.K_local, C, device=self.device)        # bit-exact fp32 master
+        self.queue_tf32 = torch.zeros(self.K_local, C, device=self.device)   # RN-rounded operand copy
         self.birth = torch.zeros(self.K_local, dtype=torch.int32, device=self.device)
         self.qstate = torch.zeros(4, dtype=torch.int64, device=self.device)
         self.ptr = 0          # host mirrors (deterministic, never read back from the device)
@@ -86,7 +87,8 @@ class NegativeQueue:
         self.ptr = int(ptr)
         self.qstate.copy_(torch.tensor([self.ptr, self.n_enq, 0, 0], dtype=torch.int64))
         self.max_key_norm = max(1.0, float(queue_ck.norm(dim=0).max().item()))
-        _cabi.call("mscl_queue_import", self.queue.data_ptr(), self.birth.data_ptr(), self.qstate.data_ptr(),
+        _cabi.call("mscl_queue_import", self.queue.data_ptr(), self.queue_tf32.data_ptr(), self.birth.data_ptr(),
+                   self.qstate.data_ptr(),
                    q_loc.data_ptr(), c_loc.data_ptr(), self.C, self.K_local, _stream())
         # keep the staging tensors alive until the kernel has consumed them
         torch.cuda.current_stream().synchronize()
@@ -115,7 +117,8 @@ class NegativeQueue:
             raise AssertionError(f"K={self.K} must be a multiple of the gathered batch size {b}")  # moco.py:432
         if self.ptr + b > self.K:
             raise _cabi.MsclError("queue pointer is not aligned to the batch size (batch size changed mid-cycle)")
-        _cabi.call("mscl_enqueue", self.queue.data_ptr(), self.birth.data_ptr(), self.qstate.data_ptr(),
+        _cabi.call("mscl_enqueue", self.queue.data_ptr(), self.queue_tf32.data_ptr(), self.birth.data_ptr(),
+                   self.qstate.data_ptr(),
                    keys_all.data_ptr(), b, self.C, self.K, self.shard_begin, self.K_local, None, None, _stream())
         self.ptr = (self.ptr + b) % self.K
         self.n_enq += 1
@@ -144,10 +147,10 @@ class _InfoNCE(torch.autograd.Function):
         else:
             qpack_all = qpack
         if impl == "simt":
-            _cabi.call("mscl_infonce_partial_simt", qpack_all.data_ptr(), M_all, nq.queue.data_ptr(), dscale.data_ptr(),
+            _cabi.call("mscl_infonce_partial_simt", qpack_all.data_ptr(), M_all, nq.queue_tf32.data_ptr(), dscale.data_ptr(),
                        nq.K_local, acc.data_ptr(), int(need_grad), st)
         else:
-            _cabi.call("mscl_infonce_partial", qpack_all.data_ptr(), M_all, nq.queue.data_ptr(), dscale.data_ptr(),
+            _cabi.call("mscl_infonce_partial", qpack_all.data_ptr(), M_all, nq.queue_tf32.data_ptr(), dscale.data_ptr(),
                        nq.K_local, acc.data_ptr(), int(need_grad), sm_count(dev), st)
         if world > 1:
             acc_local = torch.empty(M, PACK_LD, device=dev)

@@ -1,3 +1,3 @@
-from .cross_entropy_loss import CrossEntropyLoss_torch
+from .cross_entropy_loss import CrossEntropyLoss, CrossEntropyLoss_torch
 
-__all__ = ["CrossEntropyLoss_torch"]
+__all__ = ["CrossEntropyLoss", "CrossEntropyLoss_torch"]

@@ -25,3 +25,29 @@ class CrossEntropyLoss_torch(torch.nn.modules.CrossEntropyLoss):
         assert self.weight is None or isinstance(self.weight, torch.Tensor)
         return self.loss_weight * F.cross_entropy(input, target, weight=self.weight,
                                                   ignore_index=self.ignore_index, reduction=self.reduction)
+
+
+@LOSSES.register_module()
+class CrossEntropyLoss(torch.nn.Module):
+    """MMAction2's standard cross-entropy (losses/cross_entropy_loss.py:9-70, base.py): the default
+    `loss_cls` of every head, built even where it is never evaluated (MSCLWithAugPosHeadV2)."""
+
+    def __init__(self, loss_weight=1.0, class_weight=None):
+        super().__init__()
+        self.loss_weight = loss_weight
+        self.class_weight = None if class_weight is None else torch.tensor(class_weight)
+
+    def fusable(self):
+        return self.class_weight is None
+
+    def forward(self, cls_score, label, **kwargs):
+        w = None if self.class_weight is None else self.class_weight.to(cls_score.device)
+        if cls_score.size() == label.size():     # soft labels
+            lsm = F.log_softmax(cls_score, 1)
+            if w is not None:
+                lsm = lsm * w.unsqueeze(0)
+            loss = -(label * lsm).sum(1)
+            loss = loss.sum() / (w.unsqueeze(0) * label).sum() if w is not None else loss.mean()
+        else:
+            loss = F.cross_entropy(cls_score, label, weight=w, **kwargs)
+        return loss * self.loss_weight

@@ -1,0 +1,323 @@
+"""MoCoV2 recognizer on the B200 kernels (reference: recognizers/moco.py:318-554).
+
+Same constructor, same `train_step` / `forward_train(im_q, im_k, aux_info,
+return_features, update_queue)` contract, same state_dict keys (`queue` (dim,K) fp32,
+`queue_ptr` (1,) int64, `count` (K,) int64) and the same observable sequence of effects per
+call: EMA -> shuffle -> key forward -> unshuffle -> logits against the
+PRE-enqueue decayed queue -> enqueue -> iters.  What changed is how each step runs:
+
+  _momentum_update_key_encoder   one multi-tensor kernel (K4) instead of ~3 launches per tensor
+  _batch_shuffle_ddp             permutation-driven all-to-all (K6) instead of gather-everything
+  logits / CE / top-k            one fused tcgen05 pass over the queue (K1); no (N,1+K) matrix,
+                                 no decayed snapshot, no host argsort
+  _dequeue_and_enqueue           one block copy into a key-major ring buffer with implicit ages (K5)
+"""
+from math import cos, pi
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import functional as fx
+from ..registry import RECOGNIZERS, build_ssl_aug
+from .base_moco import BaseMoCoRecognizer
+from . import shuffle as shf
+
+
+def _dist_on():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+@torch.no_grad()
+def concat_all_gather(tensor):
+    """Rank-major all_gather without gradient (moco.py:558-568)."""
+    if not _dist_on():
+        return tensor
+    out = torch.empty((dist.get_world_size() * tensor.shape[0],) + tuple(tensor.shape[1:]),
+                      dtype=tensor.dtype, device=tensor.device)
+    dist.all_gather_into_tensor(out, tensor.contiguous())
+    return out
+
+
+@RECOGNIZERS.register_module()
+class MoCoV2(BaseMoCoRecognizer):
+    def __init__(self, backbone, neck, moco_head, im_key="imgs", dim_in=512, dim=128, K=65536, m_base=0.994,
+                 t_decay=0.99999, max_iters=1, T=0.07, mlp=False, aux_info=[],
+                 aug=dict(dtype="MoCoAugmentV3", moco_aug=(112, 112), t=8), train_cfg=None, test_cfg=None):
+        super().__init__(train_cfg=train_cfg, test_cfg=test_cfg)
+        self.K = K
+        self.m_base = m_base
+        self.m = m_base
+        self.iters = 0
+        self.max_iters = max_iters
+        self.batch_size = 0
+        self.T = T
+        self.dim = dim
+        self.im_key = im_key
+        self.t_decay = t_decay      # stored but unused, like the reference (the decay base is 0.99999)
+        self.aux_info = aux_info
+        if "num_classes" in backbone:
+            assert backbone["num_classes"] == dim
+        self._build_backbone(backbone, "encoder_q")
+        self._build_backbone(dict(backbone), "encoder_k")
+        self._build_neck(neck, "neck_q")
+        self._build_neck(neck, "neck_k")
+        self._build_cls_head(moco_head, "moco_head")
+        self.init_weights()
+        if mlp:
+            self.mlp_q = nn.Sequential(nn.Linear(dim_in, dim_in), nn.ReLU(), nn.Linear(dim_in, dim))
+            self.mlp_k = nn.Sequential(nn.Linear(dim_in, dim_in), nn.ReLU(), nn.Linear(dim_in, dim))
+        else:
+            self.mlp_q = nn.Linear(dim_in, dim)
+            self.mlp_k = nn.Linear(dim_in, dim)
+        for mq, mk in self._qk_modules():
+            for pq, pk in zip(mq.parameters(), mk.parameters()):
+                pk.data.copy_(pq.data)
+                pk.requires_grad = False
+        # the queue starts as unit-norm Gaussian columns with age 0 (moco.py:390-396); it is staged
+        # on the host until the module is first used on a device
+        queue0 = F.normalize(torch.randn(dim, K), dim=0)
+        self._staged = dict(queue=queue0, count=torch.zeros(K, dtype=torch.long), ptr=0)
+        self._nq = None
+        self._ema = None
+        self._weight = None
+        self._cpu_group = None
+        cfg = train_cfg or {}
+        self.shard_queue = bool(cfg.get("shard_queue", False))
+        self.keep_weight_snapshot = bool(cfg.get("keep_weight_snapshot", False))
+        self.aug_gpu = build_ssl_aug(aug)
+        self._register_state_dict_hook(MoCoV2._export_queue_hook)
+        self._register_load_state_dict_pre_hook(self._import_queue_hook)
+
+    def _qk_modules(self):
+        return ((self.encoder_q, self.encoder_k), (self.neck_q, self.neck_k), (self.mlp_q, self.mlp_k))
+
+    # ------------------------------------------------------------------ queue state
+    def negative_queue(self, device=None):
+        """The device ring buffer, created (or moved) on first use."""
+        if device is None:
+            device = next(self.parameters()).device
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise fx._cabi.MsclError("MoCoV2 needs its parameters on a CUDA device (no CPU fallback)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if self._nq is not None and self._nq.device == device:
+            return self._nq
+        if self._nq is not None:       # module was moved: carry the state over
+            self._staged = self._gathered_state()
+        rank = dist.get_rank() if _dist_on() else 0
+        world = dist.get_world_size() if _dist_on() else 1
+        nq = fx.NegativeQueue(self.K, self.dim, device, rank, world, shard=self.shard_queue and world > 1)
+        with torch.cuda.device(device):
+            nq.load(self._staged["queue"], self._staged["count"], self._staged["ptr"])
+        self._nq, self._staged = nq, None
+        return nq
+
+    def _gathered_state(self):
+        """Reference-layout state (queue (C,K), count (K,), ptr).  Collective when the queue is sharded."""
+        if self._nq is None:
+            return self._staged
+        q, c = self._nq.export()
+        if self._nq.world > 1:
+            qs = [torch.empty_like(q) for _ in range(self._nq.world)]
+            cs = [torch.empty_like(c) for _ in range(self._nq.world)]
+            dist.all_gather(qs, q)
+            dist.all_gather(cs, c)
+            q, c = torch.cat(qs, dim=1), torch.cat(cs)
+        return dict(queue=q, count=c, ptr=self._nq.ptr)
+
+    @property
+    def queue(self):
+        return self._gathered_state()["queue"]
+
+    @property
+    def count(self):
+        return self._gathered_state()["count"]
+
+    @property
+    def queue_ptr(self):
+        st = self._gathered_state()
+        return torch.tensor([st["ptr"]], dtype=torch.long, device=st["queue"].device)
+
+    @staticmethod
+    def _export_queue_hook(module, state_dict, prefix, local_metadata):
+        st = module._gathered_state()
+        state_dict[prefix + "queue"] = st["queue"].detach().clone()
+        state_dict[prefix + "queue_ptr"] = torch.tensor([st["ptr"]], dtype=torch.long, device=st["queue"].device)
+        state_dict[prefix + "count"] = st["count"].detach().clone()
+        return state_dict
+
+    def _import_queue_hook(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        keys = [prefix + k for k in ("queue", "queue_ptr", "count")]
+        if not all(k in state_dict for k in keys):
+            if strict:
+                missing_keys.extend(k for k in keys if k not in state_dict)
+            for k in keys:
+                state_dict.pop(k, None)
+            return
+        queue, ptr, count = (state_dict.pop(k) for k in keys)
+        if tuple(queue.shape) != (self.dim, self.K) or tuple(count.shape) != (self.K,):
+            error_msgs.append(f"size mismatch for {prefix}queue/count: got {tuple(queue.shape)} / {tuple(count.shape)}")
+            return
+        staged = dict(queue=queue.detach().float().cpu(), count=count.detach().long().cpu(), ptr=int(ptr.view(-1)[0]))
+        if self._nq is not None:
+            dev = self._nq.device
+            self._nq = None
+            self._staged = staged
+            self.negative_queue(dev)
+        else:
+            self._staged = staged
+
+    @property
+    def weight(self):
+        """Decayed queue snapshot (C,K) of the last forward_train, as the reference keeps in
+        `self._weight` (moco.py:488,549-551).  Materialised only on request."""
+        if self._weight is None:
+            raise RuntimeError("no snapshot kept: call forward_train(..., return_features=True) or set "
+                               "train_cfg=dict(keep_weight_snapshot=True)")
+        return self._weight
+
+    # ------------------------------------------------------------------ K4
+    @torch.no_grad()
+    def _momentum_update_key_encoder(self):
+        factor = min(self.iters / self.max_iters, 1)
+        self.m = 1 * (1 - 0.5 * (1 - self.m_base) * (cos(pi * factor) + 1))
+        if self._ema is None:
+            pk, pq = [], []
+            for mq, mk in self._qk_modules():
+                pq += list(mq.parameters())
+                pk += list(mk.parameters())
+            self._ema = fx.EmaTable(pk, pq)
+        self._ema.update(self.m)
+
+    # ------------------------------------------------------------------ K5
+    @torch.no_grad()
+    def _dequeue_and_enqueue(self, keys):
+        keys = concat_all_gather(keys.contiguous())
+        self.batch_size = keys.shape[0]
+        self.negative_queue(keys.device).enqueue(keys.contiguous())
+
+    # ------------------------------------------------------------------ K6
+    def _shuffle_group(self):
+        if self._cpu_group is None and _dist_on():
+            self._cpu_group = dist.new_group(backend="gloo")
+        return self._cpu_group
+
+    @torch.no_grad()
+    def _batch_shuffle_ddp(self, x):
+        """Returns (rows this rank feeds its key encoder, idx_unshuffle) -- moco.py:146-172."""
+        world = dist.get_world_size() if _dist_on() else 1
+        n = x.shape[0]
+        idx_shuffle = shf.draw_permutation(n * world, x.device, self._shuffle_group())
+        idx_unshuffle = torch.argsort(idx_shuffle)
+        if world == 1:
+            # one rank: the key encoder sees the same set of clips whatever their order, and the
+            # unshuffle restores it; batch-norm statistics are permutation invariant -> no copy
+            return x, idx_unshuffle
+        plan = shf.ShufflePlan(idx_shuffle, n, dist.get_rank(), world)
+        return shf.exchange(x.contiguous(), plan, fx.gather_rows), idx_unshuffle
+
+    @torch.no_grad()
+    def _batch_unshuffle_ddp(self, x, idx_unshuffle):
+        """moco.py:174-191."""
+        world = dist.get_world_size() if _dist_on() else 1
+        if world == 1:
+            return x
+        plan = shf.ShufflePlan(idx_unshuffle, x.shape[0], dist.get_rank(), world)
+        return shf.exchange(x.contiguous(), plan, fx.gather_rows)
+
+    # ------------------------------------------------------------------ encoders
+    def extract_feat(self, im_q, im_k, unshuffle_mlvl=True):
+        """Returns q, q_mlvl, k, k_mlvl, sup_loss (moco.py:517-547)."""
+        q_mlvl = self.encoder_q(im_q)
+        (q_emb, q_mlvl), sup_loss = self.neck_q(q_mlvl)
+        q = F.normalize(self.mlp_q(q_emb), dim=1)
+        with torch.no_grad():
+            self._momentum_update_key_encoder()
+            im_k, idx_unshuffle = self._batch_shuffle_ddp(im_k)
+            k_mlvl = self.encoder_k(im_k)
+            (k_emb, k_mlvl), _ = self.neck_k(k_mlvl)
+            k = F.normalize(self.mlp_k(k_emb), dim=1)
+            k = self._batch_unshuffle_ddp(k, idx_unshuffle)
+            if unshuffle_mlvl:     # never consumed by MSCLWithAug: skipped there
+                k_mlvl = [self._batch_unshuffle_ddp(lvl, idx_unshuffle) for lvl in k_mlvl]
+        return q, q_mlvl, k, k_mlvl, sup_loss
+
+    # ------------------------------------------------------------------ the objective
+    def _group(self):
+        nq = self._nq
+        return dist.group.WORLD if (nq is not None and nq.world > 1) else None
+
+    def contrast(self, terms, T=None):
+        """Fused InfoNCE of several (q, k_pos) row sets against the CURRENT queue state in one pass.
+        Returns a (len(terms), 4) tensor of [loss, top1, top5, 0] rows."""
+        n = terms[0][0].shape[0]
+        q = torch.cat([t[0] for t in terms], dim=0).contiguous()
+        kp = torch.cat([t[1].detach() for t in terms], dim=0).contiguous()
+        nq = self.negative_queue(q.device)
+        out, _ = fx.infonce(q, kp, nq, n, self.T if T is None else T, group=self._group())
+        return out
+
+    def note_branch(self, n_local, update_queue=True):
+        """Host-side bookkeeping of one forward_train call (moco.py:429,504-505): the gathered batch
+        size is recorded by the enqueue, then `iters` advances by it while training."""
+        if update_queue:
+            self.batch_size = n_local * (dist.get_world_size() if _dist_on() else 1)
+        if self.training:
+            self.iters += self.batch_size
+
+    def after_branch(self, k, update_queue=True):
+        """Enqueue + iteration bookkeeping of one forward_train call (moco.py:500-505)."""
+        if update_queue:
+            self._dequeue_and_enqueue(k)
+        self.note_branch(k.shape[0], False)
+
+    def train_step(self, data_batch, optimizer, **kwargs):
+        im_q = data_batch[self.im_key][0]
+        im_k = data_batch[self.im_key][1]
+        aux_info = {}
+        for item in self.aux_info:
+            assert item in data_batch
+            aux_info[item] = data_batch[item]
+        losses = self(im_q, im_k, aux_info, return_loss=True)
+        loss, log_vars = self._parse_losses(losses)
+        return dict(num_samples=im_q.shape[0], loss=loss, log_vars=log_vars)
+
+    def forward(self, im_q, im_k, aux_info, return_loss=True, **kwargs):
+        if kwargs.get("gradcam", False):
+            del kwargs["gradcam"]
+            return self.forward_gradcam(im_q, im_k, aux_info, **kwargs)
+        if return_loss:
+            return self.forward_train(im_q, im_k, aux_info, **kwargs)
+        raise NotImplementedError("MoCo doesnt support test mode")
+
+    def forward_train(self, im_q, im_k, aux_info, return_features=False, update_queue=True):
+        if return_features:
+            aux_info = aux_info.copy()
+        else:
+            im_q, im_k, aux_info = self.aug_gpu(im_q, im_k, aux_info)
+        q, q_mlvl, k, k_mlvl, sup_loss = self.extract_feat(im_q, im_k)
+        if not self.moco_head.can_fuse():
+            raise NotImplementedError("the fused path needs loss_cls=CrossEntropyLoss_torch without class weights")
+        out = self.contrast([(q, k)])                        # snapshot semantics: before the enqueue
+        if return_features or self.keep_weight_snapshot:    # an outer recognizer may read `.weight`
+            self._weight = self._gathered_weight()
+        self.after_branch(k, update_queue)
+        losses = self.moco_head.loss_fused(out[0])
+        losses.update(sup_loss)
+        if return_features:
+            return losses, dict(q=q, q_mlvl=q_mlvl, k=k, k_mlvl=k_mlvl, q_neg=None)
+        return losses
+
+    def _gathered_weight(self):
+        w = self._nq.weight()
+        if self._nq.world > 1:
+            ws = [torch.empty_like(w) for _ in range(self._nq.world)]
+            dist.all_gather(ws, w)
+            w = torch.cat(ws, dim=1)
+        return w
+
+    def visualize(self, data_batch):
+        pass

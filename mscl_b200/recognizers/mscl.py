@@ -1,0 +1,170 @@
+"""MSCLWithAug: RGB MoCoV2 + flow MoCoV2 (base flow and FRA-rotated flow) + cross-modal
+InfoNCE + LMCL (reference: recognizers/mscl.py:137-292).
+
+The reference evaluates 7 InfoNCE terms per step, each with its own materialised
+(N,1+K) logits, against only THREE distinct negative matrices:
+
+    W_rgb  (before this step's RGB enqueue)   <- q (own), q_f (fr), q_af (fr_aug)
+    W_flow (before the base-flow enqueue)     <- q_f (own)
+    W_flow (after the base-flow enqueue)      <- q_af (own_aug), q (rf), q (rf_aug)
+
+Here each matrix is streamed ONCE by the fused kernel with the query sets stacked
+(3N + N + 3N rows); the RGB enqueue is merely deferred until the rows that need the
+pre-enqueue RGB queue exist.  Effects visible from outside (queue contents, pointer, ages,
+`iters`, momentum, permutation draws, loss keys and values) are those of the reference.
+"""
+from collections import OrderedDict
+
+import torch
+
+from ..registry import RECOGNIZERS, build_recognizer, build_ssl_aug
+from .base_moco import BaseMoCoRecognizer
+
+
+@RECOGNIZERS.register_module()
+class MSCLWithAug(BaseMoCoRecognizer):
+    def __init__(self, recognizer, recognizer_flow, moco_mx_head, sup_head, im_key="imgs", flow_key="flow_imgs",
+                 aux_info=[], aug=dict(dtype="MoCoAugmentV3", moco_aug=(112, 112), t=8), same_kn=True,
+                 update_aug_flow=False, weight_aug_flow=(1.0, 1.0), train_cfg=None, test_cfg=None):
+        super().__init__(train_cfg=train_cfg, test_cfg=test_cfg)
+        if train_cfg:   # options such as shard_queue reach both branches
+            recognizer = dict(recognizer, train_cfg=dict(recognizer.get("train_cfg") or {}, **train_cfg))
+            recognizer_flow = dict(recognizer_flow, train_cfg=dict(recognizer_flow.get("train_cfg") or {}, **train_cfg))
+        self.recognizer = build_recognizer(recognizer)
+        self.recognizer_flow = build_recognizer(recognizer_flow)
+        self.im_key = im_key
+        self.same_kn = same_kn
+        self.update_aug_flow = update_aug_flow
+        self.weight_aug_flow = weight_aug_flow
+        if isinstance(flow_key, (list, tuple)):
+            self.cat_flow = False
+            self.flow_key = flow_key
+        else:
+            self.cat_flow = True
+            self.flow_key = (flow_key,)
+        self.aux_info = aux_info
+        self._build_cls_head(moco_mx_head, name="moco_mx_head")
+        self._build_cls_head(sup_head, name="sup_head")
+        self.aug_gpu = build_ssl_aug(aug)
+
+    def train_step(self, data_batch, optimizer, **kwargs):
+        im_q = data_batch[self.im_key][0]
+        im_k = data_batch[self.im_key][1]
+        aux_info = {}
+        for flow_key in self.flow_key:
+            aux_info[f"{flow_key}_q"] = data_batch[flow_key][0]
+            aux_info[f"{flow_key}_k"] = data_batch[flow_key][1]
+        for item in self.aux_info:
+            assert item in data_batch
+            aux_info[item] = data_batch[item]
+        losses = self(im_q, im_k, aux_info, return_loss=True)
+        loss, log_vars = self._parse_losses(losses)
+        return dict(num_samples=im_q.shape[0], loss=loss, log_vars=log_vars)
+
+    def forward(self, im_q, im_k, aux_info, return_loss=True, **kwargs):
+        if kwargs.get("gradcam", False):
+            del kwargs["gradcam"]
+            return self.forward_gradcam(im_q, im_k, aux_info, **kwargs)
+        if return_loss:
+            return self.forward_train(im_q, im_k, aux_info, **kwargs)
+        raise NotImplementedError("MoCo doesnt support test mode")
+
+    def objective(self, feats):
+        """Everything after the encoders (mscl.py:228-277 + moco.py:481-510), fused.
+
+        feats: q,k (RGB) q_f,k_f (base flow) q_af,k_af (FRA flow), each (N,128), and the
+        multi-level query features q_mlvl, q_flow_mlvl, q_aug_flow_mlvl.
+        """
+        rec, recf, mx = self.recognizer, self.recognizer_flow, self.moco_mx_head
+        q, k, q_f, k_f, q_af, k_af = (feats[n] for n in ("q", "k", "q_f", "k_f", "q_af", "k_af"))
+        for head in (rec.moco_head, recf.moco_head, mx):
+            if not head.can_fuse():
+                raise NotImplementedError("the fused path needs loss_cls=CrossEntropyLoss_torch without class weights")
+        use_aug_mx = self.weight_aug_flow[1] > 0
+
+        # which decayed queue each cross-modal term reads (heads/moco_head_v2.py:42-47)
+        rf_queue, fr_queue = ("flow_post", "rgb_pre") if self.same_kn else ("rgb_pre", "flow_post")
+        terms = {"rgb_pre": [("own", q, k, rec.T)], "flow_pre": [("own_f", q_f, k_f, recf.T)],
+                 "flow_post": [("own_af", q_af, k_af, recf.T)]}
+        terms[rf_queue].append(("rf", q, k_f, mx.T))
+        terms[fr_queue].append(("fr", q_f, k, mx.T))
+        if use_aug_mx:
+            terms[rf_queue].append(("rf_aug", q, k_af, mx.T))
+            terms[fr_queue].append(("fr_aug", q_af, k, mx.T))
+
+        rows = {}
+
+        def run(phase, owner):
+            by_T = OrderedDict()          # one pass per distinct temperature (one, in the configs)
+            for name, qq, kk, T in terms[phase]:
+                by_T.setdefault(T, []).append((name, qq, kk))
+            for T, items in by_T.items():
+                out = owner.contrast([(qq, kk) for _, qq, kk in items], T)
+                for i, (name, _, _) in enumerate(items):
+                    rows[name] = out[i]
+
+        run("rgb_pre", rec)                        # W_rgb before this step's enqueue
+        run("flow_pre", recf)                      # W_flow before the base-flow enqueue
+        rec._dequeue_and_enqueue(k)                # RGB call's enqueue (deferred past its consumers)
+        recf._dequeue_and_enqueue(k_f)             # base-flow call's enqueue
+        run("flow_post", recf)                     # W_flow containing this step's base-flow keys
+        if self.update_aug_flow:
+            recf._dequeue_and_enqueue(k_af)
+
+        losses = OrderedDict()
+        losses.update(rec.moco_head.loss_fused(rows["own"]))
+        loss_flow = recf.moco_head.loss_fused(rows["own_f"])
+        for key, val in recf.moco_head.loss_fused(rows["own_af"]).items():
+            if key.startswith("loss"):          # the FRA branch's accuracies are dropped (mscl.py:242-245)
+                loss_flow[key + "_aug"] = val * self.weight_aug_flow[0]
+        losses.update(loss_flow)
+        losses.update(mx.loss_fused_mx(rows["rf"], rows["fr"]))
+        if use_aug_mx:
+            losses.update(mx.loss_fused_mx(rows["rf_aug"], rows["fr_aug"], suffix="_aug"))
+
+        aux = {}
+        aux = self.sup_head.update_aux_info("im_features", dict(q_mlvl=feats["q_mlvl"]), aux)
+        aux = self.sup_head.update_aux_info("base_flow_features", dict(q_mlvl=feats["q_flow_mlvl"]), aux)
+        aux = self.sup_head.update_aux_info("aug_flow_features", dict(q_mlvl=feats["q_aug_flow_mlvl"]), aux)
+        aux.update(self.sup_head(**aux))
+        losses.update(self.sup_head.loss(**aux))
+        return losses
+
+    def forward_train(self, im_q, im_k, aux_info):
+        im_q, im_k, aux_info = self.aug_gpu(im_q, im_k, aux_info)
+        rec, recf = self.recognizer, self.recognizer_flow
+        if self.cat_flow:
+            cat_q, cat_k = aux_info[f"{self.flow_key[0]}_q"], aux_info[f"{self.flow_key[0]}_k"]
+            flow_q, aug_flow_q = (x.contiguous() for x in cat_q.chunk(2, 2))
+            flow_k, aug_flow_k = (x.contiguous() for x in cat_k.chunk(2, 2))
+        else:
+            flow_q, flow_k = aux_info[f"{self.flow_key[0]}_q"], aux_info[f"{self.flow_key[0]}_k"]
+            aug_flow_q, aug_flow_k = aux_info[f"{self.flow_key[1]}_q"], aux_info[f"{self.flow_key[1]}_k"]
+        # encoders in the reference's order: each call updates its key encoder by EMA and draws
+        # one shuffle permutation (RGB, base flow, FRA flow)
+        # one shuffle permutation (RGB, base flow, FRA flow); `iters` advances after each call so the
+        # second flow EMA sees the advanced schedule
+        n = im_q.shape[0]
+        q, q_mlvl, k, _, _ = rec.extract_feat(im_q, im_k, unshuffle_mlvl=False)
+        rec.note_branch(n, True)
+        q_f, qf_mlvl, k_f, _, _ = recf.extract_feat(flow_q, flow_k, unshuffle_mlvl=False)
+        recf.note_branch(n, True)
+        q_af, qaf_mlvl, k_af, _, _ = recf.extract_feat(aug_flow_q, aug_flow_k, unshuffle_mlvl=False)
+        recf.note_branch(n, self.update_aug_flow)
+        return self.objective(dict(q=q, k=k, q_f=q_f, k_f=k_f, q_af=q_af, k_af=k_af, q_mlvl=q_mlvl,
+                                   q_flow_mlvl=qf_mlvl, q_aug_flow_mlvl=qaf_mlvl))
+
+    def forward_test(self, imgs):
+        raise NotImplementedError("Not support for ssl recognizer !!!")
+
+    def forward_gradcam(self, imgs):
+        raise NotImplementedError("Not support for ssl recognizer !!!")
+
+    def extract_global_feat(self):
+        raise NotImplementedError("Not support for ssl recognizer !!!")
+
+    def extract_feat(self, im_q, im_k):
+        pass
+
+    def visualize(self, data_batch):
+        pass

@@ -1,0 +1,106 @@
+"""CPU restatement of one full MSCLWithAug training step.  TEST / BENCH INFRASTRUCTURE ONLY.
+
+The encoders, necks and projection MLPs are ordinary PyTorch modules (they stay in PyTorch in
+the product too, so the SAME module classes are instantiated here on the CPU and given the
+SAME weights); everything the hot path replaces -- momentum EMA, shuffle-BN, decayed-queue
+snapshot, logits, cross-entropy, host top-k, enqueue, LMCL -- is evaluated with the
+reference's own operation sequence through oracle/mscl_oracle.py
+(mmaction/models/recognizers/moco.py:408-547, mscl.py:225-277).
+
+Used (a) by the GPU parity tests as the checker of a whole step, (b) by bench.py as the
+CPU baseline (`--impl reference`), (c) by tests/test_oracle_vs_reference.py, which pins it
+against the unmodified reference run through oracle/ref_shim.py.
+"""
+import copy
+
+import torch
+import torch.nn.functional as F
+
+from . import mscl_oracle as O
+
+
+class OracleBranch:
+    """One MoCoV2: q/k encoder, neck, MLP on the CPU + reference-layout queue state."""
+
+    def __init__(self, rec, state=None):
+        self.encoder_q, self.encoder_k = copy.deepcopy(rec.encoder_q).cpu(), copy.deepcopy(rec.encoder_k).cpu()
+        self.neck_q, self.neck_k = copy.deepcopy(rec.neck_q).cpu(), copy.deepcopy(rec.neck_k).cpu()
+        self.mlp_q, self.mlp_k = copy.deepcopy(rec.mlp_q).cpu(), copy.deepcopy(rec.mlp_k).cpu()
+        # torchvision backbones carry the multi-level forward as an instance attribute bound to the
+        # ORIGINAL module; rebind it to the copy
+        from mscl_b200.backbones import torchvision_multilevel
+        for enc in (self.encoder_q, self.encoder_k):
+            if "forward" in enc.__dict__:
+                del enc.__dict__["forward"]
+                torchvision_multilevel(enc)
+        st = state or rec._gathered_state()
+        self.state = O.QueueState(st["queue"].cpu().float(), st["count"].cpu().long(), int(st["ptr"]))
+        self.state.iters, self.state.batch_size = rec.iters, rec.batch_size
+        self.m_base, self.max_iters, self.T = rec.m_base, rec.max_iters, rec.T
+        self.train(rec.training)
+
+    def train(self, mode=True):
+        for m in (self.encoder_q, self.encoder_k, self.neck_q, self.neck_k, self.mlp_q, self.mlp_k):
+            m.train(mode)
+
+    def q_params(self):
+        return [p for m in (self.encoder_q, self.neck_q, self.mlp_q) for p in m.parameters()]
+
+    def k_params(self):
+        return [p for m in (self.encoder_k, self.neck_k, self.mlp_k) for p in m.parameters()]
+
+    def extract_feat(self, im_q, im_k):
+        """moco.py:517-547 with world size 1 (the shuffle draws a permutation and applies it)."""
+        q_mlvl = self.encoder_q(im_q)
+        (q_emb, q_mlvl), _ = self.neck_q(q_mlvl)
+        q = F.normalize(self.mlp_q(q_emb), dim=1)
+        with torch.no_grad():
+            m = O.momentum(self.state.iters, self.max_iters, self.m_base)
+            for pk, new in zip(self.k_params(), O.ema_update([p.data for p in self.k_params()],
+                                                             [p.data for p in self.q_params()], m)):
+                pk.data = new
+            idx = torch.randperm(im_k.shape[0])
+            im_k, unshuf = O.batch_shuffle(im_k, idx, 0, 1)
+            k_mlvl = self.encoder_k(im_k)
+            (k_emb, k_mlvl), _ = self.neck_k(k_mlvl)
+            k = F.normalize(self.mlp_k(k_emb), dim=1)
+            k = O.batch_unshuffle(k, unshuf, 0, 1)
+        return q, q_mlvl, k
+
+
+class OracleMSCL:
+    def __init__(self, model):
+        self.rgb = OracleBranch(model.recognizer)
+        self.flow = OracleBranch(model.recognizer_flow)
+        self.T = model.moco_mx_head.T
+        self.t = model.sup_head.labels.shape[1]
+        self.mlvl_ids = model.sup_head.mlvl_ids
+        self.weight_aug_flow = model.weight_aug_flow
+        self.training = model.training
+
+    def parameters(self):
+        return self.rgb.q_params() + self.flow.q_params()
+
+    def train_step(self, im_q, im_k, flow_q, flow_k):
+        """Inputs already augmented: RGB (N,3,T,H,W), flow images (N,3,2T,H,W).  Returns (loss, log_vars).
+        Call order is the reference's (mscl.py:227-240): each recognizer call = encoders, logits
+        against the pre-enqueue snapshot, enqueue, iters."""
+        from collections import OrderedDict
+        tr, T = self.training, self.T
+        fq, afq = (x.contiguous() for x in flow_q.chunk(2, 2))
+        fk, afk = (x.contiguous() for x in flow_k.chunk(2, 2))
+        q, q_mlvl, k = self.rgb.extract_feat(im_q, im_k)
+        loss_img = self.rgb.state.branch(q, k, self.rgb.T, "", True, tr)
+        q_f, qf_mlvl, k_f = self.flow.extract_feat(fq, fk)
+        loss_flow = self.flow.state.branch(q_f, k_f, self.flow.T, "_flow", True, tr)
+        q_af, qaf_mlvl, k_af = self.flow.extract_feat(afq, afk)       # EMA sees the advanced iters
+        loss_aug = self.flow.state.branch(q_af, k_af, self.flow.T, "_flow", False, tr)
+        loss_flow = O.merge_flow_losses(loss_flow, loss_aug, self.weight_aug_flow)
+        feats = dict(q=q, k=k, q_f=q_f, k_f=k_f, q_af=q_af, k_af=k_af, q_map=q_mlvl[self.mlvl_ids[0]],
+                     qf_map=qf_mlvl[self.mlvl_ids[1]], qaf_map=qaf_mlvl[self.mlvl_ids[1]])
+        loss_mx, loss_sup = O.mscl_tail(feats, self.rgb.state.weight, self.flow.state.weight, T, self.t,
+                                        self.weight_aug_flow)
+        losses = OrderedDict()
+        for d in (loss_img, loss_flow, loss_mx, loss_sup):
+            losses.update(d)
+        return O.parse_losses(losses)

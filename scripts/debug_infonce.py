@@ -20,14 +20,14 @@ for impl in ("simt", "tc"):
     _cabi.call("mscl_infonce_prep", qd.data_ptr(), kd.data_ptr(), M, nq.birth.data_ptr(), nq.qstate.data_ptr(), K, inv_T, 1.0,
                qpack.data_ptr(), dscale.data_ptr(), acc.data_ptr(), M, st)
     if impl == "simt":
-        _cabi.call("mscl_infonce_partial_simt", qpack.data_ptr(), M, nq.queue.data_ptr(), dscale.data_ptr(), K, acc.data_ptr(), 1, st)
+        _cabi.call("mscl_infonce_partial_simt", qpack.data_ptr(), M, nq.queue_tf32.data_ptr(), dscale.data_ptr(), K, acc.data_ptr(), 1, st)
     else:
-        _cabi.call("mscl_infonce_partial", qpack.data_ptr(), M, nq.queue.data_ptr(), dscale.data_ptr(), K, acc.data_ptr(), 1, 148, st)
+        _cabi.call("mscl_infonce_partial", qpack.data_ptr(), M, nq.queue_tf32.data_ptr(), dscale.data_ptr(), K, acc.data_ptr(), 1, 148, st)
     torch.cuda.synchronize()
     # float64 model of the accumulators
     qp = qpack[:, :128].double()
     ds = dscale[:K].double()
-    W = nq.queue.double()                        # (K, C)
+    W = nq.queue_tf32.double()                        # (K, C)
     s2 = (qp @ W.T) * ds                         # (M, K)
     shift2 = qpack[:, 129].double().unsqueeze(1)
     pos2 = qpack[:, 128].double().unsqueeze(1)

@@ -1,0 +1,100 @@
+"""Live pin: the oracle's full training step (oracle/step.py, which re-uses the product's
+PyTorch encoder / neck modules on the CPU) against the UNMODIFIED reference executed through
+oracle/ref_shim.py.  Also proves state_dict key compatibility of the product model with the
+reference model.  Skipped where /root/reference does not exist (the GPU box)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def pair():
+    import mscl_b200
+    from mscl_b200.configs import mscl_r18_model
+    ref = ref_shim.load_reference()
+    ref_shim.ensure_process_group()
+    cfg = mscl_r18_model(K=256, aug="IdentityAug")
+    cfg["recognizer"]["max_iters"] = cfg["recognizer_flow"]["max_iters"] = 1000
+    torch.manual_seed(0)
+    ref_model = ref.builder.build_model(dict(cfg, aug=dict(type="SyncMoCoAugmentV5")))
+    mine = mscl_b200.build_model(cfg)
+    return ref, ref_model, mine
+
+
+def test_state_dict_keys_and_load(pair):
+    ref, ref_model, mine = pair
+    sd_ref = ref_model.state_dict()
+    sd_mine = mine.state_dict()
+    assert set(sd_ref.keys()) == set(sd_mine.keys())
+    for k in sd_ref:
+        assert tuple(sd_ref[k].shape) == tuple(sd_mine[k].shape), k
+        assert sd_ref[k].dtype == sd_mine[k].dtype, k
+    mine.load_state_dict(sd_ref, strict=True)
+    sd2 = mine.state_dict()
+    for k in sd_ref:
+        np.testing.assert_array_equal(sd2[k].numpy(), sd_ref[k].numpy(), err_msg=k)
+
+
+def test_parameter_counts(pair):
+    """SURVEY App. B probe facts."""
+    _, _, mine = pair
+    count = lambda ms: sum(p.numel() for m in ms for p in m.parameters())
+    r, f = mine.recognizer, mine.recognizer_flow
+    assert count([r.encoder_k, r.neck_k, r.mlp_k]) == 36_707_392
+    assert count([f.encoder_k, f.neck_k, f.mlp_k]) == 735_120
+    assert len([p for m in (r.encoder_k, r.neck_k, r.mlp_k) for p in m.parameters()]) == 88
+    assert len([p for m in (f.encoder_k, f.neck_k, f.mlp_k) for p in m.parameters()]) == 64
+
+
+def test_full_step_matches_reference(pair):
+    from oracle.step import OracleMSCL
+    ref, ref_model, mine = pair
+    mine.load_state_dict(ref_model.state_dict(), strict=True)
+    ref_model.train(), mine.train()
+    orc = OracleMSCL(mine)
+    g = torch.Generator().manual_seed(3)
+    N = 2
+    data = dict(imgs=[torch.rand(N, 3, 8, 112, 112, generator=g) for _ in range(2)],
+                flow_imgs=[torch.rand(N, 3, 16, 112, 112, generator=g) for _ in range(2)])
+    for step in range(2):      # second step exercises non-zero iters / ages / pointer
+        torch.manual_seed(100 + step)
+        out = ref_model.train_step(data, None)
+        ref_model.zero_grad()
+        out["loss"].backward()
+        torch.manual_seed(100 + step)
+        for p in orc.parameters():
+            p.grad = None
+        loss, log_vars = orc.train_step(data["imgs"][0], data["imgs"][1], data["flow_imgs"][0], data["flow_imgs"][1])
+        loss.backward()
+        assert list(log_vars) == list(out["log_vars"])
+        for k, v in out["log_vars"].items():
+            assert abs(log_vars[k] - v) <= 2e-5 * max(1.0, abs(v)), (step, k, log_vars[k], v)
+        for tag, rec, st in (("rgb", ref_model.recognizer, orc.rgb.state), ("flow", ref_model.recognizer_flow, orc.flow.state)):
+            assert int(rec.queue_ptr) == st.ptr and rec.iters == st.iters and rec.batch_size == st.batch_size
+            np.testing.assert_array_equal(rec.count.numpy(), st.count.numpy())
+            np.testing.assert_allclose(rec.queue.numpy(), st.queue.numpy(), rtol=0, atol=2e-6)
+        gr = dict(ref_model.named_parameters())
+        for name, p in (("recognizer.mlp_q.2.weight", orc.rgb.mlp_q[2].weight),
+                        ("recognizer_flow.encoder_q.stem.0.weight", orc.flow.encoder_q.stem[0].weight),
+                        ("recognizer.neck_q.tpn.fpn.lateral_convs.0.conv.weight", orc.rgb.neck_q.tpn.fpn.lateral_convs[0].conv.weight)):
+            a, b = p.grad, gr[name].grad
+            assert float((a - b).norm() / b.norm()) < 2e-4, name
+        # key encoders after the EMA(s)
+        kr = dict(ref_model.named_parameters())
+        np.testing.assert_allclose(orc.flow.mlp_k[0].weight.detach().numpy(), kr["recognizer_flow.mlp_k.0.weight"].detach().numpy(),
+                                   rtol=0, atol=1e-7)
+
+
+def test_fra_live(pair):
+    """The oracle's float32 FRA against the reference's NumPy code run here (NumPy 2: float64 rotation)."""
+    from oracle import inputs, mscl_oracle as O
+    ref = pair[0]
+    flows = inputs.flow_clip(seed=4, T=8, H=32, W=32)
+    np.random.seed(11)
+    out = ref.NormFlowWithStidedAug(ratios=(0.2, 1.8), num_chunks=8)(dict(flows=[f.copy() for f in flows]))
+    got = np.stack(O.fra(flows, int(out["ap_labels"])))
+    np.testing.assert_allclose(got, np.stack(out["flow_imgs"]), rtol=3e-6, atol=3e-7)
