@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- contrastive-step clips/s of the MSCL R3D-18 pre-training step on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's path (sm_100a kernels)
+    python bench.py --impl reference [--gpus N] [--steps K] ...      # the reference's algorithm on the host CPU
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # N > 1, one rank per GPU
+
+Workload (BASELINE.json configs[1]): the `mscl_r18_cosm_lr2e-2` model dict unchanged (R3D-18 RGB
+branch + TPN neck, slim r2d_18 flow branch, K = 65536 negatives per queue, 32 clips per GPU),
+synthetic clips: RGB (32,3,8,112,112) x 2 views, raw optical flow (32,2,8,112,112) x 2 views.
+One step = FRA (rotated-flow negatives, K3) -> GPU augmentation -> MSCLWithAug.train_step
+(3 EMA updates K4, 3 shuffle-BN draws K6, 7 InfoNCE terms in 3 fused queue passes K1, LMCL K2,
+2 enqueues K5) -> backward -> grad-norm clip (40) -> SGD step.  Nothing is skipped or cached.
+
+`value`  : clips/s over all ranks with the step's inputs already resident in HBM.
+`e2e`    : the same step fed from pinned HOST buffers (H2D inside the timed region) and its log
+           variables read back to the host every step.
+`roofline`: the kernel of ours with the largest share of the step, timed live with CUDA events on
+           the launching stream inside the timed region; `kernels` lists every kernel of the path.
+`cpu_baseline`: the oracle (CPU restatement of the reference's algorithm, oracle/step.py) timed on
+           this box's host cores on a bounded sample of the same workload.
+
+Timing: CUDA events on the current stream, barrier + synchronize on both sides, max over ranks.
+Every step touches >1 GB of activations, far more than the 126 MB L2, and alternates between
+distinct input batches, so no timed iteration finds its inputs in L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "contrastive_step_clips_per_sec"
+UNIT = "clips/s"
+WORKLOAD = "mscl_r18_cosm_lr2e-2 pretrain step (R3D-18 + r2d_18 flow, TPN neck, K=65536, 8x112x112 RGB + 8+8 flow frames)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU (config: videos_per_gpu=32)")
+    ap.add_argument("--K", type=int, default=65536, help="negatives per queue")
+    ap.add_argument("--ref-clips", type=int, default=4, help="clips per step of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shard", action="store_true", help="N>1: keep the queue replicated instead of K/N shards")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]), tf_sust=float(p["bf16_tflops_sustained"]),
+                    src="MEASURED_PEAKS.json")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic data (seeded, shapes of SURVEY.md section 8d cfg 2)
+# ----------------------------------------------------------------------------------------------
+def make_host_batch(n, seed, pin):
+    g = torch.Generator().manual_seed(seed)
+    b = dict(imgs_q=torch.rand(n, 3, 8, 112, 112, generator=g), imgs_k=torch.rand(n, 3, 8, 112, 112, generator=g),
+             flow_q=torch.randn(n, 2, 8, 112, 112, generator=g) * 3.0, flow_k=torch.randn(n, 2, 8, 112, 112, generator=g) * 3.0)
+    rs = np.random.RandomState(seed)
+    b["cid_q"] = torch.from_numpy(rs.randint(0, 8, size=n).astype(np.int32))    # transforms_motion.py:113
+    b["cid_k"] = torch.from_numpy(rs.randint(0, 8, size=n).astype(np.int32))
+    if pin:
+        b = {k: v.pin_memory() for k, v in b.items()}
+    return b
+
+
+def batch_bytes(b):
+    return int(sum(v.numel() * v.element_size() for v in b.values()))
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("uuid,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.proc, self.path, self.uuid = None, None, ""
+        try:
+            self.uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        except Exception:
+            pass
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="mscl_clocks_", suffix=".csv")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=fd, stderr=subprocess.DEVNULL)
+            os.close(fd)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = []
+        with open(self.path) as f:
+            for line in f:
+                p = [x.strip() for x in line.split(",")]
+                if len(p) == 8:
+                    rows.append(p)
+        os.unlink(self.path)
+        mine = [r for r in rows if self.uuid and self.uuid.replace("GPU-", "") in r[0]] or rows
+        if not mine:
+            return None
+        sm = []
+        for r in mine:
+            try:
+                sm.append(float(r[1]))
+            except ValueError:
+                pass
+        if not sm:
+            return None
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i] == "Active" for r in mine)]
+        load = sorted(sm)[len(sm) // 4:]           # drop the idle head of the sampling window
+        power = [float(r[3]) for r in mine if r[3].replace(".", "", 1).isdigit()]
+        return dict(sm_mhz=float(np.median(load)), sm_max_mhz=float(mine[0][2]), reasons=reasons, samples=len(mine),
+                    power_w_max=max(power) if power else None)
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's algorithm on the host CPU (oracle/step.py): --impl reference and cpu_baseline
+# ----------------------------------------------------------------------------------------------
+def cpu_step_factory(K, n_clips, threads):
+    """Returns (step_fn, description).  One call = one full training step on the CPU through the
+    oracle: NumPy FRA per clip (transforms_motion.py:103-142), augmentation, the reference's
+    operation sequence for EMA / shuffle / logits / CE / host top-k / enqueue / LMCL, backward,
+    grad clip, SGD."""
+    import mscl_b200
+    from mscl_b200.configs import mscl_r18_model
+    from oracle import mscl_oracle as O
+    from oracle.step import OracleMSCL
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = mscl_b200.build_model(mscl_r18_model(K=K))      # plain PyTorch modules on the CPU; no kernel is touched
+    model.train()
+    orc = OracleMSCL(model)
+    aug = model.aug_gpu
+    opt = torch.optim.SGD(orc.parameters(), lr=0.02, momentum=0.9, weight_decay=1e-4)
+    batches = [make_host_batch(n_clips, 1000 + i, pin=False) for i in range(2)]
+    state = dict(i=0)
+
+    def fra_cpu(flow, cid):     # (n,2,T,H,W) planar -> (n,2,2T,H,W): per-frame NumPy like the dataloader workers
+        out = []
+        for s in range(flow.shape[0]):
+            frames = [np.ascontiguousarray(flow[s, :, t].permute(1, 2, 0).numpy()) for t in range(flow.shape[2])]
+            o = np.stack(O.fra(frames, int(cid[s])))                 # (2T,H,W,2)
+            out.append(torch.from_numpy(o).permute(3, 0, 1, 2))
+        return torch.stack(out).contiguous()
+
+    def step():
+        b = batches[state["i"] % 2]
+        state["i"] += 1
+        aux = dict(flow_imgs_q=fra_cpu(b["flow_q"], b["cid_q"]), flow_imgs_k=fra_cpu(b["flow_k"], b["cid_k"]))
+        im_q, im_k, aux = aug(b["imgs_q"], b["imgs_k"], aux)
+        loss, log_vars = orc.train_step(im_q, im_k, aux["flow_imgs_q"], aux["flow_imgs_k"])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(orc.parameters(), 40.0)
+        opt.step()
+        return log_vars["loss"]
+
+    return step, f"{n_clips} clips/step, same model and K={K}, full step incl. FRA (NumPy), aug, backward, SGD"
+
+
+def time_cpu(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.ref_clips
+    step, desc = cpu_step_factory(args.K, n, threads)
+    t0 = time.perf_counter()
+    step()                                     # first warm-up step doubles as the probe
+    probe = time.perf_counter() - t0
+    budget = 240.0
+    if probe * (args.steps + args.warmup) > budget and n > 2:
+        n = 2
+        step, desc = cpu_step_factory(args.K, n, threads)
+        step()
+    sec = time_cpu(step, args.steps, max(args.warmup - 1, 0))
+    v = n / sec
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clips_per_step": n, "K": args.K, "device": "host CPU"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# this repo's path
+# ----------------------------------------------------------------------------------------------
+KERNEL_ENTRIES = ["mscl_infonce_partial", "mscl_ema_multi", "mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_fra_maxrad",
+                  "mscl_fra_apply", "mscl_enqueue", "mscl_lmcl", "mscl_infonce_prep", "mscl_infonce_finalize",
+                  "mscl_gather_rows"]
+
+
+def summarise_kernels(rec, steps, pk):
+    """Group the event-timed launches by (entry point, algorithmic bytes): one row per launch class."""
+    rows = []
+    for name, launches in rec.items():
+        groups = {}
+        for ms, nbytes, flops in launches:
+            groups.setdefault((nbytes, flops), []).append(ms)
+        for (nbytes, flops), mss in groups.items():
+            avg = float(np.mean(mss))
+            row = dict(kernel=name, launches_per_step=len(mss) / steps, avg_us=avg * 1e3, step_share_ms=sum(mss) / steps,
+                       algo_bytes=nbytes, algo_flops=flops)
+            if nbytes and avg > 0:
+                row["gbs"] = nbytes / (avg * 1e-3) / 1e9
+                row["frac_hbm"] = row["gbs"] / pk["hbm"]
+            if flops and avg > 0:
+                row["tflops"] = flops / (avg * 1e-3) / 1e12
+            rows.append(row)
+    rows.sort(key=lambda r: -r["step_share_ms"])
+    return rows
+
+
+def run_b200(args, rank, local_rank, world):
+    import mscl_b200
+    from mscl_b200 import _cabi, functional as fx
+    from mscl_b200.configs import mscl_r18_model
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this arm has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _cabi.require_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    pk = peaks()
+    N = args.batch
+    torch.manual_seed(0)
+    shard = world > 1 and not args.no_shard
+    cfg = mscl_r18_model(K=args.K)
+    cfg["train_cfg"] = dict(shard_queue=shard)
+    model = mscl_b200.build_model(cfg).to(dev)
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=0.02, momentum=0.9, weight_decay=1e-4)      # mscl_r18 config :114-118
+    runner = model
+    if world > 1:
+        runner = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
+                                                           find_unused_parameters=True)   # apis/train.py:84-88
+    table = fx.fra_table(device=dev)
+    host = [make_host_batch(N, 17 + 2 * rank + i, pin=True) for i in range(2)]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d_bytes = batch_bytes(host[0])
+
+    def train_step(b):
+        # K3: base + FRA flow frames, (N,2,8,H,W) -> (N,2,16,H,W)
+        flow_q = fx.fra(b["flow_q"], b["cid_q"], table, "planar")
+        flow_k = fx.fra(b["flow_k"], b["cid_k"], table, "planar")
+        aux = dict(flow_imgs_q=flow_q, flow_imgs_k=flow_k)
+        losses = runner(b["imgs_q"], b["imgs_k"], aux, return_loss=True)
+        loss, log_vars = model._parse_losses(losses)        # one all_reduce + the step's device->host read
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 40.0)          # config :119
+        opt.step()
+        return log_vars
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync()
+        wall = time.perf_counter() - w0
+        ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]) / 1e3 / steps, float(ms[1]) / 1e3 / steps      # seconds per step (device, wall)
+
+    # ---- device-resident inputs: `value` ----
+    for i in range(args.warmup):
+        train_step(resident[i % 2])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _cabi.launches()
+    _cabi.start_timing(KERNEL_ENTRIES)
+    last = {}
+
+    def resident_step(i):
+        last["log_vars"] = train_step(resident[i % 2])
+
+    sec, wall = timed(resident_step, args.steps)
+    rec = _cabi.stop_timing()
+    launches = _cabi.launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- host-resident inputs through the public API: `e2e` ----
+    def host_step(i):
+        b = {k: v.to(dev, non_blocking=True) for k, v in host[i % 2].items()}
+        last["log_vars"] = train_step(b)
+
+    for i in range(min(2, args.warmup)):
+        host_step(i)
+    sec_e2e, wall_e2e = timed(host_step, args.steps)
+    d2h_bytes = 4 * len(last["log_vars"])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    kernels = summarise_kernels(rec, args.steps, pk)
+    top = kernels[0] if kernels else None
+    roofline = None
+    if top is not None:
+        roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top.get("gbs"), "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": top.get("frac_hbm"), "traffic": None, "avg_us": top["avg_us"], "algo_bytes": top["algo_bytes"],
+                    "peak_source": pk["src"] + " (burst copy figure)"}
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):       # dram bytes per launch read from an ncu --set full capture (profiles/)
+            with open(traffic_file) as f:
+                roofline["traffic"] = json.load(f).get(top["kernel"])
+    clips = N * world
+    line = {"metric": METRIC, "value": clips / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (tf32 tensor-core operands, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clips_per_gpu": N, "global_batch": clips, "K": args.K,
+                       "queue": f"sharded K/{world}" if shard else "replicated", "parallelism": f"dp{world}",
+                       "l2": "each step streams >1 GB of activations and alternates input batches: inputs never L2-resident"},
+            "e2e": {"value": clips / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": sec_e2e * 1e3, "wall_ms_per_step": wall_e2e * 1e3},
+            "wall_ms_per_step": wall * 1e3, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "kernels": kernels, "loss": last["log_vars"].get("loss")}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        step, desc = cpu_step_factory(args.K, args.ref_clips, threads)
+        sec_cpu = time_cpu(step, 2, 1)
+        line["cpu_baseline"] = {"value": args.ref_clips / sec_cpu, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": desc + "; 1 warm-up + 2 timed steps", "ms_per_step": sec_cpu * 1e3}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"bench.py --gpus {args.gpus} must be launched with torch.distributed.run "
+                             f"--nproc-per-node {args.gpus} (one rank per GPU)")
+        raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

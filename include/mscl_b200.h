@@ -22,7 +22,7 @@
  *                                  reference count[j] == n_enq - birth[j]
  *                                  (moco.py:427,437).
  *   qstate  int64   [4]            {ptr, n_enq, block-done counter, reserved}.
- *   qpack   float32 [M, 132]       per query row: q[0:128] | pos2 | shift2 | 0 | 0
+ *   qpack   float32 [M, 132]       per query row: q[0:128] | pos2 | shift2 | dup slot (int bits) | dup decay
  *   acc     float32 [M, 132]       per query row: O[0:128] | sum-exp | #neg>pos | 0 | 0
  */
 #ifndef MSCL_B200_H_
@@ -160,6 +160,14 @@ int mscl_lmcl(const float *d_xq, const float *d_xf, int32_t N, int32_t C,
  *              shift2_i = |q_i| * key_norm_bound / T * log2(e)   (>= every logit)
  *              dscale_j = 0.99999^(n_enq - birth_j) / T * log2(e);  d_dscale holds
  *              ceil(K_local/64)*64 floats, the pad is written as 0
+ *              d_dup_slot (int32 [M] or NULL): GLOBAL queue slot that holds a copy of
+ *              row i's positive key (the cross-modal rf term reads the flow queue right
+ *              after k_flow was enqueued into it, mscl.py:239-248), -1 for none; dup_age
+ *              = age of those copies.  The reference scores such an entry at
+ *              pos * 0.99999^age, i.e. above the positive iff pos < 0: a 1e-5 margin that
+ *              tf32 operands cannot resolve, so `partial` skips the top-k hit test of that
+ *              one column (its softmax mass is still summed) and `finalize` adds the exact
+ *              comparison.
  *  2 partial   acc[i] += ( sum_j p_ij dscale_j queue_j | sum_j p_ij | #{j: s_ij > pos2_i} )
  *              with s_ij = (q_i . queue_j) dscale_j and p_ij = 2^(s_ij - shift2_i);
  *              tcgen05 (tf32 operands, fp32 accumulate in TMEM), queue tiles by TMA.
@@ -175,14 +183,17 @@ int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
                       const int32_t *d_birth, const int64_t *d_qstate,
                       int64_t K_local, float inv_T, float key_norm_bound,
                       float *d_qpack, float *d_dscale, float *d_acc,
-                      int32_t M_acc, mscl_stream_t stream);
+                      int32_t M_acc, const int32_t *d_dup_slot, int32_t dup_age,
+                      mscl_stream_t stream);
+/* shard_begin: global slot of d_queue[0] (0 when the queue is not sharded). */
 int mscl_infonce_partial(const float *d_qpack, int32_t M, const float *d_queue,
-                         const float *d_dscale, int64_t K_local, float *d_acc,
-                         int32_t with_grad, int32_t num_sms, mscl_stream_t stream);
+                         const float *d_dscale, int64_t K_local, int64_t shard_begin,
+                         float *d_acc, int32_t with_grad, int32_t num_sms,
+                         mscl_stream_t stream);
 /* Same contract as mscl_infonce_partial on CUDA cores in fp32: validation twin. */
 int mscl_infonce_partial_simt(const float *d_qpack, int32_t M, const float *d_queue,
-                              const float *d_dscale, int64_t K_local, float *d_acc,
-                              int32_t with_grad, mscl_stream_t stream);
+                              const float *d_dscale, int64_t K_local, int64_t shard_begin,
+                              float *d_acc, int32_t with_grad, mscl_stream_t stream);
 int mscl_infonce_finalize(const float *d_qpack, const float *d_kpos,
                           float *d_acc, int32_t M, int32_t rows_per_group,
                           float inv_T, float *d_row_loss, float *d_dq_unit,

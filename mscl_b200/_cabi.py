@@ -29,9 +29,10 @@ PROTOTYPES = {
     "mscl_hw_mean_fwd": [c_ptr, c_ptr, c_i64, c_int, c_ptr],
     "mscl_hw_mean_bwd": [c_ptr, c_ptr, c_i64, c_int, c_ptr],
     "mscl_lmcl": [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
-    "mscl_infonce_prep": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_int, c_ptr],
-    "mscl_infonce_partial": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_int, c_int, c_ptr],
-    "mscl_infonce_partial_simt": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_int, c_ptr],
+    "mscl_infonce_prep": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int,
+                          c_ptr],
+    "mscl_infonce_partial": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_int, c_int, c_ptr],
+    "mscl_infonce_partial_simt": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr],
     "mscl_infonce_finalize": [c_ptr, c_ptr, c_ptr, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr],
     "mscl_infonce_bwd": [c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr],
     "mscl_gather_rows": [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr],
@@ -74,14 +75,46 @@ def load():
     return _lib
 
 
-def call(name, *args):
-    """Invoke an entry point; raise MsclError carrying mscl_last_error() on failure."""
+# Optional device-side timing of selected entry points (bench.py's live roofline numbers):
+# while active, every call to a selected entry point is bracketed by CUDA events on torch's
+# current stream (the stream functional.py launches on) and filed with the algorithmic byte /
+# flop count the caller states for that launch.
+_timing = None
+
+
+def start_timing(names):
+    """Begin recording (start_event, end_event, algo_bytes, algo_flops) for the named entry points."""
+    global _timing
+    _timing = {n: [] for n in names}
+
+
+def stop_timing():
+    """Stop recording; returns {name: [(ms, algo_bytes, algo_flops), ...]}.  Synchronises the device."""
+    global _timing
+    import torch
+    rec, _timing = _timing, None
+    torch.cuda.synchronize()
+    return {n: [(a.elapsed_time(b), nbytes, flops) for a, b, nbytes, flops in evs] for n, evs in (rec or {}).items()}
+
+
+def call(name, *args, algo_bytes=0, algo_flops=0):
+    """Invoke an entry point; raise MsclError carrying mscl_last_error() on failure.
+    algo_bytes / algo_flops: algorithmic work of this launch, only filed
+    when timing is active."""
     global _launches
     lib = load()
+    timed = _timing is not None and name in _timing
+    if timed:
+        import torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.mscl_last_error()
         raise MsclError(f"{name} failed ({rc}): {msg.decode() if msg else ''}")
+    if timed:
+        ev1.record()
+        _timing[name].append((ev0, ev1, algo_bytes, algo_flops))
     _launches += _LAUNCHES_PER_CALL.get(name, 1)
 
 

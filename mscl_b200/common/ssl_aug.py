@@ -109,9 +109,8 @@ class SyncMoCoAugmentV5:
 
     def flip(self, clips, mask):
         """Mirror the clips selected by the boolean mask along W (deterministic piece)."""
-        out = clips.clone()
-        out[mask] = torch.flip(clips[mask], [-1])
-        return out
+        # torch.where keeps shapes static and needs no host synchronisation (a boolean-index copy does)
+        return torch.where(mask.view(-1, 1, 1, 1, 1), torch.flip(clips, [-1]), clips)
 
     def forward_flip(self, clips, aux_info, suffix="_q"):
         n = clips.shape[0]
@@ -141,21 +140,19 @@ class SyncMoCoAugmentV5:
         x = torch.where(jit, y.clamp(0, 1), x)
         gray = (torch.rand(n, device=dev) < 0.2).view(n, 1, 1, 1, 1)
         x = torch.where(gray, _rgb_to_gray(x).expand_as(x), x)
-        blur = torch.rand(n, device=dev) < 0.5
-        if bool(blur.any()):
-            sigma = float(torch.empty(1).uniform_(0.1, 2.0))
-            r = self.blur_radius
-            ax = torch.arange(r, device=dev, dtype=x.dtype) - r // 2
-            k1 = torch.exp(-ax ** 2 / (2 * sigma ** 2))
-            k1 = k1 / k1.sum()
-            xb = x[blur]
-            b, c, t, h, w = xb.shape
-            z = xb.permute(0, 2, 1, 3, 4).reshape(b * t * c, 1, h, w)
-            z = F.conv2d(F.pad(z, (r // 2, r // 2, 0, 0), mode="reflect"), k1.view(1, 1, 1, r))
-            z = F.conv2d(F.pad(z, (0, 0, r // 2, r // 2), mode="reflect"), k1.view(1, 1, r, 1))
-            x = x.clone()
-            x[blur] = z.view(b, t, c, h, w).permute(0, 2, 1, 3, 4)
-        return x
+        # Gaussian blur p=0.5, one sigma draw per call: blur every clip at a fixed shape and select,
+        # so the step has no data-dependent shapes and no host synchronisation
+        blur = (torch.rand(n, device=dev) < 0.5).view(n, 1, 1, 1, 1)
+        sigma = float(torch.empty(1).uniform_(0.1, 2.0))
+        r = self.blur_radius
+        ax = torch.arange(r, device=dev, dtype=x.dtype) - r // 2
+        k1 = torch.exp(-ax ** 2 / (2 * sigma ** 2))
+        k1 = k1 / k1.sum()
+        b, c, t, h, w = x.shape
+        z = x.reshape(b * c * t, 1, h, w)
+        z = F.conv2d(F.pad(z, (r // 2, r // 2, 0, 0), mode="reflect"), k1.view(1, 1, 1, r))
+        z = F.conv2d(F.pad(z, (0, 0, r // 2, r // 2), mode="reflect"), k1.view(1, 1, r, 1))
+        return torch.where(blur, z.view(b, c, t, h, w), x)
 
     def __call__(self, im_q, im_k, aux_info):
         im_q, aux_info = self.forward_flip(im_q, aux_info, suffix="_q")

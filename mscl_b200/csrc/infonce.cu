@@ -17,7 +17,8 @@ infonce_prep_kernel(const float *__restrict__ q, const float *__restrict__ kpos,
                     const int32_t *__restrict__ birth, const int64_t *__restrict__ qstate,
                     int64_t K_local, float inv_T, float key_norm_bound,
                     float *__restrict__ qpack, float *__restrict__ dscale,
-                    float *__restrict__ acc, int M_acc) {
+                    float *__restrict__ acc, int M_acc, const int32_t *__restrict__ dup_slot,
+                    int dup_age) {
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * 8;
   const float sc = inv_T * kLog2e;
@@ -31,9 +32,14 @@ infonce_prep_kernel(const float *__restrict__ q, const float *__restrict__ kpos,
     float4 r = make_float4(to_tf32_rn(a.x), to_tf32_rn(a.y), to_tf32_rn(a.z), to_tf32_rn(a.w));
     float *dst = qpack + (int64_t)row * kLd;
     reinterpret_cast<float4 *>(dst)[lane] = r;
-    if (lane == 0)
+    if (lane == 0) {
+      // [130] = global queue slot holding a copy of this row's positive key (int bits, -1 = none),
+      // [131] = that copy's decay factor 0.99999^age
+      const int dup = dup_slot != nullptr ? dup_slot[row] : -1;
       reinterpret_cast<float4 *>(dst)[32] =
-          make_float4(d * sc, sqrtf(ss) * key_norm_bound * sc, 0.f, 0.f);
+          make_float4(d * sc, sqrtf(ss) * key_norm_bound * sc, __int_as_float(dup),
+                      exp2f((float)dup_age * kLog2Decay));
+    }
   }
   const int64_t n_enq = qstate[1];
   const int64_t tid = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(128)
 infonce_partial_simt_kernel(const float *__restrict__ qpack, int M,
                             const float *__restrict__ queue,
                             const float *__restrict__ dscale, int64_t K_local,
-                            float *__restrict__ acc, int with_grad) {
+                            int64_t shard_begin, float *__restrict__ acc, int with_grad) {
   extern __shared__ float sm[];
   float *tile = sm;                       // [128][129]
   float *qrow = tile + kSimtKeys * 129;   // [128]
@@ -84,6 +90,8 @@ infonce_partial_simt_kernel(const float *__restrict__ qpack, int M,
     const float *qp = qpack + (int64_t)i * kLd;
     qrow[tid] = qp[tid];
     const float pos2 = qp[kC], shift2 = qp[kC + 1];
+    const int dup = __float_as_int(qp[kC + 2]);
+    const bool is_dup = dup >= 0 && (int64_t)dup - shard_begin == k0 + tid;
     __syncthreads();
     float s = 0.f;
     const float *kr = tile + tid * 129;
@@ -91,7 +99,7 @@ infonce_partial_simt_kernel(const float *__restrict__ qpack, int M,
     for (int c = 0; c < kC; ++c) s = fmaf(qrow[c], kr[c], s);
     s *= ds;
     float p = valid ? exp2f(s - shift2) : 0.f;
-    float cnt = (valid && s > pos2) ? 1.f : 0.f;
+    float cnt = (valid && !is_dup && s > pos2) ? 1.f : 0.f;
     pbuf[tid] = p * ds;
     float ps = warp_sum(p), cs = warp_sum(cnt);
     if (lane == 0) { red[warp] = ps; red[4 + warp] = cs; }
@@ -122,7 +130,13 @@ infonce_finalize_kernel(const float *__restrict__ qpack, const float *__restrict
   const float *qp = qpack + (int64_t)i * kLd;
   const float *ap = acc + (int64_t)i * kLd;
   const float pos2 = qp[kC], shift2 = qp[kC + 1];
-  const float sum = ap[kC], cnt = ap[kC + 1];
+  const float sum = ap[kC];
+  float cnt = ap[kC + 1];
+  // A queue entry that IS this row's positive key (enqueued earlier in the step, moco.py:437)
+  // scores pos * 0.99999^age in the reference: above the positive iff pos < 0.  The tensor-core
+  // pass cannot resolve a 1e-5 margin with tf32 operands, so it skips that column's hit test and
+  // the exact comparison happens here.
+  if (__float_as_int(qp[kC + 2]) >= 0 && pos2 * qp[kC + 3] > pos2) cnt += 1.f;
   const float e0 = exp2f(pos2 - shift2);
   const float Z = e0 + sum;
   const float inv_Z = 1.0f / Z;
@@ -179,7 +193,8 @@ extern "C" {
 int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
                       const int32_t *d_birth, const int64_t *d_qstate, int64_t K_local,
                       float inv_T, float key_norm_bound, float *d_qpack, float *d_dscale,
-                      float *d_acc, int32_t M_acc, mscl_stream_t stream) {
+                      float *d_acc, int32_t M_acc, const int32_t *d_dup_slot, int32_t dup_age,
+                      mscl_stream_t stream) {
   MSCL_CHECK_ARG(d_q && d_kpos && d_birth && d_qstate && d_qpack && d_dscale && d_acc,
                  "null pointer");
   MSCL_CHECK_ARG(M > 0 && M_acc >= M && K_local > 0, "bad M=%d M_acc=%d K_local=%lld", M, M_acc,
@@ -194,14 +209,14 @@ int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
   if (want > 1184) want = 1184;
   mscl::infonce_prep_kernel<<<(unsigned)want, 256, 0, mscl::as_stream(stream)>>>(
       d_q, d_kpos, M, d_birth, d_qstate, K_local, inv_T, key_norm_bound, d_qpack, d_dscale,
-      d_acc, M_acc);
+      d_acc, M_acc, d_dup_slot, dup_age);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }
 
 int mscl_infonce_partial_simt(const float *d_qpack, int32_t M, const float *d_queue,
-                              const float *d_dscale, int64_t K_local, float *d_acc,
-                              int32_t with_grad, mscl_stream_t stream) {
+                              const float *d_dscale, int64_t K_local, int64_t shard_begin,
+                              float *d_acc, int32_t with_grad, mscl_stream_t stream) {
   MSCL_CHECK_ARG(d_qpack && d_queue && d_dscale && d_acc, "null pointer");
   MSCL_CHECK_ARG(M > 0 && K_local > 0, "bad M=%d K_local=%lld", M, (long long)K_local);
   const size_t smem = sizeof(float) * (mscl::kSimtKeys * 129 + mscl::kC + mscl::kSimtKeys + 8);
@@ -209,7 +224,7 @@ int mscl_infonce_partial_simt(const float *d_qpack, int32_t M, const float *d_qu
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = (K_local + mscl::kSimtKeys - 1) / mscl::kSimtKeys;
   mscl::infonce_partial_simt_kernel<<<(unsigned)blocks, 128, smem, mscl::as_stream(stream)>>>(
-      d_qpack, M, d_queue, d_dscale, K_local, d_acc, with_grad);
+      d_qpack, M, d_queue, d_dscale, K_local, shard_begin, d_acc, with_grad);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }

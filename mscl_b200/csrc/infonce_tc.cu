@@ -197,7 +197,7 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 // One 64-key tile of one query row: S (TMEM) -> p, row sum, hit count, P' (TMEM, over S).
 template <bool GRAD, bool FULL>
 __device__ __forceinline__ void softmax_tile(uint32_t taddr0, const float *ds, float shift2, float thr,
-                                             int nvalid, float &sum, int &cnt) {
+                                             int nvalid, int dupcol, float &sum, int &cnt) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     uint32_t v[32];
@@ -214,10 +214,10 @@ __device__ __forceinline__ void softmax_tile(uint32_t taddr0, const float *ds, f
         const float tval = fmaf(__uint_as_float(v[j]), dd[e], -shift2);
         float p = ex2(tval);
         bool hit = tval > thr;
-        if (!FULL) {  // tail tile: keys beyond K_local
+        if (!FULL) {  // tail tile (keys beyond K_local) or the tile holding this row's own positive key
           const bool ok = (h * 32 + j) < nvalid;
           p = ok ? p : 0.f;
-          hit = hit && ok;
+          hit = hit && ok && (h * 32 + j) != dupcol;
         }
         sum += p;
         cnt += hit ? 1 : 0;
@@ -232,7 +232,7 @@ template <bool GRAD>
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_w2,
                   const float *__restrict__ qpack, int M, const float *__restrict__ dscale,
-                  int64_t K_local, float *__restrict__ acc) {
+                  int64_t K_local, int64_t shard_begin, float *__restrict__ acc) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -352,10 +352,13 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const int row = row0 + r;
     const bool row_ok = row < M;
     float shift2 = 0.f, thr = INFINITY;
+    int64_t dup_local = -1;   // queue slot (in this shard) holding a copy of the row's positive key
     if (row_ok) {
       const float pos2 = qpack[(int64_t)row * kLd + kC];
       shift2 = qpack[(int64_t)row * kLd + kC + 1];
       thr = pos2 - shift2;
+      const int dup = __float_as_int(qpack[(int64_t)row * kLd + kC + 2]);
+      if (dup >= 0) dup_local = (int64_t)dup - shard_begin;
     }
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     {   // this row of Q -> TMEM columns [kColQ, kColQ+128): the A operand of every MMA1
@@ -389,10 +392,14 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const int64_t key0 = (t_begin + t) * kTile;
       const int nvalid = (K_local - key0) < kTile ? (int)(K_local - key0) : kTile;
       const float *ds = ds_smem + s * kTile;
-      if (nvalid == kTile)
-        softmax_tile<GRAD, true>(lane_base + kColS + (uint32_t)b * kTile, ds, shift2, thr, nvalid, sum, cnt);
+      const int64_t dcol = dup_local - key0;
+      const bool has_dup = dcol >= 0 && dcol < kTile;
+      // warp-uniform choice (tcgen05.ld/st are .sync.aligned): slow path if any row of the warp needs it
+      if (nvalid == kTile && !__any_sync(0xffffffffu, has_dup))
+        softmax_tile<GRAD, true>(lane_base + kColS + (uint32_t)b * kTile, ds, shift2, thr, nvalid, -1, sum, cnt);
       else
-        softmax_tile<GRAD, false>(lane_base + kColS + (uint32_t)b * kTile, ds, shift2, thr, nvalid, sum, cnt);
+        softmax_tile<GRAD, false>(lane_base + kColS + (uint32_t)b * kTile, ds, shift2, thr, nvalid,
+                                  has_dup ? (int)dcol : -1, sum, cnt);
       if (GRAD) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       mbar_arrive(bar_pfull(b));
@@ -472,8 +479,9 @@ static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int ld, in
 }  // namespace mscl
 
 extern "C" int mscl_infonce_partial(const float *d_qpack, int32_t M, const float *d_queue,
-                                    const float *d_dscale, int64_t K_local, float *d_acc,
-                                    int32_t with_grad, int32_t num_sms, mscl_stream_t stream) {
+                                    const float *d_dscale, int64_t K_local, int64_t shard_begin,
+                                    float *d_acc, int32_t with_grad, int32_t num_sms,
+                                    mscl_stream_t stream) {
   using namespace mscl::tc;
   MSCL_CHECK_ARG(d_qpack && d_queue && d_dscale && d_acc, "null pointer");
   MSCL_CHECK_ARG(M > 0 && K_local > 0, "bad M=%d K_local=%lld", M, (long long)K_local);
@@ -496,11 +504,11 @@ extern "C" int mscl_infonce_partial(const float *d_qpack, int32_t M, const float
   if (with_grad) {
     MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    infonce_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(tw, tw2, d_qpack, M, d_dscale, K_local, d_acc);
+    infonce_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(tw, tw2, d_qpack, M, d_dscale, K_local, shard_begin, d_acc);
   } else {
     MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    infonce_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(tw, tw2, d_qpack, M, d_dscale, K_local, d_acc);
+    infonce_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(tw, tw2, d_qpack, M, d_dscale, K_local, shard_begin, d_acc);
   }
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;

@@ -119,7 +119,8 @@ class NegativeQueue:
             raise _cabi.MsclError("queue pointer is not aligned to the batch size (batch size changed mid-cycle)")
         _cabi.call("mscl_enqueue", self.queue.data_ptr(), self.queue_tf32.data_ptr(), self.birth.data_ptr(),
                    self.qstate.data_ptr(),
-                   keys_all.data_ptr(), b, self.C, self.K, self.shard_begin, self.K_local, None, None, _stream())
+                   keys_all.data_ptr(), b, self.C, self.K, self.shard_begin, self.K_local, None, None, _stream(),
+                   algo_bytes=2 * b * self.C * 4)
         self.ptr = (self.ptr + b) % self.K
         self.n_enq += 1
 
@@ -129,7 +130,7 @@ class NegativeQueue:
 # ----------------------------------------------------------------------------------------
 class _InfoNCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, kpos, nq, rows_per_group, inv_T, impl, group, need_grad):
+    def forward(ctx, q, kpos, nq, rows_per_group, inv_T, impl, group, need_grad, dup_slot, dup_age):
         M = q.shape[0]
         dev = q.device
         st = _stream()
@@ -140,7 +141,8 @@ class _InfoNCE(torch.autograd.Function):
         dscale = torch.empty(k_pad, device=dev)
         acc = torch.empty(M_all, PACK_LD, device=dev)
         _cabi.call("mscl_infonce_prep", q.data_ptr(), kpos.data_ptr(), M, nq.birth.data_ptr(), nq.qstate.data_ptr(),
-                   nq.K_local, inv_T, nq.max_key_norm, qpack.data_ptr(), dscale.data_ptr(), acc.data_ptr(), M_all, st)
+                   nq.K_local, inv_T, nq.max_key_norm, qpack.data_ptr(), dscale.data_ptr(), acc.data_ptr(), M_all,
+                   dup_slot.data_ptr() if dup_slot is not None else None, dup_age, st)
         if world > 1:
             qpack_all = torch.empty(M_all, PACK_LD, device=dev)
             dist.all_gather_into_tensor(qpack_all, qpack, group=group)
@@ -148,10 +150,12 @@ class _InfoNCE(torch.autograd.Function):
             qpack_all = qpack
         if impl == "simt":
             _cabi.call("mscl_infonce_partial_simt", qpack_all.data_ptr(), M_all, nq.queue_tf32.data_ptr(), dscale.data_ptr(),
-                       nq.K_local, acc.data_ptr(), int(need_grad), st)
+                       nq.K_local, nq.shard_begin, acc.data_ptr(), int(need_grad), st)
         else:
             _cabi.call("mscl_infonce_partial", qpack_all.data_ptr(), M_all, nq.queue_tf32.data_ptr(), dscale.data_ptr(),
-                       nq.K_local, acc.data_ptr(), int(need_grad), sm_count(dev), st)
+                       nq.K_local, nq.shard_begin, acc.data_ptr(), int(need_grad), sm_count(dev), st,
+                       algo_bytes=infonce_algo_bytes(M_all, nq.K_local),
+                       algo_flops=(4 if need_grad else 2) * M_all * nq.K_local * DIM)
         if world > 1:
             acc_local = torch.empty(M, PACK_LD, device=dev)
             dist.reduce_scatter_tensor(acc_local, acc, op=dist.ReduceOp.SUM, group=group)
@@ -175,24 +179,37 @@ class _InfoNCE(torch.autograd.Function):
         gout = g_group[:, 0].contiguous()
         dq = torch.empty_like(dq_unit)
         _cabi.call("mscl_infonce_bwd", dq_unit.data_ptr(), gout.data_ptr(), M, ctx.rows_per_group, dq.data_ptr(), _stream())
-        return dq, None, None, None, None, None, None, None
+        return dq, None, None, None, None, None, None, None, None, None
 
 
-def infonce(q, kpos, nq, rows_per_group, T, impl="tc", group=None):
+def infonce_algo_bytes(M, K_local):
+    """Algorithmic bytes of ONE fused pass: the queue shard once (fp32), the
+    per-key decay scale, the packed queries in and the accumulator rows out."""
+    return K_local * DIM * 4 + K_local * 4 + 2 * M * PACK_LD * 4
+
+
+def infonce(q, kpos, nq, rows_per_group, T, impl="tc", group=None, dup_slot=None, dup_age=1):
     """Fused InfoNCE over the queue `nq`.
 
     q, kpos: (M, 128) stacked query rows and the positive key of each row; consecutive
     blocks of rows_per_group rows form one loss term (one "head call" of the reference).
+    dup_slot: optional int32 (M,) GLOBAL queue slot that currently holds a copy of the row's own
+    positive key (-1: none), dup_age its age -- see include/mscl_b200.h (K1, prep).
     Returns (group_out (M/rows_per_group, 4) = [loss, top1, top5, 0], row_stats (2M,)).
     Gradient flows to q only (keys and queue are detached in the reference, moco.py:486,532).
     """
+    if dup_slot is not None:
+        _chk(dup_slot, torch.int32, "dup_slot")
+        if dup_slot.shape != (q.shape[0],):
+            raise _cabi.MsclError("dup_slot must hold one slot per query row")
     _chk(q, name="q"), _chk(kpos, name="kpos")
     if q.dim() != 2 or q.shape[1] != DIM or kpos.shape != q.shape:
         raise _cabi.MsclError(f"q and kpos must both be (M, {DIM}); got {tuple(q.shape)} and {tuple(kpos.shape)}")
     if q.shape[0] % rows_per_group:
         raise _cabi.MsclError("number of rows must be a multiple of rows_per_group")
     need_grad = bool(q.requires_grad and torch.is_grad_enabled())
-    return _InfoNCE.apply(q, kpos.detach(), nq, int(rows_per_group), float(1.0 / T), impl, group, need_grad)
+    return _InfoNCE.apply(q, kpos.detach(), nq, int(rows_per_group), float(1.0 / T), impl, group, need_grad,
+                          dup_slot, int(dup_age))
 
 
 # ----------------------------------------------------------------------------------------
@@ -205,7 +222,7 @@ class _HWMean(torch.autograd.Function):
         HW = shape[-1] * shape[-2]
         R = x.numel() // HW
         out = torch.empty(shape[:-2], device=x.device)
-        _cabi.call("mscl_hw_mean_fwd", x.data_ptr(), out.data_ptr(), R, HW, _stream())
+        _cabi.call("mscl_hw_mean_fwd", x.data_ptr(), out.data_ptr(), R, HW, _stream(), algo_bytes=4 * R * (HW + 1))
         ctx.shape = shape
         return out
 
@@ -215,7 +232,8 @@ class _HWMean(torch.autograd.Function):
         shape = ctx.shape
         HW = shape[-1] * shape[-2]
         gx = torch.empty(shape, device=g.device)
-        _cabi.call("mscl_hw_mean_bwd", g.data_ptr(), gx.data_ptr(), g.numel(), HW, _stream())
+        _cabi.call("mscl_hw_mean_bwd", g.data_ptr(), gx.data_ptr(), g.numel(), HW, _stream(),
+                   algo_bytes=4 * g.numel() * (HW + 1))
         return gx
 
 
@@ -242,7 +260,8 @@ class _LMCL(torch.autograd.Function):
         gxq = torch.empty_like(xq)
         gxf = torch.empty_like(xf)
         _cabi.call("mscl_lmcl", xq.data_ptr(), xf.data_ptr(), N, C, t, t2, inv_T, out.data_ptr(), gxq.data_ptr(),
-                   gxf.data_ptr(), part.data_ptr(), _stream())
+                   gxf.data_ptr(), part.data_ptr(), _stream(), algo_bytes=8 * N * C * (t + t2),
+                   algo_flops=6 * N * t * t2 * C)
         ctx.save_for_backward(gxq, gxf)
         return out
 
@@ -310,7 +329,8 @@ class EmaTable:
         m32 = float(np.float32(m))
         om32 = float(np.float32(1.0 - m))
         _cabi.call("mscl_ema_multi", self.k_ptrs.data_ptr(), self.q_ptrs.data_ptr(), self.sizes.data_ptr(),
-                   self.blk_tensor.data_ptr(), self.blk_start.data_ptr(), self.n_blocks, self.CHUNK, m32, om32, _stream())
+                   self.blk_tensor.data_ptr(), self.blk_start.data_ptr(), self.n_blocks, self.CHUNK, m32, om32, _stream(),
+                   algo_bytes=12 * self.numel, algo_flops=3 * self.numel)
 
 
 # ----------------------------------------------------------------------------------------
@@ -341,9 +361,10 @@ def fra(flow, cid, table, layout="planar"):
     out = torch.empty(N, 2, 2 * T, H, W, device=flow.device)
     maxrad = torch.empty(N, T, 2, device=flow.device)
     st = _stream()
-    _cabi.call("mscl_fra_maxrad", flow.data_ptr(), cid.data_ptr(), table.data_ptr(), maxrad.data_ptr(), N, T, H * W, lay, st)
+    _cabi.call("mscl_fra_maxrad", flow.data_ptr(), cid.data_ptr(), table.data_ptr(), maxrad.data_ptr(), N, T, H * W, lay, st,
+               algo_bytes=8 * N * T * H * W)
     _cabi.call("mscl_fra_apply", flow.data_ptr(), cid.data_ptr(), table.data_ptr(), maxrad.data_ptr(), out.data_ptr(),
-               N, T, H * W, lay, st)
+               N, T, H * W, lay, st, algo_bytes=24 * N * T * H * W)
     return out
 
 
@@ -356,7 +377,8 @@ def fra_rotate(flow, cid, table):
     _chk(flow, name="flow"), _chk(cid, torch.int32, "cid"), _chk(table, name="table")
     N, two, T, H, W = flow.shape
     out = torch.empty_like(flow)
-    _cabi.call("mscl_fra_rotate", flow.data_ptr(), cid.data_ptr(), table.data_ptr(), out.data_ptr(), N, T, H * W, _stream())
+    _cabi.call("mscl_fra_rotate", flow.data_ptr(), cid.data_ptr(), table.data_ptr(), out.data_ptr(), N, T, H * W, _stream(),
+               algo_bytes=16 * N * T * H * W)
     return out
 
 
@@ -369,5 +391,6 @@ def gather_rows(x, idx):
     _chk(x, name="x"), _chk(idx, torch.int64, "idx")
     row = x[0].numel()
     out = torch.empty((idx.numel(),) + tuple(x.shape[1:]), device=x.device)
-    _cabi.call("mscl_gather_rows", x.data_ptr(), idx.data_ptr(), out.data_ptr(), idx.numel(), row, _stream())
+    _cabi.call("mscl_gather_rows", x.data_ptr(), idx.data_ptr(), out.data_ptr(), idx.numel(), row, _stream(),
+               algo_bytes=8 * idx.numel() * row)
     return out

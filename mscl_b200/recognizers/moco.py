@@ -251,14 +251,28 @@ class MoCoV2(BaseMoCoRecognizer):
         return dist.group.WORLD if (nq is not None and nq.world > 1) else None
 
     def contrast(self, terms, T=None):
-        """Fused InfoNCE of several (q, k_pos) row sets against the CURRENT queue state in one pass.
+        """Fused InfoNCE of several (q, k_pos[, dup_slot]) row sets against the CURRENT queue state in
+        one pass.  dup_slot: int32 (n,) global slots holding copies of the term's own positive keys
+        (a term whose keys were enqueued before the pass), or None.
         Returns a (len(terms), 4) tensor of [loss, top1, top5, 0] rows."""
         n = terms[0][0].shape[0]
         q = torch.cat([t[0] for t in terms], dim=0).contiguous()
         kp = torch.cat([t[1].detach() for t in terms], dim=0).contiguous()
+        dups = [t[2] if len(t) > 2 else None for t in terms]
+        dup = None
+        if any(d is not None for d in dups):
+            none = torch.full((n,), -1, dtype=torch.int32, device=q.device)
+            dup = torch.cat([none if d is None else d for d in dups]).contiguous()
         nq = self.negative_queue(q.device)
-        out, _ = fx.infonce(q, kp, nq, n, self.T if T is None else T, group=self._group())
+        out, _ = fx.infonce(q, kp, nq, n, self.T if T is None else T, group=self._group(), dup_slot=dup)
         return out
+
+    def enqueue_slots(self, n_local, device):
+        """Global queue slots the NEXT enqueue writes this rank's n_local keys to (rank-major gather
+        order, moco.py:434,564-567), as int32 (n_local,)."""
+        nq = self.negative_queue(device)
+        rank = dist.get_rank() if _dist_on() else 0
+        return torch.arange(n_local, dtype=torch.int32, device=device) + int(nq.ptr + rank * n_local)
 
     def note_branch(self, n_local, update_queue=True):
         """Host-side bookkeeping of one forward_train call (moco.py:429,504-505): the gathered batch

@@ -93,15 +93,19 @@ class MSCLWithAug(BaseMoCoRecognizer):
             terms[fr_queue].append(("fr_aug", q_af, k, mx.T))
 
         rows = {}
+        # A term evaluated against W_flow(post) whose positive key IS k_f finds a copy of that key in
+        # the queue (`rf` with same_kn=True): the kernel needs the slot to rank it exactly.
+        kf_slots = recf.enqueue_slots(k_f.shape[0], k_f.device)
 
         def run(phase, owner):
             by_T = OrderedDict()          # one pass per distinct temperature (one, in the configs)
             for name, qq, kk, T in terms[phase]:
-                by_T.setdefault(T, []).append((name, qq, kk))
+                dup = kf_slots if (phase == "flow_post" and kk is k_f) else None
+                by_T.setdefault(T, []).append((name, qq, kk, dup))
             for T, items in by_T.items():
-                out = owner.contrast([(qq, kk) for _, qq, kk in items], T)
-                for i, (name, _, _) in enumerate(items):
-                    rows[name] = out[i]
+                out = owner.contrast([(qq, kk, dup) for _, qq, kk, dup in items], T)
+                for i, item in enumerate(items):
+                    rows[item[0]] = out[i]
 
         run("rgb_pre", rec)                        # W_rgb before this step's enqueue
         run("flow_pre", recf)                      # W_flow before the base-flow enqueue

@@ -256,6 +256,36 @@ def test_infonce_fresh_queue_and_after_enqueue(fx):
         nq.enqueue(keys.cuda())
 
 
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_infonce_positive_key_present_in_queue(fx, impl):
+    """The rf term of MSCLWithAug reads the flow queue right after k_flow was enqueued (mscl.py:239-248):
+    every row finds its own positive key among the negatives, scored pos*0.99999.  The reference ranks it
+    above the positive iff pos < 0; the kernel must reproduce that exactly (dup_slot)."""
+    M, K, B = 32, 2048, 32
+    q, kpos, queue, count = _make_case(21, M, K, B)
+    kpos[::3] = -kpos[::3]                       # a third of the rows get a negative positive-logit
+    ptr = 5 * B
+    queue[:, ptr:ptr + M] = kpos.t()
+    count = count + 1
+    count[ptr:ptr + M] = 1
+    ref, gref, logits = _oracle_infonce(q, kpos, queue, count, 0.07, M)
+    cnt_ref = (logits[:, 1:] > logits[:, :1]).sum(1).float()
+    assert int((logits[:, 1 + ptr:1 + ptr + M].diagonal() > logits[:, 0]).sum()) == len(range(0, M, 3))
+    nq = fx.NegativeQueue(K)
+    nq.load(queue, count, ptr + M)
+    slots = (torch.arange(M, dtype=torch.int32) + ptr).cuda()
+    qd = q.cuda().requires_grad_(True)
+    out, rows = fx.infonce(qd, kpos.cuda(), nq, M, 0.07, impl=impl, dup_slot=slots, dup_age=1)
+    out[0, 0].backward()
+    neg, pos = logits[:, 1:].clone(), logits[:, :1]
+    neg[torch.arange(M), ptr + torch.arange(M)] = 1e9          # the duplicate itself is never a close call
+    close_call = ((neg - pos).abs() < 0.02).sum(1)
+    assert bool(((rows[M:].cpu() - cnt_ref).abs() <= close_call).all()), (rows[M:].cpu(), cnt_ref)
+    assert int(close_call.sum()) < M                            # the test is not vacuous
+    assert abs(float(out[0, 0]) - float(ref[0][0])) <= 1e-3 * abs(float(ref[0][0]))
+    assert _rel(qd.grad.cpu(), gref) < 1e-3
+
+
 # ------------------------------------------------------------------ K6 gather
 def test_gather_rows(fx):
     x = torch.randn(64, 3, 8, 28, 28, device="cuda")

@@ -1,0 +1,225 @@
+"""Parity of the product's recognizer-level path on the GPU -- `MSCLWithAug.objective` and a whole
+`train_step` -- against the oracle and the golden fixtures produced by the unmodified reference.
+Needs a B200: `pytest -m gpu`."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-3     # the north star's contract: loss / gradients within 1e-3 relative (tf32 operands, fp32 accumulate)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _needs_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def head_level_model(K, t):
+    """The product's MSCLWithAug with the slim flow encoder on both branches (encoders are not run):
+    the same model dict oracle/make_golden.py hands to the reference."""
+    import mscl_b200
+    ce = dict(type="CrossEntropyLoss_torch", ignore_index=-1)
+
+    def rec(basename):
+        return dict(type="MoCoV2", backbone=dict(type="resnet_flow.r2d_18"), neck=dict(type="BaseMoCo"),
+                    moco_head=dict(type="MoCoHead", basename=basename, loss_cls=ce), im_key="imgs", dim_in=128,
+                    dim=128, K=K, m_base=0.994, max_iters=1000, T=0.07, mlp=True, aux_info=[],
+                    aug=dict(type="IdentityAug"))
+
+    cfg = dict(type="MSCLWithAug", recognizer=rec(""), recognizer_flow=rec("flow"),
+               moco_mx_head=dict(type="MSCLWithAugMxHead", basename="mx", loss_cls=ce, same_kn=True, T=0.07),
+               sup_head=dict(type="MSCLWithAugPosHeadV2", basename="", loss_pos=ce, bkb_channels=(None, None), t=t,
+                             T=0.07, aux_keys=dict(im_features=dict(q_mlvl="q_mlvl"),
+                                                   base_flow_features=dict(q_mlvl="q_flow_mlvl"),
+                                                   aug_flow_features=dict(q_mlvl="q_aug_flow_mlvl"))),
+               im_key="imgs", flow_key="flow_imgs", aux_info=[], update_aug_flow=False, weight_aug_flow=(1.0, 1.0),
+               aug=dict(type="IdentityAug"), same_kn=True)
+    return mscl_b200.build_model(cfg).cuda()
+
+
+def run_product_objective(inp, t):
+    K = inp["queue_rgb"].shape[1]
+    model = head_level_model(K, t)
+    model.train()
+    ptr = torch.tensor([inp["ptr"]])
+    missing = model.load_state_dict({
+        "recognizer.queue": inp["queue_rgb"], "recognizer.count": inp["count"], "recognizer.queue_ptr": ptr,
+        "recognizer_flow.queue": inp["queue_flow"], "recognizer_flow.count": inp["count"],
+        "recognizer_flow.queue_ptr": ptr}, strict=False)
+    assert not missing.unexpected_keys
+    leaves = {n: inp[n].cuda().requires_grad_(True) for n in ("q", "q_f", "q_af", "q_map", "qf_map", "qaf_map")}
+    feats = dict(q=leaves["q"], q_f=leaves["q_f"], q_af=leaves["q_af"], k=inp["k"].cuda(), k_f=inp["k_f"].cuda(),
+                 k_af=inp["k_af"].cuda(), q_mlvl=[leaves["q_map"]], q_flow_mlvl=[leaves["qf_map"]],
+                 q_aug_flow_mlvl=[leaves["qaf_map"]])
+    losses = model.objective(feats)
+    loss, log_vars = model._parse_losses(losses)
+    loss.backward()
+    return model, log_vars, leaves
+
+
+def _run_oracle_objective(inp, t):
+    from oracle import mscl_oracle as O
+    leaves = {n: inp[n].clone().requires_grad_(True) for n in ("q", "q_f", "q_af", "q_map", "qf_map", "qaf_map")}
+    feats = dict(k=inp["k"], k_f=inp["k_f"], k_af=inp["k_af"], **leaves)
+    rgb = O.QueueState(inp["queue_rgb"], inp["count"], inp["ptr"])
+    flow = O.QueueState(inp["queue_flow"], inp["count"], inp["ptr"])
+    loss, log_vars = O.parse_losses(O.mscl_objective(feats, rgb, flow, T=0.07, t=t))
+    loss.backward()
+    return log_vars, leaves, rgb, flow
+
+
+def check_objective(inp, t, golden=None):
+    """Product vs oracle (and vs the reference's golden numbers when given) for one objective call."""
+    from oracle import inputs
+    ref_vars, ref_leaves, rgb, flow = _run_oracle_objective(inp, t)
+    model, log_vars, leaves = run_product_objective(inp, t)
+    assert list(log_vars.keys()) == list(ref_vars.keys())         # the 23 keys, in the reference's order
+    for k, v in log_vars.items():
+        refs = [ref_vars[k]] + ([float(golden[f"logvar/{k}"])] if golden is not None else [])
+        for ref in refs:
+            if "acc" in k:
+                assert v == pytest.approx(ref, abs=1e-6), (k, v, ref)       # integer hit counts / N
+            else:
+                assert abs(v - ref) <= REL * abs(ref), (k, v, ref)
+    for n in ("q", "q_f", "q_af", "q_map", "qf_map", "qaf_map"):
+        assert _rel(leaves[n].grad, ref_leaves[n].grad) < REL, (n, _rel(leaves[n].grad, ref_leaves[n].grad))
+    if golden is not None:
+        for n in ("q", "q_f", "q_af"):
+            assert _rel(leaves[n].grad, torch.from_numpy(golden[f"grad/{n}"])) < REL, n
+        for n in ("q_map", "qf_map", "qaf_map"):
+            assert _rel(leaves[n].grad.sum(dim=(-2, -1)), torch.from_numpy(golden[f"gradsum/{n}"])) < REL, n
+    # queue pointer, enqueue contents, ages: bit-exact
+    for tag, rec, st in (("rgb", model.recognizer, rgb), ("flow", model.recognizer_flow, flow)):
+        sd = {k: v.cpu() for k, v in rec.state_dict().items() if k in ("queue", "count", "queue_ptr")}
+        assert int(sd["queue_ptr"]) == st.ptr
+        np.testing.assert_array_equal(sd["queue"].numpy(), st.queue.numpy())
+        np.testing.assert_array_equal(sd["count"].numpy(), st.count.numpy())
+        if golden is not None:
+            assert int(sd["queue_ptr"]) == int(golden[f"after/{tag}/ptr"][0])
+            np.testing.assert_array_equal(sd["count"].numpy(), golden[f"after/{tag}/count"])
+            if f"after/{tag}/queue" in golden.files:
+                np.testing.assert_array_equal(sd["queue"].numpy(), golden[f"after/{tag}/queue"])
+            else:
+                assert inputs.digest(sd["queue"]) == str(golden[f"after/{tag}/queue_digest"])
+    return log_vars
+
+
+def test_objective_head_small_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "head_small.npz"), allow_pickle=False)
+    inp = {k[3:]: (torch.from_numpy(g[k]) if g[k].ndim else int(g[k])) for k in g.files if k.startswith("in/")}
+    check_objective(inp, 4, g)
+
+
+def test_objective_cfg1_golden(golden_dir):
+    """BASELINE config 1: N=8, C=128, K=4096, t=8 (inputs regenerated from the seed, digest-guarded)."""
+    from oracle import inputs
+    g = np.load(os.path.join(golden_dir, "head_cfg1.npz"), allow_pickle=False)
+    kw = eval(str(g["kwargs"]))
+    inp = inputs.head_inputs(**kw)
+    assert inputs.digest(*[inp[k] for k in sorted(inp) if isinstance(inp[k], torch.Tensor)]) == str(g["input_digest"])
+    check_objective(inp, kw["t"], g)
+
+
+@pytest.mark.parametrize("N,K,t", [(32, 65536, 4), (64, 16384, 16)])
+def test_objective_full_size_vs_oracle(N, K, t):
+    """The r18 config's head sizes (N=32, K=65536, t=4) and BASELINE config 4's (N=64, t=16)."""
+    from oracle import inputs
+    inp = inputs.head_inputs(seed=5, N=N, K=K, t=t, hw_rgb=14, hw_flow=7, b_all=N)
+    check_objective(inp, t)
+
+
+def _synthetic_batch(N, T=8, S=112, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    imgs = [torch.rand(N, 3, T, S, S, generator=g) for _ in range(2)]
+    flows = [torch.rand(N, 3, 2 * T, S, S, generator=g) for _ in range(2)]
+    return imgs, flows
+
+
+def test_full_train_step_vs_oracle():
+    """Three whole MSCLWithAug steps (R3D-18 + r2d_18 encoders, TPN neck, K=256, N=4) against the
+    oracle's step on the CPU with identical weights: log vars, gradients of every trainable
+    parameter, key-encoder weights after the EMA (bit-exact), queue state (pointer / ages
+    bit-exact), iters / momentum bookkeeping."""
+    import mscl_b200
+    from mscl_b200.configs import mscl_r18_model
+    from oracle.step import OracleMSCL
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        cfg = mscl_r18_model(K=256, aug="IdentityAug")
+        cfg["recognizer"]["max_iters"] = cfg["recognizer_flow"]["max_iters"] = 1000
+        torch.manual_seed(0)
+        model = mscl_b200.build_model(cfg)
+        model.train()
+        orc = OracleMSCL(model)          # deep copies on the CPU, taken before the product moves
+        model = model.cuda()
+        N = 4
+        for step in range(3):
+            imgs, flows = _synthetic_batch(N, S=64, seed=10 + step)
+            torch.manual_seed(100 + step)      # the shuffle permutations come from the default CPU generator
+            loss_ref, vars_ref = orc.train_step(imgs[0], imgs[1], flows[0], flows[1])
+            for p in orc.parameters():
+                p.grad = None
+            loss_ref.backward()
+            torch.manual_seed(100 + step)
+            model.zero_grad(set_to_none=True)
+            out = model.train_step(dict(imgs=[x.cuda() for x in imgs], flow_imgs=[x.cuda() for x in flows]), None)
+            out["loss"].backward()
+            assert out["num_samples"] == N
+            assert list(out["log_vars"].keys()) == list(vars_ref.keys())
+            for k, v in out["log_vars"].items():
+                if "acc" in k:
+                    assert abs(v - vars_ref[k]) <= 1.0 / N + 1e-6, (step, k, v, vars_ref[k])   # near-ties may flip one row
+                else:
+                    assert abs(v - vars_ref[k]) <= REL * abs(vars_ref[k]), (step, k, v, vars_ref[k])
+            for tag, rec, ob in (("rgb", model.recognizer, orc.rgb), ("flow", model.recognizer_flow, orc.flow)):
+                assert rec.iters == ob.state.iters and rec.batch_size == ob.state.batch_size, tag
+                sd = rec.state_dict()
+                assert int(sd["queue_ptr"]) == ob.state.ptr
+                np.testing.assert_array_equal(sd["count"].cpu().numpy(), ob.state.count.numpy())
+                assert _rel(sd["queue"], ob.state.queue) < 1e-4, tag      # keys come from GPU vs CPU encoders
+                # EMA of the key encoder: identical inputs (weights never stepped here) -> identical bits
+                for pk, po in zip([p for m in (rec.encoder_k, rec.neck_k, rec.mlp_k) for p in m.parameters()], ob.k_params()):
+                    np.testing.assert_array_equal(pk.detach().cpu().numpy(), po.detach().numpy())
+            gp = [p for r in (model.recognizer, model.recognizer_flow) for m in (r.encoder_q, r.neck_q, r.mlp_q)
+                  for p in m.parameters()]
+            go = orc.parameters()
+            assert len(gp) == len(go)
+            num = sum(float((a.grad.cpu().double() - b.grad.double()).pow(2).sum()) for a, b in zip(gp, go)
+                      if a.grad is not None and b.grad is not None)
+            den = sum(float(b.grad.double().pow(2).sum()) for b in go if b.grad is not None)
+            assert all((a.grad is None) == (b.grad is None) for a, b in zip(gp, go))
+            assert (num / den) ** 0.5 < 5e-3, (step, (num / den) ** 0.5)     # through 18 conv layers, GPU vs CPU fp32
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_state_dict_roundtrip_on_device():
+    """Checkpoint compatibility: reference-layout buffers out, same buffers in."""
+    model = head_level_model(512, 4)
+    rec = model.recognizer
+    rec.negative_queue()
+    keys = torch.nn.functional.normalize(torch.randn(3, 16, 128, device="cuda"), dim=2)
+    for s in range(3):
+        rec._dequeue_and_enqueue(keys[s])
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    assert int(sd["recognizer.queue_ptr"]) == 48 and int(sd["recognizer.count"].max()) == 3
+    np.testing.assert_array_equal(sd["recognizer.queue"][:, 16:32].t().cpu().numpy(), keys[1].cpu().numpy())
+    other = head_level_model(512, 4)
+    other.load_state_dict(sd, strict=True)
+    sd2 = other.state_dict()
+    for k in sd:
+        np.testing.assert_array_equal(sd2[k].cpu().numpy(), sd[k].cpu().numpy(), err_msg=k)
+    np.testing.assert_allclose(other.recognizer.negative_queue().weight().cpu().numpy(),
+                               (0.99999 ** sd["recognizer.count"].float().cpu() * sd["recognizer.queue"].cpu()).numpy(),
+                               rtol=2e-6)
