@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--ref-clips", type=int, default=4, help="clips per step of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shard", action="store_true", help="N>1: keep the queue replicated instead of K/N shards")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the resident timed region (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -332,7 +334,12 @@ def run_b200(args, rank, local_rank, world):
     def resident_step(i):
         last["log_vars"] = train_step(resident[i % 2])
 
+    if args.profile_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     sec, wall = timed(resident_step, args.steps)
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     rec = _cabi.stop_timing()
     launches = _cabi.launches() - launches0
     clocks = sampler.stop() if rank == 0 else None

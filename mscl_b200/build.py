@@ -49,6 +49,8 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if os.environ.get("MSCL_TIMELINE"):      # debug build: per-CTA phase timestamps in the tcgen05 kernel
+            cmd.insert(1, "-DMSCL_TC_TIMELINE")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

@@ -194,6 +194,19 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
                : "memory");
 }
 
+#ifdef MSCL_TC_TIMELINE
+// debug build only (MSCL_TIMELINE=1 python -m mscl_b200.build): per-CTA phase timestamps
+__device__ unsigned long long g_timeline[148 * 2 * 32];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL(slot) g_timeline[(blockIdx.y * gridDim.x + blockIdx.x) * 32 + (slot)] = gtime()
+#else
+#define TL(slot)
+#endif
+
 // One 64-key tile of one query row: S (TMEM) -> p, row sum, hit count, P' (TMEM, over S).
 template <bool GRAD, bool FULL>
 __device__ __forceinline__ void softmax_tile(uint32_t taddr0, const float *ds, float shift2, float thr,
@@ -259,6 +272,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const int row0 = blockIdx.y * kRows;
 
   if (warp == 0 && lane == 0) {
+    TL(0);
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
     for (int s = 0; s < kStages; ++s) {
@@ -288,6 +302,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      TL(1);
       for (int t = 0; t < nt; ++t) {
         const int s = t % kStages;
         const uint32_t use = (uint32_t)(t / kStages);
@@ -298,6 +313,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (GRAD) tma_load_3d(sW + s * kStageBytes + kWBytes, &tmap_w2, bar_full(s), 0, (int)key0, 0);
         bulk_load_1d(sDs + s * kDsBytes, dscale + key0, kDsBytes, bar_full(s));
       }
+      TL(4);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -380,6 +396,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       mbar_arrive(bar_q);
+      if (threadIdx.x == 64) TL(2);
     }
     float sum = 0.f;
     int cnt = 0;
@@ -389,6 +406,9 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       mbar_wait(bar_full(s), (uint32_t)(t / kStages) & 1u);   // dscale slice visible
       mbar_wait(bar_sfull(b), (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
+#ifdef MSCL_TC_TIMELINE
+      if (threadIdx.x == 64 && t < 12) TL(8 + t);
+#endif
       const int64_t key0 = (t_begin + t) * kTile;
       const int nvalid = (K_local - key0) < kTile ? (int)(K_local - key0) : kTile;
       const float *ds = ds_smem + s * kTile;
@@ -403,7 +423,11 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       if (GRAD) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       mbar_arrive(bar_pfull(b));
+#ifdef MSCL_TC_TIMELINE
+      if (threadIdx.x == 64 && t < 12) TL(20 + t);
+#endif
     }
+    if (threadIdx.x == 64) TL(5);
     if (row_ok) {
       atomicAdd(acc + (int64_t)row * kLd + kC, sum);
       atomicAdd(acc + (int64_t)row * kLd + kC + 1, (float)cnt);
@@ -411,6 +435,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (GRAD && nt > 0) {
       mbar_wait(bar_ofull, 0);
       tc_fence_after();
+      if (threadIdx.x == 64) TL(6);
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
         uint32_t v[32];
@@ -427,6 +452,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     }
   }
 
+  if (threadIdx.x == 64) TL(7);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -513,3 +539,10 @@ extern "C" int mscl_infonce_partial(const float *d_qpack, int32_t M, const float
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }
+
+#ifdef MSCL_TC_TIMELINE
+extern "C" int mscl_debug_timeline(unsigned long long *host_out, int n) {
+  MSCL_CUDA(cudaMemcpyFromSymbol(host_out, mscl::tc::g_timeline, sizeof(unsigned long long) * n));
+  return MSCL_OK;
+}
+#endif

@@ -63,7 +63,8 @@ probe_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUt
     if (mode == 0 || mode == 1) {
       for (int cb = 0; cb < 4; ++cb)
         for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t bd = make_desc(sW + cb * 8192 + ks * 32, 16, 1024);
+          // lt == 1: read the K-major operand from the 32B-atom-swizzled copy (could one copy serve both MMAs?)
+          const uint64_t bd = lt == 1 ? make_desc(sW2 + cb * 8192 + ks * 32, lbo, sbo, 1) : make_desc(sW + cb * 8192 + ks * 32, 16, 1024);
           if (mode == 0)
             mma_ss(tmem, make_desc(sQ + cb * 16384 + ks * 32, 16, 1024), bd, kIdesc1, (cb | ks) ? 1u : 0u);
           else
@@ -134,7 +135,9 @@ int main() {
   Cfg cfgs[] = {{0, 16, 1024, "SS K/K"}, {1, 16, 1024, "TS K"}, {2, 8192, 1024, "SS MN lbo=8192 sbo=1024"}, {3, 8192, 1024, "TS MN lbo=8192 sbo=1024"},
                 {2, 1024, 8192, "SS MN lbo=1024 sbo=8192"}, {3, 1024, 8192, "TS MN lbo=1024 sbo=8192"},
                 {2, 8192, 512, "SS MN32 lbo=8192 sbo=512", 1}, {3, 8192, 512, "TS MN32 lbo=8192 sbo=512", 1},
-                {2, 512, 8192, "SS MN32 lbo=512 sbo=8192", 1}, {2, 8192, 1024, "SS MN32 lbo=8192 sbo=1024", 1}};
+                {2, 512, 8192, "SS MN32 lbo=512 sbo=8192", 1}, {2, 8192, 1024, "SS MN32 lbo=8192 sbo=1024", 1},
+                {1, 16, 1024, "TS K from 32B-atom copy sbo=1024", 1}, {0, 16, 1024, "SS K from 32B-atom copy sbo=1024", 1},
+                {1, 16, 512, "TS K from 32B-atom copy sbo=512", 1}, {1, 16, 256, "TS K from 32B-atom copy sbo=256", 1}};
   for (auto &c : cfgs) {
     cudaMemset(dD, 0xff, D.size() * 4);
     probe_kernel<<<1, 128, smem>>>(tq, tw, tp, tw2, dQ, dP, dD, c.mode, c.lbo, c.sbo, c.lt);
