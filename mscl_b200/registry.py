@@ -2,7 +2,7 @@
 
 Mirror of `mmaction/models/builder.py:9-97` (MODELS and its aliases, SSL_AUGS, build_*)
 for an environment without mmcv: `type=` strings of the MSCL configs resolve here.  When
-mmcv/mmaction ARE importable, `mscl_b200.integration.register_into_mmaction()` registers
+mmcv/mmaction ARE importable, `import mscl_b200.mmcv_plugin` registers
 the same classes into the reference's own registry instead.
 """
 import warnings
