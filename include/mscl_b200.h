@@ -23,7 +23,8 @@
  *                                  (moco.py:427,437).
  *   qstate  int64   [4]            {ptr, n_enq, block-done counter, reserved}.
  *   qpack   float32 [M, 132]       per query row: q[0:128] | pos2 | shift2 | dup slot (int bits) | dup decay
- *   acc     float32 [M, 132]       per query row: O[0:128] | sum-exp | #neg>pos | 0 | 0
+ *   part    float32 [P, M, 132]    per CTA slab p and query row: O[0:128] | sum-exp | #neg>pos | 0 | 0
+ *                                  (P = mscl_infonce_num_partials); summed over p in a fixed order
  */
 #ifndef MSCL_B200_H_
 #define MSCL_B200_H_
@@ -153,9 +154,9 @@ int mscl_lmcl(const float *d_xq, const float *d_xf, int32_t N, int32_t C,
  *     (core/evaluation/accuracy.py:130-149) and
  *     MSCLWithAugMxHead._forward_moco_mx/.loss (heads/moco_head_v2.py:38-100).
  *
- * Three launches per pass (a collective may sit between 2 and 3 when the queue
- * is sharded):
- *  1 prep      qpack[i] = q_i | pos2 | shift2 ; dscale[j] ; acc <- 0
+ * Three launches per pass (when the queue is sharded, reduce + a reduce-scatter sit
+ * between 2 and 3):
+ *  1 prep      qpack[i] = q_i | pos2 | shift2 | dup slot | dup decay ; dscale[j]
  *              pos2_i   = (q_i . kpos_i) / T * log2(e)
  *              shift2_i = |q_i| * key_norm_bound / T * log2(e)   (>= every logit)
  *              dscale_j = 0.99999^(n_enq - birth_j) / T * log2(e);  d_dscale holds
@@ -168,35 +169,46 @@ int mscl_lmcl(const float *d_xq, const float *d_xf, int32_t N, int32_t C,
  *              tf32 operands cannot resolve, so `partial` skips the top-k hit test of that
  *              one column (its softmax mass is still summed) and `finalize` adds the exact
  *              comparison.
- *  2 partial   acc[i] += ( sum_j p_ij dscale_j queue_j | sum_j p_ij | #{j: s_ij > pos2_i} )
- *              with s_ij = (q_i . queue_j) dscale_j and p_ij = 2^(s_ij - shift2_i);
- *              tcgen05 (tf32 operands, fp32 accumulate in TMEM), queue tiles by TMA.
- *  3 finalize  per row: Z, lse, loss_i, p0, dq_unit_i; per group of rows_per_group
- *              consecutive rows: mean loss, top-1, top-5.
+ *  2 partial   part[p][i] = ( sum_j p_ij dscale_j queue_j | sum_j p_ij | #{j: s_ij > pos2_i} )
+ *              over the keys j of CTA slab p, with s_ij = (q_i . queue_j) dscale_j and
+ *              p_ij = 2^(s_ij - shift2_i); tcgen05 (tf32 operands, fp32 accumulate in TMEM),
+ *              queue and query tiles by TMA.  Plain stores, no atomics: every (p, i) row is
+ *              written once, so the pass is bit-reproducible.  n_part CTAs along the keys
+ *              (x ceil(M/128) row blocks); ask mscl_infonce_num_partials for n_part.
+ *  2' reduce   acc[i] = sum_p part[p][i]  (only needed before a cross-GPU reduce-scatter)
+ *  3 finalize  sums the n_part slabs, then per row: Z, lse, loss_i, p0, dq_unit_i; per group of
+ *              rows_per_group consecutive rows: mean loss, top-1, top-5.
  * Row i belongs to group i / rows_per_group.  d_group_out float [n_groups, 4] =
  * {loss, top1, top5, 0}.  d_dq_unit [M, C] = d(group loss)/d q_i.
  * d_row_loss float [2*M]: loss_i for i<M, then #{j: s_ij > pos_i} (as float).
- * finalize uses acc[130] as a CTA-done counter and leaves it zero.
+ * finalize uses part[0][0][130] as a CTA-done counter and leaves it zero.
  * mscl_infonce_bwd scales: d_dq[i] = d_dq_unit[i] * d_gout[group(i)].
  */
 int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
                       const int32_t *d_birth, const int64_t *d_qstate,
                       int64_t K_local, float inv_T, float key_norm_bound,
-                      float *d_qpack, float *d_dscale, float *d_acc,
-                      int32_t M_acc, const int32_t *d_dup_slot, int32_t dup_age,
+                      float *d_qpack, float *d_dscale,
+                      const int32_t *d_dup_slot, int32_t dup_age,
                       mscl_stream_t stream);
-/* shard_begin: global slot of d_queue[0] (0 when the queue is not sharded). */
+/* Number of CTA slabs along the keys for M rows over K_local keys on num_sms SMs (> 0), or a
+ * negative MSCL_E* code. */
+int mscl_infonce_num_partials(int32_t M, int64_t K_local, int32_t num_sms);
+/* shard_begin: global slot of d_queue[0] (0 when the queue is not sharded).
+ * d_part: float [n_part, M, 132]. */
 int mscl_infonce_partial(const float *d_qpack, int32_t M, const float *d_queue,
                          const float *d_dscale, int64_t K_local, int64_t shard_begin,
-                         float *d_acc, int32_t with_grad, int32_t num_sms,
+                         float *d_part, int32_t n_part, int32_t with_grad,
                          mscl_stream_t stream);
-/* Same contract as mscl_infonce_partial on CUDA cores in fp32: validation twin. */
+/* Same sums on CUDA cores in fp32 (validation twin): ACCUMULATES into d_acc float [M, 132]
+ * (= one slab), which the caller must zero first. */
 int mscl_infonce_partial_simt(const float *d_qpack, int32_t M, const float *d_queue,
                               const float *d_dscale, int64_t K_local, int64_t shard_begin,
                               float *d_acc, int32_t with_grad, mscl_stream_t stream);
+int mscl_infonce_reduce(const float *d_part, int32_t n_part, int32_t M, float *d_acc,
+                        mscl_stream_t stream);
 int mscl_infonce_finalize(const float *d_qpack, const float *d_kpos,
-                          float *d_acc, int32_t M, int32_t rows_per_group,
-                          float inv_T, float *d_row_loss, float *d_dq_unit,
+                          float *d_part, int32_t n_part, int32_t M, int32_t rows_per_group,
+                          float inv_T, int32_t with_grad, float *d_row_loss, float *d_dq_unit,
                           float *d_group_out, mscl_stream_t stream);
 int mscl_infonce_bwd(const float *d_dq_unit, const float *d_gout, int32_t M,
                      int32_t rows_per_group, float *d_dq, mscl_stream_t stream);

@@ -29,11 +29,12 @@ PROTOTYPES = {
     "mscl_hw_mean_fwd": [c_ptr, c_ptr, c_i64, c_int, c_ptr],
     "mscl_hw_mean_bwd": [c_ptr, c_ptr, c_i64, c_int, c_ptr],
     "mscl_lmcl": [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
-    "mscl_infonce_prep": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int,
-                          c_ptr],
+    "mscl_infonce_prep": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_int, c_ptr],
+    "mscl_infonce_num_partials": [c_int, c_i64, c_int],
     "mscl_infonce_partial": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_int, c_int, c_ptr],
     "mscl_infonce_partial_simt": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr],
-    "mscl_infonce_finalize": [c_ptr, c_ptr, c_ptr, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr],
+    "mscl_infonce_reduce": [c_ptr, c_int, c_int, c_ptr, c_ptr],
+    "mscl_infonce_finalize": [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_f32, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "mscl_infonce_bwd": [c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr],
     "mscl_gather_rows": [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr],
 }
@@ -43,7 +44,7 @@ _lock = threading.Lock()
 _lib = None
 _launches = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
 # how many device kernels one successful call enqueues
-_LAUNCHES_PER_CALL = {"mscl_device_check": 0}
+_LAUNCHES_PER_CALL = {"mscl_device_check": 0, "mscl_infonce_num_partials": 0}
 
 
 class MsclError(RuntimeError):
@@ -116,6 +117,16 @@ def call(name, *args, algo_bytes=0, algo_flops=0):
         ev1.record()
         _timing[name].append((ev0, ev1, algo_bytes, algo_flops))
     _launches += _LAUNCHES_PER_CALL.get(name, 1)
+
+
+def query(name, *args):
+    """Invoke an entry point that returns a non-negative value (or a negative MSCL_E* code)."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc < 0:
+        msg = lib.mscl_last_error()
+        raise MsclError(f"{name} failed ({rc}): {msg.decode() if msg else ''}")
+    return rc
 
 
 def launches():

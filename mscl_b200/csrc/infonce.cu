@@ -9,16 +9,14 @@ constexpr int kC = MSCL_DIM;
 constexpr int kLd = MSCL_PACK_LD;
 
 // ---- 1. prep --------------------------------------------------------------
-// part A (one warp per query row): qpack row = tf32-rounded q | pos2 | shift2 | 0 | 0
+// part A (one warp per query row): qpack row = tf32-rounded q | pos2 | shift2 | dup slot | dup decay
 // part B (one thread per key)     : dscale[j]
-// part C                          : acc <- 0
 __global__ void __launch_bounds__(256)
 infonce_prep_kernel(const float *__restrict__ q, const float *__restrict__ kpos, int M,
                     const int32_t *__restrict__ birth, const int64_t *__restrict__ qstate,
                     int64_t K_local, float inv_T, float key_norm_bound,
                     float *__restrict__ qpack, float *__restrict__ dscale,
-                    float *__restrict__ acc, int M_acc, const int32_t *__restrict__ dup_slot,
-                    int dup_age) {
+                    const int32_t *__restrict__ dup_slot, int dup_age) {
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * 8;
   const float sc = inv_T * kLog2e;
@@ -55,9 +53,6 @@ infonce_prep_kernel(const float *__restrict__ q, const float *__restrict__ kpos,
     }
     dscale[j] = v;
   }
-  float4 *acc4 = reinterpret_cast<float4 *>(acc);
-  const int64_t nacc = (int64_t)M_acc * (kLd / 4);
-  for (int64_t v = tid; v < nacc; v += nthreads) acc4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---- 2'. CUDA-core twin of the tcgen05 pass (validation only) ---------------
@@ -118,20 +113,74 @@ infonce_partial_simt_kernel(const float *__restrict__ qpack, int M,
   }
 }
 
-// ---- 3. finalize -----------------------------------------------------------
-// One CTA (128 threads, thread <-> channel) per query row; the last CTA to finish
-// reduces the per-row losses / hit flags into per-group means in row order.
-__global__ void __launch_bounds__(128)
-infonce_finalize_kernel(const float *__restrict__ qpack, const float *__restrict__ kpos,
-                        float *__restrict__ acc, int M, int rows_per_group, float inv_T,
-                        float *__restrict__ row_loss, float *__restrict__ dq_unit,
-                        float *__restrict__ group_out) {
+// ---- 2''. sum of the per-CTA partial slabs (sharded path: before the reduce-scatter) ----
+__global__ void __launch_bounds__(160)
+infonce_reduce_kernel(const float *__restrict__ part, int n_part, int M, float *__restrict__ acc) {
   const int i = blockIdx.x, c = threadIdx.x;
+  if (c >= kLd) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const int64_t slab = (int64_t)M * kLd;
+  const float *src = part + (int64_t)i * kLd + c;
+  int p = 0;
+  for (; p + 4 <= n_part; p += 4) {   // fixed order, 4 independent loads in flight
+    a0 += src[(p + 0) * slab];
+    a1 += src[(p + 1) * slab];
+    a2 += src[(p + 2) * slab];
+    a3 += src[(p + 3) * slab];
+  }
+  for (; p < n_part; ++p) a0 += src[p * slab];
+  acc[(int64_t)i * kLd + c] = (a0 + a1) + (a2 + a3);
+}
+
+// ---- 3. finalize -----------------------------------------------------------
+// One CTA per query row, kFinGroups groups of 128 threads (thread <-> channel): group g sums the
+// slabs p = g, g+G, g+2G, ... of [n_part][M][132] with all its loads in flight at once (the sum over
+// 148 slabs is latency-bound otherwise), the groups are combined through shared memory in a fixed
+// order (bit-reproducible), then group 0 computes the row's loss and gradient; the last CTA to
+// finish reduces the per-row losses / hit flags into per-group means in row order.
+constexpr int kFinGroups = 8;
+constexpr int kFinMaxPer = 24;     // slabs per group held in registers per round
+__global__ void __launch_bounds__(128 * kFinGroups)
+infonce_finalize_kernel(const float *__restrict__ qpack, const float *__restrict__ kpos,
+                        float *__restrict__ part, int n_part, int M, int rows_per_group,
+                        float inv_T, int with_grad, float *__restrict__ row_loss,
+                        float *__restrict__ dq_unit, float *__restrict__ group_out) {
+  const int i = blockIdx.x, c = threadIdx.x & 127, g = threadIdx.x >> 7;
   const float *qp = qpack + (int64_t)i * kLd;
-  const float *ap = acc + (int64_t)i * kLd;
+  const int64_t slab = (int64_t)M * kLd;
+  const float *src = part + (int64_t)i * kLd;
+  __shared__ float s_o[kFinGroups][128];
+  __shared__ float s_st[kFinGroups][2];
+  {
+    float o = 0.f, st = 0.f;
+    const bool stat_thread = c < 2;
+    for (int p0 = g; p0 < n_part; p0 += kFinGroups * kFinMaxPer) {
+      float v[kFinMaxPer], w[kFinMaxPer];
+#pragma unroll
+      for (int u = 0; u < kFinMaxPer; ++u) {
+        const int p = p0 + u * kFinGroups;
+        v[u] = (with_grad && p < n_part) ? __ldg(src + p * slab + c) : 0.f;
+        w[u] = (stat_thread && p < n_part) ? __ldg(src + p * slab + kC + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kFinMaxPer; ++u) {
+        o += v[u];
+        st += w[u];
+      }
+    }
+    s_o[g][c] = o;
+    if (stat_thread) s_st[g][c] = st;
+  }
+  __syncthreads();
+  if (g != 0) return;
+  float o = 0.f, sum = 0.f, cnt = 0.f;
+#pragma unroll
+  for (int k = 0; k < kFinGroups; ++k) {
+    o += s_o[k][c];
+    sum += s_st[k][0];
+    cnt += s_st[k][1];
+  }
   const float pos2 = qp[kC], shift2 = qp[kC + 1];
-  const float sum = ap[kC];
-  float cnt = ap[kC + 1];
   // A queue entry that IS this row's positive key (enqueued earlier in the step, moco.py:437)
   // scores pos * 0.99999^age in the reference: above the positive iff pos < 0.  The tensor-core
   // pass cannot resolve a 1e-5 margin with tf32 operands, so it skips that column's hit test and
@@ -143,8 +192,8 @@ infonce_finalize_kernel(const float *__restrict__ qpack, const float *__restrict
   const float p0 = e0 * inv_Z;
   // d loss_i / d q = (1/T) [ (p0 - 1) kpos + sum_j p_j decay_j queue_j ];  the
   // accumulated O carries decay_j * log2e / T, hence the ln2 factor.
-  const float g = (p0 - 1.0f) * kpos[(int64_t)i * kC + c] * inv_T + ap[c] * inv_Z * kLn2;
-  dq_unit[(int64_t)i * kC + c] = g / (float)rows_per_group;
+  const float grad = (p0 - 1.0f) * kpos[(int64_t)i * kC + c] * inv_T + o * inv_Z * kLn2;
+  dq_unit[(int64_t)i * kC + c] = grad / (float)rows_per_group;
   __shared__ int is_last;
   if (c == 0) {
     const float loss = (shift2 + log2f(Z) - pos2) * kLn2;
@@ -152,12 +201,12 @@ infonce_finalize_kernel(const float *__restrict__ qpack, const float *__restrict
     row_loss[i] = loss;
     row_loss[M + i] = cnt;
     __threadfence();
-    unsigned *counter = reinterpret_cast<unsigned *>(acc + kC + 2);
+    unsigned *counter = reinterpret_cast<unsigned *>(part + kC + 2);   // row 0 of slab 0, a spare (zero) column
     const unsigned done = atomicAdd(counter, 1u);
     is_last = (done == (unsigned)M - 1u);
     if (is_last) *counter = 0u;
   }
-  __syncthreads();
+  asm volatile("bar.sync 1, 128;" ::: "memory");   // group 0 only (the other groups have exited)
   if (!is_last) return;
   __threadfence();
   const int n_groups = M / rows_per_group;
@@ -193,23 +242,18 @@ extern "C" {
 int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
                       const int32_t *d_birth, const int64_t *d_qstate, int64_t K_local,
                       float inv_T, float key_norm_bound, float *d_qpack, float *d_dscale,
-                      float *d_acc, int32_t M_acc, const int32_t *d_dup_slot, int32_t dup_age,
-                      mscl_stream_t stream) {
-  MSCL_CHECK_ARG(d_q && d_kpos && d_birth && d_qstate && d_qpack && d_dscale && d_acc,
-                 "null pointer");
-  MSCL_CHECK_ARG(M > 0 && M_acc >= M && K_local > 0, "bad M=%d M_acc=%d K_local=%lld", M, M_acc,
-                 (long long)K_local);
+                      const int32_t *d_dup_slot, int32_t dup_age, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_q && d_kpos && d_birth && d_qstate && d_qpack && d_dscale, "null pointer");
+  MSCL_CHECK_ARG(M > 0 && K_local > 0, "bad M=%d K_local=%lld", M, (long long)K_local);
   MSCL_CHECK_ARG(inv_T > 0.f && key_norm_bound > 0.f, "bad inv_T / key_norm_bound");
-  MSCL_CHECK_ARG((((uintptr_t)d_q | (uintptr_t)d_kpos | (uintptr_t)d_qpack | (uintptr_t)d_acc) & 15) == 0,
-                 "q/kpos/qpack/acc must be 16-byte aligned");
+  MSCL_CHECK_ARG((((uintptr_t)d_q | (uintptr_t)d_kpos | (uintptr_t)d_qpack) & 15) == 0,
+                 "q/kpos/qpack must be 16-byte aligned");
   int64_t want = (K_local + 255) / 256;
-  const int64_t want_acc = ((int64_t)M_acc * (MSCL_PACK_LD / 4) + 255) / 256;
-  if (want_acc > want) want = want_acc;
   if ((M + 7) / 8 > want) want = (M + 7) / 8;
   if (want > 1184) want = 1184;
   mscl::infonce_prep_kernel<<<(unsigned)want, 256, 0, mscl::as_stream(stream)>>>(
       d_q, d_kpos, M, d_birth, d_qstate, K_local, inv_T, key_norm_bound, d_qpack, d_dscale,
-      d_acc, M_acc, d_dup_slot, dup_age);
+      d_dup_slot, dup_age);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }
@@ -229,15 +273,25 @@ int mscl_infonce_partial_simt(const float *d_qpack, int32_t M, const float *d_qu
   return MSCL_OK;
 }
 
-int mscl_infonce_finalize(const float *d_qpack, const float *d_kpos, float *d_acc,
-                          int32_t M, int32_t rows_per_group, float inv_T, float *d_row_loss,
-                          float *d_dq_unit, float *d_group_out, mscl_stream_t stream) {
-  MSCL_CHECK_ARG(d_qpack && d_kpos && d_acc && d_row_loss && d_dq_unit && d_group_out,
+int mscl_infonce_reduce(const float *d_part, int32_t n_part, int32_t M, float *d_acc,
+                        mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_part && d_acc, "null pointer");
+  MSCL_CHECK_ARG(M > 0 && n_part > 0, "bad M=%d n_part=%d", M, n_part);
+  mscl::infonce_reduce_kernel<<<M, 160, 0, mscl::as_stream(stream)>>>(d_part, n_part, M, d_acc);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+int mscl_infonce_finalize(const float *d_qpack, const float *d_kpos, float *d_part,
+                          int32_t n_part, int32_t M, int32_t rows_per_group, float inv_T,
+                          int32_t with_grad, float *d_row_loss, float *d_dq_unit,
+                          float *d_group_out, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_qpack && d_kpos && d_part && d_row_loss && d_dq_unit && d_group_out,
                  "null pointer");
-  MSCL_CHECK_ARG(M > 0 && rows_per_group > 0 && M % rows_per_group == 0,
-                 "M=%d must be a multiple of rows_per_group=%d", M, rows_per_group);
-  mscl::infonce_finalize_kernel<<<M, 128, 0, mscl::as_stream(stream)>>>(
-      d_qpack, d_kpos, d_acc, M, rows_per_group, inv_T, d_row_loss,
+  MSCL_CHECK_ARG(M > 0 && n_part > 0 && rows_per_group > 0 && M % rows_per_group == 0,
+                 "M=%d must be a multiple of rows_per_group=%d (n_part=%d)", M, rows_per_group, n_part);
+  mscl::infonce_finalize_kernel<<<M, 128 * mscl::kFinGroups, 0, mscl::as_stream(stream)>>>(
+      d_qpack, d_kpos, d_part, n_part, M, rows_per_group, inv_T, with_grad, d_row_loss,
       d_dq_unit, d_group_out);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;

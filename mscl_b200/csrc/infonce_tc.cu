@@ -35,20 +35,28 @@ constexpr int kRows = 128;            // query rows per CTA (UMMA M)
 constexpr int kTile = 64;             // keys per stage
 constexpr int kStages = 3;
 constexpr int kCb = 4;                // channel blocks of 32 fp32 (one 128-byte swizzle row)
-constexpr int kThreads = 192;
+constexpr int kSoftmaxWarps = 8;      // two per TMEM lane quarter, each takes 32 of a tile's 64 keys
+constexpr int kThreads = (2 + kSoftmaxWarps) * 32;   // TMA producer, MMA issuer, softmax warps
 
 constexpr uint32_t kWBytes = kTile * kC * 4;          // 32768: one copy of a tile
 constexpr uint32_t kWSlab = kTile * 128;              // bytes per channel block of a W tile
-constexpr uint32_t kStageBytes = 2 * kWBytes;         // K-major copy + MN-major copy
-constexpr uint32_t kDsBytes = kTile * 4;              // 256
+constexpr uint32_t kQBytes = kRows * kC * 4;          // 65536: the Q tile, staged through one stage buffer
+constexpr uint32_t kQSlab = kRows * 128;              // bytes per channel block of the Q tile
 
 // shared memory map (offsets from the 1024-aligned base)
-constexpr uint32_t kOffW = 0;
-constexpr uint32_t kOffDs = kOffW + kStages * kStageBytes;
-constexpr uint32_t kOffBar = kOffDs + kStages * kDsBytes;
-constexpr uint32_t kNumBars = 2 * kStages + 1 + 2 + 2 + 1;  // full, empty, q, s_full[2], p_full[2], o_full
+// Two rings of kStages slots each, with separate lifetimes: ring 1 holds the 128B-swizzled (K-major)
+// copy of a tile, needed by MMA1(t) only; ring 2 the 32B-atom-swizzled (MN-major) copy, needed by
+// MMA2(t) one tile period later.  A ring-1 slot is free as soon as MMA1 has read it, so the HBM
+// prefetch runs ~kStages tiles ahead of MMA1; ring 2 is filled from L2.
+constexpr uint32_t kOffW = 0;                           // ring 1
+constexpr uint32_t kOffW2 = kOffW + kStages * kWBytes;  // ring 2
+constexpr uint32_t kOffBar = kOffW2 + kStages * kWBytes;
+constexpr uint32_t kNumBars = 4 * kStages + 1 + 2 + 2 + 1 + 2;  // full1, empty1, full2, empty2, q, s_full[2], p_full[2], o_full, qload, qfree
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
-constexpr uint32_t kSmemUsed = kOffTmemPtr + 16;
+constexpr uint32_t kOffRed = kOffTmemPtr + 16;          // [2][128] floats: sum / count of the second column half
+constexpr uint32_t kSmemUsed = kOffRed + 2 * kRows * 4;
+static_assert(kQBytes <= 2 * kWBytes && kStages >= 3, "the Q tile is staged through ring-2 slots 1 and 2");
+static_assert(kQBytes <= kStages * kWBytes, "the O tile is staged through ring 1");
 constexpr uint32_t kSmemBytes = kSmemUsed + 1024;     // slack for manual 1024-byte alignment
 
 constexpr uint32_t kTmemCols = 512;
@@ -105,6 +113,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes,
                                              uint32_t bar) {
   asm volatile(
@@ -124,6 +138,35 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
+}
+// One lane of a fully converged warp.  Issuing the tcgen05.mma stream from inside `if (elect_one())` in a
+// branch the compiler can prove warp-uniform keeps descriptors in uniform registers (UIADD3 + UTCHMMA,
+// 2 SASS instructions per dispatch); under a plain `lane == 0` branch every dispatch is wrapped in an
+// ELECT/R2UR/BRA.U.ANY waterfall (~12 instructions), and the issuing thread, not the tensor pipe, sets the pace.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred;
+}
+// D[tmem] (+)= A[tmem] . B[smem descriptor given as (lo, hi) words]
+__device__ __forceinline__ void mma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t lo, uint32_t hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // D[tmem] (+)= A[smem desc] . B[smem desc]
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
@@ -207,61 +250,76 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TL(slot)
 #endif
 
-// One 64-key tile of one query row: S (TMEM) -> p, row sum, hit count, P' (TMEM, over S).
+// 32 keys of one 64-key tile for one query row: S (TMEM) -> p, row sum, hit count, P' (TMEM, over S).
+// `ds` = the 32 per-key scales of this half tile; nvalid / dupcol are relative to the half tile.
+// Per element on the fast path: FFMA (logit - shift), MUFU.EX2, FFMA (pos - logit: its sign bit is the
+// top-k hit), one add of that sign bit, FADD (row sum), FMUL (p * scale), IADD (round to nearest tf32:
+// +half ulp, the tensor core drops the low 13 bits).  4 independent sum / count chains.
 template <bool GRAD, bool FULL>
-__device__ __forceinline__ void softmax_tile(uint32_t taddr0, const float *ds, float shift2, float thr,
+__device__ __forceinline__ void softmax_half(uint32_t taddr, const float4 *ds, float shift2, float pos2,
                                              int nvalid, int dupcol, float &sum, int &cnt) {
+  uint32_t v[32];
+  TC_LD32(taddr, v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t c4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    uint32_t v[32];
-    const uint32_t taddr = taddr0 + h * 32;
-    TC_LD32(taddr, v);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 d4 = ds[j4];
+    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      const float4 d4 = *reinterpret_cast<const float4 *>(ds + h * 32 + j4 * 4);
-      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = j4 * 4 + e;
-        const float tval = fmaf(__uint_as_float(v[j]), dd[e], -shift2);
-        float p = ex2(tval);
-        bool hit = tval > thr;
-        if (!FULL) {  // tail tile (keys beyond K_local) or the tile holding this row's own positive key
-          const bool ok = (h * 32 + j) < nvalid;
-          p = ok ? p : 0.f;
-          hit = hit && ok && (h * 32 + j) != dupcol;
-        }
-        sum += p;
-        cnt += hit ? 1 : 0;
-        v[j] = __float_as_uint(GRAD ? to_tf32_rn(p * dd[e]) : 0.f);
+    for (int e = 0; e < 4; ++e) {
+      const int j = j4 * 4 + e;
+      const float sv = __uint_as_float(v[j]);
+      float p = ex2(fmaf(sv, dd[e], -shift2));
+      uint32_t hit = __float_as_uint(fmaf(-sv, dd[e], pos2)) >> 31;    // 1 iff logit > positive logit
+      if (!FULL) {  // tail tile (keys beyond K_local) or the tile holding this row's own positive key
+        const bool ok = j < nvalid;
+        p = ok ? p : 0.f;
+        hit = (ok && j != dupcol) ? hit : 0u;
       }
+      s4[e] += p;
+      c4[e] += hit;
+      v[j] = GRAD ? __float_as_uint(p * dd[e]) + 0x1000u : 0u;
     }
-    if (GRAD) TC_ST32(taddr, v);
   }
+  sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  cnt += (int)((c4[0] + c4[1]) + (c4[2] + c4[3]));
+  if (GRAD) TC_ST32(taddr, v);
 }
 
+// part: per-CTA partial rows, float [gridDim.x][M][kLd]: O[0:128] | sum-exp | #neg>pos | 0 | 0.
+// Every (blockIdx.x, row < M) row is written exactly once (plain stores, no atomics): the cross-CTA sum
+// is taken in a fixed order by the finalize / reduce kernels, so results are bit-reproducible.
 template <bool GRAD>
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_w2,
-                  const float *__restrict__ qpack, int M, const float *__restrict__ dscale,
-                  int64_t K_local, int64_t shard_begin, float *__restrict__ acc) {
+                  const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_part,
+                  const float *__restrict__ qpack, int M,
+                  const float *__restrict__ dscale, int64_t K_local, int64_t shard_begin,
+                  float *__restrict__ part) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sW = base + kOffW;
-  const uint32_t sDs = base + kOffDs;
+  const uint32_t sW2 = base + kOffW2;
+  const uint32_t sQ = sW2 + kWBytes;                           // Q tile: ring-2 slots 1 and 2
   const uint32_t bar0 = base + kOffBar;
-  auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
-  const uint32_t bar_q = bar0 + 8u * (2 * kStages);
-  auto bar_sfull = [&](int b) { return bar0 + 8u * (2 * kStages + 1 + b); };
-  auto bar_pfull = [&](int b) { return bar0 + 8u * (2 * kStages + 3 + b); };
-  const uint32_t bar_ofull = bar0 + 8u * (2 * kStages + 5);
+  auto bar_full1 = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty1 = [&](int s) { return bar0 + 8u * (kStages + s); };
+  auto bar_full2 = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
+  auto bar_empty2 = [&](int s) { return bar0 + 8u * (3 * kStages + s); };
+  constexpr int kB = 4 * kStages;
+  const uint32_t bar_q = bar0 + 8u * kB;                       // Q rows stored to TMEM (8 warps)
+  auto bar_sfull = [&](int b) { return bar0 + 8u * (kB + 1 + b); };
+  auto bar_pfull = [&](int b) { return bar0 + 8u * (kB + 3 + b); };
+  const uint32_t bar_ofull = bar0 + 8u * (kB + 5);
+  const uint32_t bar_qload = bar0 + 8u * (kB + 6);             // Q tile landed in smem (TMA)
+  const uint32_t bar_qfree = bar0 + 8u * (kB + 7);             // Q tile read out of smem (8 warps)
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(gbase + kOffTmemPtr);
-  const float *ds_smem = reinterpret_cast<const float *>(gbase + kOffDs);
+  float *red_smem = reinterpret_cast<float *>(gbase + kOffRed);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   // this CTA's tile range
@@ -273,18 +331,27 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
   if (warp == 0 && lane == 0) {
     TL(0);
+#ifdef MSCL_TC_TIMELINE
+    g_timeline[(blockIdx.y * gridDim.x + blockIdx.x) * 32 + 30] = clock64();
+#endif
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
+    if (GRAD) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_part) : "memory");
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_full1(s), 1);
+      mbar_init(bar_empty1(s), 1);
+      mbar_init(bar_full2(s), 1);
+      mbar_init(bar_empty2(s), 1);
     }
-    mbar_init(bar_q, 128);
+    mbar_init(bar_q, kSoftmaxWarps);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_sfull(b), 1);
-      mbar_init(bar_pfull(b), 128);
+      mbar_init(bar_pfull(b), kSoftmaxWarps);
     }
     mbar_init(bar_ofull, 1);
+    mbar_init(bar_qload, 1);
+    mbar_init(bar_qfree, kSoftmaxWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -297,162 +364,245 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_ptr_smem;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       TL(1);
-      for (int t = 0; t < nt; ++t) {
+      // Q tile [128 rows x 128 ch] as 4 channel-block slabs of [128][128 B], 128B-swizzled; rows >= M are
+      // zero-filled by the TMA unit
+      mbar_arrive_expect_tx(bar_qload, kQBytes);
+      tma_load_3d(sQ, &tmap_q, bar_qload, 0, row0, 0);
+      auto load1 = [&](int t) {      // K-major copy of tile t (from HBM)
         const int s = t % kStages;
-        const uint32_t use = (uint32_t)(t / kStages);
-        mbar_wait(bar_empty(s), (use & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar_full(s), (GRAD ? 2 * kWBytes : kWBytes) + kDsBytes);
-        const int64_t key0 = (t_begin + t) * kTile;
-        tma_load_3d(sW + s * kStageBytes, &tmap_w, bar_full(s), 0, (int)key0, 0);
-        if (GRAD) tma_load_3d(sW + s * kStageBytes + kWBytes, &tmap_w2, bar_full(s), 0, (int)key0, 0);
-        bulk_load_1d(sDs + s * kDsBytes, dscale + key0, kDsBytes, bar_full(s));
+        mbar_wait(bar_empty1(s), ((uint32_t)(t / kStages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar_full1(s), kWBytes);
+        tma_load_3d(sW + s * kWBytes, &tmap_w, bar_full1(s), 0, (int)((t_begin + t) * kTile), 0);
+      };
+      auto load2 = [&](int t) {      // MN-major copy of tile t (the same bytes again: an L2 hit)
+        const int s = t % kStages;
+        if (t == 1) mbar_wait(bar_qfree, 0);        // slots 1 and 2 held the Q tile
+        mbar_wait(bar_empty2(s), ((uint32_t)(t / kStages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar_full2(s), kWBytes);
+        tma_load_3d(sW2 + s * kWBytes, &tmap_w2, bar_full2(s), 0, (int)((t_begin + t) * kTile), 0);
+      };
+      for (int t = 0; t < kStages && t < nt; ++t) load1(t);
+      for (int t = 0; t < nt; ++t) {
+        if (GRAD) load2(t);                          // waits for MMA2(t - kStages)
+        if (t + kStages < nt) load1(t + kStages);    // waits for MMA1(t), which runs after MMA2(t - 2)
       }
       TL(4);
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // descriptor words: lo = (addr >> 4) | (LBO >> 4) << 16, hi = (SBO >> 4) | version 1 << 14 | layout << 29
+    constexpr uint32_t kHi1 = (1024u >> 4) | (1u << 14) | (2u << 29);      // K-major, SWIZZLE_128B, SBO 1024
+    constexpr uint32_t kHi2 = (512u >> 4) | (1u << 14) | (1u << 29);       // MN-major, SWIZZLE_128B_BASE32B, SBO 512
+    const uint32_t lo1_base = ((sW & 0x3FFFFu) >> 4) | ((16u >> 4) << 16);              // LBO 16
+    const uint32_t lo2_base = ((sW2 & 0x3FFFFu) >> 4) | ((kWSlab >> 4) << 16);          // LBO = channel-block pitch
+    if (elect_one()) {
       auto issue_mma1 = [&](int t) {
         const int s = t % kStages;
-        mbar_wait(bar_full(s), (uint32_t)(t / kStages) & 1u);
+        mbar_wait(bar_full1(s), (uint32_t)(t / kStages) & 1u);
         tc_fence_after();
         const uint32_t d = tmem + kColS + (uint32_t)(t & 1) * kTile;
+        const uint32_t lo = lo1_base + (uint32_t)s * (kWBytes >> 4);
 #pragma unroll
         for (int cb = 0; cb < kCb; ++cb) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t bd = make_desc(sW + s * kStageBytes + cb * kWSlab + ks * 32, 16, 1024);
-            mma_ts(d, tmem + kColQ + cb * 32 + ks * 8, bd, kIdesc1, (cb | ks) ? 1u : 0u);
-          }
+          for (int ks = 0; ks < 4; ++ks)
+            mma_ts_lh(d, tmem + kColQ + cb * 32 + ks * 8, lo + ((cb * kWSlab + ks * 32) >> 4), kHi1, kIdesc1,
+                      (cb | ks) ? 1u : 0u);
         }
         tc_commit(bar_sfull(t & 1));
+        tc_commit(bar_empty1(s));      // ring-1 slot is free once MMA1 has read it
       };
       mbar_wait(bar_q, 0);
       tc_fence_after();
+#ifdef MSCL_TC_TIMELINE
+      TL(28);
+      mbar_wait(bar_full1(0), 0);
+      TL(29);
+#endif
       if (nt > 0) issue_mma1(0);
       for (int t = 0; t < nt; ++t) {
+#ifdef MSCL_TC_TIMELINE
+        if (t == 3) TL(16);
+#endif
         if (t + 1 < nt) issue_mma1(t + 1);
+#ifdef MSCL_TC_TIMELINE
+        if (t == 3) TL(17);
+#endif
         if (GRAD) {
           const int s = t % kStages;
+          mbar_wait(bar_full2(s), (uint32_t)(t / kStages) & 1u);
           mbar_wait(bar_pfull(t & 1), (uint32_t)(t >> 1) & 1u);
           tc_fence_after();
+#ifdef MSCL_TC_TIMELINE
+          if (t == 3) TL(18);
+#endif
           const uint32_t a = tmem + kColS + (uint32_t)(t & 1) * kTile;
+          const uint32_t lo = lo2_base + (uint32_t)s * (kWBytes >> 4);
+          // B = the ring-2 copy read MN-major (SWIZZLE_128B_BASE32B): 8 keys per step = two 4-row atoms
+          // 512 bytes apart (SBO); channel blocks kWSlab bytes apart (LBO)
+          if (t == 0) {
 #pragma unroll
-          for (int j = 0; j < kTile / 8; ++j) {
-            // B = the stage's second copy read MN-major (SWIZZLE_128B_BASE32B): 8 keys per step =
-            // two 4-row atoms 512 bytes apart (SBO); channel blocks kWSlab bytes apart (LBO)
-            const uint64_t bd = make_desc(sW + s * kStageBytes + kWBytes + j * 1024, kWSlab, 512, 1);
-            mma_ts(tmem + kColO, a + j * 8, bd, kIdesc2, (t | j) ? 1u : 0u);
+            for (int j = 0; j < kTile / 8; ++j)
+              mma_ts_lh(tmem + kColO, a + j * 8, lo + ((j * 1024) >> 4), kHi2, kIdesc2, j ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kTile / 8; ++j)
+              mma_ts_lh(tmem + kColO, a + j * 8, lo + ((j * 1024) >> 4), kHi2, kIdesc2, 1u);
           }
-          tc_commit(bar_empty(s));
+          tc_commit(bar_empty2(s));
+#ifdef MSCL_TC_TIMELINE
+          if (t == 3) TL(19);
+#endif
         } else {
-          // no second GEMM: the stage is free once the softmax warps have consumed dscale
-          // and MMA1 has read the tile; p_full doubles as "S consumed".
-          const int s = t % kStages;
+          // no second GEMM; p_full doubles as "S consumed" (the S buffer may be overwritten by MMA1(t+2))
           mbar_wait(bar_pfull(t & 1), (uint32_t)(t >> 1) & 1u);
-          mbar_arrive(bar_empty(s));
         }
       }
       if (GRAD) tc_commit(bar_ofull);
     }
+    __syncwarp();
   } else {
-    // ===================== softmax / epilogue warps =====================
+    // ===================== softmax / epilogue warps (8: two per TMEM lane quarter) =====================
+    const int sw = warp - 2;                      // 0..7
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = sw >> 2;                     // which 32 of a tile's 64 keys (and which half of Q / O)
     const int r = quarter * 32 + lane;            // row within the CTA's block == TMEM lane
     const int row = row0 + r;
     const bool row_ok = row < M;
-    float shift2 = 0.f, thr = INFINITY;
+    const bool warp_ok = (row0 + quarter * 32) < M;   // any valid row in this warp's lane quarter
+    float shift2 = 0.f, pos2 = INFINITY;
     int64_t dup_local = -1;   // queue slot (in this shard) holding a copy of the row's positive key
     if (row_ok) {
-      const float pos2 = qpack[(int64_t)row * kLd + kC];
-      shift2 = qpack[(int64_t)row * kLd + kC + 1];
-      thr = pos2 - shift2;
-      const int dup = __float_as_int(qpack[(int64_t)row * kLd + kC + 2]);
+      const float4 x = __ldg(reinterpret_cast<const float4 *>(qpack + (int64_t)row * kLd + kC));
+      shift2 = x.y;
+      pos2 = x.x;
+      const int dup = __float_as_int(x.z);
       if (dup >= 0) dup_local = (int64_t)dup - shard_begin;
     }
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-    {   // this row of Q -> TMEM columns [kColQ, kColQ+128): the A operand of every MMA1
-      const float4 *qsrc = reinterpret_cast<const float4 *>(qpack + (int64_t)row * kLd);
+    {   // this row of Q: smem (TMA, swizzled) -> TMEM columns [kColQ + 64*half, +64): the A operand of every MMA1
+      mbar_wait(bar_qload, 0);
+      const uint8_t *qs = gbase + kOffW2 + kWBytes;
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cb = half * 2 + hh;             // channel block (slab) of 32 channels
+        const uint8_t *rowp = qs + cb * kQSlab + r * 128;
         uint32_t v[32];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_ok) f = __ldg(qsrc + h * 8 + j4);
-          v[j4 * 4 + 0] = __float_as_uint(f.x);
-          v[j4 * 4 + 1] = __float_as_uint(f.y);
-          v[j4 * 4 + 2] = __float_as_uint(f.z);
-          v[j4 * 4 + 3] = __float_as_uint(f.w);
+        for (int c = 0; c < 8; ++c) {
+          const float4 f = *reinterpret_cast<const float4 *>(rowp + ((c ^ (r & 7)) << 4));
+          v[c * 4 + 0] = __float_as_uint(f.x);
+          v[c * 4 + 1] = __float_as_uint(f.y);
+          v[c * 4 + 2] = __float_as_uint(f.z);
+          v[c * 4 + 3] = __float_as_uint(f.w);
         }
-        TC_ST32(lane_base + kColQ + h * 32, v);
+        TC_ST32(lane_base + kColQ + cb * 32, v);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
-      mbar_arrive(bar_q);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_qfree);
+        mbar_arrive(bar_q);
+      }
       if (threadIdx.x == 64) TL(2);
     }
     float sum = 0.f;
     int cnt = 0;
     for (int t = 0; t < nt; ++t) {
-      const int s = t % kStages;
       const int b = t & 1;
-      mbar_wait(bar_full(s), (uint32_t)(t / kStages) & 1u);   // dscale slice visible
+      const int64_t key0 = (t_begin + t) * kTile + half * 32;
+      // this half tile's 32 per-key scales (L1/L2-resident, warp-uniform addresses), fetched before the wait;
+      // the array is padded to a multiple of 64 so the reads never leave it
+      float4 d4[8];
+      if (warp_ok) {
+        const float4 *dsg = reinterpret_cast<const float4 *>(dscale + key0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d4[j] = __ldg(dsg + j);
+      }
       mbar_wait(bar_sfull(b), (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
 #ifdef MSCL_TC_TIMELINE
-      if (threadIdx.x == 64 && t < 12) TL(8 + t);
+      if (threadIdx.x == 64 && t < 8) TL(8 + t);
 #endif
-      const int64_t key0 = (t_begin + t) * kTile;
-      const int nvalid = (K_local - key0) < kTile ? (int)(K_local - key0) : kTile;
-      const float *ds = ds_smem + s * kTile;
-      const int64_t dcol = dup_local - key0;
-      const bool has_dup = dcol >= 0 && dcol < kTile;
-      // warp-uniform choice (tcgen05.ld/st are .sync.aligned): slow path if any row of the warp needs it
-      if (nvalid == kTile && !__any_sync(0xffffffffu, has_dup))
-        softmax_tile<GRAD, true>(lane_base + kColS + (uint32_t)b * kTile, ds, shift2, thr, nvalid, -1, sum, cnt);
-      else
-        softmax_tile<GRAD, false>(lane_base + kColS + (uint32_t)b * kTile, ds, shift2, thr, nvalid,
-                                  has_dup ? (int)dcol : -1, sum, cnt);
-      if (GRAD) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      if (warp_ok) {
+        const int64_t left = K_local - key0;
+        const int nvalid = left < 32 ? (left < 0 ? 0 : (int)left) : 32;
+        const float4 *ds = d4;
+        const uint32_t taddr = lane_base + kColS + (uint32_t)b * kTile + half * 32;
+        const int64_t dcol = dup_local - key0;
+        const bool has_dup = dcol >= 0 && dcol < 32;
+        // warp-uniform choice (tcgen05.ld/st are .sync.aligned): slow path if any row of the warp needs it
+        if (nvalid == 32 && !__any_sync(0xffffffffu, has_dup))
+          softmax_half<GRAD, true>(taddr, ds, shift2, pos2, 32, -1, sum, cnt);
+        else
+          softmax_half<GRAD, false>(taddr, ds, shift2, pos2, nvalid, has_dup ? (int)dcol : -1, sum, cnt);
+        if (GRAD) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
       tc_fence_before();
-      mbar_arrive(bar_pfull(b));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pfull(b));
 #ifdef MSCL_TC_TIMELINE
-      if (threadIdx.x == 64 && t < 12) TL(20 + t);
+      if (threadIdx.x == 64 && t < 8) TL(20 + t);
 #endif
     }
     if (threadIdx.x == 64) TL(5);
-    if (row_ok) {
-      atomicAdd(acc + (int64_t)row * kLd + kC, sum);
-      atomicAdd(acc + (int64_t)row * kLd + kC + 1, (float)cnt);
+    // combine the two column halves of each row, then one plain store per row
+    if (half == 1) {
+      red_smem[r] = sum;
+      red_smem[kRows + r] = (float)cnt;
     }
-    if (GRAD && nt > 0) {
+    asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
+    float *prow = part + ((int64_t)blockIdx.x * M + row) * kLd;
+    if (half == 0 && row_ok)
+      *reinterpret_cast<float4 *>(prow + kC) =
+          make_float4(sum + red_smem[r], (float)cnt + red_smem[kRows + r], 0.f, 0.f);
+    if (GRAD) {
       mbar_wait(bar_ofull, 0);
       tc_fence_after();
       if (threadIdx.x == 64) TL(6);
+      // O tile: TMEM -> registers -> stage-0 buffer (all tiles are consumed by now) in the 128B-swizzled
+      // slab layout -> ONE TMA store per CTA into this CTA's slab (rows >= M are clipped by the TMA unit)
+      if (warp_ok) {
+        uint8_t *os = gbase + kOffW;
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        uint32_t v[32];
-        TC_LD32(lane_base + kColO + h * 32, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row_ok) {
-          float *dst = acc + (int64_t)row * kLd + h * 32;
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cb = half * 2 + hh;
+          uint32_t v[32];
+          TC_LD32(lane_base + kColO + cb * 32, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          uint8_t *rowp = os + cb * kQSlab + r * 128;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4 *>(rowp + ((c ^ (r & 7)) << 4)) =
+                make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
+                            __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
         }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
+      if (threadIdx.x == 64) {
+        tma_store_4d(&tmap_part, sW, 0, row0, 0, (int)blockIdx.x);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may go; the grid's end publishes the data
       }
     }
   }
 
   if (threadIdx.x == 64) TL(7);
+#ifdef MSCL_TC_TIMELINE
+  if (threadIdx.x == 0) {
+    TL(3);
+    g_timeline[(blockIdx.y * gridDim.x + blockIdx.x) * 32 + 31] = clock64();
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -501,43 +651,74 @@ static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int ld, in
   return MSCL_OK;
 }
 
+// part [n_part][M][132] viewed as {32, M, 4, n_part}: one box = the O part of one CTA's slab
+static int make_map_part(CUtensorMap *map, float *ptr, int M, int n_part) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_err(MSCL_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {32, (cuuint64_t)M, 4, (cuuint64_t)n_part};
+  cuuint64_t strides[3] = {(cuuint64_t)kLd * 4, 128, (cuuint64_t)M * kLd * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)kRows, 4, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_err(MSCL_ECUDA, "cuTensorMapEncodeTiled(part) failed with CUresult %d (M=%d n_part=%d)", (int)r, M,
+                   n_part);
+  return MSCL_OK;
+}
+
 }  // namespace tc
 }  // namespace mscl
 
 extern "C" int mscl_infonce_partial(const float *d_qpack, int32_t M, const float *d_queue,
                                     const float *d_dscale, int64_t K_local, int64_t shard_begin,
-                                    float *d_acc, int32_t with_grad, int32_t num_sms,
+                                    float *d_part, int32_t n_part, int32_t with_grad,
                                     mscl_stream_t stream) {
   using namespace mscl::tc;
-  MSCL_CHECK_ARG(d_qpack && d_queue && d_dscale && d_acc, "null pointer");
+  MSCL_CHECK_ARG(d_qpack && d_queue && d_dscale && d_part, "null pointer");
   MSCL_CHECK_ARG(M > 0 && K_local > 0, "bad M=%d K_local=%lld", M, (long long)K_local);
   MSCL_CHECK_ARG(K_local < (1ll << 31), "K_local too large for a TMA coordinate");
-  MSCL_CHECK_ARG((((uintptr_t)d_qpack | (uintptr_t)d_queue | (uintptr_t)d_dscale | (uintptr_t)d_acc) & 15) == 0,
-                 "qpack/queue/dscale/acc must be 16-byte aligned");
-  MSCL_CHECK_ARG(num_sms > 0, "num_sms=%d", num_sms);
-  CUtensorMap tw, tw2;
+  MSCL_CHECK_ARG((((uintptr_t)d_qpack | (uintptr_t)d_queue | (uintptr_t)d_dscale | (uintptr_t)d_part) & 15) == 0,
+                 "qpack/queue/dscale/part must be 16-byte aligned");
+  const int64_t n_tiles = (K_local + kTile - 1) / kTile;
+  MSCL_CHECK_ARG(n_part > 0 && n_part <= n_tiles, "n_part=%d must be in [1, %lld] (one 64-key tile per CTA at least)",
+                 n_part, (long long)n_tiles);
+  CUtensorMap tw, tw2, tq, tp;
   int rc = make_map(&tw, d_queue, K_local, kC, kTile);
   if (rc) return rc;
   rc = make_map(&tw2, d_queue, K_local, kC, kTile, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
+  rc = make_map(&tq, d_qpack, M, kLd, kRows);
+  if (rc) return rc;
+  rc = make_map_part(&tp, d_part, M, n_part);
+  if (rc) return rc;
+  const int row_blocks = (M + kRows - 1) / kRows;
+  dim3 grid((unsigned)n_part, (unsigned)row_blocks);
+  cudaStream_t s = mscl::as_stream(stream);
+  if (with_grad) {
+    MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    infonce_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(tw, tw2, tq, tp, d_qpack, M, d_dscale, K_local, shard_begin, d_part);
+  } else {
+    MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    infonce_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(tw, tw2, tq, tp, d_qpack, M, d_dscale, K_local, shard_begin, d_part);
+  }
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+// How many partial slabs (CTAs along the key axis) mscl_infonce_partial should be given.
+extern "C" int mscl_infonce_num_partials(int32_t M, int64_t K_local, int32_t num_sms) {
+  using namespace mscl::tc;
+  if (M <= 0 || K_local <= 0 || num_sms <= 0) return mscl::set_err(MSCL_EINVAL, "bad M / K_local / num_sms");
   const int64_t n_tiles = (K_local + kTile - 1) / kTile;
   const int row_blocks = (M + kRows - 1) / kRows;
   int64_t gx = num_sms / row_blocks;
   if (gx < 1) gx = 1;
   if (gx > n_tiles) gx = n_tiles;
-  dim3 grid((unsigned)gx, (unsigned)row_blocks);
-  cudaStream_t s = mscl::as_stream(stream);
-  if (with_grad) {
-    MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    infonce_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(tw, tw2, d_qpack, M, d_dscale, K_local, shard_begin, d_acc);
-  } else {
-    MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    infonce_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(tw, tw2, d_qpack, M, d_dscale, K_local, shard_begin, d_acc);
-  }
-  MSCL_LAUNCH_CHECK();
-  return MSCL_OK;
+  return (int)gx;
 }
 
 #ifdef MSCL_TC_TIMELINE

@@ -139,34 +139,38 @@ class _InfoNCE(torch.autograd.Function):
         qpack = torch.empty(M, PACK_LD, device=dev)
         k_pad = (nq.K_local + 63) // 64 * 64
         dscale = torch.empty(k_pad, device=dev)
-        acc = torch.empty(M_all, PACK_LD, device=dev)
         _cabi.call("mscl_infonce_prep", q.data_ptr(), kpos.data_ptr(), M, nq.birth.data_ptr(), nq.qstate.data_ptr(),
-                   nq.K_local, inv_T, nq.max_key_norm, qpack.data_ptr(), dscale.data_ptr(), acc.data_ptr(), M_all,
+                   nq.K_local, inv_T, nq.max_key_norm, qpack.data_ptr(), dscale.data_ptr(),
                    dup_slot.data_ptr() if dup_slot is not None else None, dup_age, st)
         if world > 1:
             qpack_all = torch.empty(M_all, PACK_LD, device=dev)
             dist.all_gather_into_tensor(qpack_all, qpack, group=group)
         else:
             qpack_all = qpack
-        if impl == "simt":
+        if impl == "simt":      # validation twin: accumulates into one zeroed slab
+            n_part = 1
+            part = torch.zeros(1, M_all, PACK_LD, device=dev)
             _cabi.call("mscl_infonce_partial_simt", qpack_all.data_ptr(), M_all, nq.queue_tf32.data_ptr(), dscale.data_ptr(),
-                       nq.K_local, nq.shard_begin, acc.data_ptr(), int(need_grad), st)
+                       nq.K_local, nq.shard_begin, part.data_ptr(), int(need_grad), st)
         else:
+            n_part = _cabi.query("mscl_infonce_num_partials", M_all, nq.K_local, sm_count(dev))
+            part = torch.empty(n_part, M_all, PACK_LD, device=dev)
             _cabi.call("mscl_infonce_partial", qpack_all.data_ptr(), M_all, nq.queue_tf32.data_ptr(), dscale.data_ptr(),
-                       nq.K_local, nq.shard_begin, acc.data_ptr(), int(need_grad), sm_count(dev), st,
+                       nq.K_local, nq.shard_begin, part.data_ptr(), n_part, int(need_grad), st,
                        algo_bytes=infonce_algo_bytes(M_all, nq.K_local),
                        algo_flops=(4 if need_grad else 2) * M_all * nq.K_local * DIM)
-        if world > 1:
-            acc_local = torch.empty(M, PACK_LD, device=dev)
-            dist.reduce_scatter_tensor(acc_local, acc, op=dist.ReduceOp.SUM, group=group)
-        else:
-            acc_local = acc
+        if world > 1:           # local slabs -> one slab, summed across ranks, each rank keeps its own rows
+            acc = torch.empty(M_all, PACK_LD, device=dev)
+            _cabi.call("mscl_infonce_reduce", part.data_ptr(), n_part, M_all, acc.data_ptr(), st)
+            part = torch.empty(1, M, PACK_LD, device=dev)
+            dist.reduce_scatter_tensor(part.view(M, PACK_LD), acc, op=dist.ReduceOp.SUM, group=group)
+            n_part = 1
         n_groups = M // rows_per_group
         row_loss = torch.empty(2 * M, device=dev)
         dq_unit = torch.empty(M, DIM, device=dev)
         group_out = torch.empty(n_groups, 4, device=dev)
-        _cabi.call("mscl_infonce_finalize", qpack.data_ptr(), kpos.data_ptr(), acc_local.data_ptr(), M, rows_per_group,
-                   inv_T, row_loss.data_ptr(), dq_unit.data_ptr(), group_out.data_ptr(), st)
+        _cabi.call("mscl_infonce_finalize", qpack.data_ptr(), kpos.data_ptr(), part.data_ptr(), n_part, M, rows_per_group,
+                   inv_T, int(need_grad), row_loss.data_ptr(), dq_unit.data_ptr(), group_out.data_ptr(), st)
         ctx.save_for_backward(dq_unit)
         ctx.rows_per_group = rows_per_group
         ctx.mark_non_differentiable(row_loss)

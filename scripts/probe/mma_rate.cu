@@ -18,6 +18,12 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d, uint32_t a, uint64_t b, u
                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
+// descriptor passed as (lo, hi) words: lo = base + constant, no dependent chain per dispatch
+__device__ __forceinline__ void mma_ts_lh(uint32_t d, uint32_t a, uint32_t lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}\n" ::"r"(d), "r"(a), "r"(lo), "r"(hi), "r"(idesc), "r"(acc) : "memory");
+}
+
 // idesc for kind::f16 with bf16 operands: c_format f32 (1<<4), a_format bf16 (1<<7), b_format bf16 (1<<10)
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -99,6 +105,39 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int rounds, long
             mma_ss(tmem, make_desc(sA + (j / 4) * 16384 + (j % 4) * 32, 16, 1024), make_desc(sB2 + j * 1024, 8192, 512, 1),
                    idesc_tf32(128, 128, 1), 1);
           break;
+        case 11: {  // tf32 MMA1 TS 16x[128x64x8], descriptors as base_lo + immediate
+          const uint64_t d0 = make_desc(sB + (r % 3) * 32768, 16, 1024);
+          const uint32_t lo = (uint32_t)d0, hi = (uint32_t)(d0 >> 32);
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_ts_lh(tmem + 128, tmem + 256 + cb * 32 + ks * 8, lo + ((cb * 8192 + ks * 32) >> 4), hi, idesc_tf32(128, 64, 0), 1);
+          break;
+        }
+        case 12: {  // tf32 MMA2 TS 8x[128x128x8] B MN 32B-atom, descriptors as base_lo + immediate
+          const uint64_t d0 = make_desc(sB2 + (r % 2) * 32768, 8192, 512, 1);
+          const uint32_t lo = (uint32_t)d0, hi = (uint32_t)(d0 >> 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            mma_ts_lh(tmem, tmem + 128 + j * 8, lo + ((j * 1024) >> 4), hi, idesc_tf32(128, 128, 1), 1);
+          break;
+        }
+        case 13: {  // the kernel's alternation: MMA1 (16 x N=64) then MMA2 (8 x N=128), lo/hi descriptors
+          const uint64_t d0 = make_desc(sB + (r % 2) * 32768, 16, 1024);
+          const uint32_t lo = (uint32_t)d0, hi = (uint32_t)(d0 >> 32);
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_ts_lh(tmem + 128 + (r & 1) * 64, tmem + 256 + cb * 32 + ks * 8, lo + ((cb * 8192 + ks * 32) >> 4), hi, idesc_tf32(128, 64, 0), (cb | ks) ? 1u : 0u);
+          const uint64_t e0 = make_desc(sB2 + (r % 2) * 32768, 8192, 512, 1);
+          const uint32_t lo2 = (uint32_t)e0, hi2 = (uint32_t)(e0 >> 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            mma_ts_lh(tmem, tmem + 128 + ((r + 1) & 1) * 64 + j * 8, lo2 + ((j * 1024) >> 4), hi2, idesc_tf32(128, 128, 1), 1);
+          break;
+        }
         case 10:  // bf16 MMA2 TS with B K-major
           for (int j = 0; j < 4; ++j)
             mma_f16_ts(tmem, tmem + 128 + j * 8, make_desc(sB2 + j * 32, 16, 1024), idesc_bf16(128, 128, 0), 1);
@@ -123,11 +162,13 @@ int main() {
   const char *names[] = {"tf32 MMA1 TS  16x[128x64x8]  B K-major", "tf32 MMA1 SS  16x[128x64x8]", "tf32 MMA2 TS  8x[128x128x8] B MN 32B-atom",
                          "tf32 MMA2 TS  8x[128x128x8] B K-major", "bf16 MMA1 TS  8x[128x64x16]", "bf16 MMA2 TS  4x[128x128x16] B MN-major",
                          "bf16 MMA1 SS  8x[128x64x16]", "tf32 MMA1 TS 16x[128x128x8]", "tf32 MMA1 TS 16x[128x256x8]",
-                         "tf32 MMA2 SS  8x[128x128x8] B MN 32B-atom", "bf16 MMA2 TS  4x[128x128x16] B K-major"};
+                         "tf32 MMA2 SS  8x[128x128x8] B MN 32B-atom", "bf16 MMA2 TS  4x[128x128x16] B K-major",
+                         "tf32 MMA1 TS 16x[128x64x8] lo/hi desc", "tf32 MMA2 TS 8x[128x128x8] MN32 lo/hi desc", "tf32 MMA1+MMA2 alternating lo/hi"};
   const double macs[] = {128. * 64 * 128, 128. * 64 * 128, 128. * 128 * 64, 128. * 128 * 64, 128. * 64 * 128, 128. * 128 * 64, 128. * 64 * 128,
-                         128. * 128 * 128, 128. * 256 * 128, 128. * 128 * 64, 128. * 128 * 64};
-  for (int grid : {1, 148}) {
-    for (int mode = 0; mode < 11; ++mode) {
+                         128. * 128 * 128, 128. * 256 * 128, 128. * 128 * 64, 128. * 128 * 64,
+                         128. * 64 * 128, 128. * 128 * 64, 2 * 128. * 64 * 128};
+  for (int grid : {148}) {
+    for (int mode = 0; mode < 14; ++mode) {
       const int rounds = 200;
       rate_kernel<<<grid, 128, smem>>>(mode, rounds, d_out);
       rate_kernel<<<grid, 128, smem>>>(mode, rounds, d_out);

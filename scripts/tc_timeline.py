@@ -26,7 +26,11 @@ for it in range(4):
     base = t[:, 0].min()
     rel = (t - base) / 1e3
     names = {0: "entry", 1: "setup done", 2: "Q staged", 8: "S0", 9: "S1", 10: "S2", 11: "S3", 12: "S4", 13: "S5", 14: "S6", 20: "P0", 21: "P1", 25: "P5", 26: "P6",
+             16: "mma: before issue M1(4)", 17: "mma: M1(4) issued", 28: "mma: Q in TMEM seen", 29: "mma: tile 0 landed", 18: "mma: P3 seen", 19: "mma: M2(3) issued", 23: "P3",
              4: "TMA issued", 5: "softmax done", 6: "O full", 7: "end"}
     print(f"iter {it}: event {rec['mscl_infonce_partial'][0][0]*1e3:.1f} us; kernel span {(t[:, 7].max() - base)/1e3:.2f} us")
+    cyc = (t[:, 31] - t[:, 30]).astype(np.float64)
+    ns = (t[:, 3] - t[:, 0]).astype(np.float64)
+    print(f"   SM clock during the kernel: {np.median(cyc / ns):.3f} GHz (clock64 / globaltimer, warp 0)")
     for k in sorted(names, key=lambda k: np.median(rel[:, k])):
-        print(f"   {names[k]:>12}: min {rel[:, k].min():6.2f}  median {np.median(rel[:, k]):6.2f}  max {rel[:, k].max():6.2f} us")
+        print(f"   {names[k]:>24}: min {rel[:, k].min():6.2f}  median {np.median(rel[:, k]):6.2f}  max {rel[:, k].max():6.2f} us")
