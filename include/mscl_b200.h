@@ -160,7 +160,7 @@ int mscl_lmcl(const float *d_xq, const float *d_xf, int32_t N, int32_t C,
  *              pos2_i   = (q_i . kpos_i) / T * log2(e)
  *              shift2_i = |q_i| * key_norm_bound / T * log2(e)   (>= every logit)
  *              dscale_j = 0.99999^(n_enq - birth_j) / T * log2(e);  d_dscale holds
- *              ceil(K_local/64)*64 floats, the pad is written as 0
+ *              ceil(K_local/128)*128 floats, the pad is written as 0
  *              d_dup_slot (int32 [M] or NULL): GLOBAL queue slot that holds a copy of
  *              row i's positive key (the cross-modal rf term reads the flow queue right
  *              after k_flow was enqueued into it, mscl.py:239-248), -1 for none; dup_age

@@ -42,9 +42,9 @@ infonce_prep_kernel(const float *__restrict__ q, const float *__restrict__ kpos,
   const int64_t n_enq = qstate[1];
   const int64_t tid = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * 256;
-  // dscale is padded to a multiple of 64 floats (the tcgen05 pass bulk-copies whole
-  // 64-key slices); the pad must be finite because P' = p * dscale feeds the second GEMM.
-  const int64_t K_pad = (K_local + 63) / 64 * 64;
+  // dscale is padded to a multiple of 128 floats (the tcgen05 pass reads whole 128-key
+  // slices); the pad must be finite because P' = p * dscale feeds the second GEMM.
+  const int64_t K_pad = (K_local + 127) / 128 * 128;
   for (int64_t j = tid; j < K_pad; j += nthreads) {
     float v = 0.f;
     if (j < K_local) {

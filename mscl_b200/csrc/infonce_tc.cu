@@ -32,43 +32,49 @@ namespace tc {
 constexpr int kC = MSCL_DIM;          // 128 channels
 constexpr int kLd = MSCL_PACK_LD;     // 132
 constexpr int kRows = 128;            // query rows per CTA (UMMA M)
-constexpr int kTile = 64;             // keys per stage
-constexpr int kStages = 3;
+constexpr int kTile = 128;            // keys per MMA1 dispatch / softmax step (a tcgen05 dispatch costs >= ~60 cycles
+                                      // whatever N is, so N = 128 keys halves the MMA1 time of N = 64)
+constexpr int kHalf = 64;             // keys per ring-2 slot (MMA2 consumes a tile in two halves)
+constexpr int kStages1 = 2;           // ring 1: K-major copies, 128 keys each
+constexpr int kStages2 = 3;           // ring 2: MN-major copies, 64 keys each
 constexpr int kCb = 4;                // channel blocks of 32 fp32 (one 128-byte swizzle row)
-constexpr int kSoftmaxWarps = 8;      // two per TMEM lane quarter, each takes 32 of a tile's 64 keys
+constexpr int kSoftmaxWarps = 8;      // two per TMEM lane quarter, each takes 64 of a tile's 128 keys
 constexpr int kThreads = (2 + kSoftmaxWarps) * 32;   // TMA producer, MMA issuer, softmax warps
 
-constexpr uint32_t kWBytes = kTile * kC * 4;          // 32768: one copy of a tile
-constexpr uint32_t kWSlab = kTile * 128;              // bytes per channel block of a W tile
-constexpr uint32_t kQBytes = kRows * kC * 4;          // 65536: the Q tile, staged through one stage buffer
+constexpr uint32_t kW1Bytes = kTile * kC * 4;         // 65536: K-major copy of a 128-key tile
+constexpr uint32_t kW1Slab = kTile * 128;             // bytes per channel block of it
+constexpr uint32_t kW2Bytes = kHalf * kC * 4;         // 32768: MN-major copy of a 64-key half tile
+constexpr uint32_t kW2Slab = kHalf * 128;
+constexpr uint32_t kQBytes = kRows * kC * 4;          // 65536: the Q tile (and the O tile on the way out)
 constexpr uint32_t kQSlab = kRows * 128;              // bytes per channel block of the Q tile
 
 // shared memory map (offsets from the 1024-aligned base)
-// Two rings of kStages slots each, with separate lifetimes: ring 1 holds the 128B-swizzled (K-major)
-// copy of a tile, needed by MMA1(t) only; ring 2 the 32B-atom-swizzled (MN-major) copy, needed by
-// MMA2(t) one tile period later.  A ring-1 slot is free as soon as MMA1 has read it, so the HBM
-// prefetch runs ~kStages tiles ahead of MMA1; ring 2 is filled from L2.
-constexpr uint32_t kOffW = 0;                           // ring 1
-constexpr uint32_t kOffW2 = kOffW + kStages * kWBytes;  // ring 2
-constexpr uint32_t kOffBar = kOffW2 + kStages * kWBytes;
-constexpr uint32_t kNumBars = 4 * kStages + 1 + 2 + 2 + 1 + 2;  // full1, empty1, full2, empty2, q, s_full[2], p_full[2], o_full, qload, qfree
+// Two rings with separate lifetimes: ring 1 holds the 128B-swizzled (K-major) copy of a tile, needed by
+// MMA1(t) only; ring 2 the 32B-atom-swizzled (MN-major) copy, needed by MMA2(t) one tile period later.
+// A ring-1 slot is free as soon as MMA1 has read it, so the HBM prefetch runs ahead of MMA1; ring 2 is
+// filled from L2 (the same bytes again).
+constexpr uint32_t kOffW = 0;                             // ring 1
+constexpr uint32_t kOffW2 = kOffW + kStages1 * kW1Bytes;  // ring 2
+constexpr uint32_t kOffBar = kOffW2 + kStages2 * kW2Bytes;
+constexpr uint32_t kNumBars = 2 * kStages1 + 2 * kStages2 + 1 + 2 + 2 + 1 + 2;  // full1, empty1, full2, empty2, q, s_full[2], p_full[2], o_full, qload, qfree
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kOffRed = kOffTmemPtr + 16;          // [2][128] floats: sum / count of the second column half
 constexpr uint32_t kSmemUsed = kOffRed + 2 * kRows * 4;
-static_assert(kQBytes <= 2 * kWBytes && kStages >= 3, "the Q tile is staged through ring-2 slots 1 and 2");
-static_assert(kQBytes <= kStages * kWBytes, "the O tile is staged through ring 1");
+static_assert(kQBytes <= 2 * kW2Bytes && kStages2 >= 3, "the Q tile is staged through ring-2 slots 1 and 2");
+static_assert(kQBytes <= kW1Bytes, "the O tile is staged through ring-1 slot 0");
 constexpr uint32_t kSmemBytes = kSmemUsed + 1024;     // slack for manual 1024-byte alignment
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColO = 0;
-constexpr uint32_t kColS = 128;
-constexpr uint32_t kColQ = 256;
+constexpr uint32_t kColS = 128;       // two S/P buffers of kTile columns
+constexpr uint32_t kColQ = 384;
 
 // instruction descriptors (cute::UMMA::InstrDescriptor bit layout):
 //  [4,6) c_format=1 (f32) | [7,10) a_format=2 (tf32) | [10,13) b_format=2 (tf32)
 //  [15] a_major | [16] b_major (1 = MN-major) | [17,23) N>>3 | [24,29) M>>4
 constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kRows >> 4) << 24);
-constexpr uint32_t kIdesc1 = kIdescBase | ((uint32_t)(kTile >> 3) << 17);               // N = 64
+constexpr uint32_t kIdesc1 = kIdescBase | ((uint32_t)(kTile >> 3) << 17);               // N = 128 keys
 constexpr uint32_t kIdesc2 = kIdescBase | (1u << 16) | ((uint32_t)(kC >> 3) << 17);     // N = 128, B MN-major
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -303,13 +309,13 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   uint8_t *gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sW = base + kOffW;
   const uint32_t sW2 = base + kOffW2;
-  const uint32_t sQ = sW2 + kWBytes;                           // Q tile: ring-2 slots 1 and 2
+  const uint32_t sQ = sW2 + kW2Bytes;                          // Q tile: ring-2 slots 1 and 2
   const uint32_t bar0 = base + kOffBar;
   auto bar_full1 = [&](int s) { return bar0 + 8u * s; };
-  auto bar_empty1 = [&](int s) { return bar0 + 8u * (kStages + s); };
-  auto bar_full2 = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
-  auto bar_empty2 = [&](int s) { return bar0 + 8u * (3 * kStages + s); };
-  constexpr int kB = 4 * kStages;
+  auto bar_empty1 = [&](int s) { return bar0 + 8u * (kStages1 + s); };
+  auto bar_full2 = [&](int s) { return bar0 + 8u * (2 * kStages1 + s); };
+  auto bar_empty2 = [&](int s) { return bar0 + 8u * (2 * kStages1 + kStages2 + s); };
+  constexpr int kB = 2 * kStages1 + 2 * kStages2;
   const uint32_t bar_q = bar0 + 8u * kB;                       // Q rows stored to TMEM (8 warps)
   auto bar_sfull = [&](int b) { return bar0 + 8u * (kB + 1 + b); };
   auto bar_pfull = [&](int b) { return bar0 + 8u * (kB + 3 + b); };
@@ -338,9 +344,11 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
     if (GRAD) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_part) : "memory");
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kStages1; ++s) {
       mbar_init(bar_full1(s), 1);
       mbar_init(bar_empty1(s), 1);
+    }
+    for (int s = 0; s < kStages2; ++s) {
       mbar_init(bar_full2(s), 1);
       mbar_init(bar_empty2(s), 1);
     }
@@ -374,23 +382,26 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       // zero-filled by the TMA unit
       mbar_arrive_expect_tx(bar_qload, kQBytes);
       tma_load_3d(sQ, &tmap_q, bar_qload, 0, row0, 0);
-      auto load1 = [&](int t) {      // K-major copy of tile t (from HBM)
-        const int s = t % kStages;
-        mbar_wait(bar_empty1(s), ((uint32_t)(t / kStages) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar_full1(s), kWBytes);
-        tma_load_3d(sW + s * kWBytes, &tmap_w, bar_full1(s), 0, (int)((t_begin + t) * kTile), 0);
+      auto load1 = [&](int t) {      // K-major copy of the 128-key tile t (from HBM)
+        const int s = t % kStages1;
+        mbar_wait(bar_empty1(s), ((uint32_t)(t / kStages1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar_full1(s), kW1Bytes);
+        tma_load_3d(sW + s * kW1Bytes, &tmap_w, bar_full1(s), 0, (int)((t_begin + t) * kTile), 0);
       };
-      auto load2 = [&](int t) {      // MN-major copy of tile t (the same bytes again: an L2 hit)
-        const int s = t % kStages;
-        if (t == 1) mbar_wait(bar_qfree, 0);        // slots 1 and 2 held the Q tile
-        mbar_wait(bar_empty2(s), ((uint32_t)(t / kStages) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar_full2(s), kWBytes);
-        tma_load_3d(sW2 + s * kWBytes, &tmap_w2, bar_full2(s), 0, (int)((t_begin + t) * kTile), 0);
+      auto load2 = [&](int u) {      // MN-major copy of the 64-key half tile u (the same bytes again: an L2 hit)
+        const int s = u % kStages2;
+        if (u == 1) mbar_wait(bar_qfree, 0);        // slots 1 and 2 held the Q tile
+        mbar_wait(bar_empty2(s), ((uint32_t)(u / kStages2) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar_full2(s), kW2Bytes);
+        tma_load_3d(sW2 + s * kW2Bytes, &tmap_w2, bar_full2(s), 0, (int)(t_begin * kTile + (int64_t)u * kHalf), 0);
       };
-      for (int t = 0; t < kStages && t < nt; ++t) load1(t);
+      for (int t = 0; t < kStages1 && t < nt; ++t) load1(t);
       for (int t = 0; t < nt; ++t) {
-        if (GRAD) load2(t);                          // waits for MMA2(t - kStages)
-        if (t + kStages < nt) load1(t + kStages);    // waits for MMA1(t), which runs after MMA2(t - 2)
+        if (GRAD) {                                    // wait for MMA2 of the half tiles kStages2 back
+          load2(2 * t);
+          load2(2 * t + 1);
+        }
+        if (t + kStages1 < nt) load1(t + kStages1);    // waits for MMA1(t)
       }
       TL(4);
     }
@@ -401,19 +412,19 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     constexpr uint32_t kHi1 = (1024u >> 4) | (1u << 14) | (2u << 29);      // K-major, SWIZZLE_128B, SBO 1024
     constexpr uint32_t kHi2 = (512u >> 4) | (1u << 14) | (1u << 29);       // MN-major, SWIZZLE_128B_BASE32B, SBO 512
     const uint32_t lo1_base = ((sW & 0x3FFFFu) >> 4) | ((16u >> 4) << 16);              // LBO 16
-    const uint32_t lo2_base = ((sW2 & 0x3FFFFu) >> 4) | ((kWSlab >> 4) << 16);          // LBO = channel-block pitch
+    const uint32_t lo2_base = ((sW2 & 0x3FFFFu) >> 4) | ((kW2Slab >> 4) << 16);         // LBO = channel-block pitch
     if (elect_one()) {
       auto issue_mma1 = [&](int t) {
-        const int s = t % kStages;
-        mbar_wait(bar_full1(s), (uint32_t)(t / kStages) & 1u);
+        const int s = t % kStages1;
+        mbar_wait(bar_full1(s), (uint32_t)(t / kStages1) & 1u);
         tc_fence_after();
         const uint32_t d = tmem + kColS + (uint32_t)(t & 1) * kTile;
-        const uint32_t lo = lo1_base + (uint32_t)s * (kWBytes >> 4);
+        const uint32_t lo = lo1_base + (uint32_t)s * (kW1Bytes >> 4);
 #pragma unroll
         for (int cb = 0; cb < kCb; ++cb) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            mma_ts_lh(d, tmem + kColQ + cb * 32 + ks * 8, lo + ((cb * kWSlab + ks * 32) >> 4), kHi1, kIdesc1,
+            mma_ts_lh(d, tmem + kColQ + cb * 32 + ks * 8, lo + ((cb * kW1Slab + ks * 32) >> 4), kHi1, kIdesc1,
                       (cb | ks) ? 1u : 0u);
         }
         tc_commit(bar_sfull(t & 1));
@@ -436,27 +447,32 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (t == 3) TL(17);
 #endif
         if (GRAD) {
-          const int s = t % kStages;
-          mbar_wait(bar_full2(s), (uint32_t)(t / kStages) & 1u);
           mbar_wait(bar_pfull(t & 1), (uint32_t)(t >> 1) & 1u);
           tc_fence_after();
 #ifdef MSCL_TC_TIMELINE
           if (t == 3) TL(18);
 #endif
-          const uint32_t a = tmem + kColS + (uint32_t)(t & 1) * kTile;
-          const uint32_t lo = lo2_base + (uint32_t)s * (kWBytes >> 4);
-          // B = the ring-2 copy read MN-major (SWIZZLE_128B_BASE32B): 8 keys per step = two 4-row atoms
-          // 512 bytes apart (SBO); channel blocks kWSlab bytes apart (LBO)
-          if (t == 0) {
 #pragma unroll
-            for (int j = 0; j < kTile / 8; ++j)
-              mma_ts_lh(tmem + kColO, a + j * 8, lo + ((j * 1024) >> 4), kHi2, kIdesc2, j ? 1u : 0u);
-          } else {
+          for (int h = 0; h < 2; ++h) {
+            const int u = 2 * t + h;
+            const int s = u % kStages2;
+            mbar_wait(bar_full2(s), (uint32_t)(u / kStages2) & 1u);
+            tc_fence_after();
+            const uint32_t a = tmem + kColS + (uint32_t)(t & 1) * kTile + h * kHalf;
+            const uint32_t lo = lo2_base + (uint32_t)s * (kW2Bytes >> 4);
+            // B = the ring-2 copy read MN-major (SWIZZLE_128B_BASE32B): 8 keys per step = two 4-row atoms
+            // 512 bytes apart (SBO); channel blocks kW2Slab bytes apart (LBO)
+            if (u == 0) {
 #pragma unroll
-            for (int j = 0; j < kTile / 8; ++j)
-              mma_ts_lh(tmem + kColO, a + j * 8, lo + ((j * 1024) >> 4), kHi2, kIdesc2, 1u);
+              for (int j = 0; j < kHalf / 8; ++j)
+                mma_ts_lh(tmem + kColO, a + j * 8, lo + ((j * 1024) >> 4), kHi2, kIdesc2, j ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int j = 0; j < kHalf / 8; ++j)
+                mma_ts_lh(tmem + kColO, a + j * 8, lo + ((j * 1024) >> 4), kHi2, kIdesc2, 1u);
+            }
+            tc_commit(bar_empty2(s));
           }
-          tc_commit(bar_empty2(s));
 #ifdef MSCL_TC_TIMELINE
           if (t == 3) TL(19);
 #endif
@@ -489,7 +505,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     {   // this row of Q: smem (TMA, swizzled) -> TMEM columns [kColQ + 64*half, +64): the A operand of every MMA1
       mbar_wait(bar_qload, 0);
-      const uint8_t *qs = gbase + kOffW2 + kWBytes;
+      const uint8_t *qs = gbase + kOffW2 + kW2Bytes;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int cb = half * 2 + hh;             // channel block (slab) of 32 channels
@@ -518,14 +534,14 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     int cnt = 0;
     for (int t = 0; t < nt; ++t) {
       const int b = t & 1;
-      const int64_t key0 = (t_begin + t) * kTile + half * 32;
-      // this half tile's 32 per-key scales (L1/L2-resident, warp-uniform addresses), fetched before the wait;
-      // the array is padded to a multiple of 64 so the reads never leave it
-      float4 d4[8];
+      const int64_t key0 = (t_begin + t) * kTile + half * 64;
+      // this warp's 64 per-key scales (L1/L2-resident, warp-uniform addresses), fetched before the wait;
+      // the array is padded to a multiple of 128 so the reads never leave it
+      float4 d4[16];
       if (warp_ok) {
         const float4 *dsg = reinterpret_cast<const float4 *>(dscale + key0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d4[j] = __ldg(dsg + j);
+        for (int j = 0; j < 16; ++j) d4[j] = __ldg(dsg + j);
       }
       mbar_wait(bar_sfull(b), (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
@@ -533,17 +549,20 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       if (threadIdx.x == 64 && t < 8) TL(8 + t);
 #endif
       if (warp_ok) {
-        const int64_t left = K_local - key0;
-        const int nvalid = left < 32 ? (left < 0 ? 0 : (int)left) : 32;
-        const float4 *ds = d4;
-        const uint32_t taddr = lane_base + kColS + (uint32_t)b * kTile + half * 32;
-        const int64_t dcol = dup_local - key0;
-        const bool has_dup = dcol >= 0 && dcol < 32;
-        // warp-uniform choice (tcgen05.ld/st are .sync.aligned): slow path if any row of the warp needs it
-        if (nvalid == 32 && !__any_sync(0xffffffffu, has_dup))
-          softmax_half<GRAD, true>(taddr, ds, shift2, pos2, 32, -1, sum, cnt);
-        else
-          softmax_half<GRAD, false>(taddr, ds, shift2, pos2, nvalid, has_dup ? (int)dcol : -1, sum, cnt);
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {          // two chunks of 32 keys
+          const int64_t k0 = key0 + ch * 32;
+          const int64_t left = K_local - k0;
+          const int nvalid = left < 32 ? (left < 0 ? 0 : (int)left) : 32;
+          const uint32_t taddr = lane_base + kColS + (uint32_t)b * kTile + half * 64 + ch * 32;
+          const int64_t dcol = dup_local - k0;
+          const bool has_dup = dcol >= 0 && dcol < 32;
+          // warp-uniform choice (tcgen05.ld/st are .sync.aligned): slow path if any row of the warp needs it
+          if (nvalid == 32 && !__any_sync(0xffffffffu, has_dup))
+            softmax_half<GRAD, true>(taddr, d4 + ch * 8, shift2, pos2, 32, -1, sum, cnt);
+          else
+            softmax_half<GRAD, false>(taddr, d4 + ch * 8, shift2, pos2, nvalid, has_dup ? (int)dcol : -1, sum, cnt);
+        }
         if (GRAD) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
       tc_fence_before();
@@ -682,12 +701,12 @@ extern "C" int mscl_infonce_partial(const float *d_qpack, int32_t M, const float
   MSCL_CHECK_ARG((((uintptr_t)d_qpack | (uintptr_t)d_queue | (uintptr_t)d_dscale | (uintptr_t)d_part) & 15) == 0,
                  "qpack/queue/dscale/part must be 16-byte aligned");
   const int64_t n_tiles = (K_local + kTile - 1) / kTile;
-  MSCL_CHECK_ARG(n_part > 0 && n_part <= n_tiles, "n_part=%d must be in [1, %lld] (one 64-key tile per CTA at least)",
+  MSCL_CHECK_ARG(n_part > 0 && n_part <= n_tiles, "n_part=%d must be in [1, %lld] (one 128-key tile per CTA at least)",
                  n_part, (long long)n_tiles);
   CUtensorMap tw, tw2, tq, tp;
   int rc = make_map(&tw, d_queue, K_local, kC, kTile);
   if (rc) return rc;
-  rc = make_map(&tw2, d_queue, K_local, kC, kTile, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  rc = make_map(&tw2, d_queue, K_local, kC, kHalf, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
   rc = make_map(&tq, d_qpack, M, kLd, kRows);
   if (rc) return rc;

@@ -137,7 +137,7 @@ class _InfoNCE(torch.autograd.Function):
         world = dist.get_world_size(group) if (group is not None and nq.world > 1) else 1
         M_all = M * world
         qpack = torch.empty(M, PACK_LD, device=dev)
-        k_pad = (nq.K_local + 63) // 64 * 64
+        k_pad = (nq.K_local + 127) // 128 * 128
         dscale = torch.empty(k_pad, device=dev)
         _cabi.call("mscl_infonce_prep", q.data_ptr(), kpos.data_ptr(), M, nq.birth.data_ptr(), nq.qstate.data_ptr(),
                    nq.K_local, inv_T, nq.max_key_norm, qpack.data_ptr(), dscale.data_ptr(),

@@ -1,0 +1,139 @@
+"""Multi-GPU parity (needs >= 2 B200s: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`).
+
+One process per GPU over NCCL.  The queue is sharded K/G; every rank's losses, gradients and the
+gathered queue state must match the single-process oracle that sees the replicated queue and the
+rank-major gathered keys.  Also the device shuffle-BN exchange against
+gather-then-index.  Skipped on a single-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        out[rank] = fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn, world):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, out), nprocs=world, join=True)
+    return [out[r] for r in range(world)]
+
+
+def _world():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    return 2 if n < 4 else 4
+
+
+def _objective_job(rank, world):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_gpu_step import head_level_model
+    from oracle import inputs, mscl_oracle as O
+    N, K, t = 8, 4096, 4
+    inp = inputs.head_inputs(seed=11, N=N * world, K=K, t=t, hw_rgb=6, hw_flow=3, b_all=N * world)
+    sl = slice(rank * N, (rank + 1) * N)
+    # product: this rank's rows, sharded queue
+    import mscl_b200
+    model = head_level_model(K, t)
+    for rec in (model.recognizer, model.recognizer_flow):
+        rec.shard_queue = True
+    model.train()
+    ptr = torch.tensor([inp["ptr"]])
+    model.load_state_dict({"recognizer.queue": inp["queue_rgb"], "recognizer.count": inp["count"], "recognizer.queue_ptr": ptr,
+                           "recognizer_flow.queue": inp["queue_flow"], "recognizer_flow.count": inp["count"],
+                           "recognizer_flow.queue_ptr": ptr}, strict=False)
+    names = ("q", "q_f", "q_af", "q_map", "qf_map", "qaf_map")
+    leaves = {n: inp[n][sl].cuda().requires_grad_(True) for n in names}
+    feats = dict(q=leaves["q"], q_f=leaves["q_f"], q_af=leaves["q_af"], k=inp["k"][sl].cuda(), k_f=inp["k_f"][sl].cuda(),
+                 k_af=inp["k_af"][sl].cuda(), q_mlvl=[leaves["q_map"]], q_flow_mlvl=[leaves["qf_map"]],
+                 q_aug_flow_mlvl=[leaves["qaf_map"]])
+    losses = model.objective(feats)
+    assert model.recognizer.negative_queue().world == world and model.recognizer.negative_queue().K_local == K // world
+    loss = sum(v.mean() for k, v in losses.items() if "loss" in k)
+    loss.backward()
+    local = {k: float(v.detach().mean()) for k, v in losses.items()}
+    sd = {k: v.cpu() for k, v in model.state_dict().items() if k.endswith(("queue", "count", "queue_ptr"))}
+    # oracle: replicated queue, this rank's rows, gathered keys for the enqueue
+    ol = {n: inp[n][sl].clone().requires_grad_(True) for n in names}
+    of = dict(k=inp["k"][sl], k_f=inp["k_f"][sl], k_af=inp["k_af"][sl], **ol)
+    rgb = O.QueueState(inp["queue_rgb"], inp["count"], inp["ptr"])
+    flow = O.QueueState(inp["queue_flow"], inp["count"], inp["ptr"])
+    ref = O.mscl_objective(of, rgb, flow, T=0.07, t=t, keys_all=dict(k=inp["k"], k_f=inp["k_f"]))
+    ref_loss = sum(v.mean() for k, v in ref.items() if "loss" in k)
+    ref_loss.backward()
+    res = dict(ok=True, msgs=[])
+
+    def check(cond, msg):
+        if not cond:
+            res["ok"] = False
+            res["msgs"].append(msg)
+
+    for k, v in local.items():
+        r = float(ref[k].detach().mean())
+        if "acc" in k:
+            check(abs(v - r) < 1e-6, f"{k}: {v} vs {r}")
+        else:
+            check(abs(v - r) <= 1e-3 * abs(r), f"{k}: {v} vs {r}")
+    for n in names:
+        a, b = leaves[n].grad.cpu().double(), ol[n].grad.double()
+        check(float((a - b).norm() / b.norm()) < 1e-3, f"grad {n}")
+    for tag, st in (("recognizer", rgb), ("recognizer_flow", flow)):
+        check(int(sd[f"{tag}.queue_ptr"]) == st.ptr, f"{tag} ptr")
+        check(bool(torch.equal(sd[f"{tag}.queue"], st.queue)), f"{tag} queue contents")
+        check(bool(torch.equal(sd[f"{tag}.count"], st.count)), f"{tag} ages")
+    return res
+
+
+def test_sharded_objective_matches_replicated_oracle():
+    world = _world()
+    for r in _run(_objective_job, world):
+        assert r["ok"], r["msgs"]
+
+
+def _shuffle_job(rank, world):
+    from mscl_b200 import functional as fx
+    from mscl_b200.recognizers import shuffle as shf
+    from oracle import mscl_oracle as O
+    n = 6
+    torch.manual_seed(50 + rank)
+    idx = shf.draw_permutation(n * world, torch.device("cuda", rank))
+    g = torch.Generator().manual_seed(1)
+    x_all = torch.randn(n * world, 3, 4, 8, 8, generator=g)
+    x = x_all[rank * n:(rank + 1) * n].cuda()
+    mine = shf.exchange(x, shf.ShufflePlan(idx, n, rank, world), fx.gather_rows)
+    want, unshuf = O.batch_shuffle(x_all, idx, rank, world)
+    back = shf.exchange(mine, shf.ShufflePlan(unshuf, n, rank, world), fx.gather_rows)
+    torch.manual_seed(50)
+    return dict(ok=bool(torch.equal(mine.cpu(), want)) and bool(torch.equal(back.cpu(), x.cpu())),
+                perm_ok=bool(torch.equal(idx, torch.randperm(n * world))))
+
+
+def test_device_shuffle_exchange():
+    world = _world()
+    for r in _run(_shuffle_job, world):
+        assert r["ok"] and r["perm_ok"], r
