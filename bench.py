@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--ref-clips", type=int, default=4, help="clips per step of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shard", action="store_true", help="N>1: keep the queue replicated instead of K/N shards")
+    ap.add_argument("--channels-last", action="store_true", help="encoders/necks in torch.channels_last_3d (experiment)")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the resident timed region (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -276,6 +277,8 @@ def run_b200(args, rank, local_rank, world):
     cfg = mscl_r18_model(K=args.K)
     cfg["train_cfg"] = dict(shard_queue=shard)
     model = mscl_b200.build_model(cfg).to(dev)
+    if args.channels_last:
+        model = model.to(memory_format=torch.channels_last_3d)
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.SGD(params, lr=0.02, momentum=0.9, weight_decay=1e-4)      # mscl_r18 config :114-118

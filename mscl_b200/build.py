@@ -51,6 +51,8 @@ def build(force=False, verbose=False):
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if os.environ.get("MSCL_TIMELINE"):      # debug build: per-CTA phase timestamps in the tcgen05 kernel
             cmd.insert(1, "-DMSCL_TC_TIMELINE")
+        for d in os.environ.get("MSCL_DEFS", "").split():      # experiment switches, e.g. MSCL_DEFS="-DMSCL_EXP_NOLOAD2"
+            cmd.insert(1, d)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

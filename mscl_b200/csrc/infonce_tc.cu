@@ -39,7 +39,7 @@ constexpr int kStages1 = 2;           // ring 1: K-major copies, 128 keys each
 constexpr int kStages2 = 3;           // ring 2: MN-major copies, 64 keys each
 constexpr int kCb = 4;                // channel blocks of 32 fp32 (one 128-byte swizzle row)
 constexpr int kSoftmaxWarps = 8;      // two per TMEM lane quarter, each takes 64 of a tile's 128 keys
-constexpr int kThreads = (2 + kSoftmaxWarps) * 32;   // TMA producer, MMA issuer, softmax warps
+constexpr int kThreads = (3 + kSoftmaxWarps) * 32;   // ring-1 producer, MMA issuer, softmax warps, ring-2 producer
 
 constexpr uint32_t kW1Bytes = kTile * kC * 4;         // 65536: K-major copy of a 128-key tile
 constexpr uint32_t kW1Slab = kTile * 128;             // bytes per channel block of it
@@ -388,22 +388,25 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         mbar_arrive_expect_tx(bar_full1(s), kW1Bytes);
         tma_load_3d(sW + s * kW1Bytes, &tmap_w, bar_full1(s), 0, (int)((t_begin + t) * kTile), 0);
       };
-      auto load2 = [&](int u) {      // MN-major copy of the 64-key half tile u (the same bytes again: an L2 hit)
+      // ring 1 only: a slot is re-armed the moment MMA1 has read it, independent of ring 2's progress
+      for (int t = 0; t < nt; ++t) load1(t);
+      TL(4);
+    }
+    __syncwarp();
+  } else if (warp == 2 + kSoftmaxWarps) {
+    // ===================== ring-2 producer (own warp: its waits on MMA2 never hold back the HBM prefetch) ======
+    if (GRAD && elect_one()) {
+      for (int u = 0; u < 2 * nt; ++u) {   // MN-major copy of the 64-key half tile u (the same bytes again: an L2 hit)
         const int s = u % kStages2;
         if (u == 1) mbar_wait(bar_qfree, 0);        // slots 1 and 2 held the Q tile
         mbar_wait(bar_empty2(s), ((uint32_t)(u / kStages2) & 1u) ^ 1u);
+#ifndef MSCL_EXP_NOLOAD2
         mbar_arrive_expect_tx(bar_full2(s), kW2Bytes);
         tma_load_3d(sW2 + s * kW2Bytes, &tmap_w2, bar_full2(s), 0, (int)(t_begin * kTile + (int64_t)u * kHalf), 0);
-      };
-      for (int t = 0; t < kStages1 && t < nt; ++t) load1(t);
-      for (int t = 0; t < nt; ++t) {
-        if (GRAD) {                                    // wait for MMA2 of the half tiles kStages2 back
-          load2(2 * t);
-          load2(2 * t + 1);
-        }
-        if (t + kStages1 < nt) load1(t + kStages1);    // waits for MMA1(t)
+#else
+        mbar_arrive(bar_full2(s));
+#endif
       }
-      TL(4);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -462,6 +465,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const uint32_t lo = lo2_base + (uint32_t)s * (kW2Bytes >> 4);
             // B = the ring-2 copy read MN-major (SWIZZLE_128B_BASE32B): 8 keys per step = two 4-row atoms
             // 512 bytes apart (SBO); channel blocks kW2Slab bytes apart (LBO)
+#ifndef MSCL_EXP_NOMMA2
             if (u == 0) {
 #pragma unroll
               for (int j = 0; j < kHalf / 8; ++j)
@@ -471,6 +475,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
               for (int j = 0; j < kHalf / 8; ++j)
                 mma_ts_lh(tmem + kColO, a + j * 8, lo + ((j * 1024) >> 4), kHi2, kIdesc2, 1u);
             }
+#endif
             tc_commit(bar_empty2(s));
           }
 #ifdef MSCL_TC_TIMELINE
@@ -548,7 +553,11 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #ifdef MSCL_TC_TIMELINE
       if (threadIdx.x == 64 && t < 8) TL(8 + t);
 #endif
+#ifdef MSCL_EXP_NOSOFTMAX
+      if (false) {
+#else
       if (warp_ok) {
+#endif
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {          // two chunks of 32 keys
           const int64_t k0 = key0 + ch * 32;

@@ -33,6 +33,18 @@ def _chk(t, dtype=torch.float32, name="tensor"):
     return t
 
 
+def _chk_dense(t, name):
+    """Like _chk, but any dense layout (row-major, channels_last, channels_last_3d) passes: the
+    elementwise EMA walks the storage, so only density and equal strides of the pair matter."""
+    if t.is_contiguous():
+        return _chk(t, name=name)
+    dense = (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)) or \
+            (t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d))
+    if not (t.is_cuda and t.dtype == torch.float32 and dense):
+        raise _cabi.MsclError(f"{name} must be a dense CUDA fp32 tensor")
+    return t
+
+
 _SM_COUNT = {}
 
 
@@ -307,9 +319,9 @@ class EmaTable:
     def _build(self):
         dev = self.params_k[0].device
         for pk, pq in zip(self.params_k, self.params_q):
-            _chk(pk.data, name="param_k"), _chk(pq.data, name="param_q")
-            if pk.shape != pq.shape:
-                raise _cabi.MsclError("key/query parameter shapes differ")
+            _chk_dense(pk.data, "param_k"), _chk_dense(pq.data, "param_q")
+            if pk.shape != pq.shape or pk.stride() != pq.stride():
+                raise _cabi.MsclError("key/query parameter shapes or strides differ")
         sizes = [p.numel() for p in self.params_k]
         blk_t, blk_s = [], []
         for i, n in enumerate(sizes):

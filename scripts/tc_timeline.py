@@ -6,6 +6,7 @@ import torch
 from mscl_b200 import functional as fx, _cabi
 
 M, K = int(sys.argv[1]) if len(sys.argv) > 1 else 96, int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+BURST = int(sys.argv[3]) if len(sys.argv) > 3 else 1      # launches back to back before the timeline is read (clock under load)
 g = torch.Generator().manual_seed(0)
 q = torch.nn.functional.normalize(torch.randn(M, 128, generator=g), dim=1).cuda()
 kp = torch.nn.functional.normalize(torch.randn(M, 128, generator=g), dim=1).cuda()
@@ -18,7 +19,8 @@ for it in range(4):
     qd = q.clone().requires_grad_(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     _cabi.start_timing(["mscl_infonce_partial"])
-    out, _ = fx.infonce(qd, kp, nq, M, 0.07)
+    for _ in range(BURST):
+        out, _ = fx.infonce(qd, kp, nq, M, 0.07)
     rec = _cabi.stop_timing()
     buf = (ctypes.c_ulonglong * (148 * 32))()
     assert lib.mscl_debug_timeline(buf, 148 * 32) == 0
@@ -28,7 +30,7 @@ for it in range(4):
     names = {0: "entry", 1: "setup done", 2: "Q staged", 8: "S0", 9: "S1", 10: "S2", 11: "S3", 12: "S4", 13: "S5", 14: "S6", 20: "P0", 21: "P1", 25: "P5", 26: "P6",
              16: "mma: before issue M1(4)", 17: "mma: M1(4) issued", 28: "mma: Q in TMEM seen", 29: "mma: tile 0 landed", 18: "mma: P3 seen", 19: "mma: M2(3) issued", 23: "P3",
              4: "TMA issued", 5: "softmax done", 6: "O full", 7: "end"}
-    print(f"iter {it}: event {rec['mscl_infonce_partial'][0][0]*1e3:.1f} us; kernel span {(t[:, 7].max() - base)/1e3:.2f} us")
+    print(f"iter {it}: event {rec['mscl_infonce_partial'][-1][0]*1e3:.1f} us; kernel span {(t[:, 7].max() - base)/1e3:.2f} us")
     cyc = (t[:, 31] - t[:, 30]).astype(np.float64)
     ns = (t[:, 3] - t[:, 0]).astype(np.float64)
     print(f"   SM clock during the kernel: {np.median(cyc / ns):.3f} GHz (clock64 / globaltimer, warp 0)")
