@@ -63,6 +63,30 @@ __device__ __forceinline__ float4 to_tf32_rn(float4 v) {
   return make_float4(to_tf32_rn(v.x), to_tf32_rn(v.y), to_tf32_rn(v.z), to_tf32_rn(v.w));
 }
 
+// ---- programmatic dependent launch (PDL) ----
+// A kernel launched through launch_pdl may start while its predecessor in the stream is still
+// running; it must execute pdl_wait() before touching anything the predecessor writes.  The
+// predecessor calls pdl_trigger() as early as it likes (it only opens the gate for the successor's
+// launch; memory visibility is pdl_wait's job, which blocks until the predecessor has completed).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // streaming 128-bit accesses (read-once / write-once data)
 __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
   float4 r;

@@ -17,6 +17,8 @@ infonce_prep_kernel(const float *__restrict__ q, const float *__restrict__ kpos,
                     int64_t K_local, float inv_T, float key_norm_bound,
                     float *__restrict__ qpack, float *__restrict__ dscale,
                     const int32_t *__restrict__ dup_slot, int dup_age) {
+  pdl_trigger();   // the tcgen05 pass may launch now and prefetch queue tiles; it waits for this grid before reading qpack / dscale
+  pdl_wait();      // this grid itself may have been launched early behind a finalize (back-to-back objectives)
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * 8;
   const float sc = inv_T * kLog2e;
@@ -146,6 +148,8 @@ infonce_finalize_kernel(const float *__restrict__ qpack, const float *__restrict
                         float inv_T, int with_grad, float *__restrict__ row_loss,
                         float *__restrict__ dq_unit, float *__restrict__ group_out) {
   const int i = blockIdx.x, c = threadIdx.x & 127, g = threadIdx.x >> 7;
+  pdl_wait();      // launched early (PDL): the partial slabs are complete and visible from here on
+  pdl_trigger();   // a following prep may be launched; it waits for this grid before reading or writing anything
   const float *qp = qpack + (int64_t)i * kLd;
   const int64_t slab = (int64_t)M * kLd;
   const float *src = part + (int64_t)i * kLd;
@@ -251,10 +255,9 @@ int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
   int64_t want = (K_local + 255) / 256;
   if ((M + 7) / 8 > want) want = (M + 7) / 8;
   if (want > 1184) want = 1184;
-  mscl::infonce_prep_kernel<<<(unsigned)want, 256, 0, mscl::as_stream(stream)>>>(
-      d_q, d_kpos, M, d_birth, d_qstate, K_local, inv_T, key_norm_bound, d_qpack, d_dscale,
-      d_dup_slot, dup_age);
-  MSCL_LAUNCH_CHECK();
+  MSCL_CUDA(mscl::launch_pdl(mscl::infonce_prep_kernel, dim3((unsigned)want), dim3(256), 0, mscl::as_stream(stream), d_q,
+                             d_kpos, M, d_birth, d_qstate, K_local, inv_T, key_norm_bound, d_qpack, d_dscale, d_dup_slot,
+                             dup_age));
   return MSCL_OK;
 }
 
@@ -290,10 +293,9 @@ int mscl_infonce_finalize(const float *d_qpack, const float *d_kpos, float *d_pa
                  "null pointer");
   MSCL_CHECK_ARG(M > 0 && n_part > 0 && rows_per_group > 0 && M % rows_per_group == 0,
                  "M=%d must be a multiple of rows_per_group=%d (n_part=%d)", M, rows_per_group, n_part);
-  mscl::infonce_finalize_kernel<<<M, 128 * mscl::kFinGroups, 0, mscl::as_stream(stream)>>>(
-      d_qpack, d_kpos, d_part, n_part, M, rows_per_group, inv_T, with_grad, d_row_loss,
-      d_dq_unit, d_group_out);
-  MSCL_LAUNCH_CHECK();
+  MSCL_CUDA(mscl::launch_pdl(mscl::infonce_finalize_kernel, dim3(M), dim3(128 * mscl::kFinGroups), 0,
+                             mscl::as_stream(stream), d_qpack, d_kpos, d_part, n_part, M, rows_per_group, inv_T,
+                             with_grad, d_row_loss, d_dq_unit, d_group_out));
   return MSCL_OK;
 }
 

@@ -256,17 +256,14 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TL(slot)
 #endif
 
-// 32 keys of one 64-key tile for one query row: S (TMEM) -> p, row sum, hit count, P' (TMEM, over S).
+// 32 keys of one tile for one query row, on registers: S -> p, row sum, hit count, P' (written back over S by the caller).
 // `ds` = the 32 per-key scales of this half tile; nvalid / dupcol are relative to the half tile.
 // Per element on the fast path: FFMA (logit - shift), MUFU.EX2, FFMA (pos - logit: its sign bit is the
 // top-k hit), one add of that sign bit, FADD (row sum), FMUL (p * scale), IADD (round to nearest tf32:
 // +half ulp, the tensor core drops the low 13 bits).  4 independent sum / count chains.
 template <bool GRAD, bool FULL>
-__device__ __forceinline__ void softmax_half(uint32_t taddr, const float4 *ds, float shift2, float pos2,
+__device__ __forceinline__ void softmax_half(uint32_t (&v)[32], const float4 *ds, float shift2, float pos2,
                                              int nvalid, int dupcol, float &sum, int &cnt) {
-  uint32_t v[32];
-  TC_LD32(taddr, v);
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   float s4[4] = {0.f, 0.f, 0.f, 0.f};
   uint32_t c4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -291,7 +288,6 @@ __device__ __forceinline__ void softmax_half(uint32_t taddr, const float4 *ds, f
   }
   sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
   cnt += (int)((c4[0] + c4[1]) + (c4[2] + c4[3]));
-  if (GRAD) TC_ST32(taddr, v);
 }
 
 // part: per-CTA partial rows, float [gridDim.x][M][kLd]: O[0:128] | sum-exp | #neg>pos | 0 | 0.
@@ -373,23 +369,28 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  pdl_trigger();   // the finalize kernel may be launched; it waits for this grid's completion before reading the slabs
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       TL(1);
-      // Q tile [128 rows x 128 ch] as 4 channel-block slabs of [128][128 B], 128B-swizzled; rows >= M are
-      // zero-filled by the TMA unit
-      mbar_arrive_expect_tx(bar_qload, kQBytes);
-      tma_load_3d(sQ, &tmap_q, bar_qload, 0, row0, 0);
       auto load1 = [&](int t) {      // K-major copy of the 128-key tile t (from HBM)
         const int s = t % kStages1;
         mbar_wait(bar_empty1(s), ((uint32_t)(t / kStages1) & 1u) ^ 1u);
         mbar_arrive_expect_tx(bar_full1(s), kW1Bytes);
         tma_load_3d(sW + s * kW1Bytes, &tmap_w, bar_full1(s), 0, (int)((t_begin + t) * kTile), 0);
       };
+      // The queue is older than the prep kernel this grid may overlap with (PDL): start streaming it
+      // before waiting for prep's qpack / dscale.
+      for (int t = 0; t < kStages1 && t < nt; ++t) load1(t);
+      pdl_wait();
+      // Q tile [128 rows x 128 ch] as 4 channel-block slabs of [128][128 B], 128B-swizzled; rows >= M are
+      // zero-filled by the TMA unit
+      mbar_arrive_expect_tx(bar_qload, kQBytes);
+      tma_load_3d(sQ, &tmap_q, bar_qload, 0, row0, 0);
       // ring 1 only: a slot is re-armed the moment MMA1 has read it, independent of ring 2's progress
-      for (int t = 0; t < nt; ++t) load1(t);
+      for (int t = kStages1; t < nt; ++t) load1(t);
       TL(4);
     }
     __syncwarp();
@@ -500,6 +501,7 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const bool warp_ok = (row0 + quarter * 32) < M;   // any valid row in this warp's lane quarter
     float shift2 = 0.f, pos2 = INFINITY;
     int64_t dup_local = -1;   // queue slot (in this shard) holding a copy of the row's positive key
+    pdl_wait();               // qpack and dscale come from the prep kernel this grid may have overlapped with
     if (row_ok) {
       const float4 x = __ldg(reinterpret_cast<const float4 *>(qpack + (int64_t)row * kLd + kC));
       shift2 = x.y;
@@ -558,19 +560,26 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 #else
       if (warp_ok) {
 #endif
+        // both 32-key chunks of this warp's 64 keys are fetched from TMEM up front (one wait)
+        const uint32_t taddr = lane_base + kColS + (uint32_t)b * kTile + half * 64;
+        uint32_t v0[32], v1[32];
+        TC_LD32(taddr, v0);
+        TC_LD32(taddr + 32, v1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {          // two chunks of 32 keys
           const int64_t k0 = key0 + ch * 32;
           const int64_t left = K_local - k0;
           const int nvalid = left < 32 ? (left < 0 ? 0 : (int)left) : 32;
-          const uint32_t taddr = lane_base + kColS + (uint32_t)b * kTile + half * 64 + ch * 32;
           const int64_t dcol = dup_local - k0;
           const bool has_dup = dcol >= 0 && dcol < 32;
+          uint32_t(&v)[32] = ch ? v1 : v0;
           // warp-uniform choice (tcgen05.ld/st are .sync.aligned): slow path if any row of the warp needs it
           if (nvalid == 32 && !__any_sync(0xffffffffu, has_dup))
-            softmax_half<GRAD, true>(taddr, d4 + ch * 8, shift2, pos2, 32, -1, sum, cnt);
+            softmax_half<GRAD, true>(v, d4 + ch * 8, shift2, pos2, 32, -1, sum, cnt);
           else
-            softmax_half<GRAD, false>(taddr, d4 + ch * 8, shift2, pos2, nvalid, has_dup ? (int)dcol : -1, sum, cnt);
+            softmax_half<GRAD, false>(v, d4 + ch * 8, shift2, pos2, nvalid, has_dup ? (int)dcol : -1, sum, cnt);
+          if (GRAD) TC_ST32(taddr + ch * 32, v);
         }
         if (GRAD) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
@@ -724,14 +733,18 @@ extern "C" int mscl_infonce_partial(const float *d_qpack, int32_t M, const float
   const int row_blocks = (M + kRows - 1) / kRows;
   dim3 grid((unsigned)n_part, (unsigned)row_blocks);
   cudaStream_t s = mscl::as_stream(stream);
+  static bool configured = false;      // once per process (idempotent, so a race between threads is harmless)
+  if (!configured) {
+    MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    configured = true;
+  }
   if (with_grad) {
-    MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    infonce_tc_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(tw, tw2, tq, tp, d_qpack, M, d_dscale, K_local, shard_begin, d_part);
+    MSCL_CUDA(mscl::launch_pdl(infonce_tc_kernel<true>, grid, dim3(kThreads), kSmemBytes, s, tw, tw2, tq, tp, d_qpack, M,
+                               d_dscale, K_local, shard_begin, d_part));
   } else {
-    MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    infonce_tc_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(tw, tw2, tq, tp, d_qpack, M, d_dscale, K_local, shard_begin, d_part);
+    MSCL_CUDA(mscl::launch_pdl(infonce_tc_kernel<false>, grid, dim3(kThreads), kSmemBytes, s, tw, tw2, tq, tp, d_qpack, M,
+                               d_dscale, K_local, shard_begin, d_part));
   }
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;

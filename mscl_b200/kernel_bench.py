@@ -1,0 +1,284 @@
+"""Per-kernel roofline probe: every kernel of the MSCL hot path timed ALONE at BASELINE.json's shapes.
+
+bench.py times whole steps; its in-step per-launch events include ~3 us of launch gap, which
+swamps kernels that run for 5-20 us.  Here each kernel is launched back to back over a ring of
+distinct buffer sets whose total footprint exceeds twice the L2 (so every launch streams from
+HBM), with one pair of CUDA events around the whole train on the launching stream:
+
+    us per launch = elapsed / launches;   achieved = algorithmic bytes / us;   frac = achieved / measured HBM peak
+
+Algorithmic bytes per launch are the ones `functional.py` states.
+
+    python -m mscl_b200.kernel_bench [--configs cfg2,cfg3,cfg4,cfg5] [--out gpurun_out/kernel_rooflines.json]
+"""
+import argparse
+import json
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _cabi, functional as fx
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+L2_BYTES = 126 * 1024 * 1024
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream      # evaluated per call: the capturing stream during graph capture
+
+
+def n_rot(bytes_per_set):
+    return max(2, min(64, -(-2 * L2_BYTES // max(int(bytes_per_set), 1))))
+
+
+def time_train(fn, iters, warm=3):
+    """us per launch of `fn(i)`, i = 0..iters-1, replayed from ONE CUDA graph so the host (Python, ctypes,
+    tensor-map encoding) is out of the measurement: what remains is device time, launch gaps included."""
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(iters):
+                fn(i)
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / iters
+
+
+def row(cfg, kernel, shape, us, algo_bytes, algo_flops, pk, bound="hbm", note=None):
+    r = dict(config=cfg, kernel=kernel, shape=shape, us=us, algo_bytes=int(algo_bytes), algo_flops=int(algo_flops),
+             bound=bound)
+    if algo_bytes:
+        r["gbs"] = algo_bytes / us / 1e3
+        r["frac_hbm"] = r["gbs"] / pk
+    if algo_flops:
+        r["tflops"] = algo_flops / us / 1e6
+    if note:
+        r["note"] = note
+    return r
+
+
+# ------------------------------------------------------------------------------------------ K1
+def bench_k1(cfg, M, K, pk, dev, iters=30):
+    rot = n_rot(K * 512)
+    g = torch.Generator().manual_seed(K + M)
+    queues = []
+    for s in range(rot):
+        nq = fx.NegativeQueue(K, 128, dev)
+        nq.load(F.normalize(torch.randn(128, K, generator=g), dim=0), torch.randint(0, 2000, (K,), generator=g), 0)
+        queues.append(nq)
+    q = F.normalize(torch.randn(M, 128, generator=g), dim=1).to(dev)
+    k = F.normalize(torch.randn(M, 128, generator=g), dim=1).to(dev)
+    qpack = torch.empty(M, fx.PACK_LD, device=dev)
+    dscales = [torch.empty((K + 127) // 128 * 128, device=dev) for _ in queues]
+    n_part = _cabi.query("mscl_infonce_num_partials", M, K, fx.sm_count(dev))
+    part = torch.empty(n_part, M, fx.PACK_LD, device=dev)
+    row_loss, dq, gout = torch.empty(2 * M, device=dev), torch.empty(M, 128, device=dev), torch.empty(1, 4, device=dev)
+
+    def prep(i):
+        nq = queues[i % rot]
+        _cabi.call("mscl_infonce_prep", q.data_ptr(), k.data_ptr(), M, nq.birth.data_ptr(), nq.qstate.data_ptr(), K, 1 / 0.07,
+                   1.0, qpack.data_ptr(), dscales[i % rot].data_ptr(), None, 1, _st())
+
+    def partial(i):
+        _cabi.call("mscl_infonce_partial", qpack.data_ptr(), M, queues[i % rot].queue_tf32.data_ptr(),
+                   dscales[i % rot].data_ptr(), K, 0, part.data_ptr(), n_part, 1, _st())
+
+    def finalize(i):
+        _cabi.call("mscl_infonce_finalize", qpack.data_ptr(), k.data_ptr(), part.data_ptr(), n_part, M, M, 1 / 0.07, 1,
+                   row_loss.data_ptr(), dq.data_ptr(), gout.data_ptr(), _st())
+
+    def whole(i):
+        prep(i), partial(i), finalize(i)
+
+    for i in range(rot):
+        prep(i)
+    ab = fx.infonce_algo_bytes(M, K)
+    fl = 4 * M * K * 128
+    shape = f"M={M} K={K}"
+    out = [row(cfg, "infonce_tc_kernel<grad> (K1 pass)", shape, time_train(partial, iters), ab, fl, pk,
+               note=f"{n_part} CTAs along the keys; queue ring of {rot}"),
+           row(cfg, "K1 op = prep + pass + finalize", shape, time_train(whole, iters), ab, fl, pk)]
+    del queues
+    return out
+
+
+# ------------------------------------------------------------------------------------------ K2
+def bench_k2(cfg, N, t, pk, dev, iters=30):
+    out = []
+    for name, shp in (("rgb", (N, 128, t, 28, 28)), ("flow", (N, 128, 2 * t, 7, 7))):
+        nbytes = 4 * int(np.prod(shp))
+        rot = n_rot(nbytes)
+        xs = [torch.randn(shp, device=dev) for _ in range(rot)]
+        HW = shp[-1] * shp[-2]
+        R = xs[0].numel() // HW
+        o = torch.empty(shp[:3], device=dev)
+        us = time_train(lambda i: _cabi.call("mscl_hw_mean_fwd", xs[i % rot].data_ptr(), o.data_ptr(), R, HW, _st()), iters)
+        out.append(row(cfg, "hw_mean_fwd", f"{name} {shp}", us, 4 * R * (HW + 1), 0, pk))
+        us = time_train(lambda i: _cabi.call("mscl_hw_mean_bwd", o.data_ptr(), xs[i % rot].data_ptr(), R, HW, _st()), iters)
+        out.append(row(cfg, "hw_mean_bwd", f"{name} {shp}", us, 4 * R * (HW + 1), 0, pk))
+        del xs
+    xq = torch.randn(N, 128, t, device=dev)
+    xf = torch.randn(N, 128, 2 * t, device=dev)
+    us = time_train(lambda i: fx._LMCL.apply(xq, xf, 1 / 0.07), iters)
+    out.append(row(cfg, "lmcl_kernel (fwd+bwd)", f"N={N} t={t}", us, 8 * N * 128 * 3 * t, 6 * N * t * 2 * t * 128, pk,
+                   bound="latency", note="one CTA per clip, KFLOPs: launch-latency bound"))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ K3
+def bench_k3(cfg, N, T, pk, dev, iters=30):
+    HW = 112 * 112
+    in_bytes = N * 2 * T * HW * 4
+    rot = n_rot(3 * in_bytes)
+    flows = [torch.randn(N, 2, T, 112, 112, device=dev) for _ in range(rot)]
+    outs = [torch.empty(N, 2, 2 * T, 112, 112, device=dev) for _ in range(rot)]
+    cid = torch.from_numpy(np.random.RandomState(0).randint(0, 8, size=N).astype(np.int32)).to(dev)
+    tab = fx.fra_table(device=dev)
+    maxrad = torch.empty(N, T, 2, device=dev)
+    us1 = time_train(lambda i: _cabi.call("mscl_fra_maxrad", flows[i % rot].data_ptr(), cid.data_ptr(), tab.data_ptr(),
+                                          maxrad.data_ptr(), N, T, HW, 0, _st()), iters)
+    us2 = time_train(lambda i: _cabi.call("mscl_fra_apply", flows[i % rot].data_ptr(), cid.data_ptr(), tab.data_ptr(),
+                                          maxrad.data_ptr(), outs[i % rot].data_ptr(), N, T, HW, 0, _st()), iters)
+    shape = f"({N},2,{T},112,112)"
+    return [row(cfg, "fra_maxrad", shape, us1, 8 * N * T * HW, 0, pk, note="includes the 2-float-per-frame memset"),
+            row(cfg, "fra_apply", shape, us2, 24 * N * T * HW, 0, pk)]
+
+
+# ------------------------------------------------------------------------------------------ K4
+def r3d18_key_sizes():
+    """Parameter sizes of the r18 RGB key side (R3D-18 + TPN neck + MLP): 36.7 M elements."""
+    sizes = [3 * 64 * 3 * 49, 64, 64]
+    cin = 64
+    for planes, blocks in ((64, 2), (128, 2), (256, 2), (512, 2)):
+        for b in range(blocks):
+            sizes += [cin * planes * 27, planes, planes, planes * planes * 27, planes, planes]
+            if b == 0 and cin != planes:
+                sizes += [cin * planes, planes, planes]
+            cin = planes
+    sizes += [128 * 128, 128, 256 * 128, 128, 512 * 128, 128] + [128 * 128 * 9, 128] * 3 + [128 * 128 * 27, 128] * 3
+    sizes += [512 * 512, 512, 512 * 128, 128]
+    return sizes
+
+
+def slowonly_r50_key_sizes():
+    """SlowOnly-R50 key side, cfg 5: 159 backbone tensors (min 64, max 3,145,728 elements) + neck + MLP = 38.4 M."""
+    sizes = [3 * 64 * 49, 64, 64]
+    cin = 64
+    for planes, blocks, kt in ((64, 3, 1), (128, 4, 1), (256, 6, 3), (512, 3, 3)):
+        for b in range(blocks):
+            sizes += [cin * planes * kt, planes, planes, planes * planes * 9, planes, planes, planes * planes * 4,
+                      planes * 4, planes * 4]
+            if b == 0:
+                sizes += [cin * planes * 4, planes * 4, planes * 4]
+            cin = planes * 4
+    sizes += [512 * 128, 128, 1024 * 128, 128, 2048 * 128, 128] + [128 * 128 * 9, 128] * 3 + [128 * 128 * 27, 128] * 3
+    sizes += [2048 * 2048, 2048, 2048 * 128, 128]
+    return sizes
+
+
+def bench_k4(cfg, name, sizes, pk, dev, iters=20):
+    total = sum(sizes)
+    rot = n_rot(8 * total)
+    tables = []
+    for _ in range(rot):
+        flat_k, flat_q = torch.randn(total, device=dev), torch.randn(total, device=dev)
+        ks, qs, o = [], [], 0
+        for n in sizes:       # views into one allocation per side: same access pattern as separate 256B-aligned tensors
+            ks.append(flat_k[o:o + n]), qs.append(flat_q[o:o + n])
+            o += n
+        tables.append(fx.EmaTable(ks, qs))
+    us = time_train(lambda i: tables[i % rot].update(0.997), iters)
+    return [row(cfg, "ema_multi_kernel", f"{name}: {total} elements / {len(sizes)} tensors", us, 12 * total, 3 * total, pk)]
+
+
+# ------------------------------------------------------------------------------------------ K5 / K6
+def bench_k5(cfg, B_all, K, pk, dev, iters=30):
+    nq = fx.NegativeQueue(K, 128, dev)
+    nq.load(F.normalize(torch.randn(128, K), dim=0), torch.zeros(K, dtype=torch.long), 0)
+    keys = F.normalize(torch.randn(B_all, 128, device=dev), dim=1)
+    us = time_train(lambda i: nq.enqueue(keys), iters)
+    return [row(cfg, "enqueue_kernel", f"B_all={B_all} K={K}", us, 2 * B_all * 128 * 4, 0, pk, bound="latency",
+                note="64-256 KB per call: launch-latency bound")]
+
+
+def bench_k6(cfg, shape, pk, dev, iters=20):
+    nbytes = 4 * int(np.prod(shape))
+    rot = n_rot(2 * nbytes)
+    xs = [torch.randn(shape, device=dev) for _ in range(rot)]
+    idx = torch.randperm(shape[0]).to(dev)
+    us = time_train(lambda i: fx.gather_rows(xs[i % rot], idx), iters)
+    return [row(cfg, "gather_rows_kernel (shuffle-BN)", str(tuple(shape)), us, 2 * nbytes, 0, pk)]
+
+
+def run(configs=("cfg2", "cfg3", "cfg4", "cfg5"), device=0, verbose=True):
+    dev = torch.device("cuda", device)
+    torch.cuda.set_device(dev)
+    _cabi.require_device(device)
+    pk, src = hbm_peak()
+    rows = []
+
+    def add(rs):
+        rows.extend(rs)
+        if verbose:
+            for r in rs:
+                frac = f"{100 * r['frac_hbm']:5.1f}% of HBM peak" if "frac_hbm" in r else ""
+                print(f"[{r['config']}] {r['kernel']:<34} {r['shape']:<44} {r['us']:8.1f} us  "
+                      f"{r.get('gbs', 0):7.0f} GB/s  {frac}", flush=True)
+        torch.cuda.empty_cache()
+
+    if "cfg2" in configs:      # the r18 pre-training step, 32 clips/GPU, K = 65536
+        for M in (96, 32):
+            add(bench_k1("cfg2", M, 65536, pk, dev))
+        add(bench_k2("cfg2", 32, 4, pk, dev))
+        add(bench_k3("cfg2", 32, 8, pk, dev))
+        add(bench_k4("cfg2", "r18 RGB key side", r3d18_key_sizes(), pk, dev))
+        add(bench_k5("cfg2", 32, 65536, pk, dev))
+    if "cfg3" in configs:      # queue sweep, N = 64 per GPU
+        for K in (16384, 65536, 262144, 1048576):
+            add(bench_k1("cfg3", 64, K, pk, dev, iters=20))
+    if "cfg4" in configs:      # LMCL + FRA, N = 64, t = 16
+        add(bench_k2("cfg4", 64, 16, pk, dev, iters=15))
+        add(bench_k3("cfg4", 64, 16, pk, dev, iters=15))
+    if "cfg5" in configs:      # large-parameter key encoder
+        add(bench_k4("cfg5", "SlowOnly-R50 key side", slowonly_r50_key_sizes(), pk, dev))
+        add(bench_k6("cfg5", (32, 3, 8, 224, 224), pk, dev))
+        add(bench_k5("cfg5", 256, 65536, pk, dev))
+    return dict(hbm_peak_gbs=pk, peak_source=src, timing="back-to-back launches over a buffer ring > 2x L2, one CUDA-event pair",
+                rows=rows)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="cfg2,cfg3,cfg4,cfg5")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernel_rooflines.json"))
+    args = ap.parse_args()
+    res = run(tuple(args.configs.split(",")))
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
