@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--K", type=int, default=65536, help="negatives per queue")
     ap.add_argument("--ref-clips", type=int, default=4, help="clips per step of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-rooflines", action="store_true",
+                    help="skip the stand-alone per-kernel roofline probe (mscl_b200/kernel_bench.py) appended at N=1")
     ap.add_argument("--no-shard", action="store_true", help="N>1: keep the queue replicated instead of K/N shards")
     ap.add_argument("--channels-last", action="store_true", help="encoders/necks in torch.channels_last_3d (experiment)")
     ap.add_argument("--profile-range", action="store_true",
@@ -232,8 +234,8 @@ def run_reference(args, rank):
 # ----------------------------------------------------------------------------------------------
 # this repo's path
 # ----------------------------------------------------------------------------------------------
-KERNEL_ENTRIES = ["mscl_infonce_partial", "mscl_ema_multi", "mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_fra_maxrad",
-                  "mscl_fra_apply", "mscl_enqueue", "mscl_lmcl", "mscl_infonce_prep", "mscl_infonce_finalize",
+KERNEL_ENTRIES = ["mscl_infonce_partial", "mscl_ema_multi", "mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_fra_fused",
+                  "mscl_fra_maxrad", "mscl_fra_apply", "mscl_enqueue", "mscl_lmcl", "mscl_infonce_prep", "mscl_infonce_finalize",
                   "mscl_gather_rows"]
 
 
@@ -383,6 +385,15 @@ def run_b200(args, rank, local_rank, world):
                     "ms_per_step": sec_e2e * 1e3, "wall_ms_per_step": wall_e2e * 1e3},
             "wall_ms_per_step": wall * 1e3, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "kernels": kernels, "loss": last["log_vars"].get("loss")}
+    if world == 1 and not args.no_kernel_rooflines:
+        # every kernel of the path alone, at this workload's shapes (cfg2) and at the queue sweep's (cfg3): graph-replayed
+        # launch trains over L2-cold buffer rings -- device time without the per-launch event gap of the in-step numbers
+        from mscl_b200 import kernel_bench
+        del resident
+        torch.cuda.empty_cache()
+        kr = kernel_bench.run(("cfg2", "cfg3"), device=local_rank, verbose=False)
+        line["kernel_rooflines"] = dict(timing=kr["timing"], hbm_peak_gbs=kr["hbm_peak_gbs"], rows=[
+            {k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items() if k != "note"} for r in kr["rows"]])
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         step, desc = cpu_step_factory(args.K, args.ref_clips, threads)

@@ -118,6 +118,12 @@ int mscl_fra_maxrad(const float *d_flow, const int32_t *d_cid, const float *d_cs
 int mscl_fra_apply(const float *d_flow, const int32_t *d_cid, const float *d_cs,
                    const float *d_maxrad, float *d_out, int32_t N, int32_t T,
                    int32_t HW, int32_t layout, mscl_stream_t stream);
+/* One-pass form of the two calls above for frames of up to 204800 pixels: a cluster of 8 CTAs per
+ * frame stages the frame in (distributed) shared memory, so the flow is read once -- 24 B instead of
+ * 32 B per (u,v) pair -- and no scratch is needed.  Same output, bit for bit. */
+int mscl_fra_fused(const float *d_flow, const int32_t *d_cid, const float *d_cs,
+                   float *d_out, int32_t N, int32_t T, int32_t HW, int32_t layout,
+                   mscl_stream_t stream);
 /* Rotation only on an already normalised planar clip [N,2,T,HW] -> [N,2,T,HW]
  * (Appendix A.10 of SURVEY.md: rotation preserves the per-frame maximum). */
 int mscl_fra_rotate(const float *d_flow, const int32_t *d_cid, const float *d_cs,

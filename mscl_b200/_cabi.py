@@ -25,6 +25,7 @@ PROTOTYPES = {
     "mscl_ema_multi": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_f32, c_f32, c_ptr],
     "mscl_fra_maxrad": [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "mscl_fra_apply": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
+    "mscl_fra_fused": [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
     "mscl_fra_rotate": [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr],
     "mscl_hw_mean_fwd": [c_ptr, c_ptr, c_i64, c_int, c_ptr],
     "mscl_hw_mean_bwd": [c_ptr, c_ptr, c_i64, c_int, c_ptr],

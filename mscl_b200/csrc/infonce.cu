@@ -214,21 +214,24 @@ infonce_finalize_kernel(const float *__restrict__ qpack, const float *__restrict
   if (!is_last) return;
   __threadfence();
   const int n_groups = M / rows_per_group;
-  volatile const float *rl = row_loss;
-  for (int gidx = c; gidx < n_groups; gidx += 128) {
+  // one warp per loss term: lane l sums rows l, l+32, ... in order, then a fixed shuffle tree (bit-reproducible)
+  const int lane = c & 31;
+  for (int gidx = c >> 5; gidx < n_groups; gidx += 4) {
     float sl = 0.f, s1 = 0.f, s5 = 0.f;
-    for (int r = 0; r < rows_per_group; ++r) {
+    for (int r = lane; r < rows_per_group; r += 32) {
       const int row = gidx * rows_per_group + r;
-      sl += rl[row];
-      const float k = rl[M + row];
+      sl += __ldcg(row_loss + row);
+      const float k = __ldcg(row_loss + M + row);
       s1 += (k < 1.f) ? 1.f : 0.f;
       s5 += (k < 5.f) ? 1.f : 0.f;
     }
-    const float inv = 1.0f / (float)rows_per_group;
-    group_out[gidx * 4 + 0] = sl * inv;
-    group_out[gidx * 4 + 1] = s1 * inv;
-    group_out[gidx * 4 + 2] = s5 * inv;
-    group_out[gidx * 4 + 3] = 0.f;
+    sl = warp_sum(sl);
+    s1 = warp_sum(s1);
+    s5 = warp_sum(s5);
+    if (lane == 0) {
+      const float inv = 1.0f / (float)rows_per_group;
+      *reinterpret_cast<float4 *>(group_out + gidx * 4) = make_float4(sl * inv, s1 * inv, s5 * inv, 0.f);
+    }
   }
 }
 

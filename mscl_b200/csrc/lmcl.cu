@@ -63,68 +63,128 @@ hw_mean_bwd_kernel(const float *__restrict__ gout, float *__restrict__ gx, int64
   }
 }
 
-// One CTA (256 threads) per clip.
-// smem floats: y[C*tt] | dy[C*tt] | sim[t*t2] | nrm[tt] | dot[tt] | red[8*3]   with tt = t + t2
-// Columns 0..t-1 of y are the RGB frames, t..tt-1 the flow frames (base then FRA).
+// Small planes (H*W < 128, e.g. the 7x7 flow maps): a warp per 49-element row leaves most lanes idle and
+// issues 196-byte requests.  Here a CTA stages 64 consecutive rows -- one contiguous 16-byte-aligned span --
+// through shared memory with 128-bit loads, then 4 threads per row sum it (odd H*W: conflict-free pitch).
+constexpr int kSmallRows = 64;
 __global__ void __launch_bounds__(256)
+hw_mean_fwd_small_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t R, int HW,
+                         float inv_hw) {
+  extern __shared__ float4 buf4[];
+  float *buf = reinterpret_cast<float *>(buf4);
+  const int tid = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * kSmallRows;
+  const int nrows = (int)((R - row0) < kSmallRows ? (R - row0) : kSmallRows);
+  const int nfl = nrows * HW;
+  const float *base = x + row0 * HW;
+  const int n4 = nfl >> 2;
+  for (int v = tid; v < n4; v += 256) buf4[v] = ldg_stream(reinterpret_cast<const float4 *>(base) + v);
+  for (int i = (n4 << 2) + tid; i < nfl; i += 256) buf[i] = __ldg(base + i);
+  __syncthreads();
+  const int r = tid >> 2, part = tid & 3;
+  float acc = 0.f;
+  if (r < nrows) {
+    const float *p = buf + r * HW;
+    for (int i = part; i < HW; i += 4) acc += p[i];
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (part == 0 && r < nrows) out[row0 + r] = acc * inv_hw;
+}
+
+// backward of the same: plain element-wise fill, one float4 per thread, row index by division
+__global__ void __launch_bounds__(256)
+hw_mean_bwd_small_kernel(const float *__restrict__ gout, float *__restrict__ gx, int64_t total4, int HW,
+                         float inv_hw) {
+  const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (v >= total4) return;
+  const int64_t e = v << 2;
+  const int64_t r = e / HW;
+  const int rem = (int)(e - r * HW);
+  const float g0 = __ldg(gout + r) * inv_hw;
+  float g1 = g0;
+  if (rem + 3 >= HW) g1 = __ldg(gout + r + 1) * inv_hw;     // HW >= 4: at most one row boundary inside a float4
+  float4 o;
+  o.x = g0;
+  o.y = (rem + 1 >= HW) ? g1 : g0;
+  o.z = (rem + 2 >= HW) ? g1 : g0;
+  o.w = (rem + 3 >= HW) ? g1 : g0;
+  stg_stream(reinterpret_cast<float4 *>(gx) + v, o);
+}
+
+// One CTA (256 threads) per clip.
+// smem floats: y[C*ld] | dy[C*ld] | sim[t*sp] | nrm[tt] | dot[tt] | red[32*3]   with tt = t + t2,
+// ld = tt | 1 and sp = t2 | 1: odd pitches, so the column walks (norms, dy) hit 32 different banks.
+// Columns 0..t-1 of y are the RGB frames, t..tt-1 the flow frames (base then FRA).
+__global__ void __launch_bounds__(1024)
 lmcl_kernel(const float *__restrict__ xq, const float *__restrict__ xf, int N, int C, int t,
             int t2, float inv_T, float *__restrict__ out, float *__restrict__ gxq,
             float *__restrict__ gxf, float *__restrict__ part) {
   extern __shared__ float sm[];
   const int tt = t + t2;
+  const int ld = tt | 1, sp = t2 | 1;
   float *y = sm;
-  float *dy = y + C * tt;
-  float *sim = dy + C * tt;
-  float *nrm = sim + t * t2;
+  float *dy = y + C * ld;
+  float *sim = dy + C * ld;
+  float *nrm = sim + t * sp;
   float *dot = nrm + tt;
   float *red = dot + tt;
   const int n = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthr = blockDim.x, nwarps = nthr >> 5;
   const float *xq_n = xq + (int64_t)n * C * t;
   const float *xf_n = xf + (int64_t)n * C * t2;
 
-  // 1. stage: y[c*tt + col]
-  for (int i = tid; i < C * t; i += 256) {
+  // 1. stage: y[c*ld + col]
+  for (int i = tid; i < C * t; i += nthr) {
     const int c = i / t, col = i - c * t;
-    y[c * tt + col] = __ldg(xq_n + i);
+    y[c * ld + col] = __ldg(xq_n + i);
   }
-  for (int i = tid; i < C * t2; i += 256) {
+  for (int i = tid; i < C * t2; i += nthr) {
     const int c = i / t2, col = i - c * t2;
-    y[c * tt + t + col] = __ldg(xf_n + i);
+    y[c * ld + t + col] = __ldg(xf_n + i);
   }
   __syncthreads();
   // 2. column norms (F.normalize: x / max(||x||_2, 1e-12))
-  for (int col = warp; col < tt; col += 8) {
+  for (int col = warp; col < tt; col += nwarps) {
     float ss = 0.f;
     for (int c = lane; c < C; c += 32) {
-      const float v = y[c * tt + col];
+      const float v = y[c * ld + col];
       ss = fmaf(v, v, ss);
     }
     ss = warp_sum(ss);
     if (lane == 0) nrm[col] = fmaxf(sqrtf(ss), 1e-12f);
   }
   __syncthreads();
-  for (int i = tid; i < C * tt; i += 256) y[i] = __fdiv_rn(y[i], nrm[i % tt]);
+  for (int i = tid; i < C * tt; i += nthr) {
+    const int c = i / tt, col = i - c * tt;
+    y[c * ld + col] = __fdiv_rn(y[c * ld + col], nrm[col]);
+  }
   __syncthreads();
   // 3. similarities / T
-  for (int ij = tid; ij < t * t2; ij += 256) {
+  for (int ij = tid; ij < t * t2; ij += nthr) {
     const int i = ij / t2, j = ij - i * t2;
-    float acc = 0.f;
-    for (int c = 0; c < C; ++c) acc = fmaf(y[c * tt + i], y[c * tt + t + j], acc);
-    sim[ij] = acc * inv_T;
+    float a0 = 0.f, a1 = 0.f;
+    int c = 0;
+    for (; c + 1 < C; c += 2) {
+      a0 = fmaf(y[c * ld + i], y[c * ld + t + j], a0);
+      a1 = fmaf(y[(c + 1) * ld + i], y[(c + 1) * ld + t + j], a1);
+    }
+    if (c < C) a0 = fmaf(y[c * ld + i], y[c * ld + t + j], a0);
+    sim[i * sp + j] = (a0 + a1) * inv_T;
   }
   __syncthreads();
   // 4. per-row cross-entropy against column i; sim <- d loss / d sim (unit upstream)
   float l_loss = 0.f, l_t1 = 0.f, l_t5 = 0.f;
   const float gscale = inv_T / (float)(N * t);
-  for (int i = warp; i < t; i += 8) {
-    const float spos = sim[i * t2 + i];
+  for (int i = warp; i < t; i += nwarps) {
+    const float spos = sim[i * sp + i];
     float mx = -INFINITY;
-    for (int j = lane; j < t2; j += 32) mx = fmaxf(mx, sim[i * t2 + j]);
+    for (int j = lane; j < t2; j += 32) mx = fmaxf(mx, sim[i * sp + j]);
     mx = warp_max(mx);
     float se = 0.f, cnt = 0.f;
     for (int j = lane; j < t2; j += 32) {
-      const float s = sim[i * t2 + j];
+      const float s = sim[i * sp + j];
       se += __expf(s - mx);
       cnt += (j != i && s > spos) ? 1.f : 0.f;
     }
@@ -132,8 +192,8 @@ lmcl_kernel(const float *__restrict__ xq, const float *__restrict__ xf, int N, i
     cnt = warp_sum(cnt);
     const float lse = mx + __logf(se);
     for (int j = lane; j < t2; j += 32) {
-      const float p = __expf(sim[i * t2 + j] - lse);
-      sim[i * t2 + j] = (p - (j == i ? 1.f : 0.f)) * gscale;
+      const float p = __expf(sim[i * sp + j] - lse);
+      sim[i * sp + j] = (p - (j == i ? 1.f : 0.f)) * gscale;
     }
     if (lane == 0) {
       l_loss += lse - spos;
@@ -148,65 +208,72 @@ lmcl_kernel(const float *__restrict__ xq, const float *__restrict__ xf, int N, i
   }
   __syncthreads();
   // 5. dy = d loss / d y
-  for (int i = tid; i < C * tt; i += 256) {
+  for (int i = tid; i < C * tt; i += nthr) {
     const int c = i / tt, col = i - c * tt;
     float acc = 0.f;
     if (col < t) {
-      for (int j = 0; j < t2; ++j) acc = fmaf(sim[col * t2 + j], y[c * tt + t + j], acc);
+      for (int j = 0; j < t2; ++j) acc = fmaf(sim[col * sp + j], y[c * ld + t + j], acc);
     } else {
       const int j = col - t;
-      for (int r = 0; r < t; ++r) acc = fmaf(sim[r * t2 + j], y[c * tt + r], acc);
+      for (int r = 0; r < t; ++r) acc = fmaf(sim[r * sp + j], y[c * ld + r], acc);
     }
-    dy[i] = acc;
+    dy[c * ld + col] = acc;
   }
   __syncthreads();
   // 6. back through the normalisation: dx = (dy - y (y . dy)) / ||x||
-  for (int col = warp; col < tt; col += 8) {
+  for (int col = warp; col < tt; col += nwarps) {
     float d = 0.f;
-    for (int c = lane; c < C; c += 32) d = fmaf(y[c * tt + col], dy[c * tt + col], d);
+    for (int c = lane; c < C; c += 32) d = fmaf(y[c * ld + col], dy[c * ld + col], d);
     d = warp_sum(d);
     if (lane == 0) dot[col] = d;
   }
   __syncthreads();
   float *gq_n = gxq + (int64_t)n * C * t;
   float *gf_n = gxf + (int64_t)n * C * t2;
-  for (int i = tid; i < C * tt; i += 256) {
-    const int c = i / tt, col = i - c * tt;
-    const float g = (dy[i] - y[i] * dot[col]) / nrm[col];
-    if (col < t)
-      gq_n[c * t + col] = g;
-    else
-      gf_n[c * t2 + (col - t)] = g;
+  for (int i = tid; i < C * t; i += nthr) {        // coalesced stores, one output tensor at a time
+    const int c = i / t, col = i - c * t;
+    gq_n[i] = (dy[c * ld + col] - y[c * ld + col] * dot[col]) / nrm[col];
   }
-  // 7. per-clip partials, last CTA reduces in clip order (deterministic)
+  for (int i = tid; i < C * t2; i += nthr) {
+    const int c = i / t2, col = t + i - c * t2;
+    gf_n[i] = (dy[c * ld + col] - y[c * ld + col] * dot[col]) / nrm[col];
+  }
+  // 7. per-clip partials; the last CTA to finish sums them with one warp: lane k takes clips k, k+32, ...
+  //    in order, then a fixed shuffle tree -> the same bits on every run (no float atomics)
+  __shared__ int is_last;
   if (tid == 0) {
     float a = 0.f, b = 0.f, c5 = 0.f;
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < nwarps; ++w) {
       a += red[w * 3 + 0];
       b += red[w * 3 + 1];
       c5 += red[w * 3 + 2];
     }
-    part[n * 4 + 0] = a;
-    part[n * 4 + 1] = b;
-    part[n * 4 + 2] = c5;
+    *reinterpret_cast<float4 *>(part + n * 4) = make_float4(a, b, c5, 0.f);
     __threadfence();
     unsigned *counter = reinterpret_cast<unsigned *>(part + (int64_t)N * 4);
     const unsigned done = atomicAdd(counter, 1u);
-    if (done == (unsigned)N - 1u) {
-      __threadfence();
-      float sl = 0.f, s1 = 0.f, s5 = 0.f;
-      volatile float *vp = part;
-      for (int k = 0; k < N; ++k) {
-        sl += vp[k * 4 + 0];
-        s1 += vp[k * 4 + 1];
-        s5 += vp[k * 4 + 2];
-      }
+    is_last = (done == (unsigned)N - 1u);
+  }
+  __syncthreads();
+  if (is_last && warp == 0) {
+    __threadfence();
+    float sl = 0.f, s1 = 0.f, s5 = 0.f;
+    for (int k = lane; k < N; k += 32) {
+      const float4 v = __ldcg(reinterpret_cast<const float4 *>(part) + k);
+      sl += v.x;
+      s1 += v.y;
+      s5 += v.z;
+    }
+    sl = warp_sum(sl);
+    s1 = warp_sum(s1);
+    s5 = warp_sum(s5);
+    if (lane == 0) {
       const float inv = 1.f / (float)(N * t);
       out[0] = sl * inv;
       out[1] = s1 * inv;
       out[2] = s5 * inv;
       out[3] = 0.f;
-      *counter = 0u;
+      *reinterpret_cast<unsigned *>(part + (int64_t)N * 4) = 0u;
     }
   }
 }
@@ -219,6 +286,14 @@ int mscl_hw_mean_fwd(const float *d_x, float *d_out, int64_t R, int32_t HW,
                      mscl_stream_t stream) {
   MSCL_CHECK_ARG(d_x && d_out, "null pointer");
   MSCL_CHECK_ARG(R > 0 && HW > 0, "bad R=%lld HW=%d", (long long)R, HW);
+  if (HW >= 4 && HW < 128 && (((uintptr_t)d_x) & 15) == 0) {
+    const int64_t nb = (R + mscl::kSmallRows - 1) / mscl::kSmallRows;
+    MSCL_CHECK_ARG(nb < (1ll << 31), "too many rows");
+    mscl::hw_mean_fwd_small_kernel<<<(unsigned)nb, 256, (size_t)mscl::kSmallRows * HW * 4, mscl::as_stream(stream)>>>(
+        d_x, d_out, R, HW, 1.0f / (float)HW);
+    MSCL_LAUNCH_CHECK();
+    return MSCL_OK;
+  }
   const int64_t blocks = (R + 7) / 8;
   MSCL_CHECK_ARG(blocks < (1ll << 31), "too many rows");
   mscl::hw_mean_fwd_kernel<<<(unsigned)blocks, 256, 0, mscl::as_stream(stream)>>>(
@@ -231,6 +306,15 @@ int mscl_hw_mean_bwd(const float *d_gout, float *d_gx, int64_t R, int32_t HW,
                      mscl_stream_t stream) {
   MSCL_CHECK_ARG(d_gout && d_gx, "null pointer");
   MSCL_CHECK_ARG(R > 0 && HW > 0, "bad R=%lld HW=%d", (long long)R, HW);
+  if (HW >= 4 && HW < 128 && (((uintptr_t)d_gx) & 15) == 0 && ((R * HW) & 3) == 0) {
+    const int64_t total4 = (R * HW) >> 2;
+    const int64_t nb = (total4 + 255) / 256;
+    MSCL_CHECK_ARG(nb < (1ll << 31), "too many elements");
+    mscl::hw_mean_bwd_small_kernel<<<(unsigned)nb, 256, 0, mscl::as_stream(stream)>>>(d_gout, d_gx, total4, HW,
+                                                                                     1.0f / (float)HW);
+    MSCL_LAUNCH_CHECK();
+    return MSCL_OK;
+  }
   const int64_t blocks = (R + 7) / 8;
   MSCL_CHECK_ARG(blocks < (1ll << 31), "too many rows");
   mscl::hw_mean_bwd_kernel<<<(unsigned)blocks, 256, 0, mscl::as_stream(stream)>>>(
@@ -245,7 +329,7 @@ int mscl_lmcl(const float *d_xq, const float *d_xf, int32_t N, int32_t C, int32_
   MSCL_CHECK_ARG(d_xq && d_xf && d_out && d_gxq && d_gxf && d_part, "null pointer");
   MSCL_CHECK_ARG(N > 0 && C > 0 && t > 0 && t2 >= t, "bad N=%d C=%d t=%d t2=%d", N, C, t, t2);
   const int tt = t + t2;
-  const size_t smem = sizeof(float) * ((size_t)2 * C * tt + (size_t)t * t2 + 2 * tt + 24);
+  const size_t smem = sizeof(float) * ((size_t)2 * C * (tt | 1) + (size_t)t * (t2 | 1) + 2 * tt + 96);
   MSCL_CHECK_ARG(smem <= 200 * 1024, "C*(t+t2) too large for one CTA (%zu B of shared memory)",
                  smem);
   static thread_local size_t configured = 0;
@@ -254,7 +338,8 @@ int mscl_lmcl(const float *d_xq, const float *d_xf, int32_t N, int32_t C, int32_
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  mscl::lmcl_kernel<<<N, 256, smem, mscl::as_stream(stream)>>>(d_xq, d_xf, N, C, t, t2, inv_T,
+  const int threads = (C * tt >= 4096) ? 1024 : ((C * tt >= 2048) ? 512 : 256);     // one thread per ~6 staged elements
+  mscl::lmcl_kernel<<<N, threads, smem, mscl::as_stream(stream)>>>(d_xq, d_xf, N, C, t, t2, inv_T,
                                                               d_out, d_gxq, d_gxf, d_part);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;

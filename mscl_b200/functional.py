@@ -361,8 +361,11 @@ def fra_table(ratios=(0.2, 1.8), num_chunks=8, device="cuda"):
     return torch.tensor(np.array(tab, dtype=np.float64).astype(np.float32), device=device).contiguous()
 
 
+FRA_FUSED_MAX_PIXELS = 204800
+
+
 @torch.no_grad()
-def fra(flow, cid, table, layout="planar"):
+def fra(flow, cid, table, layout="planar", one_pass=None):
     """Normalised base + rotated flow.  flow: planar (N,2,T,H,W) or interleaved (N,T,H,W,2);
     cid int32 (N,).  Returns (N,2,2T,H,W): base frames then FRA frames (transforms_motion.py:111-142)."""
     _chk(flow, name="flow"), _chk(cid, torch.int32, "cid"), _chk(table, name="table")
@@ -375,8 +378,14 @@ def fra(flow, cid, table, layout="planar"):
     if two != 2:
         raise _cabi.MsclError("flow must have exactly two components (u, v)")
     out = torch.empty(N, 2, 2 * T, H, W, device=flow.device)
-    maxrad = torch.empty(N, T, 2, device=flow.device)
     st = _stream()
+    if one_pass is None:
+        one_pass = H * W <= FRA_FUSED_MAX_PIXELS
+    if one_pass:                           # one pass: a cluster of 8 CTAs keeps the frame in shared memory
+        _cabi.call("mscl_fra_fused", flow.data_ptr(), cid.data_ptr(), table.data_ptr(), out.data_ptr(), N, T, H * W, lay, st,
+                   algo_bytes=24 * N * T * H * W)
+        return out
+    maxrad = torch.empty(N, T, 2, device=flow.device)
     _cabi.call("mscl_fra_maxrad", flow.data_ptr(), cid.data_ptr(), table.data_ptr(), maxrad.data_ptr(), N, T, H * W, lay, st,
                algo_bytes=8 * N * T * H * W)
     _cabi.call("mscl_fra_apply", flow.data_ptr(), cid.data_ptr(), table.data_ptr(), maxrad.data_ptr(), out.data_ptr(),

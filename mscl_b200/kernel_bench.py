@@ -161,9 +161,12 @@ def bench_k3(cfg, N, T, pk, dev, iters=30):
                                           maxrad.data_ptr(), N, T, HW, 0, _st()), iters)
     us2 = time_train(lambda i: _cabi.call("mscl_fra_apply", flows[i % rot].data_ptr(), cid.data_ptr(), tab.data_ptr(),
                                           maxrad.data_ptr(), outs[i % rot].data_ptr(), N, T, HW, 0, _st()), iters)
+    us3 = time_train(lambda i: _cabi.call("mscl_fra_fused", flows[i % rot].data_ptr(), cid.data_ptr(), tab.data_ptr(),
+                                          outs[i % rot].data_ptr(), N, T, HW, 0, _st()), iters)
     shape = f"({N},2,{T},112,112)"
-    return [row(cfg, "fra_maxrad", shape, us1, 8 * N * T * HW, 0, pk, note="includes the 2-float-per-frame memset"),
-            row(cfg, "fra_apply", shape, us2, 24 * N * T * HW, 0, pk)]
+    return [row(cfg, "fra_fused_kernel (one pass)", shape, us3, 24 * N * T * HW, 0, pk),
+            row(cfg, "fra_maxrad", shape, us1, 8 * N * T * HW, 0, pk, note="includes the 2-float-per-frame memset"),
+            row(cfg, "fra_apply", shape, us2, 24 * N * T * HW, 0, pk, note="two-pass form, frames too large for a cluster")]
 
 
 # ------------------------------------------------------------------------------------------ K4

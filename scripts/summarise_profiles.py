@@ -20,8 +20,9 @@ OUT = os.path.join(ROOT, "profiles")
 GP = os.path.join(ROOT, "gpurun_out")
 OURS = ("infonce", "ema_multi", "fra_", "hw_mean", "enqueue_kernel", "lmcl_kernel", "queue_transpose", "gather_rows")
 ENTRY = {"infonce_tc_kernel": "mscl_infonce_partial", "ema_multi_kernel": "mscl_ema_multi", "fra_maxrad_kernel": "mscl_fra_maxrad",
-         "fra_apply_kernel": "mscl_fra_apply", "fra_fused_kernel": "mscl_fra", "hw_mean_fwd_kernel": "mscl_hw_mean_fwd",
-         "hw_mean_bwd_kernel": "mscl_hw_mean_bwd", "enqueue_kernel": "mscl_enqueue", "lmcl_kernel": "mscl_lmcl"}
+         "fra_apply_kernel": "mscl_fra_apply", "fra_fused_kernel": "mscl_fra_fused", "hw_mean_fwd_kernel": "mscl_hw_mean_fwd",
+         "hw_mean_bwd_kernel": "mscl_hw_mean_bwd", "hw_mean_fwd_small_kernel": "mscl_hw_mean_fwd",
+         "hw_mean_bwd_small_kernel": "mscl_hw_mean_bwd", "enqueue_kernel": "mscl_enqueue", "lmcl_kernel": "mscl_lmcl"}
 
 
 def launch_shares(tag):

@@ -121,22 +121,43 @@ def test_fra_golden(fx, golden_dir):
             np.testing.assert_allclose(got, ref, rtol=3e-6, atol=3e-7)
 
 
-def test_fra_oracle_bit_exact_full_size(fx):
+@pytest.mark.parametrize("one_pass,hw", [(True, (112, 112)), (False, (112, 112)), (True, (36, 52)), (True, (224, 224))])
+def test_fra_oracle_bit_exact_full_size(fx, one_pass, hw):
+    """one_pass=True: the cluster kernel (frame staged in distributed shared memory); False: max pre-pass + apply."""
     from oracle import inputs, mscl_oracle as O
-    N, T, H, W = 3, 8, 112, 112
+    N, T, (H, W) = 3, 8, hw
     rs = np.random.RandomState(0)
     cids = rs.randint(0, 8, size=N)
     clips = [inputs.flow_clip(seed=10 + n, T=T, H=H, W=W) for n in range(N)]
     ref = np.stack([np.stack(O.fra(c, int(k))) for c, k in zip(clips, cids)])      # (N,2T,H,W,2)
     x = torch.from_numpy(np.stack([np.stack(c) for c in clips])).cuda()            # (N,T,H,W,2)
-    out = fx.fra(x, torch.from_numpy(cids.astype(np.int32)).cuda(), fx.fra_table(), "interleaved")
+    out = fx.fra(x, torch.from_numpy(cids.astype(np.int32)).cuda(), fx.fra_table(), "interleaved", one_pass=one_pass)
     got = out.permute(0, 2, 3, 4, 1).cpu().numpy()
     np.testing.assert_array_equal(got, ref)   # same float32 operation sequence -> same bits
+    planar = x.permute(0, 4, 1, 2, 3).contiguous()
+    out_p = fx.fra(planar, torch.from_numpy(cids.astype(np.int32)).cuda(), fx.fra_table(), "planar", one_pass=one_pass)
+    np.testing.assert_array_equal(out_p.cpu().numpy(), out.cpu().numpy())
     rot = fx.fra_rotate(out[:, :, :T].contiguous(), torch.from_numpy(cids.astype(np.int32)).cuda(), fx.fra_table())
     np.testing.assert_allclose(rot.permute(0, 2, 3, 4, 1).cpu().numpy(), ref[:, T:], rtol=1e-5, atol=1e-6)
 
 
 # ------------------------------------------------------------------ K2 LMCL
+@pytest.mark.parametrize("shape", [(2, 128, 8, 7, 7), (3, 5, 3, 7, 7), (2, 128, 4, 28, 28), (1, 7, 3, 2, 2), (2, 3, 5, 1, 3),
+                                   (2, 16, 4, 10, 10), (1, 130, 1, 9, 14)])
+def test_hw_mean_matches_torch(fx, shape):
+    """AdaptiveAvgPool3d((None,1,1)) (local_cl_head.py:61-62): both kernels (warp-per-row, and the staged form
+    used for planes under 128 pixels), forward and backward, ragged row counts."""
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g).cuda().requires_grad_(True)
+    w = torch.randn(shape[:3], generator=g).cuda()
+    out = fx.hw_mean(x)
+    ref = x.detach().double().mean(dim=(-2, -1))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    (out * w).sum().backward()
+    want = (w / (shape[-1] * shape[-2]))[..., None, None].expand(shape)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), want.cpu().numpy(), rtol=1e-6, atol=0)
+
+
 def _oracle_lmcl(q_map, qf_map, qaf_map, T, t):
     from oracle import mscl_oracle as O
     leaves = [x.clone().requires_grad_(True) for x in (q_map, qf_map, qaf_map)]
