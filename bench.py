@@ -286,8 +286,12 @@ def run_b200(args, rank, local_rank, world):
     opt = torch.optim.SGD(params, lr=0.02, momentum=0.9, weight_decay=1e-4)      # mscl_r18 config :114-118
     runner = model
     if world > 1:
+        # apis/train.py:84-88 (broadcast_buffers=False, find_unused_parameters=True); the set of unused TPN level convs
+        # is the same every step, so the graph is declared static: DDP finds them once instead of traversing the
+        # autograd graph every step
         runner = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
-                                                           find_unused_parameters=True)   # apis/train.py:84-88
+                                                           static_graph=True,
+                                                           gradient_as_bucket_view=True)
     table = fx.fra_table(device=dev)
     host = [make_host_batch(N, 17 + 2 * rank + i, pin=True) for i in range(2)]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]

@@ -56,11 +56,19 @@ def draw_permutation(b_all, device, group=None):
     return idx
 
 
+def _upload(idx, dev):
+    """Host index tensor -> device without stalling the host: a pageable source makes the copy synchronous,
+    which would stop the CPU from running ahead of the GPU six times per step."""
+    if dev.type != "cuda":
+        return idx.to(dev)
+    return idx.pin_memory().to(dev, non_blocking=True)
+
+
 def exchange(x, plan, gather_rows):
     """Run a ShufflePlan on device tensor x (n_local, ...) with torch.distributed all_to_all.
     `gather_rows(x, idx)` is the row-gather kernel (functional.gather_rows)."""
     dev = x.device
-    send = gather_rows(x, plan.send_idx.to(dev))
+    send = gather_rows(x, _upload(plan.send_idx, dev))
     recv = torch.empty_like(x)
     dist.all_to_all_single(recv, send, output_split_sizes=plan.out_splits, input_split_sizes=plan.in_splits)
-    return gather_rows(recv, plan.recv_pos.to(dev))
+    return gather_rows(recv, _upload(plan.recv_pos, dev))
