@@ -228,6 +228,17 @@ int mscl_infonce_bwd(const float *d_dq_unit, const float *d_gout, int32_t M,
 int mscl_gather_rows(const float *d_x, const int64_t *d_idx, float *d_out,
                      int32_t n_rows, int64_t row_elems, mscl_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * K7  trilinear up-sampling between pyramid levels of the TPN neck.   replaces
+ *     F.interpolate(x, size=[T,H,W], mode="trilinear") (align_corners=False) in
+ *     mmaction/models/necks/sepc.py:126-130.  x [NC, Ti, Hi, Wi] -> y [NC, To, Ho, Wo], fp32, contiguous.
+ * The backward is a gather over the outputs that read each input element (no atomics).
+ */
+int mscl_upsample_trilinear_fwd(const float *d_x, float *d_y, int64_t NC, int32_t Ti, int32_t Hi,
+                                int32_t Wi, int32_t To, int32_t Ho, int32_t Wo, mscl_stream_t stream);
+int mscl_upsample_trilinear_bwd(const float *d_gy, float *d_gx, int64_t NC, int32_t Ti, int32_t Hi,
+                                int32_t Wi, int32_t To, int32_t Ho, int32_t Wo, mscl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,8 @@ PROTOTYPES = {
     "mscl_infonce_finalize": [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_f32, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "mscl_infonce_bwd": [c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr],
     "mscl_gather_rows": [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr],
+    "mscl_upsample_trilinear_fwd": [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
+    "mscl_upsample_trilinear_bwd": [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
 }
 EXPORTS = ["mscl_abi_version", "mscl_last_error"] + list(PROTOTYPES)
 

@@ -1,0 +1,154 @@
+// K7: trilinear up-sampling of the TPN neck's pyramid levels
+// (mmaction/models/necks/sepc.py:126-130: F.interpolate(..., size=[T,H,W], mode="trilinear"), align_corners=False).
+//
+// Adjacent to the contrastive path: PyTorch's upsample_trilinear3d kernels walk N*C inside
+// one thread per output position and run at ~30 GB/s on these shapes (7.5 ms of an 87 ms step); this is a plain
+// streaming pass -- one thread per 4 consecutive outputs along W, 128-bit stores, the 8x smaller input served
+// from L1/L2 -- and a gather-form backward (no atomics: bit-reproducible).
+//
+// Source coordinate (ATen area_pixel_compute_source_index, align_corners=False):
+//   src = max(0, (dst + 0.5) * in/out - 0.5);  i0 = floor(src);  i1 = min(i0 + 1, in - 1);  l1 = src - i0;  l0 = 1 - l1
+#include "common.cuh"
+
+namespace mscl {
+
+struct AxisTap {
+  int i0, i1;
+  float l0, l1;
+};
+
+__device__ __forceinline__ AxisTap axis_tap(int dst, float scale, int in_size) {
+  float src = ((float)dst + 0.5f) * scale - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  AxisTap a;
+  a.i0 = (int)src;
+  if (a.i0 > in_size - 1) a.i0 = in_size - 1;
+  a.i1 = a.i0 + (a.i0 < in_size - 1 ? 1 : 0);
+  a.l1 = src - (float)a.i0;
+  a.l0 = 1.f - a.l1;
+  return a;
+}
+
+// x [NC, Ti, Hi, Wi] -> y [NC, To, Ho, Wo]; one thread per 4 outputs along W (Wo % 4 == 0) or per output
+template <int VEC>
+__global__ void __launch_bounds__(256)
+upsample_trilinear_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t total_v, int Ti, int Hi,
+                              int Wi, int To, int Ho, int Wo, float st, float sh, float sw) {
+  const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (v >= total_v) return;
+  const int wv = Wo / VEC;
+  const int ow0 = (int)(v % wv) * VEC;
+  int64_t r = v / wv;
+  const int oh = (int)(r % Ho);
+  r /= Ho;
+  const int ot = (int)(r % To);
+  const int64_t nc = r / To;
+  const AxisTap at = axis_tap(ot, st, Ti), ah = axis_tap(oh, sh, Hi);
+  const float *p = x + nc * (int64_t)Ti * Hi * Wi;
+  const float *r00 = p + ((int64_t)at.i0 * Hi + ah.i0) * Wi, *r01 = p + ((int64_t)at.i0 * Hi + ah.i1) * Wi;
+  const float *r10 = p + ((int64_t)at.i1 * Hi + ah.i0) * Wi, *r11 = p + ((int64_t)at.i1 * Hi + ah.i1) * Wi;
+  float o[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    const AxisTap aw = axis_tap(ow0 + e, sw, Wi);
+    // same association as ATen's upsample_trilinear3d_out_frame
+    o[e] = at.l0 * (ah.l0 * (aw.l0 * __ldg(r00 + aw.i0) + aw.l1 * __ldg(r00 + aw.i1)) +
+                    ah.l1 * (aw.l0 * __ldg(r01 + aw.i0) + aw.l1 * __ldg(r01 + aw.i1))) +
+           at.l1 * (ah.l0 * (aw.l0 * __ldg(r10 + aw.i0) + aw.l1 * __ldg(r10 + aw.i1)) +
+                    ah.l1 * (aw.l0 * __ldg(r11 + aw.i0) + aw.l1 * __ldg(r11 + aw.i1)));
+  }
+  float *dst = y + ((nc * To + ot) * (int64_t)Ho + oh) * Wo + ow0;
+  if (VEC == 4)
+    stg_stream(reinterpret_cast<float4 *>(dst), make_float4(o[0], o[1], o[2], o[3]));
+  else
+    dst[0] = o[0];
+}
+
+// Range of outputs whose taps can touch input index i: src(o) in (i - 1, i + 1)  (plus the clamped ends)
+__device__ __forceinline__ void out_range(int i, float inv_scale, int out_size, int &lo, int &hi) {
+  lo = (int)floorf(((float)i - 0.5f) * inv_scale - 0.5f) - 1;
+  hi = (int)ceilf(((float)i + 1.5f) * inv_scale - 0.5f) + 1;
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > out_size - 1 ? out_size - 1 : hi;
+}
+__device__ __forceinline__ float tap_weight(const AxisTap &a, int i) {
+  return (a.i0 == i ? a.l0 : 0.f) + (a.i1 == i ? a.l1 : 0.f);
+}
+
+// gx [NC, Ti, Hi, Wi] = sum over the outputs that read it; one thread per input element, fixed summation order
+__global__ void __launch_bounds__(256)
+upsample_trilinear_bwd_kernel(const float *__restrict__ gy, float *__restrict__ gx, int64_t total, int Ti, int Hi,
+                              int Wi, int To, int Ho, int Wo, float st, float sh, float sw) {
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= total) return;
+  const int iw = (int)(e % Wi);
+  int64_t r = e / Wi;
+  const int ih = (int)(r % Hi);
+  r /= Hi;
+  const int it = (int)(r % Ti);
+  const int64_t nc = r / Ti;
+  int t0, t1, h0, h1, w0, w1;
+  out_range(it, 1.f / st, To, t0, t1);
+  out_range(ih, 1.f / sh, Ho, h0, h1);
+  out_range(iw, 1.f / sw, Wo, w0, w1);
+  const float *g = gy + nc * (int64_t)To * Ho * Wo;
+  float acc = 0.f;
+  for (int ot = t0; ot <= t1; ++ot) {
+    const float wt = tap_weight(axis_tap(ot, st, Ti), it);
+    if (wt == 0.f) continue;
+    for (int oh = h0; oh <= h1; ++oh) {
+      const float wh = tap_weight(axis_tap(oh, sh, Hi), ih);
+      if (wh == 0.f) continue;
+      const float *row = g + ((int64_t)ot * Ho + oh) * Wo;
+      float racc = 0.f;
+      for (int ow = w0; ow <= w1; ++ow) racc = fmaf(tap_weight(axis_tap(ow, sw, Wi), iw), __ldg(row + ow), racc);
+      acc = fmaf(wt * wh, racc, acc);
+    }
+  }
+  gx[e] = acc;
+}
+
+}  // namespace mscl
+
+extern "C" {
+
+static int resample_check(const void *a, const void *b, int64_t NC, int Ti, int Hi, int Wi, int To, int Ho, int Wo) {
+  MSCL_CHECK_ARG(a && b, "null pointer");
+  MSCL_CHECK_ARG(NC > 0 && Ti > 0 && Hi > 0 && Wi > 0 && To > 0 && Ho > 0 && Wo > 0, "bad shape");
+  MSCL_CHECK_ARG((((uintptr_t)a | (uintptr_t)b) & 15) == 0, "tensors must be 16-byte aligned");
+  return MSCL_OK;
+}
+
+int mscl_upsample_trilinear_fwd(const float *d_x, float *d_y, int64_t NC, int32_t Ti, int32_t Hi, int32_t Wi,
+                                int32_t To, int32_t Ho, int32_t Wo, mscl_stream_t stream) {
+  int rc = resample_check(d_x, d_y, NC, Ti, Hi, Wi, To, Ho, Wo);
+  if (rc) return rc;
+  const float st = (float)Ti / (float)To, sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  const int vec = (Wo % 4 == 0) ? 4 : 1;
+  const int64_t total_v = NC * To * Ho * (Wo / vec);
+  const int64_t blocks = (total_v + 255) / 256;
+  MSCL_CHECK_ARG(blocks < (1ll << 31), "too many elements");
+  cudaStream_t s = mscl::as_stream(stream);
+  if (vec == 4)
+    mscl::upsample_trilinear_fwd_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(d_x, d_y, total_v, Ti, Hi, Wi, To, Ho, Wo, st, sh, sw);
+  else
+    mscl::upsample_trilinear_fwd_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(d_x, d_y, total_v, Ti, Hi, Wi, To, Ho, Wo, st, sh, sw);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+int mscl_upsample_trilinear_bwd(const float *d_gy, float *d_gx, int64_t NC, int32_t Ti, int32_t Hi, int32_t Wi,
+                                int32_t To, int32_t Ho, int32_t Wo, mscl_stream_t stream) {
+  int rc = resample_check(d_gy, d_gx, NC, Ti, Hi, Wi, To, Ho, Wo);
+  if (rc) return rc;
+  const float st = (float)Ti / (float)To, sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  const int64_t total = NC * Ti * Hi * Wi;
+  const int64_t blocks = (total + 255) / 256;
+  MSCL_CHECK_ARG(blocks < (1ll << 31), "too many elements");
+  mscl::upsample_trilinear_bwd_kernel<<<(unsigned)blocks, 256, 0, mscl::as_stream(stream)>>>(d_gy, d_gx, total, Ti, Hi, Wi, To,
+                                                                                            Ho, Wo, st, sh, sw);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+}  // extern "C"

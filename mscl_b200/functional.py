@@ -419,3 +419,37 @@ def gather_rows(x, idx):
     _cabi.call("mscl_gather_rows", x.data_ptr(), idx.data_ptr(), out.data_ptr(), idx.numel(), row, _stream(),
                algo_bytes=8 * idx.numel() * row)
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# K7: trilinear up-sampling (TPN neck)
+# ----------------------------------------------------------------------------------------
+class _UpsampleTrilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size):
+        n, c, ti, hi, wi = x.shape
+        to, ho, wo = size
+        y = torch.empty(n, c, to, ho, wo, device=x.device)
+        _cabi.call("mscl_upsample_trilinear_fwd", x.data_ptr(), y.data_ptr(), n * c, ti, hi, wi, to, ho, wo, _stream(),
+                   algo_bytes=4 * (x.numel() + y.numel()))
+        ctx.in_shape = tuple(x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, c, ti, hi, wi = ctx.in_shape
+        gy = gy.contiguous()
+        to, ho, wo = gy.shape[2:]
+        gx = torch.empty(ctx.in_shape, device=gy.device)
+        _cabi.call("mscl_upsample_trilinear_bwd", gy.data_ptr(), gx.data_ptr(), n * c, ti, hi, wi, to, ho, wo, _stream(),
+                   algo_bytes=4 * (gx.numel() + gy.numel()))
+        return gx, None
+
+
+def upsample_trilinear(x, size):
+    """F.interpolate(x, size=size, mode="trilinear") with align_corners=False (necks/sepc.py:126-130) for a
+    contiguous fp32 (N,C,T,H,W) CUDA tensor."""
+    _chk(x, name="x")
+    if x.dim() != 5 or len(size) != 3:
+        raise _cabi.MsclError("upsample_trilinear takes (N,C,T,H,W) and a (T,H,W) size")
+    return _UpsampleTrilinear.apply(x, tuple(int(v) for v in size))

@@ -6,10 +6,21 @@ TPNMoCo  : the same embedding, plus a 3-level pyramid = FPN with (1,3,3) convs
            (necks/fpn.py:146-227) followed by SEPC pyramid convolutions
            (necks/sepc.py:17-135) -- (necks/base.py:137-175, fpn_video.py:43-136).
 """
+import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from ..registry import NECKS
+
+
+def _trilinear(x, size):
+    """F.interpolate(x, size, mode="trilinear") (necks/sepc.py:126-130).  On a CUDA tensor this is the K7 kernel
+    (PyTorch's upsample_trilinear3d runs at ~30 GB/s on these shapes); CPU tensors -- the oracle runs these
+    modules on the host -- take the PyTorch op."""
+    if x.is_cuda and x.dtype == torch.float32:
+        from .. import functional as fx
+        return fx.upsample_trilinear(x.contiguous(), size)
+    return F.interpolate(x, size=size, mode="trilinear")
 
 
 class _Conv(nn.Module):
@@ -54,7 +65,7 @@ class _PConv3D(nn.Module):
             if lvl > 0:
                 y = y + self.Pconv[2](xs[lvl - 1])
             if lvl < len(xs) - 1:
-                y = y + F.interpolate(self.Pconv[0](xs[lvl + 1]), size=list(y.shape[2:]), mode="trilinear")
+                y = y + _trilinear(self.Pconv[0](xs[lvl + 1]), list(y.shape[2:]))
             out.append(self.relu(y))
         return out
 

@@ -312,3 +312,23 @@ def test_gather_rows(fx):
     x = torch.randn(64, 3, 8, 28, 28, device="cuda")
     idx = torch.randperm(64)[:16].cuda()
     np.testing.assert_array_equal(fx.gather_rows(x, idx).cpu().numpy(), x[idx].cpu().numpy())
+
+
+# ------------------------------------------------------------------ K7 trilinear up-sampling (TPN neck)
+@pytest.mark.parametrize("shape,size", [((2, 8, 2, 14, 14), (4, 28, 28)), ((2, 5, 1, 7, 7), (2, 14, 14)), ((1, 3, 3, 5, 6), (7, 9, 11)),
+                                        ((2, 4, 4, 6, 6), (4, 6, 6)), ((1, 2, 2, 3, 3), (5, 8, 12))])
+def test_upsample_trilinear_matches_torch(fx, shape, size):
+    """necks/sepc.py:126-130: F.interpolate(mode="trilinear", align_corners=False); forward and the gather backward."""
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g).cuda().requires_grad_(True)
+    w = torch.randn(shape[:2] + size, generator=g).cuda()
+    y = fx.upsample_trilinear(x, size)
+    xr = x.detach().clone().requires_grad_(True)
+    yr = F.interpolate(xr, size=size, mode="trilinear")
+    np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+    (y * w).sum().backward()
+    (yr * w).sum().backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), xr.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    xc = x.detach().cpu().requires_grad_(True)       # and against the host op the oracle uses
+    yc = F.interpolate(xc, size=size, mode="trilinear")
+    np.testing.assert_allclose(y.detach().cpu().numpy(), yc.detach().numpy(), rtol=1e-5, atol=1e-6)
