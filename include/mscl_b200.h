@@ -239,6 +239,29 @@ int mscl_upsample_trilinear_fwd(const float *d_x, float *d_y, int64_t NC, int32_
 int mscl_upsample_trilinear_bwd(const float *d_gy, float *d_gx, int64_t NC, int32_t Ti, int32_t Hi,
                                 int32_t Wi, int32_t To, int32_t Ho, int32_t Wo, mscl_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * K8  flow visualisation + flip.   replaces FlowVisualizer.__call__ / flow_uv_to_colors
+ *     (mmaction/models/common/ssl_aug.py:87-136, colour wheel tools/RAFT/core/utils/flow_viz.py:20-67) and the
+ *     mirror of SyncMoCoAugmentV5.forward_flip (common/ssl_aug_v2.py:109-117) for the flow images.
+ * flow planar [N, 2, T, H, W] -> out [N, 3, T, H, W] in {0, 1/255, ..., 1}.  d_flip uint8 [N] (mirror along W;
+ * may be NULL); d_norm float[6] = mean[3], std[3] applied after the colour lookup (NULL: normalize_flow=False).
+ * Arithmetic follows the reference's dtypes: float32 up to f = fk - k0 and (1 - f), float64 for the interpolation.
+ */
+int mscl_flow_visualize(const float *d_flow, const uint8_t *d_flip, const float *d_norm, float *d_out,
+                        int32_t N, int32_t T, int32_t H, int32_t W, mscl_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * K9  RGB colour pipeline of SyncMoCoAugmentV5 (common/ssl_aug_v2.py:31-48,66-68, common/ssl_aug.py:138-174):
+ *     flip -> ColorJitter(brightness, contrast, saturation, hue) -> grayscale -> separable Gaussian blur
+ *     (reflect border) -> Normalize, decisions and parameters per clip, drawn by the caller.
+ * x [N, 3, T, H, W] in [0,1] -> out same shape.  d_params float [N][16]: flip, jitter?, brightness, contrast,
+ * saturation, hue matrix[9] (row major, RGB -> RGB), gray?, blur?.  d_taps float[n_taps] (odd, <= 31) the 1-D blur
+ * kernel; d_norm float[6] = mean[3], std[3]; d_gray_partial float [N][n_chunks] scratch for the clip luminance sums.
+ */
+int mscl_color_pipeline(const float *d_x, const float *d_params, const float *d_taps, int32_t n_taps,
+                        const float *d_norm, float *d_gray_partial, int32_t n_chunks, float *d_out,
+                        int32_t N, int32_t T, int32_t H, int32_t W, mscl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,281 @@
+// K8 / K9: the GPU augmentation front-end that feeds the encoders every step.
+//
+//  K8 flow_visualize : (u,v) flow -> Middlebury colour-wheel image, the reference's FlowVisualizer
+//                      (mmaction/models/common/ssl_aug.py:87-136, wheel tools/RAFT/core/utils/flow_viz.py:20-67),
+//                      fused with the per-sample horizontal flip of SyncMoCoAugmentV5.forward_flip
+//                      (common/ssl_aug_v2.py:109-117: only the image is mirrored, u keeps its sign) and the optional
+//                      normalisation.  One thread per 4 pixels: 8 B read, 12 B written per pixel.
+//  K9 color_pipeline : the RGB branch of SyncMoCoAugmentV5 (ssl_aug_v2.py:31-48,66-68): flip, ColorJitter
+//                      (brightness, contrast, saturation, hue) p=.8, RandomGrayscale p=.2, Gaussian blur p=.5
+//                      (separable, reflect border), Normalize -- decisions and parameters per clip, drawn by the
+//                      caller.  clip_gray_sum (the contrast step needs the clip's mean luminance) + one CTA per
+//                      frame that keeps the frame in shared memory through both blur passes: 12 B read (x2 for the
+//                      mean) and 12 B written per pixel instead of ~25 element-wise passes and two convolutions.
+#include "common.cuh"
+
+namespace mscl {
+
+// ------------------------------------------------------------------------------------------- K8
+__constant__ double c_wheel[55 * 3];        // colour wheel / 255 (float64, as the reference's tmp[k] / 255.0)
+
+struct WheelTap {
+  int k0, k1;
+  float f, omf, rad;
+};
+
+__device__ __forceinline__ WheelTap wheel_tap(float u, float v) {
+  WheelTap w;
+  w.rad = __fsqrt_rn(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)));
+  const float a = __fdiv_rn(atan2f(-v, -u), 3.14159265358979323846f);
+  const float fk = __fmul_rn(__fdiv_rn(__fadd_rn(a, 1.f), 2.f), 54.f);
+  const float fl = floorf(fk);
+  w.k0 = (int)fl;
+  w.k1 = w.k0 + 1;
+  if (w.k1 == 55) w.k1 = 0;
+  w.f = __fsub_rn(fk, fl);
+  w.omf = __fsub_rn(1.f, w.f);      // (1 - f) is a float32 op in the reference; the products below are float64
+  return w;
+}
+
+// `wheel`: the shared-memory copy (the lookup index differs per lane: constant memory would serialise it)
+__device__ __forceinline__ float wheel_color(const WheelTap &w, int ch, const double *wheel) {
+  double col = __dadd_rn(__dmul_rn((double)w.omf, wheel[w.k0 * 3 + ch]), __dmul_rn((double)w.f, wheel[w.k1 * 3 + ch]));
+  if (w.rad <= 1.f)
+    col = __dsub_rn(1.0, __dmul_rn((double)w.rad, __dsub_rn(1.0, col)));
+  else
+    col = __dmul_rn(col, 0.75);
+  const float q = (float)(unsigned char)floor(__dmul_rn(255.0, col));     // uint8 round trip (ssl_aug.py:121)
+  return __fdiv_rn(q, 255.f);
+}
+
+// flow planar [N, 2, T, H, W] -> out [N, 3, T, H, W].  flip: uint8 [N] or null.  norm: float [6] = mean[3], std[3] or null.
+__global__ void __launch_bounds__(256)
+flow_visualize_kernel(const float *__restrict__ flow, const uint8_t *__restrict__ flip, const float *__restrict__ norm,
+                      float *__restrict__ out, int T, int H, int W, int64_t total4) {
+  __shared__ double s_wheel[55 * 3];
+  if (threadIdx.x < 55 * 3) s_wheel[threadIdx.x] = c_wheel[threadIdx.x];
+  __syncthreads();
+  const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (g >= total4) return;
+  const int w4 = W >> 2;
+  const int wq = (int)(g % w4);
+  int64_t r = g / w4;                       // (n, t, h) row index
+  const int64_t HW = (int64_t)H * W, THW = (int64_t)T * HW;
+  const int64_t row_in_clip = r % ((int64_t)T * H);
+  const int n = (int)(r / ((int64_t)T * H));
+  const bool fl = flip != nullptr && flip[n] != 0;
+  const int w_src = fl ? (W - 4 - 4 * wq) : 4 * wq;
+  const float *pu = flow + ((int64_t)n * 2 + 0) * THW + row_in_clip * W + w_src;
+  const float *pv = flow + ((int64_t)n * 2 + 1) * THW + row_in_clip * W + w_src;
+  float4 u4 = ldg_stream(reinterpret_cast<const float4 *>(pu));
+  float4 v4 = ldg_stream(reinterpret_cast<const float4 *>(pv));
+  if (fl) {
+    u4 = make_float4(u4.w, u4.z, u4.y, u4.x);
+    v4 = make_float4(v4.w, v4.z, v4.y, v4.x);
+  }
+  const float us[4] = {u4.x, u4.y, u4.z, u4.w}, vs[4] = {v4.x, v4.y, v4.z, v4.w};
+  float o[3][4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const WheelTap tap = wheel_tap(us[e], vs[e]);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float c = wheel_color(tap, ch, s_wheel);
+      if (norm != nullptr) c = __fdiv_rn(__fsub_rn(c, norm[ch]), norm[3 + ch]);
+      o[ch][e] = c;
+    }
+  }
+  float *po = out + (int64_t)n * 3 * THW + row_in_clip * W + 4 * wq;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch)
+    stg_stream(reinterpret_cast<float4 *>(po + ch * THW), make_float4(o[ch][0], o[ch][1], o[ch][2], o[ch][3]));
+}
+
+// ------------------------------------------------------------------------------------------- K9
+__device__ __forceinline__ float gray_of(float r, float g, float b) {
+  return 0.299f * r + 0.587f * g + 0.114f * b;
+}
+
+// partial[n][chunk] = sum over this chunk of the clip's pixels of gray(x); grid (chunks, N)
+__global__ void __launch_bounds__(256)
+clip_gray_sum_kernel(const float *__restrict__ x, float *__restrict__ partial, int64_t THW) {
+  const int n = blockIdx.y;
+  const float *pr = x + (int64_t)n * 3 * THW, *pg = pr + THW, *pb = pg + THW;
+  const int64_t n4 = THW >> 2;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 r = ldg_stream(reinterpret_cast<const float4 *>(pr) + i);
+    const float4 g = ldg_stream(reinterpret_cast<const float4 *>(pg) + i);
+    const float4 b = ldg_stream(reinterpret_cast<const float4 *>(pb) + i);
+    acc += (gray_of(r.x, g.x, b.x) + gray_of(r.y, g.y, b.y)) + (gray_of(r.z, g.z, b.z) + gray_of(r.w, g.w, b.w));
+  }
+  acc = warp_sum(acc);
+  __shared__ float s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s[w];
+    partial[n * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// Per-clip parameters, float [N][kColorParams]:
+//  0 flip  1 jitter?  2 brightness  3 contrast  4 saturation  5..13 hue matrix (row major)  14 gray?  15 blur?
+constexpr int kColorParams = 16;
+constexpr int kMaxTaps = 31;
+
+// One CTA per frame (n, t).  smem: a[H*W] | b[H*W] floats.
+__global__ void __launch_bounds__(512)
+color_pipeline_kernel(const float *__restrict__ x, const float *__restrict__ params, const float *__restrict__ gray_partial,
+                      int n_chunks, const float *__restrict__ taps, int n_taps, const float *__restrict__ norm,
+                      float *__restrict__ out, int T, int H, int W) {
+  extern __shared__ float sm[];
+  const int HW = H * W;
+  float *a = sm, *b = sm + HW;
+  __shared__ float s_taps[kMaxTaps];
+  const int frame = blockIdx.x;
+  const int n = frame / T, t = frame - n * T;
+  const float *p = params + n * kColorParams;
+  const bool flip = p[0] != 0.f, jit = p[1] != 0.f, to_gray = p[14] != 0.f, blur = p[15] != 0.f;
+  const float br = p[2], ct = p[3], sat = p[4];
+  float hm[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) hm[i] = p[5 + i];
+  const int64_t THW = (int64_t)T * HW;
+  // clip mean of gray(x * brightness): the partial sums in a fixed order
+  float gsum = 0.f;
+  for (int c = 0; c < n_chunks; ++c) gsum += __ldg(gray_partial + n * n_chunks + c);
+  const float m = br * (gsum / (float)THW);     // mean over (1, T, H, W) of the luminance
+  if (threadIdx.x < n_taps) s_taps[threadIdx.x] = taps[threadIdx.x];
+  const float *pr = x + (int64_t)n * 3 * THW + (int64_t)t * HW, *pg = pr + THW, *pb = pg + THW;
+  float *po = out + (int64_t)n * 3 * THW + (int64_t)t * HW;
+  const int half = n_taps >> 1;
+  // point-wise colour ops of one pixel (flip applied on the way in)
+  auto shade = [&](int i, float &r, float &g, float &bl) {
+    const int h = i / W, w = i - h * W;
+    const int src = flip ? (h * W + (W - 1 - w)) : i;
+    r = __ldg(pr + src), g = __ldg(pg + src), bl = __ldg(pb + src);
+    if (jit) {
+      float y0 = r * br, y1 = g * br, y2 = bl * br;                       // brightness
+      y0 = (y0 - m) * ct + m, y1 = (y1 - m) * ct + m, y2 = (y2 - m) * ct + m;   // contrast about the clip mean
+      const float gy = gray_of(y0, y1, y2);
+      y0 = (y0 - gy) * sat + gy, y1 = (y1 - gy) * sat + gy, y2 = (y2 - gy) * sat + gy;   // saturation
+      const float z0 = hm[0] * y0 + hm[1] * y1 + hm[2] * y2;             // hue rotation in YIQ space
+      const float z1 = hm[3] * y0 + hm[4] * y1 + hm[5] * y2;
+      const float z2 = hm[6] * y0 + hm[7] * y1 + hm[8] * y2;
+      r = fminf(fmaxf(z0, 0.f), 1.f), g = fminf(fmaxf(z1, 0.f), 1.f), bl = fminf(fmaxf(z2, 0.f), 1.f);
+    }
+    if (to_gray) r = g = bl = gray_of(r, g, bl);
+  };
+  if (!blur) {      // one pass, three planes out
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      float r, g, bl;
+      shade(i, r, g, bl);
+      po[i] = (r - norm[0]) / norm[3];
+      po[THW + i] = (g - norm[1]) / norm[4];
+      po[2 * THW + i] = (bl - norm[2]) / norm[5];
+    }
+    return;
+  }
+  __syncthreads();   // s_taps
+  for (int ch = 0; ch < 3; ++ch) {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      float r, g, bl;
+      shade(i, r, g, bl);
+      a[i] = ch == 0 ? r : (ch == 1 ? g : bl);
+    }
+    __syncthreads();
+    // ---- horizontal pass a -> b, reflect border (F.pad mode="reflect": index -k -> k, W-1+k -> W-1-k)
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const int h = i / W, w = i - h * W;
+      float acc = 0.f;
+      for (int k = 0; k < n_taps; ++k) {
+        int ww = w + k - half;
+        ww = ww < 0 ? -ww : (ww >= W ? 2 * W - 2 - ww : ww);
+        acc = fmaf(s_taps[k], a[h * W + ww], acc);
+      }
+      b[i] = acc;
+    }
+    __syncthreads();
+    // ---- vertical pass b -> out, normalised
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const int h = i / W, w = i - h * W;
+      float acc = 0.f;
+      for (int k = 0; k < n_taps; ++k) {
+        int hh = h + k - half;
+        hh = hh < 0 ? -hh : (hh >= H ? 2 * H - 2 - hh : hh);
+        acc = fmaf(s_taps[k], b[hh * W + w], acc);
+      }
+      po[ch * THW + i] = (acc - norm[ch]) / norm[3 + ch];
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace mscl
+
+extern "C" {
+
+int mscl_flow_visualize(const float *d_flow, const uint8_t *d_flip, const float *d_norm, float *d_out, int32_t N,
+                        int32_t T, int32_t H, int32_t W, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_flow && d_out, "null pointer");
+  MSCL_CHECK_ARG(N > 0 && T > 0 && H > 0 && W > 0 && W % 4 == 0, "bad shape N=%d T=%d H=%d W=%d (W must be a multiple of 4)", N,
+                 T, H, W);
+  MSCL_CHECK_ARG((((uintptr_t)d_flow | (uintptr_t)d_out) & 15) == 0, "flow / out must be 16-byte aligned");
+  static bool wheel_ready = false;
+  if (!wheel_ready) {
+    // 55-entry Middlebury wheel (tools/RAFT/core/utils/flow_viz.py:33-67): six hue segments, floor(255*i/len) ramps
+    const int seg_len[6] = {15, 6, 4, 11, 13, 6};
+    const int full[6] = {0, 1, 1, 2, 2, 0}, ramp[6] = {1, 0, 2, 1, 0, 2}, rising[6] = {1, 0, 1, 0, 1, 0};
+    double wheel[55 * 3];
+    int k = 0;
+    for (int s = 0; s < 6; ++s)
+      for (int i = 0; i < seg_len[s]; ++i, ++k) {
+        double rgb[3] = {0.0, 0.0, 0.0};
+        const double r = (double)((255 * i) / seg_len[s]);
+        rgb[full[s]] = 255.0;
+        rgb[ramp[s]] = rising[s] ? r : 255.0 - r;
+        for (int c = 0; c < 3; ++c) wheel[k * 3 + c] = rgb[c] / 255.0;
+      }
+    MSCL_CUDA(cudaMemcpyToSymbol(mscl::c_wheel, wheel, sizeof(wheel)));
+    wheel_ready = true;
+  }
+  const int64_t total4 = (int64_t)N * T * H * (W / 4);
+  const int64_t blocks = (total4 + 255) / 256;
+  MSCL_CHECK_ARG(blocks < (1ll << 31), "too many pixels");
+  mscl::flow_visualize_kernel<<<(unsigned)blocks, 256, 0, mscl::as_stream(stream)>>>(d_flow, d_flip, d_norm, d_out, T, H, W,
+                                                                                    total4);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+int mscl_color_pipeline(const float *d_x, const float *d_params, const float *d_taps, int32_t n_taps, const float *d_norm,
+                        float *d_gray_partial, int32_t n_chunks, float *d_out, int32_t N, int32_t T, int32_t H, int32_t W,
+                        mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_x && d_params && d_taps && d_norm && d_gray_partial && d_out, "null pointer");
+  MSCL_CHECK_ARG(N > 0 && T > 0 && H > 0 && W > 0, "bad shape");
+  MSCL_CHECK_ARG(n_taps >= 1 && n_taps <= mscl::kMaxTaps && (n_taps & 1), "n_taps=%d must be odd and <= %d", n_taps,
+                 mscl::kMaxTaps);
+  MSCL_CHECK_ARG(n_taps / 2 < H && n_taps / 2 < W, "blur radius exceeds the frame (reflect border)");
+  MSCL_CHECK_ARG(n_chunks > 0 && n_chunks <= 1024, "bad n_chunks");
+  const int64_t THW = (int64_t)T * H * W;
+  MSCL_CHECK_ARG(THW % 4 == 0 && (((uintptr_t)d_x) & 15) == 0, "T*H*W must be a multiple of 4 and x 16-byte aligned");
+  const size_t smem = (size_t)2 * H * W * sizeof(float);
+  MSCL_CHECK_ARG(smem <= 200 * 1024, "frame of %dx%d does not fit in shared memory", H, W);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    MSCL_CUDA(cudaFuncSetAttribute(mscl::color_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  cudaStream_t s = mscl::as_stream(stream);
+  mscl::clip_gray_sum_kernel<<<dim3(n_chunks, N), 256, 0, s>>>(d_x, d_gray_partial, THW);
+  MSCL_LAUNCH_CHECK();
+  mscl::color_pipeline_kernel<<<N * T, 512, smem, s>>>(d_x, d_params, d_gray_partial, n_chunks, d_taps, n_taps, d_norm, d_out,
+                                                       T, H, W);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+}  // extern "C"

@@ -91,6 +91,15 @@ upsample_trilinear_bwd_kernel(const float *__restrict__ gy, float *__restrict__ 
   out_range(it, 1.f / st, To, t0, t1);
   out_range(ih, 1.f / sh, Ho, h0, h1);
   out_range(iw, 1.f / sw, Wo, w0, w1);
+  // the W-axis weights do not depend on (ot, oh): evaluate them once (the candidate range is short: <= 2/scale + 4)
+  constexpr int kMaxW = 12;
+  float ww[kMaxW];
+  const int nw = w1 - w0 + 1;
+  const bool cached = nw <= kMaxW;
+  if (cached) {
+#pragma unroll
+    for (int k = 0; k < kMaxW; ++k) ww[k] = (k < nw) ? tap_weight(axis_tap(w0 + k, sw, Wi), iw) : 0.f;
+  }
   const float *g = gy + nc * (int64_t)To * Ho * Wo;
   float acc = 0.f;
   for (int ot = t0; ot <= t1; ++ot) {
@@ -99,9 +108,15 @@ upsample_trilinear_bwd_kernel(const float *__restrict__ gy, float *__restrict__ 
     for (int oh = h0; oh <= h1; ++oh) {
       const float wh = tap_weight(axis_tap(oh, sh, Hi), ih);
       if (wh == 0.f) continue;
-      const float *row = g + ((int64_t)ot * Ho + oh) * Wo;
+      const float *row = g + ((int64_t)ot * Ho + oh) * Wo + w0;
       float racc = 0.f;
-      for (int ow = w0; ow <= w1; ++ow) racc = fmaf(tap_weight(axis_tap(ow, sw, Wi), iw), __ldg(row + ow), racc);
+      if (cached) {
+#pragma unroll
+        for (int k = 0; k < kMaxW; ++k)
+          if (k < nw) racc = fmaf(ww[k], __ldg(row + k), racc);
+      } else {
+        for (int k = 0; k < nw; ++k) racc = fmaf(tap_weight(axis_tap(w0 + k, sw, Wi), iw), __ldg(row + k), racc);
+      }
       acc = fmaf(wt * wh, racc, acc);
     }
   }

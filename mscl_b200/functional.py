@@ -453,3 +453,44 @@ def upsample_trilinear(x, size):
     if x.dim() != 5 or len(size) != 3:
         raise _cabi.MsclError("upsample_trilinear takes (N,C,T,H,W) and a (T,H,W) size")
     return _UpsampleTrilinear.apply(x, tuple(int(v) for v in size))
+
+
+# ----------------------------------------------------------------------------------------
+# K8 / K9: augmentation front-end
+# ----------------------------------------------------------------------------------------
+@torch.no_grad()
+def flow_visualize(flow, flip=None, norm=None):
+    """Colour-wheel image of a planar flow clip (N,2,T,H,W) -> (N,3,T,H,W) (ssl_aug.py:87-136), mirrored along W
+    for the samples of the uint8 mask `flip` (ssl_aug_v2.py:109-117), optionally normalised by norm = [mean3, std3]."""
+    _chk(flow, name="flow")
+    if flow.dim() != 5 or flow.shape[1] != 2:
+        raise _cabi.MsclError("flow must be (N,2,T,H,W)")
+    N, _, T, H, W = flow.shape
+    if flip is not None:
+        _chk(flip, torch.uint8, "flip")
+    if norm is not None:
+        _chk(norm, name="norm")
+    out = torch.empty(N, 3, T, H, W, device=flow.device)
+    _cabi.call("mscl_flow_visualize", flow.data_ptr(), flip.data_ptr() if flip is not None else None,
+               norm.data_ptr() if norm is not None else None, out.data_ptr(), N, T, H, W, _stream(),
+               algo_bytes=20 * N * T * H * W)
+    return out
+
+
+COLOR_PARAMS = 16
+_GRAY_CHUNKS = 16
+
+
+@torch.no_grad()
+def color_pipeline(x, params, taps, norm):
+    """Fused flip / colour jitter / grayscale / Gaussian blur / normalise of RGB clips (N,3,T,H,W); params (N,16)
+    as described in include/mscl_b200.h (K9), taps the odd-length 1-D blur kernel, norm = [mean3, std3]."""
+    _chk(x, name="clips"), _chk(params, name="params"), _chk(taps, name="taps"), _chk(norm, name="norm")
+    if x.dim() != 5 or x.shape[1] != 3 or tuple(params.shape) != (x.shape[0], COLOR_PARAMS):
+        raise _cabi.MsclError("clips must be (N,3,T,H,W) and params (N,16)")
+    N, _, T, H, W = x.shape
+    out = torch.empty_like(x)
+    scratch = torch.empty(N, _GRAY_CHUNKS, device=x.device)
+    _cabi.call("mscl_color_pipeline", x.data_ptr(), params.data_ptr(), taps.data_ptr(), taps.numel(), norm.data_ptr(),
+               scratch.data_ptr(), _GRAY_CHUNKS, out.data_ptr(), N, T, H, W, _stream(), algo_bytes=36 * N * T * H * W)
+    return out

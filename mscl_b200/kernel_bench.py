@@ -235,6 +235,56 @@ def bench_k6(cfg, shape, pk, dev, iters=20):
     return [row(cfg, "gather_rows_kernel (shuffle-BN)", str(tuple(shape)), us, 2 * nbytes, 0, pk)]
 
 
+# ------------------------------------------------------------------------------------------ K7 / K8 / K9
+def bench_k789(cfg, N, pk, dev, iters=20):
+    out = []
+    # K7: the two SEPC up-sampling steps of the r18 TPN (necks/sepc.py:126-130)
+    for shp, size in (((N, 128, 2, 14, 14), (4, 28, 28)), ((N, 128, 1, 7, 7), (2, 14, 14))):
+        nout = N * 128 * size[0] * size[1] * size[2]
+        nin = int(np.prod(shp))
+        rot = n_rot(4 * (nin + nout))
+        xs = [torch.randn(shp, device=dev) for _ in range(rot)]
+        ys = [torch.empty((N, 128) + size, device=dev) for _ in range(rot)]
+        us = time_train(lambda i: _cabi.call("mscl_upsample_trilinear_fwd", xs[i % rot].data_ptr(), ys[i % rot].data_ptr(),
+                                             N * 128, *shp[2:], *size, _st()), iters)
+        out.append(row(cfg, "upsample_trilinear_fwd", f"{shp} -> {size}", us, 4 * (nin + nout), 0, pk))
+        us = time_train(lambda i: _cabi.call("mscl_upsample_trilinear_bwd", ys[i % rot].data_ptr(), xs[i % rot].data_ptr(),
+                                             N * 128, *shp[2:], *size, _st()), iters)
+        out.append(row(cfg, "upsample_trilinear_bwd", f"{size} -> {shp}", us, 4 * (nin + nout), 0, pk))
+        del xs, ys
+    # K8: (N,2,16,112,112) flow -> colour image, K9: (N,3,8,112,112) RGB clips
+    T2, HW = 16, 112 * 112
+    rot = n_rot(20 * N * T2 * HW)
+    flows = [torch.randn(N, 2, T2, 112, 112, device=dev) for _ in range(rot)]
+    imgs = [torch.empty(N, 3, T2, 112, 112, device=dev) for _ in range(rot)]
+    flip = (torch.arange(N, device=dev) % 2).to(torch.uint8)
+    us = time_train(lambda i: _cabi.call("mscl_flow_visualize", flows[i % rot].data_ptr(), flip.data_ptr(), None,
+                                         imgs[i % rot].data_ptr(), N, T2, 112, 112, _st()), iters)
+    out.append(row(cfg, "flow_visualize_kernel", f"({N},2,{T2},112,112)", us, 20 * N * T2 * HW, 0, pk,
+                   note="atan2 + float64 interpolation per pixel: ALU-heavy for an element-wise pass"))
+    del flows, imgs
+    from .common.ssl_aug import SyncMoCoAugmentV5
+    aug = SyncMoCoAugmentV5(crop_size=112, sync_level=("batch", "batch"), t=(8, 8), flow_suffix="flow_imgs")
+    T = 8
+    rot = n_rot(24 * N * T * HW)
+    xs = [torch.rand(N, 3, T, 112, 112, device=dev) for _ in range(rot)]
+    ys = [torch.empty(N, 3, T, 112, 112, device=dev) for _ in range(rot)]
+    torch.manual_seed(0)
+    prm = aug._color_params(N, dev)
+    norm = torch.cat([aug.mean.view(-1), aug.std.view(-1)]).to(dev)
+    scratch = torch.empty(N, fx._GRAY_CHUNKS, device=dev)
+    for name, blur in (("drawn decisions (p_blur=.5)", None), ("all clips blurred", True), ("no clip blurred", False)):
+        if blur is not None:
+            prm["blur"] = torch.full((N,), blur, device=dev)
+        params = aug._pack_params(prm, flip.bool(), False)
+        taps = prm["taps"].contiguous()
+        us = time_train(lambda i: _cabi.call("mscl_color_pipeline", xs[i % rot].data_ptr(), params.data_ptr(), taps.data_ptr(),
+                                             taps.numel(), norm.data_ptr(), scratch.data_ptr(), fx._GRAY_CHUNKS,
+                                             ys[i % rot].data_ptr(), N, T, 112, 112, _st()), iters)
+        out.append(row(cfg, "clip_gray_sum + color_pipeline", f"({N},3,{T},112,112) {name}", us, 36 * N * T * HW, 0, pk))
+    return out
+
+
 def run(configs=("cfg2", "cfg3", "cfg4", "cfg5"), device=0, verbose=True):
     dev = torch.device("cuda", device)
     torch.cuda.set_device(dev)
@@ -258,6 +308,7 @@ def run(configs=("cfg2", "cfg3", "cfg4", "cfg5"), device=0, verbose=True):
         add(bench_k3("cfg2", 32, 8, pk, dev))
         add(bench_k4("cfg2", "r18 RGB key side", r3d18_key_sizes(), pk, dev))
         add(bench_k5("cfg2", 32, 65536, pk, dev))
+        add(bench_k789("cfg2", 32, pk, dev))
     if "cfg3" in configs:      # queue sweep, N = 64 per GPU
         for K in (16384, 65536, 262144, 1048576):
             add(bench_k1("cfg3", 64, K, pk, dev, iters=20))

@@ -177,6 +177,23 @@ def golden_shuffle(ref):
     np.savez_compressed(os.path.join(OUT, "shuffle.npz"), **res)
 
 
+def golden_flowvis(ref):
+    """The reference's own FlowVisualizer / flow_uv_to_colors (common/ssl_aug.py:87-136) with the reference's colour
+    wheel (tools/RAFT/core/utils/flow_viz.py:20-67), executed from the reference tree; kornia is only needed by the
+    other definitions of that file, so just these three are loaded."""
+    import math
+    viz = ref_shim._load("mscl_ref_flow_viz", "tools/RAFT/core/utils/flow_viz.py")
+    defs = ref_shim.load_defs("mmaction/models/common/ssl_aug.py", ["flow_uv_to_colors", "FlowVisualizer"],
+                              dict(torch=torch, math=math, make_colorwheel=viz.make_colorwheel))
+    g = torch.Generator().manual_seed(7)
+    flows = torch.randn(2, 2, 3, 12, 16, generator=g) * torch.tensor([0.4, 1.5]).view(2, 1, 1, 1, 1)
+    flows[0, :, 0, 0, :4] = torch.tensor([[0.0, 1.0, -1.0, 0.0], [0.0, 0.0, 0.0, -1.0]])   # axis-aligned / zero vectors
+    out = defs.FlowVisualizer()(flows.clone())
+    np.savez_compressed(os.path.join(OUT, "flowvis.npz"), flows=flows.numpy(), out=out.numpy(),
+                        wheel=viz.make_colorwheel())
+    print("flowvis:", tuple(out.shape), out.dtype, float(out.mean()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load_reference()
@@ -187,6 +204,7 @@ def main():
     golden_ema(ref)
     golden_fra(ref)
     golden_shuffle(ref)
+    golden_flowvis(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -150,6 +150,22 @@ def _load(modname, relpath, strip_lines=(), inject=None):
     return mod
 
 
+def load_defs(relpath, names, extra_globals=None):
+    """Execute ONLY the named top-level functions / classes of a reference file (read from REF_ROOT at run time,
+    never copied): for files whose module-level imports cannot be satisfied here (kornia in common/ssl_aug.py)."""
+    import ast
+    path = os.path.join(REF_ROOT, relpath)
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    keep = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
+    missing = set(names) - {n.name for n in keep}
+    if missing:
+        raise RuntimeError(f"{relpath}: no top-level definition of {sorted(missing)}")
+    ns = dict(extra_globals or {})
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return types.SimpleNamespace(**{n: ns[n] for n in names})
+
+
 _LOADED = None
 
 

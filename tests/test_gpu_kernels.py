@@ -332,3 +332,71 @@ def test_upsample_trilinear_matches_torch(fx, shape, size):
     xc = x.detach().cpu().requires_grad_(True)       # and against the host op the oracle uses
     yc = F.interpolate(xc, size=size, mode="trilinear")
     np.testing.assert_allclose(y.detach().cpu().numpy(), yc.detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ K8 / K9 augmentation front-end
+def _flowvis_close(got, ref):
+    """Every op of the visualiser is exactly rounded except atan2 (device vs host libm differ in the last ulp), which can
+    move a pixel across a floor(255 * col) boundary: values are k/255, so a mismatch is exactly one level, and rare."""
+    d = np.abs(got - ref)
+    assert d.max() <= 1.0 / 255 + 1e-7, d.max()
+    assert (d > 0).mean() <= 5e-3, (d > 0).mean()
+
+
+def test_flow_visualize_golden_and_oracle(fx, golden_dir):
+    from oracle import mscl_oracle as O
+    g = _load(golden_dir, "flowvis.npz")
+    got = fx.flow_visualize(torch.from_numpy(g["flows"]).cuda())
+    _flowvis_close(got.cpu().numpy(), g["out"])
+    gen = torch.Generator().manual_seed(3)
+    flows = torch.randn(4, 2, 16, 112, 112, generator=gen) * torch.tensor([0.2, 0.6, 1.0, 3.0]).view(4, 1, 1, 1, 1)
+    ref = O.flow_visualize(flows)
+    flip = torch.tensor([1, 0, 1, 0], dtype=torch.uint8)
+    got = fx.flow_visualize(flows.cuda(), flip.cuda())
+    want = torch.where(flip.bool().view(-1, 1, 1, 1, 1), torch.flip(ref, [-1]), ref)    # ssl_aug_v2.py:109-117
+    _flowvis_close(got.cpu().numpy(), want.numpy())
+    norm = torch.tensor([0.485, 0.456, 0.406, 0.229, 0.224, 0.225])
+    got_n = fx.flow_visualize(flows.cuda(), None, norm.cuda())
+    want_n = (ref - norm[:3].view(1, 3, 1, 1, 1)) / norm[3:].view(1, 3, 1, 1, 1)
+    d = np.abs(got_n.cpu().numpy() - want_n.numpy())
+    assert d.max() <= (1.0 / 255) / 0.224 + 1e-5 and (d > 1e-6).mean() <= 5e-3
+
+
+@pytest.mark.parametrize("shape", [(6, 3, 4, 32, 48), (3, 3, 8, 112, 112)])
+def test_color_pipeline_matches_torch_ops(fx, shape):
+    """K9 against the same pipeline written as PyTorch ops (SyncMoCoAugmentV5._color_torch, the host path): every
+    combination of jitter / grayscale / blur / flip decisions, given parameters."""
+    from mscl_b200.common.ssl_aug import SyncMoCoAugmentV5
+    aug = SyncMoCoAugmentV5(crop_size=112, sync_level=("batch", "batch"), t=(8, 8), flow_suffix="flow_imgs")
+    n = shape[0]
+    gen = torch.Generator().manual_seed(n)
+    x = torch.rand(shape, generator=gen)
+    torch.manual_seed(5)
+    prm = aug._color_params(n, torch.device("cpu"))
+    combos = [(1, 1, 1), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (0, 0, 0)]
+    prm["jit"] = torch.tensor([combos[i % 6][0] for i in range(n)], dtype=torch.bool)
+    prm["gray"] = torch.tensor([combos[i % 6][1] for i in range(n)], dtype=torch.bool)
+    prm["blur"] = torch.tensor([combos[i % 6][2] for i in range(n)], dtype=torch.bool)
+    flip = torch.tensor([i % 2 == 0 for i in range(n)])
+    want = aug._normalize(aug._color_torch(aug.flip(x, flip), prm))
+    dev = torch.device("cuda")
+    prm_d = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in prm.items()}
+    norm = torch.cat([aug.mean.view(-1), aug.std.view(-1)]).to(dev)
+    got = fx.color_pipeline(x.to(dev), aug._pack_params(prm_d, flip.to(dev), False), prm_d["taps"].contiguous(), norm)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-5, atol=2e-5)
+    weak = fx.color_pipeline(x.to(dev), aug._pack_params(prm_d, flip.to(dev), True), prm_d["taps"].contiguous(), norm)
+    np.testing.assert_allclose(weak.cpu().numpy(), aug._normalize(aug.flip(x, flip)).numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_augmentation_module_on_device(fx):
+    """SyncMoCoAugmentV5.__call__ on CUDA tensors: shapes, value ranges, flow images are k/255 levels."""
+    from mscl_b200.common.ssl_aug import SyncMoCoAugmentV5
+    aug = SyncMoCoAugmentV5(crop_size=112, sync_level=("batch", "batch"), t=(8, 8), flow_suffix="flow_imgs")
+    torch.manual_seed(0)
+    q, k = torch.rand(4, 3, 8, 112, 112).cuda(), torch.rand(4, 3, 8, 112, 112).cuda()
+    aux = dict(flow_imgs_q=torch.randn(4, 2, 16, 112, 112).cuda(), flow_imgs_k=torch.randn(4, 2, 16, 112, 112).cuda())
+    a, b, c = aug(q, k, aux)
+    assert a.shape == q.shape and b.shape == k.shape and c["flow_imgs_q"].shape == (4, 3, 16, 112, 112)
+    lv = c["flow_imgs_k"] * 255
+    assert torch.all((lv - lv.round()).abs() < 1e-4) and lv.min() >= 0 and lv.max() <= 255
+    assert torch.isfinite(a).all() and a.min() >= (0 - 0.485) / 0.229 - 1e-4 and a.max() <= (1 - 0.406) / 0.225 + 1e-4

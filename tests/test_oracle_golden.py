@@ -136,3 +136,16 @@ def test_topk_known_answers():
     assert O.top_k_accuracy(scores, [1, 0, 3, 2], (1, 3, 5)) == [0, 0, 1.0]
     assert O.top_k_accuracy(scores, [1, 3, 4, 0], (1, 3, 5)) == [0, 0.5, 1.0]
     assert O.top_k_accuracy(scores, [2, 3, 0, 2], (1, 3, 5)) == [0.25, 0.75, 1.0]
+
+
+def test_flow_visualizer_matches_reference(golden_dir):
+    """K8 oracle vs the reference's own FlowVisualizer (common/ssl_aug.py:87-136) and colour wheel
+    (tools/RAFT/core/utils/flow_viz.py:20-67), run from the reference tree by oracle/make_golden.py."""
+    from oracle import mscl_oracle as O
+    g = _load(golden_dir, "flowvis.npz")
+    np.testing.assert_array_equal(O.colorwheel(), g["wheel"])
+    out = O.flow_visualize(torch.from_numpy(g["flows"]))
+    np.testing.assert_array_equal(out.numpy(), g["out"])
+    # the host path of the product's registry class is the same op sequence
+    from mscl_b200.common.ssl_aug import FlowVisualizer
+    np.testing.assert_array_equal(FlowVisualizer()._torch(torch.from_numpy(g["flows"])).numpy(), g["out"])
