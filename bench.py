@@ -58,7 +58,8 @@ def parse_args():
     ap.add_argument("--no-kernel-rooflines", action="store_true",
                     help="skip the stand-alone per-kernel roofline probe (mscl_b200/kernel_bench.py) appended at N=1")
     ap.add_argument("--no-shard", action="store_true", help="N>1: keep the queue replicated instead of K/N shards")
-    ap.add_argument("--channels-last", action="store_true", help="encoders/necks in torch.channels_last_3d (experiment)")
+    ap.add_argument("--nchw", action="store_true",
+                    help="keep the encoders' activations NCDHW (PyTorch default) instead of torch.channels_last_3d")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the resident timed region (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -279,7 +280,10 @@ def run_b200(args, rank, local_rank, world):
     cfg = mscl_r18_model(K=args.K)
     cfg["train_cfg"] = dict(shard_queue=shard)
     model = mscl_b200.build_model(cfg).to(dev)
-    if args.channels_last:
+    if not args.nchw:
+        # NDHWC activations: cuDNN's tf32 convolutions and batch-norm kernels are native in this layout (no
+        # nchw<->nhwc transposes, NHWC batch-norm kernels); 62 ms -> 32 ms of kernel time per step on one B200
+        # (profiles/r01_step_profile_*.txt).  An execution detail: the model dict and the state_dict are unchanged.
         model = model.to(memory_format=torch.channels_last_3d)
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
@@ -382,7 +386,7 @@ def run_b200(args, rank, local_rank, world):
     line = {"metric": METRIC, "value": clips / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (tf32 tensor-core operands, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "clips_per_gpu": N, "global_batch": clips, "K": args.K,
+            "config": {"workload": WORKLOAD, "memory_format": "NCDHW" if args.nchw else "channels_last_3d", "clips_per_gpu": N, "global_batch": clips, "K": args.K,
                        "queue": f"sharded K/{world}" if shard else "replicated", "parallelism": f"dp{world}",
                        "l2": "each step streams >1 GB of activations and alternates input batches: inputs never L2-resident"},
             "e2e": {"value": clips / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

@@ -8,7 +8,7 @@ from mscl_b200 import functional as fx
 from mscl_b200.configs import mscl_r18_model
 from bench import make_host_batch
 
-cl = "--channels-last" in sys.argv
+cl = "--nchw" not in sys.argv
 dev = torch.device("cuda", 0)
 torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
