@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--no-kernel-rooflines", action="store_true",
                     help="skip the stand-alone per-kernel roofline probe (mscl_b200/kernel_bench.py) appended at N=1")
     ap.add_argument("--no-shard", action="store_true", help="N>1: keep the queue replicated instead of K/N shards")
+    ap.add_argument("--no-graphs", action="store_true",
+                    help="run the encoder paths eagerly instead of replaying CUDA graphs (mscl_b200/graphed.py)")
     ap.add_argument("--nchw", action="store_true",
                     help="keep the encoders' activations NCDHW (PyTorch default) instead of torch.channels_last_3d")
     ap.add_argument("--profile-range", action="store_true",
@@ -288,6 +290,29 @@ def run_b200(args, rank, local_rank, world):
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.SGD(params, lr=0.02, momentum=0.9, weight_decay=1e-4)      # mscl_r18 config :114-118
+    table = fx.fra_table(device=dev)
+    host = [make_host_batch(N, 17 + 2 * rank + i, pin=True) for i in range(2)]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d_bytes = batch_bytes(host[0])
+    graph_state = None
+    if not args.no_graphs:
+        # the encoders' ~4000 launches per step replayed from CUDA graphs (one per call site); EMA, shuffle, the fused
+        # objective and the optimizer stay eager
+        from mscl_b200 import graphed
+        b0 = resident[0]
+        with torch.no_grad():
+            aux0 = dict(flow_imgs_q=fx.fra(b0["flow_q"], b0["cid_q"], table, "planar"),
+                        flow_imgs_k=fx.fra(b0["flow_k"], b0["cid_k"], table, "planar"))
+            im_q0, _, aux0 = model.aug_gpu(b0["imgs_q"], b0["imgs_k"], aux0)
+            flow0 = aux0["flow_imgs_q"][:, :, :8].contiguous()
+
+        def eager_fwd_bwd():
+            aux = dict(flow_imgs_q=fx.fra(b0["flow_q"], b0["cid_q"], table, "planar"),
+                       flow_imgs_k=fx.fra(b0["flow_k"], b0["cid_k"], table, "planar"))
+            loss, _ = model._parse_losses(model(b0["imgs_q"], b0["imgs_k"], aux, return_loss=True))
+            loss.backward()
+
+        graph_state = graphed.enable(model, im_q0, flow0, eager_fwd_bwd)
     runner = model
     if world > 1:
         # apis/train.py:84-88 (broadcast_buffers=False, find_unused_parameters=True); the set of unused TPN level convs
@@ -296,10 +321,6 @@ def run_b200(args, rank, local_rank, world):
         runner = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
                                                            static_graph=True,
                                                            gradient_as_bucket_view=True)
-    table = fx.fra_table(device=dev)
-    host = [make_host_batch(N, 17 + 2 * rank + i, pin=True) for i in range(2)]
-    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
-    h2d_bytes = batch_bytes(host[0])
 
     def train_step(b):
         # K3: base + FRA flow frames, (N,2,8,H,W) -> (N,2,16,H,W)
@@ -310,6 +331,8 @@ def run_b200(args, rank, local_rank, world):
         loss, log_vars = model._parse_losses(losses)        # one all_reduce + the step's device->host read
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        if graph_state is not None:
+            graph_state.after_backward()                      # grads PyTorch eager would have left as None
         torch.nn.utils.clip_grad_norm_(params, 40.0)          # config :119
         opt.step()
         return log_vars
@@ -386,7 +409,8 @@ def run_b200(args, rank, local_rank, world):
     line = {"metric": METRIC, "value": clips / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (tf32 tensor-core operands, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "memory_format": "NCDHW" if args.nchw else "channels_last_3d", "clips_per_gpu": N, "global_batch": clips, "K": args.K,
+            "config": {"workload": WORKLOAD, "memory_format": "NCDHW" if args.nchw else "channels_last_3d",
+                       "encoders": "eager" if args.no_graphs else "CUDA graphs per call site (mscl_b200/graphed.py)", "clips_per_gpu": N, "global_batch": clips, "K": args.K,
                        "queue": f"sharded K/{world}" if shard else "replicated", "parallelism": f"dp{world}",
                        "l2": "each step streams >1 GB of activations and alternates input batches: inputs never L2-resident"},
             "e2e": {"value": clips / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

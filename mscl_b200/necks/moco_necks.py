@@ -103,7 +103,7 @@ class BaseMoCo(nn.Module):
         super().__init__()
         self.tofc = nn.Sequential(nn.AdaptiveAvgPool3d((1, 1, 1)), nn.Flatten(1))
 
-    def forward(self, x):
+    def forward(self, x, target=None, pyramid=True):
         return (self.tofc(x[-1]), x), dict()
 
     def init_weights(self):
@@ -129,10 +129,12 @@ class TPNMoCo(nn.Module):
                 if m.bias is not None:
                     nn.init.constant_(m.bias, 0)
 
-    def forward(self, x, target=None):
+    def forward(self, x, target=None, pyramid=True):
+        """pyramid=False: the caller consumes only the embedding (the key side of MSCLWithAug never reads k_mlvl,
+        SURVEY.md section 2.4); with emb_from_bkb the embedding does not depend on the pyramid, so it is not built."""
         if self.emb_from_bkb:
             emb = self.tofc(x[-1])
-            x = self.tpn(x)
+            x = self.tpn(x) if pyramid else list(x)
         else:
             x = self.tpn(x)
             emb = self.tofc(x[-1])

@@ -229,17 +229,34 @@ class MoCoV2(BaseMoCoRecognizer):
         return shf.exchange(x.contiguous(), plan, fx.gather_rows)
 
     # ------------------------------------------------------------------ encoders
-    def extract_feat(self, im_q, im_k, unshuffle_mlvl=True):
-        """Returns q, q_mlvl, k, k_mlvl, sup_loss (moco.py:517-547)."""
+    def q_path(self, im_q):
+        """Query side: encoder -> neck -> projection -> L2 norm (moco.py:520-529).  Returns (q, q_mlvl, sup_loss)."""
         q_mlvl = self.encoder_q(im_q)
         (q_emb, q_mlvl), sup_loss = self.neck_q(q_mlvl)
-        q = F.normalize(self.mlp_q(q_emb), dim=1)
+        return F.normalize(self.mlp_q(q_emb), dim=1), q_mlvl, sup_loss
+
+    def k_path(self, im_k, pyramid=True):
+        """Key side (moco.py:538-541), no gradient.  Returns (k, k_mlvl)."""
+        k_mlvl = self.encoder_k(im_k)
+        (k_emb, k_mlvl), _ = self.neck_k(k_mlvl, pyramid=pyramid)
+        return F.normalize(self.mlp_k(k_emb), dim=1), k_mlvl
+
+    def extract_feat(self, im_q, im_k, unshuffle_mlvl=True, site=0):
+        """Returns q, q_mlvl, k, k_mlvl, sup_loss (moco.py:517-547).  `site` names the call site within a step (the
+        flow recognizer is called twice): CUDA-graphed encoder paths (mscl_b200/graphed.py) keep one set of static
+        activations per site."""
+        graphed = getattr(self, "_graphed_paths", None)
+        if graphed is not None and self.training and torch.is_grad_enabled():
+            q, q_mlvl, sup_loss = graphed.q(site, im_q)
+        else:
+            q, q_mlvl, sup_loss = self.q_path(im_q)
         with torch.no_grad():
             self._momentum_update_key_encoder()
             im_k, idx_unshuffle = self._batch_shuffle_ddp(im_k)
-            k_mlvl = self.encoder_k(im_k)
-            (k_emb, k_mlvl), _ = self.neck_k(k_mlvl)
-            k = F.normalize(self.mlp_k(k_emb), dim=1)
+            if graphed is not None and self.training and not unshuffle_mlvl:
+                k, k_mlvl = graphed.k(site, im_k)
+            else:
+                k, k_mlvl = self.k_path(im_k, pyramid=unshuffle_mlvl)
             k = self._batch_unshuffle_ddp(k, idx_unshuffle)
             if unshuffle_mlvl:     # never consumed by MSCLWithAug (SURVEY.md section 2.4): skipped there
                 k_mlvl = [self._batch_unshuffle_ddp(lvl, idx_unshuffle) for lvl in k_mlvl]

@@ -153,7 +153,7 @@ class MSCLWithAug(BaseMoCoRecognizer):
         rec.note_branch(n, True)
         q_f, qf_mlvl, k_f, _, _ = recf.extract_feat(flow_q, flow_k, unshuffle_mlvl=False)
         recf.note_branch(n, True)
-        q_af, qaf_mlvl, k_af, _, _ = recf.extract_feat(aug_flow_q, aug_flow_k, unshuffle_mlvl=False)
+        q_af, qaf_mlvl, k_af, _, _ = recf.extract_feat(aug_flow_q, aug_flow_k, unshuffle_mlvl=False, site=1)
         recf.note_branch(n, self.update_aug_flow)
         return self.objective(dict(q=q, k=k, q_f=q_f, k_f=k_f, q_af=q_af, k_af=k_af, q_mlvl=q_mlvl,
                                    q_flow_mlvl=qf_mlvl, q_aug_flow_mlvl=qaf_mlvl))

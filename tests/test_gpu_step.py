@@ -204,6 +204,63 @@ def test_full_train_step_vs_oracle():
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+def test_graphed_encoder_paths_match_eager():
+    """mscl_b200/graphed.py: CUDA-graphed query/key encoder paths (one graph per call site, the flow recognizer is called
+    twice per step) against the eager model with identical weights: log vars, gradients (incl. which parameters get
+    None), key features / queue state, over three steps."""
+    import mscl_b200
+    from mscl_b200 import graphed
+    from mscl_b200.configs import mscl_r18_model
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        cfg = mscl_r18_model(K=256, aug="IdentityAug")
+        cfg["recognizer"]["max_iters"] = cfg["recognizer_flow"]["max_iters"] = 1000
+        torch.manual_seed(0)
+        eager = mscl_b200.build_model(cfg)
+        torch.manual_seed(0)             # a second build from the same seed (a deepcopy would keep torchvision's
+        fast = mscl_b200.build_model(cfg)  # patched forward bound to the original encoder)
+        eager, fast = eager.train().cuda(), fast.train().cuda()
+        N = 4
+        imgs, flows = _synthetic_batch(N, S=64, seed=3)
+
+        def batch(seed):
+            im, fl = _synthetic_batch(N, S=64, seed=seed)
+            return dict(imgs=[x.cuda() for x in im], flow_imgs=[x.cuda() for x in fl])
+
+        def warm():     # the step graphed.enable() runs eagerly to find the parameters no loss reaches
+            fast.train_step(batch(3), None)["loss"].backward()
+
+        torch.manual_seed(50)
+        state = graphed.enable(fast, imgs[0].cuda(), flows[0][:, :, :8].contiguous().cuda(), warm)
+        assert len(state.unused) > 0            # some pyramid convolutions feed no loss
+        torch.manual_seed(50)
+        eager.train_step(batch(3), None)["loss"].backward()       # same step on the eager twin (queue, iters advance)
+        for step in range(3):
+            outs = []
+            for m in (eager, fast):
+                torch.manual_seed(200 + step)
+                m.zero_grad(set_to_none=True)
+                out = m.train_step(batch(20 + step), None)
+                out["loss"].backward()
+                outs.append(out)
+            state.after_backward()
+            for k, v in outs[0]["log_vars"].items():
+                assert abs(v - outs[1]["log_vars"][k]) <= 2e-4 * max(1.0, abs(v)), (step, k, v, outs[1]["log_vars"][k])
+            for (n, a), b in zip(eager.named_parameters(), fast.parameters()):
+                assert (a.grad is None) == (b.grad is None), n
+                if a.grad is not None:
+                    assert _rel(b.grad, a.grad) < 2e-3, (step, n, _rel(b.grad, a.grad))
+            for ra, rb in ((eager.recognizer, fast.recognizer), (eager.recognizer_flow, fast.recognizer_flow)):
+                sa, sb = ra.state_dict(), rb.state_dict()
+                assert int(sa["queue_ptr"]) == int(sb["queue_ptr"]) and ra.iters == rb.iters
+                np.testing.assert_array_equal(sa["count"].cpu().numpy(), sb["count"].cpu().numpy())
+                assert _rel(sb["queue"], sa["queue"]) < 1e-4
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 def test_state_dict_roundtrip_on_device():
     """Checkpoint compatibility: reference-layout buffers out, same buffers in."""
     model = head_level_model(512, 4)
