@@ -239,6 +239,7 @@ def run_reference(args, rank):
 # ----------------------------------------------------------------------------------------------
 KERNEL_ENTRIES = ["mscl_infonce_partial", "mscl_ema_multi", "mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_fra_fused",
                   "mscl_fra_maxrad", "mscl_fra_apply", "mscl_enqueue", "mscl_lmcl", "mscl_infonce_prep", "mscl_infonce_finalize",
+                  "mscl_infonce_reduce_scatter", "mscl_flow_visualize", "mscl_color_pipeline",
                   "mscl_gather_rows"]
 
 

@@ -195,7 +195,18 @@ int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
                       int64_t K_local, float inv_T, float key_norm_bound,
                       float *d_qpack, float *d_dscale,
                       const int32_t *d_dup_slot, int32_t dup_age,
+                      float *const *d_peer_qpack, int32_t n_peers, int32_t row_offset,
                       mscl_stream_t stream);
+/* Sharded queue, exchange over NVLink peer memory (the reference replicates the queue and has no counterpart;
+ * these replace an all_gather of the packed queries and a reduce-scatter of the partial results):
+ *  - prep: with n_peers > 0, d_peer_qpack[p] (device table of n_peers pointers into every rank's gathered query
+ *    table, this rank's own included) receives rows row_offset .. row_offset+M-1 by peer stores;
+ *  - mscl_infonce_reduce_scatter: sums this rank's n_part CTA slabs of row i (i < M_all) and stores the 132 floats
+ *    into d_peer_acc[i / M_local] + (my_rank * M_local + i % M_local) * 132, i.e. slot my_rank of the owner's
+ *    accumulator [G, M_local, 132], which mscl_infonce_finalize then reads as G slabs.
+ * The caller puts a device-side barrier across the ranks after each of the two (torch symmetric memory). */
+int mscl_infonce_reduce_scatter(const float *d_part, int32_t n_part, int32_t M_all, int32_t M_local,
+                                float *const *d_peer_acc, int32_t my_rank, mscl_stream_t stream);
 /* Number of CTA slabs along the keys for M rows over K_local keys on num_sms SMs (> 0), or a
  * negative MSCL_E* code. */
 int mscl_infonce_num_partials(int32_t M, int64_t K_local, int32_t num_sms);

@@ -30,7 +30,9 @@ PROTOTYPES = {
     "mscl_hw_mean_fwd": [c_ptr, c_ptr, c_i64, c_int, c_ptr],
     "mscl_hw_mean_bwd": [c_ptr, c_ptr, c_i64, c_int, c_ptr],
     "mscl_lmcl": [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
-    "mscl_infonce_prep": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_int, c_ptr],
+    "mscl_infonce_prep": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int,
+                          c_ptr],
+    "mscl_infonce_reduce_scatter": [c_ptr, c_int, c_int, c_int, c_ptr, c_int, c_ptr],
     "mscl_infonce_num_partials": [c_int, c_i64, c_int],
     "mscl_infonce_partial": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_int, c_int, c_ptr],
     "mscl_infonce_partial_simt": [c_ptr, c_int, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr],

@@ -16,7 +16,8 @@ infonce_prep_kernel(const float *__restrict__ q, const float *__restrict__ kpos,
                     const int32_t *__restrict__ birth, const int64_t *__restrict__ qstate,
                     int64_t K_local, float inv_T, float key_norm_bound,
                     float *__restrict__ qpack, float *__restrict__ dscale,
-                    const int32_t *__restrict__ dup_slot, int dup_age) {
+                    const int32_t *__restrict__ dup_slot, int dup_age,
+                    float *const *__restrict__ peer_qpack, int n_peers, int row_offset) {
   pdl_trigger();   // the tcgen05 pass may launch now and prefetch queue tiles; it waits for this grid before reading qpack / dscale
   pdl_wait();      // this grid itself may have been launched early behind a finalize (back-to-back objectives)
   const int lane = threadIdx.x & 31;
@@ -32,13 +33,18 @@ infonce_prep_kernel(const float *__restrict__ q, const float *__restrict__ kpos,
     float4 r = make_float4(to_tf32_rn(a.x), to_tf32_rn(a.y), to_tf32_rn(a.z), to_tf32_rn(a.w));
     float *dst = qpack + (int64_t)row * kLd;
     reinterpret_cast<float4 *>(dst)[lane] = r;
-    if (lane == 0) {
-      // [130] = global queue slot holding a copy of this row's positive key (int bits, -1 = none),
-      // [131] = that copy's decay factor 0.99999^age
-      const int dup = dup_slot != nullptr ? dup_slot[row] : -1;
-      reinterpret_cast<float4 *>(dst)[32] =
-          make_float4(d * sc, sqrtf(ss) * key_norm_bound * sc, __int_as_float(dup),
-                      exp2f((float)dup_age * kLog2Decay));
+    // [130] = global queue slot holding a copy of this row's positive key (int bits, -1 = none),
+    // [131] = that copy's decay factor 0.99999^age
+    const int dup = dup_slot != nullptr ? dup_slot[row] : -1;
+    const float4 tail = make_float4(d * sc, sqrtf(ss) * key_norm_bound * sc, __int_as_float(dup),
+                                    exp2f((float)dup_age * kLog2Decay));
+    if (lane == 0) reinterpret_cast<float4 *>(dst)[32] = tail;
+    // sharded queue: the row goes straight into every rank's gathered table over NVLink (peer stores replace
+    // the all_gather; a device barrier follows before any rank's pass reads its table)
+    for (int p = 0; p < n_peers; ++p) {
+      float *pd = peer_qpack[p] + (int64_t)(row_offset + row) * kLd;
+      reinterpret_cast<float4 *>(pd)[lane] = r;
+      if (lane == 0) reinterpret_cast<float4 *>(pd)[32] = tail;
     }
   }
   const int64_t n_enq = qstate[1];
@@ -132,6 +138,33 @@ infonce_reduce_kernel(const float *__restrict__ part, int n_part, int M, float *
   }
   for (; p < n_part; ++p) a0 += src[p * slab];
   acc[(int64_t)i * kLd + c] = (a0 + a1) + (a2 + a3);
+}
+
+// ---- 2x. fused reduce + scatter over NVLink (sharded path) ----------------------------------
+// Row i of the gathered query table belongs to rank i / M_local.  This rank's partial result for it (the sum of its
+// CTA slabs, fixed order) is stored straight into the OWNER's accumulator, slot `my_rank`:
+//   peer_acc[owner][my_rank][i % M_local][0:132]
+// so the reduce-scatter is peer stores from the kernel that does the reduction; the owner's finalize then sums
+// the G slots in rank order (bit-reproducible, unlike a ring reduce-scatter whose order depends on the rank).
+__global__ void __launch_bounds__(160)
+infonce_reduce_scatter_kernel(const float *__restrict__ part, int n_part, int M_all, int M_local,
+                              float *const *__restrict__ peer_acc, int my_rank) {
+  const int i = blockIdx.x, c = threadIdx.x;
+  if (c >= kLd) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const int64_t slab = (int64_t)M_all * kLd;
+  const float *src = part + (int64_t)i * kLd + c;
+  int p = 0;
+  for (; p + 4 <= n_part; p += 4) {
+    a0 += src[(p + 0) * slab];
+    a1 += src[(p + 1) * slab];
+    a2 += src[(p + 2) * slab];
+    a3 += src[(p + 3) * slab];
+  }
+  for (; p < n_part; ++p) a0 += src[p * slab];
+  const int owner = i / M_local, r = i - owner * M_local;
+  float *dst = peer_acc[owner] + ((int64_t)my_rank * M_local + r) * kLd + c;
+  *dst = (a0 + a1) + (a2 + a3);
 }
 
 // ---- 3. finalize -----------------------------------------------------------
@@ -249,10 +282,12 @@ extern "C" {
 int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
                       const int32_t *d_birth, const int64_t *d_qstate, int64_t K_local,
                       float inv_T, float key_norm_bound, float *d_qpack, float *d_dscale,
-                      const int32_t *d_dup_slot, int32_t dup_age, mscl_stream_t stream) {
+                      const int32_t *d_dup_slot, int32_t dup_age, float *const *d_peer_qpack,
+                      int32_t n_peers, int32_t row_offset, mscl_stream_t stream) {
   MSCL_CHECK_ARG(d_q && d_kpos && d_birth && d_qstate && d_qpack && d_dscale, "null pointer");
   MSCL_CHECK_ARG(M > 0 && K_local > 0, "bad M=%d K_local=%lld", M, (long long)K_local);
   MSCL_CHECK_ARG(inv_T > 0.f && key_norm_bound > 0.f, "bad inv_T / key_norm_bound");
+  MSCL_CHECK_ARG((n_peers == 0) || (d_peer_qpack != nullptr && n_peers > 0 && row_offset >= 0), "bad peer table");
   MSCL_CHECK_ARG((((uintptr_t)d_q | (uintptr_t)d_kpos | (uintptr_t)d_qpack) & 15) == 0,
                  "q/kpos/qpack must be 16-byte aligned");
   int64_t want = (K_local + 255) / 256;
@@ -260,7 +295,7 @@ int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
   if (want > 1184) want = 1184;
   MSCL_CUDA(mscl::launch_pdl(mscl::infonce_prep_kernel, dim3((unsigned)want), dim3(256), 0, mscl::as_stream(stream), d_q,
                              d_kpos, M, d_birth, d_qstate, K_local, inv_T, key_norm_bound, d_qpack, d_dscale, d_dup_slot,
-                             dup_age));
+                             dup_age, d_peer_qpack, n_peers, row_offset));
   return MSCL_OK;
 }
 
@@ -284,6 +319,17 @@ int mscl_infonce_reduce(const float *d_part, int32_t n_part, int32_t M, float *d
   MSCL_CHECK_ARG(d_part && d_acc, "null pointer");
   MSCL_CHECK_ARG(M > 0 && n_part > 0, "bad M=%d n_part=%d", M, n_part);
   mscl::infonce_reduce_kernel<<<M, 160, 0, mscl::as_stream(stream)>>>(d_part, n_part, M, d_acc);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+int mscl_infonce_reduce_scatter(const float *d_part, int32_t n_part, int32_t M_all, int32_t M_local,
+                                float *const *d_peer_acc, int32_t my_rank, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_part && d_peer_acc, "null pointer");
+  MSCL_CHECK_ARG(M_all > 0 && n_part > 0 && M_local > 0 && M_all % M_local == 0 && my_rank >= 0 && my_rank < M_all / M_local,
+                 "bad M_all=%d M_local=%d n_part=%d rank=%d", M_all, M_local, n_part, my_rank);
+  mscl::infonce_reduce_scatter_kernel<<<M_all, 160, 0, mscl::as_stream(stream)>>>(d_part, n_part, M_all, M_local, d_peer_acc,
+                                                                                  my_rank);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }

@@ -140,6 +140,44 @@ class NegativeQueue:
 # ----------------------------------------------------------------------------------------
 # K1: fused InfoNCE
 # ----------------------------------------------------------------------------------------
+class PeerWorkspace:
+    """Symmetric (same offset on every rank) device buffers mapped into every peer over NVLink, for the sharded
+    queue's exchange: each rank's kernels STORE into their peers' buffers, a device-side barrier orders the phases.
+
+        qp_all  [G * rows, 132]   the gathered packed queries: rank r's prep writes rows [r*M, (r+1)*M) on every rank
+        acc     [G, rows, 132]    slot s = rank s's partial result for THIS rank's rows (written by rank s)
+
+    Built on torch's symmetric memory (allocation, handle exchange, barrier); the data path is this repo's kernels.
+    Creating one is collective over `group`."""
+
+    def __init__(self, group, rows, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group, self.rows = group, int(rows)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        n = self.world * self.rows * PACK_LD
+        self.buf = symm_mem.empty(2 * n, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.qp_all, self.acc = self.buf[:n], self.buf[n:]
+        self.qp_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.acc_ptrs = torch.tensor([p + 4 * n for p in ptrs], dtype=torch.int64, device=device)
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+
+def peer_workspace(nq, group, rows):
+    """The queue's exchange workspace, (re)created collectively when more rows are needed."""
+    ws = getattr(nq, "_peer_ws", None)
+    if ws is None or ws.rows < rows or ws.group is not group:
+        ws = PeerWorkspace(group, rows, nq.device)
+        nq._peer_ws = ws
+    return ws
+
+
+EXCHANGE = "peer"      # "peer": NVLink peer stores from the kernels + device barriers; "nccl": all_gather / reduce_scatter
+
+
 class _InfoNCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, kpos, nq, rows_per_group, inv_T, impl, group, need_grad, dup_slot, dup_age):
@@ -151,10 +189,16 @@ class _InfoNCE(torch.autograd.Function):
         qpack = torch.empty(M, PACK_LD, device=dev)
         k_pad = (nq.K_local + 127) // 128 * 128
         dscale = torch.empty(k_pad, device=dev)
+        peer = world > 1 and EXCHANGE == "peer" and impl != "simt"
+        ws = peer_workspace(nq, group, M) if peer else None
         _cabi.call("mscl_infonce_prep", q.data_ptr(), kpos.data_ptr(), M, nq.birth.data_ptr(), nq.qstate.data_ptr(),
                    nq.K_local, inv_T, nq.max_key_norm, qpack.data_ptr(), dscale.data_ptr(),
-                   dup_slot.data_ptr() if dup_slot is not None else None, dup_age, st)
-        if world > 1:
+                   dup_slot.data_ptr() if dup_slot is not None else None, dup_age,
+                   ws.qp_ptrs.data_ptr() if peer else None, world if peer else 0, ws.rank * M if peer else 0, st)
+        if peer:                # every rank's rows were stored into every rank's table: wait for all of them
+            ws.barrier()
+            qpack_all = ws.qp_all[:M_all * PACK_LD].view(M_all, PACK_LD)
+        elif world > 1:
             qpack_all = torch.empty(M_all, PACK_LD, device=dev)
             dist.all_gather_into_tensor(qpack_all, qpack, group=group)
         else:
@@ -171,7 +215,14 @@ class _InfoNCE(torch.autograd.Function):
                        nq.K_local, nq.shard_begin, part.data_ptr(), n_part, int(need_grad), st,
                        algo_bytes=infonce_algo_bytes(M_all, nq.K_local),
                        algo_flops=(4 if need_grad else 2) * M_all * nq.K_local * DIM)
-        if world > 1:           # local slabs -> one slab, summed across ranks, each rank keeps its own rows
+        if peer:
+            # the sum over this rank's CTA slabs goes straight into the row owners' accumulators (peer stores), then
+            # every rank holds G slabs -- one per shard -- of its own rows, which finalize adds in rank order
+            _cabi.call("mscl_infonce_reduce_scatter", part.data_ptr(), n_part, M_all, M, ws.acc_ptrs.data_ptr(), ws.rank, st,
+                       algo_bytes=4 * PACK_LD * M_all * (n_part + 1))
+            ws.barrier()
+            part, n_part = ws.acc, world
+        elif world > 1:         # local slabs -> one slab, summed across ranks, each rank keeps its own rows
             acc = torch.empty(M_all, PACK_LD, device=dev)
             _cabi.call("mscl_infonce_reduce", part.data_ptr(), n_part, M_all, acc.data_ptr(), st)
             part = torch.empty(1, M, PACK_LD, device=dev)

@@ -99,7 +99,7 @@ def bench_k1(cfg, M, K, pk, dev, iters=30):
     def prep(i):
         nq = queues[i % rot]
         _cabi.call("mscl_infonce_prep", q.data_ptr(), k.data_ptr(), M, nq.birth.data_ptr(), nq.qstate.data_ptr(), K, 1 / 0.07,
-                   1.0, qpack.data_ptr(), dscales[i % rot].data_ptr(), None, 1, _st())
+                   1.0, qpack.data_ptr(), dscales[i % rot].data_ptr(), None, 1, None, 0, 0, _st())
 
     def partial(i):
         _cabi.call("mscl_infonce_partial", qpack.data_ptr(), M, queues[i % rot].queue_tf32.data_ptr(),

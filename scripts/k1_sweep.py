@@ -75,7 +75,7 @@ def main():
             dscales = [torch.empty(k_pad, device=dev) for _ in queues]
             for nq, ds in zip(queues, dscales):
                 _cabi.call("mscl_infonce_prep", q.data_ptr(), k.data_ptr(), M, nq.birth.data_ptr(), nq.qstate.data_ptr(),
-                           K, 1 / 0.07, 1.0, qpack.data_ptr(), ds.data_ptr(), None, 1, st)
+                           K, 1 / 0.07, 1.0, qpack.data_ptr(), ds.data_ptr(), None, 1, None, 0, 0, st)
             n_part = _cabi.query("mscl_infonce_num_partials", M, K, sms)
             part = torch.empty(n_part, M, fx.PACK_LD, device=dev)
             row_loss = torch.empty(2 * M, device=dev)
@@ -100,7 +100,7 @@ def main():
                 nq = queues[i % n_rot]
                 ds = dscales[i % n_rot]
                 _cabi.call("mscl_infonce_prep", q.data_ptr(), k.data_ptr(), M, nq.birth.data_ptr(), nq.qstate.data_ptr(),
-                           K, 1 / 0.07, 1.0, qpack.data_ptr(), ds.data_ptr(), None, 1, st)
+                           K, 1 / 0.07, 1.0, qpack.data_ptr(), ds.data_ptr(), None, 1, None, 0, 0, st)
                 _cabi.call("mscl_infonce_partial", qpack.data_ptr(), M, nq.queue_tf32.data_ptr(), ds.data_ptr(), K, 0,
                            part.data_ptr(), n_part, 1, st)
                 _cabi.call("mscl_infonce_finalize", qpack.data_ptr(), k.data_ptr(), part.data_ptr(), n_part, M, M, 1 / 0.07, 1,
