@@ -273,6 +273,23 @@ int mscl_color_pipeline(const float *d_x, const float *d_params, const float *d_
                         const float *d_norm, float *d_gray_partial, int32_t n_chunks, float *d_out,
                         int32_t N, int32_t T, int32_t H, int32_t W, mscl_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * K10  gradient-norm clip + SGD-momentum step, multi-tensor.   replaces torch.nn.utils.clip_grad_norm_(max_norm=40)
+ *      (mmcv OptimizerHook, optimizer_config.grad_clip) followed by torch.optim.SGD(lr, momentum, weight_decay).step()
+ *      (configs/recognition/moco/mscl_r18_cosm_lr2e-2.py:112-119).  Tables as for mscl_ema_multi.
+ * mscl_grad_norm_multi: d_stats[0] = ||g||_2 over all tensors, d_stats[1] = min(1, max_norm / (||g|| + 1e-6));
+ *   d_partial float[n_blocks] scratch (per-CTA sums, reduced in a fixed order).
+ * mscl_clip_sgd_multi:  g <- g * d_stats[1] (d_stats NULL: no clipping); d = g + weight_decay * p;
+ *   buf <- momentum * buf + d (first_step != 0: buf <- d);  p <- p - lr * buf.
+ */
+int mscl_grad_norm_multi(const float *const *d_g_ptrs, const int64_t *d_sizes, const int32_t *d_blk_tensor,
+                         const int64_t *d_blk_start, int32_t n_blocks, int32_t chunk_elems, float max_norm,
+                         float *d_partial, float *d_stats, mscl_stream_t stream);
+int mscl_clip_sgd_multi(float *const *d_g_ptrs, float *const *d_p_ptrs, float *const *d_buf_ptrs,
+                        const int64_t *d_sizes, const int32_t *d_blk_tensor, const int64_t *d_blk_start,
+                        int32_t n_blocks, int32_t chunk_elems, const float *d_stats, float weight_decay,
+                        float momentum, float lr, int32_t first_step, mscl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

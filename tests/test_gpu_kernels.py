@@ -362,12 +362,14 @@ def test_flow_visualize_golden_and_oracle(fx, golden_dir):
     assert d.max() <= (1.0 / 255) / 0.224 + 1e-5 and (d > 1e-6).mean() <= 5e-3
 
 
-@pytest.mark.parametrize("shape", [(6, 3, 4, 32, 48), (3, 3, 8, 112, 112)])
-def test_color_pipeline_matches_torch_ops(fx, shape):
+@pytest.mark.parametrize("shape,crop", [((6, 3, 4, 32, 48), 112), ((3, 3, 8, 112, 112), 112), ((6, 3, 2, 24, 36), 64),
+                                        ((2, 3, 2, 130, 132), 112)])
+def test_color_pipeline_matches_torch_ops(fx, shape, crop):
     """K9 against the same pipeline written as PyTorch ops (SyncMoCoAugmentV5._color_torch, the host path): every
-    combination of jitter / grayscale / blur / flip decisions, given parameters."""
+    combination of jitter / grayscale / blur / flip decisions, given parameters.  crop 112 -> 11 taps (frames up to 128
+    wide take the in-place shared-memory kernel, wider ones the generic one), crop 64 -> 7 taps (generic kernel)."""
     from mscl_b200.common.ssl_aug import SyncMoCoAugmentV5
-    aug = SyncMoCoAugmentV5(crop_size=112, sync_level=("batch", "batch"), t=(8, 8), flow_suffix="flow_imgs")
+    aug = SyncMoCoAugmentV5(crop_size=crop, sync_level=("batch", "batch"), t=(8, 8), flow_suffix="flow_imgs")
     n = shape[0]
     gen = torch.Generator().manual_seed(n)
     x = torch.rand(shape, generator=gen)
@@ -400,3 +402,39 @@ def test_augmentation_module_on_device(fx):
     lv = c["flow_imgs_k"] * 255
     assert torch.all((lv - lv.round()).abs() < 1e-4) and lv.min() >= 0 and lv.max() <= 255
     assert torch.isfinite(a).all() and a.min() >= (0 - 0.485) / 0.229 - 1e-4 and a.max() <= (1 - 0.406) / 0.225 + 1e-4
+
+
+# ------------------------------------------------------------------ K10 clip + SGD
+def test_fused_clip_sgd_matches_torch(fx):
+    """FusedClipSGD against torch.nn.utils.clip_grad_norm_(40) + torch.optim.SGD(lr=.02, momentum=.9, wd=1e-4)
+    (mscl_r18_cosm_lr2e-2.py:112-119): ragged sizes, a channels_last_3d weight, a parameter without gradient,
+    clipping active and inactive, four steps (first step: buf = d)."""
+    from mscl_b200.optim import FusedClipSGD
+    g = torch.Generator().manual_seed(0)
+    shapes = [(64, 3, 3, 7, 7), (5,), (128, 64, 3, 3, 3), (33, 17), (1,), (100003,), (16, 16, 1, 3, 3)]
+    base = [torch.randn(s, generator=g) for s in shapes]
+    pa = [torch.nn.Parameter(b.clone().cuda()) for b in base]
+    pb = [torch.nn.Parameter(b.clone().cuda()) for b in base]
+    for ps in (pa, pb):
+        ps[2].data = ps[2].data.contiguous(memory_format=torch.channels_last_3d)
+    ref = torch.optim.SGD(pa, lr=0.02, momentum=0.9, weight_decay=1e-4)
+    opt = FusedClipSGD(pb, lr=0.02, momentum=0.9, weight_decay=1e-4, max_norm=40.0)
+    for step in range(4):
+        scale = (30.0, 0.01, 5.0, 0.5)[step]          # clip active on steps 0 and 2
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if i == 4 and step != 2:                  # a parameter the loss does not reach (grad None), most steps
+                a.grad = b.grad = None
+                continue
+            gr = torch.randn(shapes[i], generator=g).cuda() * scale
+            a.grad = gr.clone()
+            b.grad = gr.clone() if i != 2 else gr.clone().contiguous(memory_format=torch.channels_last_3d)
+        norm = torch.nn.utils.clip_grad_norm_(pa, 40.0)
+        ref.step()
+        opt.step()
+        assert abs(float(opt.last_grad_norm[0]) - float(norm)) <= 1e-5 * float(norm)
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            np.testing.assert_allclose(b.detach().cpu().numpy(), a.detach().cpu().numpy(), rtol=2e-6, atol=1e-7, err_msg=f"step {step} param {i}")
+            if a.grad is not None:
+                np.testing.assert_allclose(b.grad.cpu().numpy(), a.grad.cpu().numpy(), rtol=2e-6, atol=1e-7)
+    sd = opt.state_dict()
+    assert "momentum_buffer" in sd["state"][0]
