@@ -166,7 +166,7 @@ def cpu_step_factory(K, n_clips, threads):
     grad clip, SGD."""
     import mscl_b200
     from mscl_b200.configs import mscl_r18_model
-    from oracle import mscl_oracle as O
+    from oracle import aug_oracle, mscl_oracle as O
     from oracle.step import OracleMSCL
     torch.set_num_threads(threads)
     torch.manual_seed(0)
@@ -190,7 +190,7 @@ def cpu_step_factory(K, n_clips, threads):
         b = batches[state["i"] % 2]
         state["i"] += 1
         aux = dict(flow_imgs_q=fra_cpu(b["flow_q"], b["cid_q"]), flow_imgs_k=fra_cpu(b["flow_k"], b["cid_k"]))
-        im_q, im_k, aux = aug(b["imgs_q"], b["imgs_k"], aux)
+        im_q, im_k, aux = aug_oracle.augment(aug, b["imgs_q"], b["imgs_k"], aux)
         loss, log_vars = orc.train_step(im_q, im_k, aux["flow_imgs_q"], aux["flow_imgs_k"])
         opt.zero_grad(set_to_none=True)
         loss.backward()

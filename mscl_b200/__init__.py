@@ -10,6 +10,6 @@ from .registry import (BACKBONES, HEADS, LOSSES, MODELS, NECKS, PIPELINES, RECOG
                        build_head, build_loss, build_model, build_neck, build_recognizer, build_ssl_aug)
 from .config import Config
 from . import losses, necks, backbones, common, heads, recognizers  # noqa: F401  (populate the registries)
-from .recognizers import MoCoV2, MSCLWithAug
+from .recognizers import MoCo, MoCoV2, MoDist, MSCL, MSCLWithAug
 
 __version__ = "0.1.0"

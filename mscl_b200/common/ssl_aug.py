@@ -2,17 +2,20 @@
 
 Adjacent to the hot path: it has to exist for the config to build
 and for (N,2,2T,H,W) flow input to become the 3-channel images the flow encoder eats.
-PyTorch ops on the device; the deterministic pieces (flow colour-wheel visualisation,
-flip given a mask, normalisation) follow common/ssl_aug.py:87-136 and
+Two kernels do the pixel work (K8 flow_visualize, K9 color_pipeline); this file only draws the
+random decisions on the device and packs them.  The deterministic pieces (flow colour-wheel
+visualisation, flip given a mask, normalisation) follow common/ssl_aug.py:87-136 and
 common/ssl_aug_v2.py:50-133 exactly, the random colour pipeline reproduces the
 reference's distribution (ColorJitter(0.4,0.4,0.4,0.1) p=.8, grayscale p=.2, Gaussian blur
 p=.5, decisions shared by the frames of a clip) but not kornia's random stream.
+
+CUDA tensors only: a host tensor raises MsclError.  The same pipeline written as PyTorch ops
+lives in oracle/aug_oracle.py (test / CPU-baseline infrastructure).
 """
 import math
 
 import torch
-import torch.nn.functional as F
-
+from .._cabi import MsclError
 from ..registry import SSL_AUGS
 
 
@@ -38,38 +41,10 @@ class FlowVisualizer:
         self.colorwheel = make_colorwheel()
 
     def __call__(self, flows, flip=None):
-        """flip: optional bool (N,) mask; the colour image of those samples is mirrored along W."""
-        if flows.is_cuda:       # K8: lookup + flip in one pass
-            from .. import functional as fx
-            return fx.flow_visualize(flows.contiguous(), None if flip is None else flip.to(torch.uint8))
-        img = self._torch(flows)
-        if flip is not None:
-            img = torch.where(flip.view(-1, 1, 1, 1, 1), torch.flip(img, [-1]), img)
-        return img
-
-    def _torch(self, flows):
-        """The reference's op sequence and dtypes (float32 up to f and 1 - f, float64 interpolation)."""
-        wheel = self.colorwheel.to(flows.device)
-        ncols = wheel.shape[0]
-        u, v = flows[:, 0], flows[:, 1]                       # (N,T,H,W)
-        rad = torch.sqrt(torch.square(u) + torch.square(v))
-        a = torch.atan2(-v, -u) / math.pi
-        fk = (a + 1) / 2 * (ncols - 1)
-        k0 = torch.floor(fk).long()
-        k1 = k0 + 1
-        k1[k1 == ncols] = 0
-        f = fk - k0                    # float32 (ssl_aug.py:108); (1 - f) below is a float32 op as well
-        omf = (1 - f).double()
-        f = f.double()
-        inside = rad <= 1
-        rad_d = rad.double()
-        chans = []
-        for i in range(3):
-            tmp = wheel[:, i]
-            col = omf * (tmp[k0] / 255.0) + f * (tmp[k1] / 255.0)
-            col = torch.where(inside, 1 - rad_d * (1 - col), col * 0.75)
-            chans.append(torch.floor(255 * col).to(torch.uint8).float() / 255)   # uint8 round trip as in the reference
-        return torch.stack(chans, dim=1)
+        """flip: optional bool (N,) mask; the colour image of those samples is mirrored along W (K8: lookup +
+        flip in one pass)."""
+        from .. import functional as fx
+        return fx.flow_visualize(flows.contiguous(), None if flip is None else flip.to(torch.uint8))
 
 
 @SSL_AUGS.register_module()
@@ -81,10 +56,6 @@ class IdentityAug:
         if im_k is None and aux_info is None:
             return clips                     # reference signature (common/ssl_aug.py:178-183)
         return clips, im_k, aux_info
-
-
-def _rgb_to_gray(x):
-    return (0.299 * x[:, 0:1] + 0.587 * x[:, 1:2] + 0.114 * x[:, 2:3])
 
 
 def _hue_matrix(h):
@@ -99,11 +70,6 @@ def _hue_matrix(h):
     return inv.unsqueeze(0) @ rot @ yiq.unsqueeze(0)
 
 
-def _hue_shift(x, h):
-    """Rotate hue by h (fraction of a turn, per sample) in YIQ space."""
-    return torch.einsum("nij,njthw->nithw", _hue_matrix(h), x)
-
-
 @SSL_AUGS.register_module()
 class SyncMoCoAugmentV5:
     def __init__(self, crop_size, flip_transform=dict(p=0.5, same_on_batch=False), sync_level="batch", t=None,
@@ -113,6 +79,7 @@ class SyncMoCoAugmentV5:
         assert all(v in ("batch", "params") for v in sync_level)
         self.mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1, 1)
         self.std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1, 1)
+        self.visualize = bool(visualize)
         self.visualizer = FlowVisualizer() if visualize else (lambda x: x)
         self.flow_suffix = flow_suffix
         self.img_width = img_width
@@ -161,29 +128,6 @@ class SyncMoCoAugmentV5:
         prm["taps"] = k1 / k1.sum()
         return prm
 
-    def _color_torch(self, x, prm):
-        """The colour pipeline as PyTorch ops (host tensors, and the reference the fused kernel is tested against)."""
-        v = lambda t: t.view(-1, 1, 1, 1, 1)
-        y = x * v(prm["brightness"])                                          # brightness
-        m = _rgb_to_gray(y).mean(dim=(1, 2, 3, 4), keepdim=True)
-        y = (y - m) * v(prm["contrast"]) + m                                 # contrast
-        g = _rgb_to_gray(y)
-        y = (y - g) * v(prm["saturation"]) + g                               # saturation
-        y = _hue_shift(y, prm["hue"])                                         # hue
-        x = torch.where(v(prm["jit"]), y.clamp(0, 1), x)
-        x = torch.where(v(prm["gray"]), _rgb_to_gray(x).expand_as(x), x)
-        # blur every clip at a fixed shape and select: no data-dependent shapes, no host synchronisation
-        r = self.blur_radius
-        k1 = prm["taps"].to(x.dtype)
-        b, c, t, h, w = x.shape
-        z = x.reshape(b * c * t, 1, h, w)
-        z = F.conv2d(F.pad(z, (r // 2, r // 2, 0, 0), mode="reflect"), k1.view(1, 1, 1, r))
-        z = F.conv2d(F.pad(z, (0, 0, r // 2, r // 2), mode="reflect"), k1.view(1, 1, r, 1))
-        return torch.where(v(prm["blur"]), z.view(b, c, t, h, w), x)
-
-    def _color(self, x):
-        return self._color_torch(x, self._color_params(x.shape[0], x.device))
-
     def _pack_params(self, prm, flip, weak):
         """(n,16) float rows for the fused kernel (include/mscl_b200.h, K9)."""
         n = flip.shape[0]
@@ -194,19 +138,70 @@ class SyncMoCoAugmentV5:
         return torch.cat([f32(flip), f32(prm["jit"]), f32(prm["brightness"]), f32(prm["contrast"]), f32(prm["saturation"]),
                           _hue_matrix(prm["hue"]).reshape(n, 9), f32(prm["gray"]), f32(prm["blur"])], dim=1).contiguous()
 
-    def _view(self, clips, aux_info, suffix, weak):
-        """One view: flip decision, flow images, RGB colour pipeline + Normalize."""
+    def _view(self, clips, aux_info, suffix, weak, flow=None):
+        """One view: flip decision, flow images, RGB colour pipeline + Normalize.  `flow`: an optional flow clip that
+        is mirrored for the same samples (SyncMoCoAugmentV2.forward_with_flow)."""
         if not clips.is_cuda:
-            clips, aux_info, _ = self.forward_flip(clips, aux_info, suffix)
-            return self._normalize(clips if weak else self._color(clips)), aux_info
+            raise MsclError(f"{type(self).__name__} runs on CUDA tensors only (no CPU fallback)")
         from .. import functional as fx      # K9: flip + colour + blur + normalise in one pass over the clip
         clips, aux_info, mask = self.forward_flip(clips, aux_info, suffix, flip_clips=False)
         prm = self._color_params(clips.shape[0], clips.device)
         norm = torch.cat([self.mean.view(-1), self.std.view(-1)]).to(clips.device)
         out = fx.color_pipeline(clips.contiguous().float(), self._pack_params(prm, mask, weak), prm["taps"].contiguous(), norm)
-        return out, aux_info
+        if flow is not None:
+            flow = self.flip(flow, mask)
+        return out, aux_info, flow
 
     def __call__(self, im_q, im_k, aux_info):
-        im_q, aux_info = self._view(im_q, aux_info, "_q", self.weak_aug[0])
-        im_k, aux_info = self._view(im_k, aux_info, "_k", self.weak_aug[1])
+        im_q, aux_info, _ = self._view(im_q, aux_info, "_q", self.weak_aug[0])
+        im_k, aux_info, _ = self._view(im_k, aux_info, "_k", self.weak_aug[1])
         return im_q, im_k, aux_info
+
+
+@SSL_AUGS.register_module()
+class SyncMoCoAugmentV2(SyncMoCoAugmentV5):
+    """Temporally consistent MoCo-v2 augmentation of the `moco_r*_consistent_*` configs (common/ssl_aug.py:249-332):
+    per-clip flip, ColorJitter(0.4,0.4,0.4,0.1) p=.8, grayscale p=.2, Gaussian blur p=.5, Normalize -- V5 without the
+    flow visualiser and the weak-augmentation switch, plus `forward_with_flow` (MoDist), which mirrors a flow clip for
+    the same samples as its RGB clip when `with_flow` is set."""
+
+    def __init__(self, crop_size, flip_transform=dict(p=0.5, same_on_batch=False), sync_level="batch", t=None,
+                 with_flow=False, img_width=112):
+        assert sync_level in ("batch", "params")
+        super().__init__(crop_size, flip_transform=flip_transform, sync_level=sync_level, t=t, flow_suffix=None,
+                         img_width=img_width, visualize=False, weak_aug=(False, False), normalize_flow=False)
+        self.with_flow = with_flow
+
+    def forward_with_flow(self, im_q, im_k, flow_q, flow_k, aux_info):
+        im_q, aux_info, fq = self._view(im_q, aux_info, "_q", False, flow_q if self.with_flow else None)
+        im_k, aux_info, fk = self._view(im_k, aux_info, "_k", False, flow_k if self.with_flow else None)
+        return im_q, im_k, (fq if self.with_flow else flow_q), (fk if self.with_flow else flow_k), aux_info
+
+
+@SSL_AUGS.register_module()
+class MoCoAugmentV2(SyncMoCoAugmentV5):
+    """Frame-level (temporally inconsistent) MoCo-v2 augmentation of `moco_r18_lr3e-2.py` (common/ssl_aug.py:214-246):
+    the clip is treated as N*T independent images -- colour-jitter parameters, grayscale and flip are drawn per FRAME;
+    the two `RandomApply` wrappers (jitter p=.8, blur p=.5) draw ONE decision per call for the whole batch.
+    Same K9 kernel, launched on the frames as one-frame clips."""
+
+    def __init__(self, crop_size):
+        super().__init__(crop_size, flow_suffix=None, visualize=False)
+
+    def single_cal(self, clips):
+        if not clips.is_cuda:
+            raise MsclError("MoCoAugmentV2 runs on CUDA tensors only (no CPU fallback)")
+        from .. import functional as fx
+        n, c, t, h, w = clips.shape
+        frames = clips.permute(0, 2, 1, 3, 4).reshape(n * t, c, 1, h, w).contiguous().float()
+        dev = clips.device
+        prm = self._color_params(n * t, dev)
+        prm["jit"] = (torch.rand(1, device=dev) < 0.8).expand(n * t)
+        prm["blur"] = (torch.rand(1, device=dev) < 0.5).expand(n * t)
+        mask = torch.rand(n * t, device=dev) < 0.5
+        norm = torch.cat([self.mean.view(-1), self.std.view(-1)]).to(dev)
+        out = fx.color_pipeline(frames, self._pack_params(prm, mask, False), prm["taps"].contiguous(), norm)
+        return out.view(n, t, c, h, w).permute(0, 2, 1, 3, 4).contiguous()
+
+    def __call__(self, im_q, im_k, aux_info):
+        return self.single_cal(im_q), self.single_cal(im_k), aux_info

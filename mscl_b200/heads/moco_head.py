@@ -1,6 +1,7 @@
 """Contrastive heads under the reference's names.
 
 MoCoHead           (heads/moco_head.py:9-81)
+MoCoHeadV2         (heads/moco_head_v3.py:15-85)
 MSCLWithAugMxHead  (heads/moco_head_v2.py:15-106)
 
 In the reference these receive a materialised (N, 1+K) logits matrix, copy it to the host
@@ -73,6 +74,33 @@ class MoCoHead(_ContrastHead):
 
     def loss(self, cls_score, labels, basename=None, **kwargs):
         return self._loss_from_logits(cls_score, labels, self.basename if basename is None else basename)
+
+    def loss_mx(self, **kwargs):
+        return dict()
+
+
+@HEADS.register_module()
+class MoCoHeadV2(_ContrastHead):
+    """MoCoHead that also owns the logits step and its temperature (heads/moco_head_v3.py:15-85).
+
+    `forward(q, k, weight)` keeps the reference's materialised form ((N,1+K) logits against a decayed snapshot);
+    `forward_fused(q, k, recognizer)` runs the same term through the recognizer's fused queue pass and returns the
+    [loss, top1, top5] row for `loss_fused`."""
+
+    def __init__(self, basename="", loss_cls=dict(type="CrossEntropyLoss"), num_classes=2, in_channels=128, T=0.07):
+        super().__init__(basename, loss_cls, num_classes, in_channels)
+        self.T = T
+
+    def forward(self, q, k, weight, **kwargs):
+        logits = torch.cat([(q * k).sum(1, keepdim=True), q @ weight], dim=1) / self.T
+        ssl_label = torch.zeros(logits.shape[0], dtype=torch.long, device=logits.device)
+        return dict(cls_score=logits, ssl_label=ssl_label)
+
+    def forward_fused(self, q, k, recognizer, dup_slot=None):
+        return recognizer.contrast([(q, k, dup_slot)], self.T)[0]
+
+    def loss(self, cls_score, ssl_label, basename=None, **kwargs):
+        return self._loss_from_logits(cls_score, ssl_label, self.basename if basename is None else basename)
 
     def loss_mx(self, **kwargs):
         return dict()

@@ -9,9 +9,10 @@ Importing this module without mmaction raises ImportError (it is never imported 
 """
 import mscl_b200
 
-MODEL_NAMES = ("MSCLWithAug", "MoCoV2", "MoCoHead", "MSCLWithAugMxHead", "MSCLWithAugPosHeadV2",
-               "CrossEntropyLoss_torch", "TPNMoCo", "BaseMoCo")
-AUG_NAMES = ("SyncMoCoAugmentV5", "IdentityAug")
+MODEL_NAMES = ("MSCLWithAug", "MSCL", "MoDist", "MoCoV2", "MoCo", "MoCoHead", "MoCoHeadV2", "MSCLWithAugMxHead",
+               "MSCLWithAugPosHeadV2", "MSCLWithAugPosHead", "MoDistv2PosHead", "MlvlMSCLWithAugPosHead",
+               "MSCLWithAugSimpleHead", "CrossEntropyLoss_torch", "TPNMoCo", "BaseMoCo", "ResNet3dSlowOnly")
+AUG_NAMES = ("SyncMoCoAugmentV5", "SyncMoCoAugmentV2", "MoCoAugmentV2", "IdentityAug")
 
 
 def register_into_mmaction():

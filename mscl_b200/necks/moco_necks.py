@@ -14,13 +14,12 @@ from ..registry import NECKS
 
 
 def _trilinear(x, size):
-    """F.interpolate(x, size, mode="trilinear") (necks/sepc.py:126-130).  On a CUDA tensor this is the K7 kernel
-    (PyTorch's upsample_trilinear3d runs at ~30 GB/s on these shapes); CPU tensors -- the oracle runs these
-    modules on the host -- take the PyTorch op."""
-    if x.is_cuda and x.dtype == torch.float32:
-        from .. import functional as fx
-        return fx.upsample_trilinear(x.contiguous(), size)
-    return F.interpolate(x, size=size, mode="trilinear")
+    """F.interpolate(x, size, mode="trilinear") (necks/sepc.py:126-130) as the K7 kernel (PyTorch's
+    upsample_trilinear3d runs at ~30 GB/s on these shapes).  fp32 CUDA tensors only: anything else raises MsclError.
+    The oracle, which re-uses these module classes on the host, replaces the `upsample` attribute of ITS copies
+    (oracle/step.py)."""
+    from .. import functional as fx
+    return fx.upsample_trilinear(x.contiguous(), size)
 
 
 class _Conv(nn.Module):
@@ -57,6 +56,7 @@ class _PConv3D(nn.Module):
         self.Pconv = nn.ModuleList([nn.Conv3d(cin, cout, 3, padding=1), nn.Conv3d(cin, cout, 3, padding=1),
                                     nn.Conv3d(cin, cout, 3, padding=1, stride=stride)])
         self.relu = nn.ReLU()
+        self.upsample = _trilinear
 
     def forward(self, xs):
         out = []
@@ -65,7 +65,7 @@ class _PConv3D(nn.Module):
             if lvl > 0:
                 y = y + self.Pconv[2](xs[lvl - 1])
             if lvl < len(xs) - 1:
-                y = y + _trilinear(self.Pconv[0](xs[lvl + 1]), list(y.shape[2:]))
+                y = y + self.upsample(self.Pconv[0](xs[lvl + 1]), list(y.shape[2:]))
             out.append(self.relu(y))
         return out
 

@@ -1,5 +1,6 @@
 from .base_moco import BaseMoCoRecognizer
-from .moco import MoCoV2, concat_all_gather
-from .mscl import MSCLWithAug
+from .moco import MoCo, MoCoV2, concat_all_gather
+from .mscl import MSCL, MSCLWithAug
+from .modist import MoDist
 
-__all__ = ["BaseMoCoRecognizer", "MoCoV2", "MSCLWithAug", "concat_all_gather"]
+__all__ = ["BaseMoCoRecognizer", "MoCo", "MoCoV2", "MSCL", "MSCLWithAug", "MoDist", "concat_all_gather"]

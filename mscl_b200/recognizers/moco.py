@@ -181,9 +181,13 @@ class MoCoV2(BaseMoCoRecognizer):
 
     # ------------------------------------------------------------------ K4
     @torch.no_grad()
-    def _momentum_update_key_encoder(self):
+    def _next_momentum(self):
+        """Cosine-annealed momentum of this update (moco.py:413-415)."""
         factor = min(self.iters / self.max_iters, 1)
-        self.m = 1 * (1 - 0.5 * (1 - self.m_base) * (cos(pi * factor) + 1))
+        return 1 * (1 - 0.5 * (1 - self.m_base) * (cos(pi * factor) + 1))
+
+    def _momentum_update_key_encoder(self):
+        self.m = self._next_momentum()
         if self._ema is None:
             pk, pq = [], []
             for mq, mk in self._qk_modules():
@@ -352,3 +356,21 @@ class MoCoV2(BaseMoCoRecognizer):
 
     def visualize(self, data_batch):
         pass
+
+
+@RECOGNIZERS.register_module()
+class MoCo(MoCoV2):
+    """The reference's first MoCo recognizer (recognizers/moco.py:30-316): everything MoCoV2 does -- decay-by-age
+    negatives included (:270-273) -- with a CONSTANT key-encoder momentum `m` (:114-124) instead of the cosine
+    schedule.  Used by the four `moco_r*.py` configs.  (In the reference MoCoV2 derives from MoCo; here the
+    machinery lives in MoCoV2 and this class only pins the momentum.)"""
+
+    def __init__(self, backbone, neck, moco_head, im_key="imgs", dim_in=512, dim=128, K=65536, m=0.999, T=0.07,
+                 mlp=False, aux_info=[], aug=dict(dtype="MoCoAugmentV3", moco_aug=(112, 112), t=8),
+                 train_cfg=None, test_cfg=None):
+        super().__init__(backbone, neck, moco_head, im_key=im_key, dim_in=dim_in, dim=dim, K=K, m_base=m, max_iters=1,
+                         T=T, mlp=mlp, aux_info=aux_info, aug=aug, train_cfg=train_cfg, test_cfg=test_cfg)
+        self.m = m
+
+    def _next_momentum(self):
+        return self.m

@@ -1,5 +1,6 @@
 """MSCLWithAug: RGB MoCoV2 + flow MoCoV2 (base flow and FRA-rotated flow) + cross-modal
-InfoNCE + LMCL (reference: recognizers/mscl.py:137-292).
+InfoNCE + LMCL (reference: recognizers/mscl.py:137-292), and MSCL, the same model without the
+FRA branch (recognizers/mscl.py:9-134).
 
 The reference evaluates 7 InfoNCE terms per step, each with its own materialised
 (N,1+K) logits, against only THREE distinct negative matrices:
@@ -19,6 +20,129 @@ import torch
 
 from ..registry import RECOGNIZERS, build_recognizer, build_ssl_aug
 from .base_moco import BaseMoCoRecognizer
+
+
+def two_branch_rows(rec, recf, q, k, q_f, k_f, same_kn, T_mx):
+    """The four InfoNCE terms of a two-branch step without the FRA call (mscl.py:92-113, modist.py:84-118): own RGB,
+    own flow, rf (q vs k_flow) and fr (q_flow vs k).  Every term reads a PRE-enqueue decayed queue (each recognizer
+    snapshots its weight before its own enqueue, moco.py:484-502), so each queue is streamed once with the two row
+    sets that need it stacked; then both enqueues run.  Returns {name: [loss, top1, top5, 0] row}."""
+    for head in (rec.moco_head, recf.moco_head):
+        if not head.can_fuse():
+            raise NotImplementedError("the fused path needs loss_cls=CrossEntropyLoss_torch without class weights")
+    rf_queue, fr_queue = ("flow", "rgb") if same_kn else ("rgb", "flow")
+    terms = {"rgb": [("own", q, k, rec.T)], "flow": [("own_f", q_f, k_f, recf.T)]}
+    terms[rf_queue].append(("rf", q, k_f, T_mx))
+    terms[fr_queue].append(("fr", q_f, k, T_mx))
+    rows = {}
+    for phase, owner in (("rgb", rec), ("flow", recf)):
+        by_T = OrderedDict()          # one pass per distinct temperature (one, in the configs)
+        for name, qq, kk, T in terms[phase]:
+            by_T.setdefault(T, []).append((name, qq, kk))
+        for T, items in by_T.items():
+            out = owner.contrast([(qq, kk) for _, qq, kk in items], T)
+            for i, item in enumerate(items):
+                rows[item[0]] = out[i]
+    rec._dequeue_and_enqueue(k)
+    recf._dequeue_and_enqueue(k_f)
+    return rows
+
+
+def _wants(head, name):
+    """Does the head's aux_keys map ask for feature `name` (e.g. the unshuffled key pyramid `k_mlvl`)?"""
+    return any(name in v for v in getattr(head, "aux_keys", {}).values())
+
+
+@RECOGNIZERS.register_module()
+class MSCL(BaseMoCoRecognizer):
+    """RGB MoCo + flow MoCo + cross-modal InfoNCE (`moco_mx_head`) + a frame-level head (`sup_head`, e.g.
+    MoDistv2PosHead) on the base flow only (recognizers/mscl.py:9-134)."""
+
+    def __init__(self, recognizer, recognizer_flow, moco_mx_head, sup_head, im_key="imgs", flow_key="flows",
+                 flow_img_key="flow_imgs", aux_info=[], aug=dict(dtype="MoCoAugmentV3", moco_aug=(112, 112), t=8),
+                 same_kn=True, update_aug_flow=False, weight_aug_flow=(1.0, 1.0), train_cfg=None, test_cfg=None):
+        super().__init__(train_cfg=train_cfg, test_cfg=test_cfg)
+        if train_cfg:
+            recognizer = dict(recognizer, train_cfg=dict(recognizer.get("train_cfg") or {}, **train_cfg))
+            recognizer_flow = dict(recognizer_flow, train_cfg=dict(recognizer_flow.get("train_cfg") or {}, **train_cfg))
+        self.recognizer = build_recognizer(recognizer)
+        self.recognizer_flow = build_recognizer(recognizer_flow)
+        self.im_key = im_key
+        self.same_kn = same_kn
+        self.update_aug_flow = update_aug_flow        # stored, unused (as the reference)
+        self.weight_aug_flow = weight_aug_flow
+        self.flow_key = flow_key
+        self.flow_img_key = flow_img_key
+        self.aux_info = aux_info
+        self._build_cls_head(moco_mx_head, name="moco_mx_head")
+        self._build_cls_head(sup_head, name="sup_head")
+        self.aug_gpu = build_ssl_aug(aug)
+
+    def train_step(self, data_batch, optimizer, **kwargs):
+        im_q = data_batch[self.im_key][0]
+        im_k = data_batch[self.im_key][1]
+        aux_info = {f"{self.flow_key}_q": data_batch[self.flow_key][0], f"{self.flow_key}_k": data_batch[self.flow_key][1]}
+        for item in self.aux_info:
+            assert item in data_batch
+            aux_info[item] = data_batch[item]
+        losses = self(im_q, im_k, aux_info, return_loss=True)
+        loss, log_vars = self._parse_losses(losses)
+        return dict(num_samples=im_q.shape[0], loss=loss, log_vars=log_vars)
+
+    def forward(self, im_q, im_k, aux_info, return_loss=True, **kwargs):
+        if kwargs.get("gradcam", False):
+            del kwargs["gradcam"]
+            return self.forward_gradcam(im_q, im_k, aux_info, **kwargs)
+        if return_loss:
+            return self.forward_train(im_q, im_k, aux_info, **kwargs)
+        raise NotImplementedError("MoCo doesnt support test mode")
+
+    def objective(self, feats):
+        """Everything after the encoders (mscl.py:92-120).  feats: q, k, q_f, k_f (N,128) and the feature dicts
+        `im_features` / `flow_features` handed to the frame-level head."""
+        rec, recf, mx = self.recognizer, self.recognizer_flow, self.moco_mx_head
+        if not mx.can_fuse():
+            raise NotImplementedError("the fused path needs loss_cls=CrossEntropyLoss_torch without class weights")
+        rows = two_branch_rows(rec, recf, feats["q"], feats["k"], feats["q_f"], feats["k_f"], mx.same_kn, mx.T)
+        losses = OrderedDict()
+        losses.update(rec.moco_head.loss_fused(rows["own"]))
+        losses.update(recf.moco_head.loss_fused(rows["own_f"]))
+        losses.update(mx.loss_fused_mx(rows["rf"], rows["fr"]))
+        aux = dict(feats.get("aux_info") or {})
+        aux = self.sup_head.update_aux_info("im_features", feats["im_features"], aux)
+        aux = self.sup_head.update_aux_info("base_flow_features", feats["flow_features"], aux)
+        aux.update(self.sup_head(**aux))
+        losses.update(self.sup_head.loss(**aux))
+        return losses
+
+    def forward_train(self, im_q, im_k, aux_info):
+        im_q, im_k, aux_info = self.aug_gpu(im_q, im_k, aux_info)
+        rec, recf = self.recognizer, self.recognizer_flow
+        flow_q, flow_k = aux_info[f"{self.flow_img_key}_q"], aux_info[f"{self.flow_img_key}_k"]
+        n = im_q.shape[0]
+        need_k = _wants(self.sup_head, "k_mlvl")
+        q, q_mlvl, k, k_mlvl, _ = rec.extract_feat(im_q, im_k, unshuffle_mlvl=need_k)
+        rec.note_branch(n, True)
+        q_f, qf_mlvl, k_f, kf_mlvl, _ = recf.extract_feat(flow_q, flow_k, unshuffle_mlvl=need_k)
+        recf.note_branch(n, True)
+        return self.objective(dict(q=q, k=k, q_f=q_f, k_f=k_f, aux_info=aux_info,
+                                   im_features=dict(q=q, q_mlvl=q_mlvl, k=k, k_mlvl=k_mlvl, q_neg=None),
+                                   flow_features=dict(q=q_f, q_mlvl=qf_mlvl, k=k_f, k_mlvl=kf_mlvl, q_neg=None)))
+
+    def forward_test(self, imgs):
+        raise NotImplementedError("Not support for ssl recognizer !!!")
+
+    def forward_gradcam(self, imgs):
+        raise NotImplementedError("Not support for ssl recognizer !!!")
+
+    def extract_global_feat(self):
+        raise NotImplementedError("Not support for ssl recognizer !!!")
+
+    def extract_feat(self, im_q, im_k):
+        pass
+
+    def visualize(self, data_batch):
+        pass
 
 
 @RECOGNIZERS.register_module()

@@ -48,6 +48,33 @@ def head_inputs(seed=0, N=8, C=128, K=4096, t=8, hw_rgb=28, hw_flow=7, b_all=Non
     return out
 
 
+def sibling_head_cases():
+    """(name, reference class name, ctor kwargs, rgb level shapes, flow level shapes, uses FRA flow) -- shared with the
+    GPU parity test, which rebuilds the same inputs from the seed."""
+    return [
+        ("pos_head", "MSCLWithAugPosHead", dict(bkb_channels=(48, 24), t=4, T=0.07, mlvl_ids=(0, -1)),
+         [(3, 48, 4, 6, 6)], [(3, 24, 4, 3, 3)], True),
+        ("pos_head_identity_rgb", "MSCLWithAugPosHead", dict(bkb_channels=(None, 24), t=4, T=0.07, mlvl_ids=(0, -1)),
+         [(3, 128, 4, 5, 5)], [(3, 24, 4, 3, 3)], True),
+        ("modist_pos_head", "MoDistv2PosHead", dict(bkb_channels=(None, 32), t=8, T=0.1, mlvl_ids=(0, -1)),
+         [(2, 128, 8, 7, 7)], [(2, 32, 8, 4, 4)], False),
+        ("mlvl_pos_head", "MlvlMSCLWithAugPosHead", dict(bkb_channels=(None, 16), t=4, T=0.07, mlvl_ids=(0, 1, 2),
+                                                         mlvl_flow_ids=(-1, -1, -1)),
+         [(3, 128, 4, 8, 8), (3, 128, 4, 4, 4), (3, 128, 4, 2, 2)], [(3, 16, 4, 3, 3)], True),
+    ]
+
+
+def sibling_head_inputs(case, seed=7):
+    name, _, kw, rgb_shapes, flow_shapes, with_aug = case
+    g = torch.Generator().manual_seed(seed + len(name))
+    t = kw["t"]
+    zt = [torch.randn(rgb_shapes[0][0], 1, t, 1, 1, generator=g) for _ in range(2)]
+    q_mlvl = [torch.randn(*s, generator=g) * 0.3 + zt[0] for s in rgb_shapes]
+    qf_mlvl = [torch.randn(*s, generator=g) * 0.3 + zt[0] + 0.3 * zt[1] for s in flow_shapes]
+    qaf_mlvl = [torch.randn(*s, generator=g) * 0.3 + zt[1] for s in flow_shapes] if with_aug else None
+    return q_mlvl, qf_mlvl, qaf_mlvl
+
+
 def flow_clip(seed=0, T=8, H=112, W=112):
     """One clip of raw optical flow, list of T float32 (H, W, 2) frames."""
     g = _gen(seed)

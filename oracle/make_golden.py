@@ -194,6 +194,117 @@ def golden_flowvis(ref):
     print("flowvis:", tuple(out.shape), out.dtype, float(out.mean()))
 
 
+class _AttrDict(dict):
+    """Enough of mmcv's ConfigDict for modist.py:43-44 (`moco_head.copy(); moco_head_r.basename += '_r'`)."""
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+    def copy(self):
+        return _AttrDict(self)
+
+
+def golden_sibling_heads(ref):
+    """MSCLWithAugPosHead, MoDistv2PosHead, MlvlMSCLWithAugPosHead of the unmodified reference
+    (heads/moco_head_v2.py:128-441): weights, losses, accuracies and input gradients."""
+    import sys
+    mod = sys.modules["mmaction.models.heads.moco_head_v2"]
+    res = {}
+    for case in inputs.sibling_head_cases():
+        name, cls_name, kw, _, _, with_aug = case
+        torch.manual_seed(11)
+        head = getattr(mod, cls_name)(basename="", loss_pos=LOSS, loss_cls=LOSS, **kw)
+        q_mlvl, qf_mlvl, qaf_mlvl = inputs.sibling_head_inputs(case)
+        leaves = [x.requires_grad_(True) for x in q_mlvl + qf_mlvl + (qaf_mlvl or [])]
+        args = dict(q_mlvl=q_mlvl, q_flow_mlvl=qf_mlvl)
+        if with_aug:
+            args["q_aug_flow_mlvl"] = qaf_mlvl
+        out = head(**args)
+        losses = head.loss(**out)
+        total = sum(v for k, v in losses.items() if "loss" in k)
+        total.backward()
+        for k, v in head.state_dict().items():
+            res[f"{name}/state/{k}"] = v.detach().numpy().copy()
+        for k, v in losses.items():
+            res[f"{name}/out/{k}"] = np.float64(float(v))
+        res[f"{name}/out_order"] = np.array(list(losses.keys()))
+        for i, x in enumerate(leaves):
+            res[f"{name}/gradsum/{i}"] = (x.grad.sum(dim=(-2, -1)).numpy() if x.grad is not None
+                                          else np.zeros(x.shape[:3], dtype=np.float32))
+        for k, p_ in head.named_parameters():
+            res[f"{name}/pgrad/{k}"] = p_.grad.numpy().copy()
+        print(name, {k: round(float(v), 6) for k, v in losses.items()})
+    np.savez_compressed(os.path.join(OUT, "sibling_heads.npz"), **res)
+
+
+def _two_branch_model(ref, kind, K, t, mlvl_ids=(0, -1)):
+    import sys
+    if kind == "mscl":
+        cfg = dict(type="MSCL", recognizer=_flow_recognizer_cfg(K, ""), recognizer_flow=_flow_recognizer_cfg(K, "flow"),
+                   moco_mx_head=dict(type="MSCLWithAugMxHead", basename="mx", loss_cls=LOSS, same_kn=True, T=0.07),
+                   sup_head=dict(type="MoDistv2PosHead", basename="", loss_pos=LOSS, bkb_channels=(None, 128), t=t, T=0.07,
+                                 mlvl_ids=mlvl_ids, aux_keys=dict(im_features=dict(q_mlvl="q_mlvl"),
+                                               base_flow_features=dict(q_mlvl="q_flow_mlvl"))),
+                   im_key="imgs", flow_key="flow_imgs", flow_img_key="flow_imgs", aux_info=[], aug=dict(type="IdentityAug"),
+                   same_kn=True)
+        return ref.builder.build_model(cfg)
+    if "mmaction.models.recognizers.modist" not in sys.modules:
+        from . import ref_shim
+        ref_shim._load("mmaction.models.recognizers.modist", "mmaction/models/recognizers/modist.py")
+    cfg = dict(type="MoDist", recognizer=_flow_recognizer_cfg(K, ""), recognizer_flow=_flow_recognizer_cfg(K, "flow"),
+               moco_head=_AttrDict(type="MoCoHead", basename="mx", loss_cls=LOSS), im_key="imgs", flow_key="flow_imgs",
+               aux_info=[], aug=dict(type="IdentityAug"), same_kn=True)
+    m = ref.builder.build_model(cfg)
+    m.aug_gpu.forward_with_flow = lambda a, b, c, d, e: (a, b, c, d, e)
+    return m
+
+
+def golden_two_branch(ref):
+    """MSCL (with a MoDistv2PosHead) and MoDist of the unmodified reference (recognizers/mscl.py:9-134,
+    recognizers/modist.py:9-132), driven at head level like golden_head: encoder outputs given, two consecutive
+    steps so that the second one sees non-trivial ages / pointer / iters."""
+    kw = dict(seed=2, N=4, C=128, K=256, t=4, hw_rgb=6, hw_flow=3)
+    res = {"kwargs": np.array(repr(kw))}
+    for kind in ("mscl", "modist"):
+        inp = inputs.head_inputs(**kw)
+        torch.manual_seed(13)
+        m = _two_branch_model(ref, kind, kw["K"], kw["t"])
+        m.train()
+        for rec, qn in ((m.recognizer, "queue_rgb"), (m.recognizer_flow, "queue_flow")):
+            rec.queue.copy_(inp[qn])
+            rec.count.copy_(inp["count"])
+            rec.queue_ptr[0] = inp["ptr"]
+        if kind == "mscl":
+            for k, v in m.sup_head.state_dict().items():
+                res[f"mscl/sup_state/{k}"] = v.numpy().copy()
+        N = kw["N"]
+        dummy = torch.zeros(N, 3, 2, 4, 4)
+        for step in range(2):
+            x = inputs.head_inputs(**dict(kw, seed=kw["seed"] + step))
+            leaves = {n: x[n].clone().requires_grad_(True) for n in ("q", "q_f", "q_map", "qf_map")}
+            calls_rgb = [(leaves["q"], [leaves["q_map"]], x["k"], [], {})]
+            calls_flow = [(leaves["q_f"], [leaves["qf_map"]], x["k_f"], [], {})]
+            m.recognizer.extract_feat = lambda a, b: calls_rgb.pop(0)
+            m.recognizer_flow.extract_feat = lambda a, b: calls_flow.pop(0)
+            out = m.train_step(dict(imgs=[dummy, dummy], flow_imgs=[dummy, dummy]), None)
+            out["loss"].backward()
+            tag = f"{kind}/step{step}"
+            for k, v in out["log_vars"].items():
+                res[f"{tag}/logvar/{k}"] = np.float64(v)
+            res[f"{tag}/logvar_order"] = np.array(list(out["log_vars"].keys()))
+            for n in ("q", "q_f"):
+                res[f"{tag}/grad/{n}"] = leaves[n].grad.numpy()
+            if kind == "mscl":
+                for n in ("q_map", "qf_map"):
+                    res[f"{tag}/gradsum/{n}"] = leaves[n].grad.sum(dim=(-2, -1)).numpy()
+            for br, rec in (("rgb", m.recognizer), ("flow", m.recognizer_flow)):
+                res[f"{tag}/after/{br}/queue"] = rec.queue.numpy().copy()
+                res[f"{tag}/after/{br}/count"] = rec.count.numpy().copy()
+                res[f"{tag}/after/{br}/ptr"] = rec.queue_ptr.numpy().copy()
+                res[f"{tag}/after/{br}/iters"] = np.int64(rec.iters)
+            print(tag, {k: round(float(v), 5) for k, v in out["log_vars"].items()})
+    np.savez_compressed(os.path.join(OUT, "two_branch.npz"), **res)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load_reference()
@@ -205,6 +316,8 @@ def main():
     golden_fra(ref)
     golden_shuffle(ref)
     golden_flowvis(ref)
+    golden_sibling_heads(ref)
+    golden_two_branch(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

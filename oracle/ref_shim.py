@@ -114,6 +114,15 @@ def _normal_init(module, mean=0, std=1, bias=0):
         nn.init.constant_(module.bias, bias)
 
 
+def _kaiming_init(module, a=0, mode="fan_out", nonlinearity="relu", bias=0, distribution="normal"):
+    if distribution == "uniform":
+        nn.init.kaiming_uniform_(module.weight, a=a, mode=mode, nonlinearity=nonlinearity)
+    else:
+        nn.init.kaiming_normal_(module.weight, a=a, mode=mode, nonlinearity=nonlinearity)
+    if getattr(module, "bias", None) is not None:
+        nn.init.constant_(module.bias, bias)
+
+
 def _auto_fp16(*a, **k):
     def deco(f):
         return f
@@ -192,8 +201,14 @@ def load_reference():
     cnn.constant_init = _constant_init
     cnn.normal_init = _normal_init
     cnn.MODELS = _Registry("mmcv_models")
+    cnn.NonLocal3d = None
+    cnn.build_activation_layer = lambda cfg: nn.ReLU(inplace=bool(cfg.get("inplace", False)))
+    cnn.kaiming_init = _kaiming_init
+    runner.load_checkpoint = lambda *a, **k: {}
     utils = _pkg("mmcv.utils")
     utils.Registry = _Registry
+    utils._BatchNorm = nn.modules.batchnorm._BatchNorm
+    utils.print_log = lambda *a, **k: None
     mmcv.runner, mmcv.cnn, mmcv.utils = runner, cnn, utils
 
     # --- fake mmaction parents ---
@@ -265,6 +280,18 @@ def load_reference():
     )
     _LOADED = ns
     return ns
+
+
+def load_slowonly():
+    """The reference's ResNet3dSlowOnly class (backbones/resnet3d_slowonly.py:16-52; its line 2 is a stray
+    `from turtle import forward`, which needs tkinter, and is skipped)."""
+    load_reference()
+    if "mmaction.models.backbones.resnet3d_slowonly" not in sys.modules:
+        _load("mmaction.models.backbones.resnet3d", "mmaction/models/backbones/resnet3d.py")
+        _load("mmaction.models.backbones.resnet3d_slowfast", "mmaction/models/backbones/resnet3d_slowfast.py")
+        _load("mmaction.models.backbones.resnet3d_slowonly", "mmaction/models/backbones/resnet3d_slowonly.py",
+              strip_lines=(2,))
+    return sys.modules["mmaction.models.backbones.resnet3d_slowonly"].ResNet3dSlowOnly
 
 
 def ensure_process_group():

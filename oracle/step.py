@@ -33,10 +33,17 @@ class OracleBranch:
             if "forward" in enc.__dict__:
                 del enc.__dict__["forward"]
                 torchvision_multilevel(enc)
+        # the product's pyramid convolutions up-sample with the K7 kernel; the host copies take the library op
+        for neck in (self.neck_q, self.neck_k):
+            for mod in neck.modules():
+                if hasattr(mod, "upsample"):
+                    mod.upsample = lambda x, size: F.interpolate(x, size=size, mode="trilinear")
         st = state or rec._gathered_state()
         self.state = O.QueueState(st["queue"].cpu().float(), st["count"].cpu().long(), int(st["ptr"]))
         self.state.iters, self.state.batch_size = rec.iters, rec.batch_size
         self.m_base, self.max_iters, self.T = rec.m_base, rec.max_iters, rec.T
+        # the first MoCo recognizer keeps a constant momentum (moco.py:114-124); MoCoV2 anneals it (:413-415)
+        self.fixed_m = rec.m if type(rec).__name__ == "MoCo" else None
         self.train(rec.training)
 
     def train(self, mode=True):
@@ -55,7 +62,7 @@ class OracleBranch:
         (q_emb, q_mlvl), _ = self.neck_q(q_mlvl)
         q = F.normalize(self.mlp_q(q_emb), dim=1)
         with torch.no_grad():
-            m = O.momentum(self.state.iters, self.max_iters, self.m_base)
+            m = self.fixed_m if self.fixed_m is not None else O.momentum(self.state.iters, self.max_iters, self.m_base)
             for pk, new in zip(self.k_params(), O.ema_update([p.data for p in self.k_params()],
                                                              [p.data for p in self.q_params()], m)):
                 pk.data = new
@@ -103,4 +110,60 @@ class OracleMSCL:
         losses = OrderedDict()
         for d in (loss_img, loss_flow, loss_mx, loss_sup):
             losses.update(d)
+        return O.parse_losses(losses)
+
+
+class OracleMoCo:
+    """One MoCo / MoCoV2 recognizer trained on its own (`moco_r*.py` configs): train_step = extract_feat, logits
+    against the pre-enqueue decayed snapshot, enqueue, iters (moco.py:236-296 / :473-515)."""
+
+    def __init__(self, model):
+        self.branch = OracleBranch(model)
+        self.basename = model.moco_head.basename
+        self.training = model.training
+
+    def parameters(self):
+        return self.branch.q_params()
+
+    def train_step(self, im_q, im_k):
+        q, _, k = self.branch.extract_feat(im_q, im_k)
+        losses = self.branch.state.branch(q, k, self.branch.T, self.basename, True, self.training)
+        return O.parse_losses(losses)
+
+
+class OracleTwoBranch:
+    """MSCL (kind="mscl", recognizers/mscl.py:85-120) or MoDist (kind="modist", recognizers/modist.py:77-118) with the
+    product's encoder modules on the CPU."""
+
+    def __init__(self, model, kind):
+        self.kind = kind
+        self.rgb = OracleBranch(model.recognizer)
+        self.flow = OracleBranch(model.recognizer_flow)
+        self.training = model.training
+        if kind == "mscl":
+            head = model.sup_head
+            self.T, self.same_kn, self.mx_basename = model.moco_mx_head.T, model.moco_mx_head.same_kn, model.moco_mx_head.basename
+            self.sup = dict(t=head.labels.shape[1], T=head.T, ids=head.mlvl_ids, trans_rgb=copy.deepcopy(head.trans_rgb).cpu(),
+                            trans_flow=copy.deepcopy(head.trans_flow).cpu(), with_aug=type(head).__name__ != "MoDistv2PosHead")
+        else:
+            self.T, self.same_kn, self.mx_basename, self.sup = model.T, model.same_kn, model.moco_head.basename, None
+
+    def parameters(self):
+        extra = []
+        if self.sup is not None:
+            extra = list(self.sup["trans_rgb"].parameters()) + list(self.sup["trans_flow"].parameters())
+        return self.rgb.q_params() + self.flow.q_params() + extra
+
+    def train_step(self, im_q, im_k, flow_q, flow_k):
+        q, q_mlvl, k = self.rgb.extract_feat(im_q, im_k)
+        # the reference runs the whole RGB call (snapshot, enqueue, iters) before the flow encoders; the enqueue does
+        # not feed the flow call, so only the EMA schedule (iters) and the permutation draw order matter here
+        q_f, qf_mlvl, k_f = self.flow.extract_feat(flow_q, flow_k)
+        sup = None
+        if self.sup is not None:
+            s = self.sup
+            sup = lambda: O.frame_contrast(q_mlvl[s["ids"][0]], qf_mlvl[s["ids"][1]], s["T"], s["t"], s["trans_rgb"], s["trans_flow"])
+        losses = O.two_branch_objective(dict(q=q, k=k, q_f=q_f, k_f=k_f), self.rgb.state, self.flow.state, T=self.T,
+                                        same_kn=self.same_kn, kind=self.kind, mx_basename=self.mx_basename, sup=sup,
+                                        training=self.training)
         return O.parse_losses(losses)

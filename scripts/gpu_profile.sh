@@ -8,7 +8,7 @@ timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --profile
 echo "launchlist rc=$?"
 # full capture of our kernels (regex on kernel names), a few launches each
 timeout 1200 ncu --set full --clock-control none --import-source on \
-    -k regex:"infonce_tc_kernel|ema_multi_kernel|fra_|hw_mean|enqueue_kernel|lmcl_kernel" -c 40 --profile-from-start off \
+    -k regex:"infonce_tc_kernel|ema_multi_kernel|fra_|hw_mean|enqueue_kernel|lmcl_kernel|clip_sgd_multi|grad_sqnorm_multi|color_pipeline|flow_visualize|upsample_trilinear" -c 60 --profile-from-start off \
     -o gpurun_out/prof_kernels -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-kernel-rooflines --profile-range > gpurun_out/prof_kernels.log 2>&1
 echo "full rc=$?"
 ls -la gpurun_out

@@ -365,11 +365,13 @@ def test_flow_visualize_golden_and_oracle(fx, golden_dir):
 @pytest.mark.parametrize("shape,crop", [((6, 3, 4, 32, 48), 112), ((3, 3, 8, 112, 112), 112), ((6, 3, 2, 24, 36), 64),
                                         ((2, 3, 2, 130, 132), 112)])
 def test_color_pipeline_matches_torch_ops(fx, shape, crop):
-    """K9 against the same pipeline written as PyTorch ops (SyncMoCoAugmentV5._color_torch, the host path): every
+    """K9 against the same pipeline written as PyTorch ops (oracle/aug_oracle.py): every
     combination of jitter / grayscale / blur / flip decisions, given parameters.  crop 112 -> 11 taps (frames up to 128
     wide take the in-place shared-memory kernel, wider ones the generic one), crop 64 -> 7 taps (generic kernel)."""
     from mscl_b200.common.ssl_aug import SyncMoCoAugmentV5
+    from oracle import aug_oracle as A
     aug = SyncMoCoAugmentV5(crop_size=crop, sync_level=("batch", "batch"), t=(8, 8), flow_suffix="flow_imgs")
+    mean, std = aug.mean.view(-1), aug.std.view(-1)
     n = shape[0]
     gen = torch.Generator().manual_seed(n)
     x = torch.rand(shape, generator=gen)
@@ -380,14 +382,14 @@ def test_color_pipeline_matches_torch_ops(fx, shape, crop):
     prm["gray"] = torch.tensor([combos[i % 6][1] for i in range(n)], dtype=torch.bool)
     prm["blur"] = torch.tensor([combos[i % 6][2] for i in range(n)], dtype=torch.bool)
     flip = torch.tensor([i % 2 == 0 for i in range(n)])
-    want = aug._normalize(aug._color_torch(aug.flip(x, flip), prm))
+    want = A.normalize(A.color_pipeline(A.flip(x, flip), prm, aug.blur_radius), mean, std)
     dev = torch.device("cuda")
     prm_d = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in prm.items()}
     norm = torch.cat([aug.mean.view(-1), aug.std.view(-1)]).to(dev)
     got = fx.color_pipeline(x.to(dev), aug._pack_params(prm_d, flip.to(dev), False), prm_d["taps"].contiguous(), norm)
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-5, atol=2e-5)
     weak = fx.color_pipeline(x.to(dev), aug._pack_params(prm_d, flip.to(dev), True), prm_d["taps"].contiguous(), norm)
-    np.testing.assert_allclose(weak.cpu().numpy(), aug._normalize(aug.flip(x, flip)).numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(weak.cpu().numpy(), A.normalize(A.flip(x, flip), mean, std).numpy(), rtol=1e-6, atol=1e-6)
 
 
 def test_augmentation_module_on_device(fx):

@@ -146,6 +146,110 @@ def test_flow_visualizer_matches_reference(golden_dir):
     np.testing.assert_array_equal(O.colorwheel(), g["wheel"])
     out = O.flow_visualize(torch.from_numpy(g["flows"]))
     np.testing.assert_array_equal(out.numpy(), g["out"])
-    # the host path of the product's registry class is the same op sequence
-    from mscl_b200.common.ssl_aug import FlowVisualizer
-    np.testing.assert_array_equal(FlowVisualizer()._torch(torch.from_numpy(g["flows"])).numpy(), g["out"])
+
+
+# ------------------------------------------------------------------ sibling heads / recognizers
+def _projections(g, name, kw):
+    """trans_rgb / trans_flow of a frame-level head rebuilt from the reference's stored state_dict."""
+    import torch.nn as nn
+    b_rgb, b_flow = kw["bkb_channels"]
+    cls = str(name)
+    trans_rgb = trans_flow = None
+    keys = [k for k in g.files if k.startswith(f"{cls}/state/")]
+    if any("trans_rgb.0.weight" in k for k in keys):
+        trans_rgb = nn.Sequential(nn.Conv1d(b_rgb, 128, 1), nn.ReLU(), nn.Conv1d(128, 128, 1))
+    elif any("trans_rgb.weight" in k for k in keys):
+        trans_rgb = nn.Conv1d(b_rgb, 128, 1)
+    if any("trans_flow.weight" in k for k in keys):
+        trans_flow = nn.Conv1d(b_flow, 128, 1)
+    for mod, pre in ((trans_rgb, "trans_rgb."), (trans_flow, "trans_flow.")):
+        if mod is not None:
+            mod.load_state_dict({k.split("/state/")[1][len(pre):]: torch.from_numpy(g[k]) for k in keys
+                                 if k.split("/state/")[1].startswith(pre)}, strict=True)
+    return trans_rgb, trans_flow
+
+
+def run_oracle_sibling_head(g, case):
+    """Oracle losses + leaves (with grads) for one sibling-head case; shared with the GPU parity test."""
+    name, cls_name, kw, _, _, with_aug = case
+    q_mlvl, qf_mlvl, qaf_mlvl = inputs.sibling_head_inputs(case)
+    leaves = [x.requires_grad_(True) for x in q_mlvl + qf_mlvl + (qaf_mlvl or [])]
+    trans_rgb, trans_flow = _projections(g, name, kw)
+    if cls_name == "MlvlMSCLWithAugPosHead":
+        losses = O.mlvl_lmcl(q_mlvl, qf_mlvl, qaf_mlvl, kw["mlvl_ids"], kw["mlvl_flow_ids"], kw["T"], kw["t"], trans_rgb, trans_flow)
+    elif cls_name == "MoDistv2PosHead":
+        losses = O.frame_contrast(q_mlvl[kw["mlvl_ids"][0]], qf_mlvl[kw["mlvl_ids"][1]], kw["T"], kw["t"], trans_rgb, trans_flow)
+    else:
+        losses = O.lmcl(q_mlvl[kw["mlvl_ids"][0]], qf_mlvl[kw["mlvl_ids"][1]], qaf_mlvl[kw["mlvl_ids"][1]], kw["T"], kw["t"],
+                        trans_rgb, trans_flow)
+    sum(v for k, v in losses.items() if "loss" in k).backward()
+    params = {}
+    for mod, pre in ((trans_rgb, "trans_rgb."), (trans_flow, "trans_flow.")):
+        if mod is not None:
+            params.update({pre + k: p for k, p in mod.named_parameters()})
+    return losses, leaves, params
+
+
+def test_sibling_heads_oracle_matches_reference(golden_dir):
+    """frame_contrast / lmcl / mlvl_lmcl vs the reference's MSCLWithAugPosHead, MoDistv2PosHead and
+    MlvlMSCLWithAugPosHead (heads/moco_head_v2.py:128-441)."""
+    g = _load(golden_dir, "sibling_heads.npz")
+    for case in inputs.sibling_head_cases():
+        name = case[0]
+        losses, leaves, params = run_oracle_sibling_head(g, case)
+        assert list(losses.keys()) == [str(k) for k in g[f"{name}/out_order"]]
+        for k, v in losses.items():
+            ref = float(g[f"{name}/out/{k}"])
+            assert abs(float(v) - ref) <= 2e-6 * max(1.0, abs(ref)), (name, k, float(v), ref)
+        for i, x in enumerate(leaves):
+            got = x.grad.sum(dim=(-2, -1)).numpy() if x.grad is not None else np.zeros(x.shape[:3], dtype=np.float32)
+            np.testing.assert_allclose(got, g[f"{name}/gradsum/{i}"], rtol=1e-4, atol=2e-6, err_msg=f"{name} leaf {i}")
+        for k, p in params.items():
+            np.testing.assert_allclose(p.grad.numpy(), g[f"{name}/pgrad/{k}"], rtol=1e-4, atol=2e-6, err_msg=f"{name} {k}")
+
+
+def run_oracle_two_branch(g, kind):
+    """Two consecutive MSCL / MoDist steps through the oracle; yields per step (log_vars, leaves, rgb, flow)."""
+    import torch.nn as nn
+    kw = eval(str(g["kwargs"]))
+    inp = inputs.head_inputs(**kw)
+    rgb = O.QueueState(inp["queue_rgb"], inp["count"], inp["ptr"])
+    flow = O.QueueState(inp["queue_flow"], inp["count"], inp["ptr"])
+    trans_flow = None
+    if kind == "mscl":
+        trans_flow = nn.Conv1d(128, 128, 1)
+        trans_flow.load_state_dict({"weight": torch.from_numpy(g["mscl/sup_state/trans_flow.weight"]),
+                                    "bias": torch.from_numpy(g["mscl/sup_state/trans_flow.bias"])})
+    for step in range(2):
+        x = inputs.head_inputs(**dict(kw, seed=kw["seed"] + step))
+        leaves = {n: x[n].clone().requires_grad_(True) for n in ("q", "q_f", "q_map", "qf_map")}
+        feats = dict(k=x["k"], k_f=x["k_f"], **leaves)
+        sup = None
+        if kind == "mscl":
+            sup = lambda: O.frame_contrast(leaves["q_map"], leaves["qf_map"], 0.07, kw["t"], None, trans_flow)
+        losses = O.two_branch_objective(feats, rgb, flow, T=0.07, same_kn=True, kind=kind, sup=sup)
+        loss, log_vars = O.parse_losses(losses)
+        loss.backward()
+        yield step, log_vars, leaves, rgb, flow
+
+
+def test_two_branch_oracle_matches_reference(golden_dir):
+    """two_branch_objective vs the reference's MSCL (recognizers/mscl.py:9-134) and MoDist
+    (recognizers/modist.py:9-132) over two consecutive steps."""
+    g = _load(golden_dir, "two_branch.npz")
+    for kind in ("mscl", "modist"):
+        for step, log_vars, leaves, rgb, flow in run_oracle_two_branch(g, kind):
+            tag = f"{kind}/step{step}"
+            assert list(log_vars.keys()) == [str(k) for k in g[f"{tag}/logvar_order"]]
+            for k, v in log_vars.items():
+                ref = float(g[f"{tag}/logvar/{k}"])
+                assert abs(v - ref) <= 2e-6 * max(1.0, abs(ref)), (tag, k, v, ref)
+            for n in ("q", "q_f"):
+                np.testing.assert_allclose(leaves[n].grad.numpy(), g[f"{tag}/grad/{n}"], rtol=1e-5, atol=2e-6)
+            if kind == "mscl":
+                for n in ("q_map", "qf_map"):
+                    np.testing.assert_allclose(leaves[n].grad.sum(dim=(-2, -1)).numpy(), g[f"{tag}/gradsum/{n}"], rtol=1e-4, atol=2e-6)
+            for br, st in (("rgb", rgb), ("flow", flow)):
+                assert st.ptr == int(g[f"{tag}/after/{br}/ptr"][0]) and st.iters == int(g[f"{tag}/after/{br}/iters"])
+                np.testing.assert_array_equal(st.count.numpy(), g[f"{tag}/after/{br}/count"])
+                np.testing.assert_array_equal(st.queue.numpy(), g[f"{tag}/after/{br}/queue"])

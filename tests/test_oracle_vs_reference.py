@@ -98,3 +98,122 @@ def test_fra_live(pair):
     out = ref.NormFlowWithStidedAug(ratios=(0.2, 1.8), num_chunks=8)(dict(flows=[f.copy() for f in flows]))
     got = np.stack(O.fra(flows, int(out["ap_labels"])))
     np.testing.assert_allclose(got, np.stack(out["flow_imgs"]), rtol=3e-6, atol=3e-7)
+
+
+# ------------------------------------------------------------------ sibling recognizers / backbone
+def test_slowonly_backbone_matches_reference():
+    """mscl_b200's ResNet3dSlowOnly against the reference class with the r50 configs' arguments: state_dict keys,
+    parameter count of BASELINE config 5 (31,672,128 in 159 tensors), identical init stream and forward outputs."""
+    from mscl_b200.backbones import ResNet3dSlowOnly
+    Ref = ref_shim.load_slowonly()
+    kw = dict(depth=50, pretrained=None, pretrained2d=False, lateral=False, num_stages=4, conv1_kernel=(5, 7, 7),
+              conv1_stride_t=2, pool1_stride_t=1, spatial_strides=(1, 2, 2, 2), out_indices=(0, 1, 2, 3))
+    r, m = Ref(**kw), ResNet3dSlowOnly(**kw)
+    torch.manual_seed(1)
+    r.init_weights()
+    torch.manual_seed(1)
+    m.init_weights()
+    sr, sm = r.state_dict(), m.state_dict()
+    assert list(sr) == list(sm)
+    for k in sr:
+        assert torch.equal(sr[k], sm[k]), k
+    assert sum(p.numel() for p in m.parameters()) == 31_672_128 and len(list(m.parameters())) == 159
+    for k, v in sr.items():     # the zero-initialised last batch norms would hide the residual branches
+        if ".bn." in k and k.endswith(("weight", "bias")):
+            v.uniform_(0.5, 1.5)
+    m.load_state_dict(sr, strict=True)
+    x = torch.rand(2, 3, 8, 64, 64)
+    for mode in (False, True):
+        r.train(mode), m.train(mode)
+        for a, b in zip(r(x), m(x)):
+            assert a.shape == b.shape and torch.equal(a, b)
+
+
+def _small_moco_cfg(typ, K, **kw):
+    cfg = dict(type=typ, backbone=dict(type="resnet_flow.r2d_18"), neck=dict(type="BaseMoCo"),
+               moco_head=dict(type="MoCoHead", basename="", loss_cls=dict(type="CrossEntropyLoss_torch", ignore_index=-1)),
+               im_key="imgs", dim_in=128, dim=128, K=K, T=0.07, mlp=True, aux_info=[], aug=dict(type="IdentityAug"))
+    cfg.update(kw)
+    return cfg
+
+
+def test_moco_v1_full_step_matches_reference():
+    """`MoCo` (constant momentum, recognizers/moco.py:30-316) -- oracle step vs the unmodified reference, 2 steps."""
+    import mscl_b200
+    from oracle.step import OracleMoCo
+    ref = ref_shim.load_reference()
+    ref_shim.ensure_process_group()
+    cfg = _small_moco_cfg("MoCo", 64, m=0.99)
+    torch.manual_seed(0)
+    ref_model = ref.builder.build_model(cfg)
+    mine = mscl_b200.build_model(cfg)
+    assert set(ref_model.state_dict()) == set(mine.state_dict())
+    mine.load_state_dict(ref_model.state_dict(), strict=True)
+    ref_model.train(), mine.train()
+    orc = OracleMoCo(mine)
+    g = torch.Generator().manual_seed(5)
+    data = dict(imgs=[torch.rand(4, 3, 8, 32, 32, generator=g) for _ in range(2)])
+    for step in range(2):
+        torch.manual_seed(100 + step)
+        out = ref_model.train_step(data, None)
+        ref_model.zero_grad()
+        out["loss"].backward()
+        torch.manual_seed(100 + step)
+        for p in orc.parameters():
+            p.grad = None
+        loss, log_vars = orc.train_step(data["imgs"][0], data["imgs"][1])
+        loss.backward()
+        assert list(log_vars) == list(out["log_vars"])
+        for k, v in out["log_vars"].items():
+            assert abs(log_vars[k] - v) <= 2e-5 * max(1.0, abs(v)), (step, k, log_vars[k], v)
+        st = orc.branch.state
+        assert int(ref_model.queue_ptr) == st.ptr
+        np.testing.assert_array_equal(ref_model.count.numpy(), st.count.numpy())
+        np.testing.assert_allclose(ref_model.queue.numpy(), st.queue.numpy(), rtol=0, atol=2e-6)
+        kr = dict(ref_model.named_parameters())
+        np.testing.assert_allclose(orc.branch.mlp_k[0].weight.detach().numpy(), kr["mlp_k.0.weight"].detach().numpy(), rtol=0, atol=1e-7)
+        a, b = orc.branch.mlp_q[2].weight.grad, kr["mlp_q.2.weight"].grad
+        assert float((a - b).norm() / b.norm()) < 2e-4
+
+
+@pytest.mark.parametrize("kind", ["mscl", "modist"])
+def test_two_branch_full_step_matches_reference(kind):
+    """MSCL (+ MoDistv2PosHead) and MoDist: oracle step (oracle/step.py OracleTwoBranch) vs the unmodified reference."""
+    import mscl_b200
+    from oracle import make_golden as G
+    from oracle.step import OracleTwoBranch
+    ref = ref_shim.load_reference()
+    ref_shim.ensure_process_group()
+    K, t = 64, 4
+    torch.manual_seed(0)
+    ref_model = G._two_branch_model(ref, kind, K, t, mlvl_ids=(-1, -1))
+    if kind == "mscl":
+        cfg = dict(type="MSCL", recognizer=G._flow_recognizer_cfg(K, ""), recognizer_flow=G._flow_recognizer_cfg(K, "flow"),
+                   moco_mx_head=dict(type="MSCLWithAugMxHead", basename="mx", loss_cls=G.LOSS, same_kn=True, T=0.07),
+                   sup_head=dict(type="MoDistv2PosHead", basename="", loss_pos=G.LOSS, bkb_channels=(None, 128), t=t, T=0.07,
+                                 mlvl_ids=(-1, -1), aux_keys=dict(im_features=dict(q_mlvl="q_mlvl"), base_flow_features=dict(q_mlvl="q_flow_mlvl"))),
+                   im_key="imgs", flow_key="flow_imgs", flow_img_key="flow_imgs", aux_info=[], aug=dict(type="IdentityAug"), same_kn=True)
+    else:
+        cfg = dict(type="MoDist", recognizer=G._flow_recognizer_cfg(K, ""), recognizer_flow=G._flow_recognizer_cfg(K, "flow"),
+                   moco_head=dict(type="MoCoHead", basename="mx", loss_cls=G.LOSS), im_key="imgs", flow_key="flow_imgs",
+                   aux_info=[], aug=dict(type="IdentityAug"), same_kn=True)
+    mine = mscl_b200.build_model(cfg)
+    assert set(ref_model.state_dict()) == set(mine.state_dict())
+    mine.load_state_dict(ref_model.state_dict(), strict=True)
+    ref_model.train(), mine.train()
+    orc = OracleTwoBranch(mine, kind)
+    g = torch.Generator().manual_seed(6)
+    data = dict(imgs=[torch.rand(4, 3, 8, 32, 32, generator=g) for _ in range(2)],
+                flow_imgs=[torch.rand(4, 3, 8, 32, 32, generator=g) for _ in range(2)])
+    for step in range(2):
+        torch.manual_seed(100 + step)
+        out = ref_model.train_step(data, None)
+        torch.manual_seed(100 + step)
+        loss, log_vars = orc.train_step(data["imgs"][0], data["imgs"][1], data["flow_imgs"][0], data["flow_imgs"][1])
+        assert list(log_vars) == list(out["log_vars"])
+        for k, v in out["log_vars"].items():
+            assert abs(log_vars[k] - v) <= 2e-5 * max(1.0, abs(v)), (kind, step, k, log_vars[k], v)
+        for rec, st in ((ref_model.recognizer, orc.rgb.state), (ref_model.recognizer_flow, orc.flow.state)):
+            assert int(rec.queue_ptr) == st.ptr and rec.iters == st.iters and rec.batch_size == st.batch_size
+            np.testing.assert_array_equal(rec.count.numpy(), st.count.numpy())
+            np.testing.assert_allclose(rec.queue.numpy(), st.queue.numpy(), rtol=0, atol=2e-6)
