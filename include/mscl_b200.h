@@ -290,6 +290,22 @@ int mscl_clip_sgd_multi(float *const *d_g_ptrs, float *const *d_p_ptrs, float *c
                         int32_t n_blocks, int32_t chunk_elems, const float *d_stats, float weight_decay,
                         float momentum, float lr, int32_t first_step, mscl_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * K11  nearest-neighbour retrieval evaluation.   replaces tools/test_retrival.py:286-304:
+ *        feature -= feature.mean(dim=0); feature = F.normalize(feature, p=2, dim=1)           (train and test)
+ *        sim = test @ train.T                    (a plain library GEMM: cuBLAS, done by the caller)
+ *        for k in (1,5,10,20,50): acc = any(train_label[topk(sim, k).indices] == test_label[:, None], dim=1).mean()
+ * mscl_center_normalize: x [N, D] row-major -> out [N, D]; d_partial double [n_chunks][D] and d_mean float [D] scratch
+ *   (column sums in double, fixed order).
+ * mscl_retrieval_rank:   sim [n_test, ld >= n_train] -> rank int32 [n_test] = number of train items scoring strictly
+ *   above the test item's best same-label train item (n_train if the label never occurs), so that the reference's
+ *   acc@k == mean(rank < k) for every k at once (ties at the k-th value aside, which torch.topk breaks arbitrarily).
+ */
+int mscl_center_normalize(const float *d_x, int64_t N, int32_t D, double *d_partial, int32_t n_chunks, float *d_mean,
+                          float *d_out, mscl_stream_t stream);
+int mscl_retrieval_rank(const float *d_sim, int64_t ld, const int64_t *d_train_label, const int64_t *d_test_label,
+                        int32_t n_test, int32_t n_train, int32_t *d_rank, mscl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

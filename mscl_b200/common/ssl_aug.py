@@ -57,6 +57,10 @@ class IdentityAug:
             return clips                     # reference signature (common/ssl_aug.py:178-183)
         return clips, im_k, aux_info
 
+    def forward_with_flow(self, im_q, im_k, flow_q, flow_k, aux_info):
+        """What MoDist.forward_train calls (recognizers/modist.py:79)."""
+        return im_q, im_k, flow_q, flow_k, aux_info
+
 
 def _hue_matrix(h):
     """(n,3,3) RGB->RGB matrices rotating hue by h (fraction of a turn, per sample) in YIQ space."""

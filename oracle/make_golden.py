@@ -12,7 +12,7 @@ import sys
 import numpy as np
 import torch
 
-from . import inputs, ref_shim
+from . import inputs, mscl_oracle as O, ref_shim
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 LOSS = dict(type="CrossEntropyLoss_torch", ignore_index=-1)
@@ -305,6 +305,30 @@ def golden_two_branch(ref):
     np.savez_compressed(os.path.join(OUT, "two_branch.npz"), **res)
 
 
+def golden_retrieval(ref):
+    """Lines 286-304 of the reference's tools/test_retrival.py (the script body after feature extraction), executed
+    from the reference tree on seeded features: the five kNN accuracies."""
+    import textwrap
+    import torch.nn.functional as F
+    path = os.path.join(ref_shim.REF_ROOT, "tools", "test_retrival.py")
+    with open(path) as f:
+        lines = f.read().split("\n")
+    start = next(i for i, l in enumerate(lines) if l.strip().startswith("ks = [1,5,10,20,50]"))
+    end = next(i for i, l in enumerate(lines) if i > start and l.strip().startswith("print('%dNN acc"))
+    body = textwrap.dedent("\n".join(lines[start:end + 1]))
+    res = {}
+    for name, kw in (("small", dict(seed=0)), ("wide", dict(seed=1, n_train=1500, n_test=400, dim=512, n_classes=101, noise=6.0))):
+        train, test, train_label, test_label = O.retrieval_inputs(**kw)
+        ns = dict(torch=torch, F=F, train_feature=train.clone(), test_feature=test.clone(), train_label=train_label,
+                  test_label=test_label)
+        exec(compile(body, path, "exec"), ns)
+        res[f"{name}/acc"] = np.array(ns["NN_acc"], dtype=np.float64)
+        res[f"{name}/kwargs"] = np.array(repr(kw))
+        res[f"{name}/digest"] = np.array(inputs.digest(train, test, train_label, test_label))
+        print("retrieval", name, ns["NN_acc"])
+    np.savez_compressed(os.path.join(OUT, "retrieval.npz"), **res)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load_reference()
@@ -318,6 +342,7 @@ def main():
     golden_flowvis(ref)
     golden_sibling_heads(ref)
     golden_two_branch(ref)
+    golden_retrieval(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

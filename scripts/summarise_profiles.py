@@ -18,11 +18,16 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 GP = os.path.join(ROOT, "gpurun_out")
-OURS = ("infonce", "ema_multi", "fra_", "hw_mean", "enqueue_kernel", "lmcl_kernel", "queue_transpose", "gather_rows")
+OURS = ("infonce", "ema_multi", "fra_", "hw_mean", "enqueue_kernel", "lmcl_kernel", "queue_transpose", "gather_rows",
+        "clip_sgd_multi", "grad_sqnorm_multi", "grad_norm_finish", "color_pipeline", "clip_gray_sum", "flow_visualize",
+        "upsample_trilinear")
 ENTRY = {"infonce_tc_kernel": "mscl_infonce_partial", "ema_multi_kernel": "mscl_ema_multi", "fra_maxrad_kernel": "mscl_fra_maxrad",
          "fra_apply_kernel": "mscl_fra_apply", "fra_fused_kernel": "mscl_fra_fused", "hw_mean_fwd_kernel": "mscl_hw_mean_fwd",
          "hw_mean_bwd_kernel": "mscl_hw_mean_bwd", "hw_mean_fwd_small_kernel": "mscl_hw_mean_fwd",
-         "hw_mean_bwd_small_kernel": "mscl_hw_mean_bwd", "enqueue_kernel": "mscl_enqueue", "lmcl_kernel": "mscl_lmcl"}
+         "hw_mean_bwd_small_kernel": "mscl_hw_mean_bwd", "enqueue_kernel": "mscl_enqueue", "lmcl_kernel": "mscl_lmcl", "clip_sgd_multi_kernel": "mscl_clip_sgd_multi",
+         "grad_sqnorm_multi_kernel": "mscl_grad_sqnorm_multi", "color_pipeline_fast_kernel": "mscl_color_pipeline",
+         "color_pipeline_kernel": "mscl_color_pipeline", "flow_visualize_kernel": "mscl_flow_visualize",
+         "upsample_trilinear_fwd_kernel": "mscl_upsample_trilinear_fwd", "upsample_trilinear_bwd_kernel": "mscl_upsample_trilinear_bwd"}
 
 
 def launch_shares(tag):
@@ -61,9 +66,13 @@ def launch_shares(tag):
 
 def kernel_metrics(tag):
     rep = os.path.join(GP, "prof_kernels.ncu-rep")
-    if not os.path.exists(rep):
+    raw_csv = os.path.join(GP, "prof_kernels_raw.csv")       # exported on the GPU box (the .ncu-rep may be too big to travel)
+    if os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    elif os.path.exists(raw_csv):
+        raw = open(raw_csv).read()
+    else:
         return
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(raw.splitlines()))
     hdr, units, rows = r[0], r[1], r[2:]
     want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",

@@ -1,0 +1,327 @@
+"""GPU parity of the sibling heads / recognizers / augmentations against the golden fixtures
+produced by the unmodified reference (oracle/make_golden.py) and against the oracle.  Needs a B200: `pytest -m gpu`."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-3          # InfoNCE terms: tf32 operands, fp32 accumulate (the north star's contract)
+REL_FRAME = 1e-4    # frame-level heads: fp32 throughout
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _needs_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the Conv1d projections / encoders are compared with fp32 CPU runs
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+LOSS = dict(type="CrossEntropyLoss_torch", ignore_index=-1)
+
+
+# ------------------------------------------------------------------ frame-level heads
+def test_sibling_heads_vs_reference_golden(golden_dir):
+    """MSCLWithAugPosHead, MoDistv2PosHead, MlvlMSCLWithAugPosHead (heads/moco_head_v2.py:128-441) on the hw_mean + lmcl
+    kernels: losses, accuracies, input and projection gradients against the reference's numbers and the oracle."""
+    import mscl_b200
+    from oracle import inputs
+    from test_oracle_golden import run_oracle_sibling_head
+    g = np.load(os.path.join(golden_dir, "sibling_heads.npz"), allow_pickle=False)
+    for case in inputs.sibling_head_cases():
+        name, cls_name, kw, _, _, with_aug = case
+        head = mscl_b200.build_head(dict(type=cls_name, basename="", loss_pos=LOSS, loss_cls=LOSS, **kw))
+        state = {k.split("/state/")[1]: torch.from_numpy(g[k]) for k in g.files if k.startswith(f"{name}/state/")}
+        head.load_state_dict(state, strict=True)
+        head = head.cuda()
+        q_mlvl, qf_mlvl, qaf_mlvl = inputs.sibling_head_inputs(case)
+        n_rgb, n_flow = len(q_mlvl), len(qf_mlvl)
+        leaves = [x.cuda().requires_grad_(True) for x in q_mlvl + qf_mlvl + (qaf_mlvl or [])]
+        args = dict(q_mlvl=leaves[:n_rgb], q_flow_mlvl=leaves[n_rgb:n_rgb + n_flow])
+        if with_aug:
+            args["q_aug_flow_mlvl"] = leaves[n_rgb + n_flow:]
+        losses = head.loss(**head(**args))
+        sum(v for k, v in losses.items() if "loss" in k).backward()
+        ref_losses, ref_leaves, ref_params = run_oracle_sibling_head(g, case)
+        assert list(losses.keys()) == [str(k) for k in g[f"{name}/out_order"]] == list(ref_losses.keys())
+        for k, v in losses.items():
+            for ref in (float(g[f"{name}/out/{k}"]), float(ref_losses[k])):
+                if "acc" in k:
+                    assert float(v) == pytest.approx(ref, abs=1e-6), (name, k, float(v), ref)
+                else:
+                    assert abs(float(v) - ref) <= REL_FRAME * abs(ref), (name, k, float(v), ref)
+        for i, (x, xr) in enumerate(zip(leaves, ref_leaves)):
+            if xr.grad is None:           # a pyramid level no (rgb, flow) pair reads
+                assert x.grad is None or float(x.grad.abs().max()) == 0.0
+                continue
+            assert _rel(x.grad, xr.grad) < REL_FRAME, (name, i, _rel(x.grad, xr.grad))
+            assert _rel(x.grad.sum(dim=(-2, -1)), torch.from_numpy(g[f"{name}/gradsum/{i}"])) < REL_FRAME, (name, i)
+        for k, p in head.named_parameters():
+            assert _rel(p.grad, torch.from_numpy(g[f"{name}/pgrad/{k}"])) < REL_FRAME, (name, k)
+            assert _rel(p.grad, ref_params[k].grad) < REL_FRAME, (name, k)
+
+
+def test_moco_head_v2_fused_vs_materialised():
+    """MoCoHeadV2 (heads/moco_head_v3.py:15-85): the fused row equals the head's own materialised logits + CE + top-k."""
+    import mscl_b200
+    from oracle import inputs
+    inp = inputs.head_inputs(seed=9, N=16, K=1024, t=4, hw_rgb=2, hw_flow=2)
+    rec = mscl_b200.build_model(_moco_cfg("MoCoV2", 1024, m_base=0.994, max_iters=100)).cuda().train()
+    rec.load_state_dict({"queue": inp["queue_rgb"], "count": inp["count"], "queue_ptr": torch.tensor([inp["ptr"]])}, strict=False)
+    head = mscl_b200.build_head(dict(type="MoCoHeadV2", basename="v2", loss_cls=LOSS, T=0.2)).cuda()
+    q, k = inp["q"].cuda().requires_grad_(True), inp["k"].cuda()
+    fused = head.loss_fused(head.forward_fused(q, k, rec))
+    fused["loss_cls_v2"].backward()
+    g_fused = q.grad.clone()
+    q.grad = None
+    w = rec.negative_queue().weight()
+    mat = head.loss(**head(q, k, w))
+    mat["loss_cls_v2"].backward()
+    assert list(fused.keys()) == list(mat.keys())
+    for key in fused:
+        if "acc" in key:
+            assert float(fused[key]) == pytest.approx(float(mat[key]), abs=1e-6), key
+        else:
+            assert abs(float(fused[key]) - float(mat[key])) <= REL * abs(float(mat[key])), key
+    assert _rel(g_fused, q.grad) < REL
+
+
+# ------------------------------------------------------------------ two-branch recognizers at head level
+def _moco_cfg(typ, K, basename="", **kw):
+    cfg = dict(type=typ, backbone=dict(type="resnet_flow.r2d_18"), neck=dict(type="BaseMoCo"),
+               moco_head=dict(type="MoCoHead", basename=basename, loss_cls=LOSS), im_key="imgs", dim_in=128, dim=128, K=K,
+               T=0.07, mlp=True, aux_info=[], aug=dict(type="IdentityAug"))
+    cfg.update(kw)
+    return cfg
+
+
+def _two_branch_cfg(kind, K, t, mlvl_ids=(0, -1)):
+    rec = lambda b: _moco_cfg("MoCoV2", K, b, m_base=0.994, max_iters=1000)
+    if kind == "mscl":
+        return dict(type="MSCL", recognizer=rec(""), recognizer_flow=rec("flow"),
+                    moco_mx_head=dict(type="MSCLWithAugMxHead", basename="mx", loss_cls=LOSS, same_kn=True, T=0.07),
+                    sup_head=dict(type="MoDistv2PosHead", basename="", loss_pos=LOSS, bkb_channels=(None, 128), t=t, T=0.07,
+                                  mlvl_ids=mlvl_ids, aux_keys=dict(im_features=dict(q_mlvl="q_mlvl"),
+                                                                   base_flow_features=dict(q_mlvl="q_flow_mlvl"))),
+                    im_key="imgs", flow_key="flow_imgs", flow_img_key="flow_imgs", aux_info=[], aug=dict(type="IdentityAug"),
+                    same_kn=True)
+    return dict(type="MoDist", recognizer=rec(""), recognizer_flow=rec("flow"),
+                moco_head=dict(type="MoCoHead", basename="mx", loss_cls=LOSS), im_key="imgs", flow_key="flow_imgs",
+                aux_info=[], aug=dict(type="IdentityAug"), same_kn=True)
+
+
+@pytest.mark.parametrize("kind", ["mscl", "modist"])
+def test_two_branch_objective_vs_reference_golden(kind, golden_dir):
+    """MSCL / MoDist `objective` (4 InfoNCE terms in two fused queue passes + the frame-level head) over two consecutive
+    steps: log vars in the reference's order, query / feature-map gradients, queue contents / ages / pointer bit-exact."""
+    import mscl_b200
+    from oracle import inputs
+    from test_oracle_golden import run_oracle_two_branch
+    g = np.load(os.path.join(golden_dir, "two_branch.npz"), allow_pickle=False)
+    kw = eval(str(g["kwargs"]))
+    inp = inputs.head_inputs(**kw)
+    model = mscl_b200.build_model(_two_branch_cfg(kind, kw["K"], kw["t"])).train()
+    ptr = torch.tensor([inp["ptr"]])
+    state = {"recognizer.queue": inp["queue_rgb"], "recognizer.count": inp["count"], "recognizer.queue_ptr": ptr,
+             "recognizer_flow.queue": inp["queue_flow"], "recognizer_flow.count": inp["count"], "recognizer_flow.queue_ptr": ptr}
+    if kind == "mscl":
+        state.update({f"sup_head.{k.split('/sup_state/')[1]}": torch.from_numpy(g[k]) for k in g.files if "/sup_state/" in k})
+    assert not model.load_state_dict(state, strict=False).unexpected_keys
+    model = model.cuda()
+    N = kw["N"]
+    for step, ref_vars, ref_leaves, rgb, flow in run_oracle_two_branch(g, kind):
+        x = inputs.head_inputs(**dict(kw, seed=kw["seed"] + step))
+        leaves = {n: x[n].cuda().requires_grad_(True) for n in ("q", "q_f", "q_map", "qf_map")}
+        k, k_f = x["k"].cuda(), x["k_f"].cuda()
+        model.recognizer.note_branch(N, True)          # what forward_train does after each encoder call
+        model.recognizer_flow.note_branch(N, True)
+        if kind == "mscl":
+            losses = model.objective(dict(q=leaves["q"], k=k, q_f=leaves["q_f"], k_f=k_f, aux_info={},
+                                          im_features=dict(q_mlvl=[leaves["q_map"]]),
+                                          flow_features=dict(q_mlvl=[leaves["qf_map"]])))
+        else:
+            losses = model.objective(leaves["q"], k, leaves["q_f"], k_f)
+        loss, log_vars = model._parse_losses(losses)
+        loss.backward()
+        tag = f"{kind}/step{step}"
+        assert list(log_vars.keys()) == [str(s) for s in g[f"{tag}/logvar_order"]]
+        for key, v in log_vars.items():
+            for ref in (float(g[f"{tag}/logvar/{key}"]), ref_vars[key]):
+                if "acc" in key:
+                    assert v == pytest.approx(ref, abs=1e-6), (tag, key, v, ref)
+                else:
+                    assert abs(v - ref) <= REL * abs(ref), (tag, key, v, ref)
+        for n in ("q", "q_f"):
+            assert _rel(leaves[n].grad, torch.from_numpy(g[f"{tag}/grad/{n}"])) < REL, (tag, n)
+            assert _rel(leaves[n].grad, ref_leaves[n].grad) < REL, (tag, n)
+        if kind == "mscl":
+            for n in ("q_map", "qf_map"):
+                assert _rel(leaves[n].grad, ref_leaves[n].grad) < REL_FRAME, (tag, n)
+                assert _rel(leaves[n].grad.sum(dim=(-2, -1)), torch.from_numpy(g[f"{tag}/gradsum/{n}"])) < REL_FRAME, (tag, n)
+        for br, rec, st in (("rgb", model.recognizer, rgb), ("flow", model.recognizer_flow, flow)):
+            sd = {kk: vv.cpu() for kk, vv in rec.state_dict().items() if kk in ("queue", "count", "queue_ptr")}
+            assert int(sd["queue_ptr"]) == st.ptr == int(g[f"{tag}/after/{br}/ptr"][0])
+            assert rec.iters == st.iters == int(g[f"{tag}/after/{br}/iters"])
+            np.testing.assert_array_equal(sd["count"].numpy(), g[f"{tag}/after/{br}/count"])
+            np.testing.assert_array_equal(sd["queue"].numpy(), g[f"{tag}/after/{br}/queue"])
+
+
+# ------------------------------------------------------------------ whole steps through the encoders
+def _check_step_state(rec, ob, tag):
+    sd = rec.state_dict()
+    assert int(sd["queue_ptr"]) == ob.state.ptr, tag
+    np.testing.assert_array_equal(sd["count"].cpu().numpy(), ob.state.count.numpy())
+    assert _rel(sd["queue"], ob.state.queue) < 1e-4, tag              # keys come from GPU vs CPU encoders
+    for pk, po in zip([p for m in (rec.encoder_k, rec.neck_k, rec.mlp_k) for p in m.parameters()], ob.k_params()):
+        np.testing.assert_array_equal(pk.detach().cpu().numpy(), po.detach().numpy())     # EMA: bit-exact
+
+
+def _grad_rel(gp, go):
+    assert len(gp) == len(go)
+    assert all((a.grad is None) == (b.grad is None) for a, b in zip(gp, go))
+    num = sum(float((a.grad.cpu().double() - b.grad.double()).pow(2).sum()) for a, b in zip(gp, go) if b.grad is not None)
+    den = sum(float(b.grad.double().pow(2).sum()) for b in go if b.grad is not None)
+    return (num / den) ** 0.5
+
+
+def test_moco_v1_train_step_vs_oracle():
+    """`MoCo` (constant momentum; the recognizer of the four moco_r*.py configs): three whole train_steps against the
+    oracle with identical weights -- log vars, encoder gradients, EMA'd key encoder (bit-exact), queue state."""
+    import mscl_b200
+    from oracle.step import OracleMoCo
+    torch.manual_seed(0)
+    model = mscl_b200.build_model(_moco_cfg("MoCo", 256, m=0.99)).train()
+    orc = OracleMoCo(model)
+    model = model.cuda()
+    N = 8
+    for step in range(3):
+        g = torch.Generator().manual_seed(20 + step)
+        imgs = [torch.rand(N, 3, 8, 64, 64, generator=g) for _ in range(2)]
+        torch.manual_seed(100 + step)
+        loss_ref, vars_ref = orc.train_step(imgs[0], imgs[1])
+        for p in orc.parameters():
+            p.grad = None
+        loss_ref.backward()
+        torch.manual_seed(100 + step)
+        model.zero_grad(set_to_none=True)
+        out = model.train_step(dict(imgs=[x.cuda() for x in imgs]), None)
+        out["loss"].backward()
+        assert list(out["log_vars"].keys()) == list(vars_ref.keys())
+        for k, v in out["log_vars"].items():
+            tol = 1.0 / N + 1e-6 if "acc" in k else REL * abs(vars_ref[k])
+            assert abs(v - vars_ref[k]) <= tol, (step, k, v, vars_ref[k])
+        assert model.m == 0.99
+        _check_step_state(model, orc.branch, f"step{step}")
+        gp = [p for m in (model.encoder_q, model.neck_q, model.mlp_q) for p in m.parameters()]
+        assert _grad_rel(gp, orc.parameters()) < 5e-3
+
+
+@pytest.mark.parametrize("kind", ["mscl", "modist"])
+def test_two_branch_train_step_vs_oracle(kind):
+    """MSCL / MoDist whole train_steps (slim encoders on both branches, K=256) against the oracle."""
+    import mscl_b200
+    from oracle.step import OracleTwoBranch
+    torch.manual_seed(0)
+    model = mscl_b200.build_model(_two_branch_cfg(kind, 256, 4, mlvl_ids=(-1, -1))).train()
+    orc = OracleTwoBranch(model, kind)
+    model = model.cuda()
+    N = 8
+    for step in range(2):
+        g = torch.Generator().manual_seed(30 + step)
+        imgs = [torch.rand(N, 3, 8, 64, 64, generator=g) for _ in range(2)]
+        flows = [torch.rand(N, 3, 8, 64, 64, generator=g) for _ in range(2)]
+        torch.manual_seed(100 + step)
+        loss_ref, vars_ref = orc.train_step(imgs[0], imgs[1], flows[0], flows[1])
+        for p in orc.parameters():
+            p.grad = None
+        loss_ref.backward()
+        torch.manual_seed(100 + step)
+        model.zero_grad(set_to_none=True)
+        out = model.train_step(dict(imgs=[x.cuda() for x in imgs], flow_imgs=[x.cuda() for x in flows]), None)
+        out["loss"].backward()
+        assert list(out["log_vars"].keys()) == list(vars_ref.keys())
+        for k, v in out["log_vars"].items():
+            tol = 1.0 / N + 1e-6 if "acc" in k and "pos" not in k else (1.0 / (4 * N) + 1e-6 if "acc" in k else REL * abs(vars_ref[k]))
+            assert abs(v - vars_ref[k]) <= tol, (kind, step, k, v, vars_ref[k])
+        for tag, rec, ob in (("rgb", model.recognizer, orc.rgb), ("flow", model.recognizer_flow, orc.flow)):
+            assert rec.iters == ob.state.iters and rec.batch_size == ob.state.batch_size, tag
+            _check_step_state(rec, ob, f"{kind}/{tag}/step{step}")
+        gp = [p for r in (model.recognizer, model.recognizer_flow) for m in (r.encoder_q, r.neck_q, r.mlp_q) for p in m.parameters()]
+        if kind == "mscl":
+            gp += list(model.sup_head.trans_rgb.parameters()) + list(model.sup_head.trans_flow.parameters())
+        assert _grad_rel(gp, orc.parameters()) < 5e-3
+
+
+# ------------------------------------------------------------------ augmentations
+def test_sync_aug_v2_and_frame_level_aug_on_device():
+    """SyncMoCoAugmentV2 (incl. forward_with_flow: the flow clip is mirrored for exactly the samples whose RGB clip is)
+    and MoCoAugmentV2 on CUDA tensors: shapes, value ranges, flip coupling."""
+    import mscl_b200
+    torch.manual_seed(0)
+    q, k = torch.rand(4, 3, 8, 112, 112).cuda(), torch.rand(4, 3, 8, 112, 112).cuda()
+    fq, fk = torch.rand(4, 3, 8, 112, 112).cuda(), torch.rand(4, 3, 8, 112, 112).cuda()
+    lo, hi = (0 - 0.485) / 0.229 - 1e-4, (1 - 0.406) / 0.225 + 1e-4
+    for p_flip in (0.0, 1.0):
+        aug = mscl_b200.build_ssl_aug(dict(type="SyncMoCoAugmentV2", crop_size=112, sync_level="params", t=(8, 8),
+                                           with_flow=True, flip_transform=dict(p=p_flip, same_on_batch=False)))
+        a, b, fa, fb, aux = aug.forward_with_flow(q, k, fq, fk, {})
+        assert a.shape == q.shape and b.shape == k.shape and torch.isfinite(a).all() and a.min() >= lo and a.max() <= hi
+        want = torch.flip(fq, [-1]) if p_flip == 1.0 else fq
+        assert torch.equal(fa, want) and torch.equal(fb, torch.flip(fk, [-1]) if p_flip == 1.0 else fk)
+    aug = mscl_b200.build_ssl_aug(dict(type="SyncMoCoAugmentV2", crop_size=112, sync_level="batch", t=8))
+    a, b, aux = aug(q, k, {})
+    assert a.shape == q.shape and torch.isfinite(b).all()
+    aug = mscl_b200.build_ssl_aug(dict(type="MoCoAugmentV2", crop_size=112))
+    a, b, aux = aug(q, k, {})
+    assert a.shape == q.shape and b.shape == k.shape and torch.isfinite(a).all() and a.min() >= lo and a.max() <= hi
+    # frame-level decisions: within one clip some frames are mirrored and some are not (p = 2^-7 of a miss per clip)
+    weak = mscl_b200.build_ssl_aug(dict(type="MoCoAugmentV2", crop_size=112))
+    weak._color_params = lambda n, dev, f=weak._color_params: dict(f(n, dev), gray=torch.zeros(n, dtype=torch.bool, device=dev))
+    torch.manual_seed(3)
+    ramp = torch.linspace(0, 1, 112).view(1, 1, 1, 1, 112).expand(2, 3, 8, 112, 112).contiguous().cuda()
+    out = weak.single_cal(ramp)
+    slope = (out[..., -1] - out[..., 0]).mean(dim=(1, 3))            # (n, t): sign = flip decision of the frame
+    assert (slope > 0).any() and (slope < 0).any()
+
+
+# ------------------------------------------------------------------ K11 retrieval evaluation
+def test_retrieval_accuracy_vs_reference_golden(golden_dir):
+    """nn_retrieval_accuracy (center_normalize + cuBLAS fp32 GEMM + retrieval_rank kernels) against the numbers of the
+    reference's script (tools/test_retrival.py:286-304) and the oracle; the two kernels against their PyTorch forms."""
+    from mscl_b200 import retrieval as R
+    from oracle import inputs, mscl_oracle as O
+    g = np.load(os.path.join(golden_dir, "retrieval.npz"), allow_pickle=False)
+    for name in ("small", "wide"):
+        kw = eval(str(g[f"{name}/kwargs"]))
+        train, test, train_label, test_label = O.retrieval_inputs(**kw)
+        assert inputs.digest(train, test, train_label, test_label) == str(g[f"{name}/digest"])
+        acc = R.nn_retrieval_accuracy(train.cuda(), test.cuda(), train_label.cuda(), test_label.cuda())
+        want = O.retrieval_nn_accuracy(train, test, train_label, test_label)
+        # a near-tie between the best same-label item and its neighbour may flip one test item (GPU vs host summation)
+        np.testing.assert_allclose(acc, g[f"{name}/acc"], rtol=0, atol=1.0 / len(test) + 1e-7)
+        np.testing.assert_allclose(acc, want, rtol=0, atol=1.0 / len(test) + 1e-7)
+        cn = R.center_normalize(train.cuda()).cpu()
+        ref = torch.nn.functional.normalize(train - train.mean(dim=0, keepdim=True), p=2, dim=1)
+        np.testing.assert_allclose(cn.numpy(), ref.numpy(), rtol=2e-6, atol=2e-7)
+        sim = (torch.nn.functional.normalize(test - test.mean(0, keepdim=True), dim=1) @ ref.t()).contiguous()
+        same = train_label.view(1, -1) == test_label.view(-1, 1)
+        best = torch.where(same, sim, torch.full_like(sim, float("-inf"))).amax(dim=1, keepdim=True)
+        rank = (sim > best).sum(dim=1)
+        rank[~same.any(dim=1)] = sim.shape[1]
+        got = R.retrieval_rank(sim.cuda(), train_label.cuda(), test_label.cuda()).cpu()
+        np.testing.assert_array_equal(got.numpy(), rank.to(torch.int32).numpy())        # same sim matrix: exact
+    # ragged sizes: rows not a multiple of the warp / chunk counts, D not a multiple of 32
+    x = torch.randn(37, 45)
+    np.testing.assert_allclose(R.center_normalize(x.cuda()).cpu().numpy(),
+                               torch.nn.functional.normalize(x - x.mean(0, keepdim=True), dim=1).numpy(), rtol=2e-6, atol=2e-7)

@@ -1,0 +1,176 @@
+"""Host-side logic of the sibling recognizers / heads on the CPU: which row sets are stacked against which queue state,
+enqueue order, loss-dict keys and their order, 1/num_ids scaling, aux-key routing.
+
+The CUDA kernels cannot run here, so THIS TEST substitutes the four kernel entry points the classes call
+(`MoCoV2.contrast`, `MoCoV2._dequeue_and_enqueue`, `functional.hw_mean`, `functional.lmcl`) with the oracle's arithmetic
+(test infrastructure only -- the product has no such path) and checks the assembled result against the golden fixtures
+of the unmodified reference.  The kernels themselves are checked on the GPU (tests/test_gpu_siblings.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mscl_b200
+from mscl_b200 import functional as fx
+from mscl_b200.recognizers.moco import MoCoV2
+from oracle import inputs, mscl_oracle as O
+
+LOSS = dict(type="CrossEntropyLoss_torch", ignore_index=-1)
+
+
+def _fake_lmcl(xq, xf, T):
+    """[loss, top1, top5, 0] of normalise -> bmm -> /T -> CE vs the diagonal (what kernel `mscl_lmcl` returns)."""
+    t = xq.shape[2]
+    a, b = torch.nn.functional.normalize(xq, dim=1), torch.nn.functional.normalize(xf, dim=1)
+    scores = torch.bmm(a.transpose(1, 2), b).flatten(0, 1) / T
+    labels = torch.arange(t).repeat(xq.shape[0])
+    acc = O.top_k_accuracy(scores.detach().numpy(), labels.numpy(), (1, 5))
+    return torch.stack([O.cross_entropy_torch(scores, labels), torch.tensor(acc[0], dtype=torch.float32),
+                        torch.tensor(acc[1], dtype=torch.float32), torch.zeros(())])
+
+
+def _fake_contrast(self, terms, T=None):
+    T = self.T if T is None else T
+    st = self._cpu_state
+    w = O.decayed_weight(st.queue, st.count)
+    rows = []
+    for term in terms:
+        logits = O.infonce_logits(term[0], term[1].detach(), w, T)
+        labels = torch.zeros(logits.shape[0], dtype=torch.long)
+        acc = O.top_k_accuracy(logits.detach().numpy(), labels.numpy(), (1, 5))
+        rows.append(torch.stack([O.cross_entropy_torch(logits, labels), torch.tensor(acc[0], dtype=torch.float32),
+                                 torch.tensor(acc[1], dtype=torch.float32), torch.zeros(())]))
+    return torch.stack(rows)
+
+
+def _fake_enqueue(self, keys):
+    st = self._cpu_state
+    st.ptr = O.enqueue(st.queue, st.count, st.ptr, keys.detach())
+    self.batch_size = keys.shape[0]
+
+
+@pytest.fixture
+def cpu_kernels(monkeypatch):
+    monkeypatch.setattr(MoCoV2, "contrast", _fake_contrast)
+    monkeypatch.setattr(MoCoV2, "_dequeue_and_enqueue", _fake_enqueue)
+    monkeypatch.setattr(fx, "hw_mean", lambda x: x.mean(dim=(-2, -1)))
+    monkeypatch.setattr(fx, "lmcl", _fake_lmcl)
+
+
+def test_sibling_heads_host_logic(cpu_kernels, golden_dir):
+    g = np.load(os.path.join(golden_dir, "sibling_heads.npz"), allow_pickle=False)
+    for case in inputs.sibling_head_cases():
+        name, cls_name, kw, _, _, with_aug = case
+        head = mscl_b200.build_head(dict(type=cls_name, basename="", loss_pos=LOSS, loss_cls=LOSS, **kw))
+        head.load_state_dict({k.split("/state/")[1]: torch.from_numpy(g[k]) for k in g.files if k.startswith(f"{name}/state/")},
+                             strict=True)
+        q_mlvl, qf_mlvl, qaf_mlvl = inputs.sibling_head_inputs(case)
+        leaves = [x.requires_grad_(True) for x in q_mlvl + qf_mlvl + (qaf_mlvl or [])]
+        args = dict(q_mlvl=q_mlvl, q_flow_mlvl=qf_mlvl)
+        if with_aug:
+            args["q_aug_flow_mlvl"] = qaf_mlvl
+        losses = head.loss(**head(**args))
+        sum(v for k, v in losses.items() if "loss" in k).backward()
+        assert list(losses.keys()) == [str(k) for k in g[f"{name}/out_order"]]
+        for k, v in losses.items():
+            ref = float(g[f"{name}/out/{k}"])
+            assert abs(float(v) - ref) <= 2e-6 * max(1.0, abs(ref)), (name, k, float(v), ref)
+        for i, x in enumerate(leaves):
+            got = x.grad.sum(dim=(-2, -1)).numpy() if x.grad is not None else np.zeros(x.shape[:3], dtype=np.float32)
+            np.testing.assert_allclose(got, g[f"{name}/gradsum/{i}"], rtol=1e-4, atol=2e-6)
+        for k, p in head.named_parameters():
+            np.testing.assert_allclose(p.grad.numpy(), g[f"{name}/pgrad/{k}"], rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("kind", ["mscl", "modist"])
+def test_two_branch_host_logic(cpu_kernels, kind, golden_dir):
+    from test_gpu_siblings import _two_branch_cfg
+    g = np.load(os.path.join(golden_dir, "two_branch.npz"), allow_pickle=False)
+    kw = eval(str(g["kwargs"]))
+    inp = inputs.head_inputs(**kw)
+    model = mscl_b200.build_model(_two_branch_cfg(kind, kw["K"], kw["t"])).train()
+    if kind == "mscl":
+        model.sup_head.load_state_dict({k.split("/sup_state/")[1]: torch.from_numpy(g[k]) for k in g.files if "/sup_state/" in k})
+    model.recognizer._cpu_state = O.QueueState(inp["queue_rgb"], inp["count"], inp["ptr"])
+    model.recognizer_flow._cpu_state = O.QueueState(inp["queue_flow"], inp["count"], inp["ptr"])
+    N = kw["N"]
+    for step in range(2):
+        x = inputs.head_inputs(**dict(kw, seed=kw["seed"] + step))
+        leaves = {n: x[n].clone().requires_grad_(True) for n in ("q", "q_f", "q_map", "qf_map")}
+        model.recognizer.note_branch(N, True)
+        model.recognizer_flow.note_branch(N, True)
+        if kind == "mscl":
+            losses = model.objective(dict(q=leaves["q"], k=x["k"], q_f=leaves["q_f"], k_f=x["k_f"], aux_info={},
+                                          im_features=dict(q_mlvl=[leaves["q_map"]]), flow_features=dict(q_mlvl=[leaves["qf_map"]])))
+        else:
+            losses = model.objective(leaves["q"], x["k"], leaves["q_f"], x["k_f"])
+        loss, log_vars = model._parse_losses(losses)
+        loss.backward()
+        tag = f"{kind}/step{step}"
+        assert list(log_vars.keys()) == [str(s) for s in g[f"{tag}/logvar_order"]]
+        for key, v in log_vars.items():
+            ref = float(g[f"{tag}/logvar/{key}"])
+            assert abs(v - ref) <= 2e-6 * max(1.0, abs(ref)), (tag, key, v, ref)
+        for n in ("q", "q_f"):
+            np.testing.assert_allclose(leaves[n].grad.numpy(), g[f"{tag}/grad/{n}"], rtol=1e-5, atol=2e-6)
+        for br, rec in (("rgb", model.recognizer), ("flow", model.recognizer_flow)):
+            st = rec._cpu_state
+            assert st.ptr == int(g[f"{tag}/after/{br}/ptr"][0]) and rec.iters == int(g[f"{tag}/after/{br}/iters"])
+            np.testing.assert_array_equal(st.count.numpy(), g[f"{tag}/after/{br}/count"])
+            np.testing.assert_array_equal(st.queue.numpy(), g[f"{tag}/after/{br}/queue"])
+
+
+class _FakeEma:
+    """fx.EmaTable stand-in: the reference's `k*m + q*(1-m)` through the oracle."""
+
+    def __init__(self, params_k, params_q):
+        self.k, self.q = list(params_k), list(params_q)
+
+    def update(self, m):
+        for pk, new in zip(self.k, O.ema_update([p.data for p in self.k], [p.data for p in self.q], m)):
+            pk.data = new
+
+
+def _attach_cpu_state(rec):
+    st = rec._staged
+    rec._cpu_state = O.QueueState(st["queue"], st["count"], st["ptr"])
+
+
+@pytest.mark.parametrize("kind", ["moco", "mscl", "modist"])
+def test_whole_train_step_host_logic(cpu_kernels, monkeypatch, kind):
+    """forward_train plumbing of MoCo / MSCL / MoDist (EMA -> shuffle draw -> key path -> stacked terms -> enqueues ->
+    iters) against the oracle's step, both on the CPU with identical weights."""
+    from oracle.step import OracleMoCo, OracleTwoBranch
+    from test_gpu_siblings import _moco_cfg, _two_branch_cfg
+    monkeypatch.setattr(fx, "EmaTable", _FakeEma)
+    torch.manual_seed(0)
+    if kind == "moco":
+        model = mscl_b200.build_model(_moco_cfg("MoCo", 64, m=0.99)).train()
+        orc = OracleMoCo(model)
+        recs = [(model, orc.branch)]
+    else:
+        model = mscl_b200.build_model(_two_branch_cfg(kind, 64, 4, mlvl_ids=(-1, -1))).train()
+        orc = OracleTwoBranch(model, kind)
+        recs = [(model.recognizer, orc.rgb), (model.recognizer_flow, orc.flow)]
+    for rec, _ in recs:
+        _attach_cpu_state(rec)
+    N = 4
+    for step in range(2):
+        g = torch.Generator().manual_seed(40 + step)
+        imgs = [torch.rand(N, 3, 8, 32, 32, generator=g) for _ in range(2)]
+        flows = [torch.rand(N, 3, 8, 32, 32, generator=g) for _ in range(2)]
+        torch.manual_seed(100 + step)
+        _, vars_ref = orc.train_step(*(imgs if kind == "moco" else imgs + flows)) if kind == "moco" else \
+            orc.train_step(imgs[0], imgs[1], flows[0], flows[1])
+        torch.manual_seed(100 + step)
+        batch = dict(imgs=imgs) if kind == "moco" else dict(imgs=imgs, flow_imgs=flows)
+        out = model.train_step(batch, None)
+        assert out["num_samples"] == N and list(out["log_vars"].keys()) == list(vars_ref.keys())
+        for k, v in out["log_vars"].items():
+            assert abs(v - vars_ref[k]) <= 5e-5 * max(1.0, abs(vars_ref[k])), (kind, step, k, v, vars_ref[k])
+        for rec, ob in recs:
+            assert rec._cpu_state.ptr == ob.state.ptr and rec.iters == ob.state.iters and rec.batch_size == ob.state.batch_size
+            np.testing.assert_array_equal(rec._cpu_state.count.numpy(), ob.state.count.numpy())
+            for pk, po in zip([p for m in (rec.encoder_k, rec.neck_k, rec.mlp_k) for p in m.parameters()], ob.k_params()):
+                np.testing.assert_array_equal(pk.detach().numpy(), po.detach().numpy())

@@ -253,3 +253,25 @@ def test_two_branch_oracle_matches_reference(golden_dir):
                 assert st.ptr == int(g[f"{tag}/after/{br}/ptr"][0]) and st.iters == int(g[f"{tag}/after/{br}/iters"])
                 np.testing.assert_array_equal(st.count.numpy(), g[f"{tag}/after/{br}/count"])
                 np.testing.assert_array_equal(st.queue.numpy(), g[f"{tag}/after/{br}/queue"])
+
+
+def test_retrieval_oracle_matches_reference(golden_dir):
+    """K11 oracle vs the reference's own script lines (tools/test_retrival.py:286-304, executed by oracle/make_golden.py),
+    and the rank formulation the kernel uses: acc@k == mean(#{train items above the best same-label item} < k)."""
+    import torch.nn.functional as F
+    g = _load(golden_dir, "retrieval.npz")
+    for name in ("small", "wide"):
+        kw = eval(str(g[f"{name}/kwargs"]))
+        train, test, train_label, test_label = O.retrieval_inputs(**kw)
+        assert inputs.digest(train, test, train_label, test_label) == str(g[f"{name}/digest"])
+        acc = O.retrieval_nn_accuracy(train, test, train_label, test_label)
+        np.testing.assert_allclose(acc, g[f"{name}/acc"], rtol=0, atol=1e-7)
+        a = F.normalize(test - test.mean(0, keepdim=True), dim=1)
+        b = F.normalize(train - train.mean(0, keepdim=True), dim=1)
+        sim = a @ b.t()
+        same = train_label.view(1, -1) == test_label.view(-1, 1)
+        best = torch.where(same, sim, torch.full_like(sim, float("-inf"))).amax(dim=1, keepdim=True)
+        rank = (sim > best).sum(dim=1)
+        rank[~same.any(dim=1)] = sim.shape[1]
+        by_rank = [(rank < k).float().mean().item() for k in (1, 5, 10, 20, 50)]
+        np.testing.assert_allclose(by_rank, g[f"{name}/acc"], rtol=0, atol=1e-7)
