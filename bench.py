@@ -13,8 +13,9 @@ One step = FRA (rotated-flow negatives, K3) -> GPU augmentation -> MSCLWithAug.t
 2 enqueues K5) -> backward -> grad-norm clip (40) -> SGD step.  Nothing is skipped or cached.
 
 `value`  : clips/s over all ranks with the step's inputs already resident in HBM.
-`e2e`    : the same step fed from pinned HOST buffers (H2D inside the timed region) and its log
-           variables read back to the host every step.
+`e2e`    : the same step fed from pinned HOST buffers -- every step's inputs are copied H2D inside the timed region,
+           on a copy stream one step ahead of the compute stream (two device slots) -- and its log variables read
+           back to the host every step (one step late, so the device never waits for the host between steps).
 `roofline`: the kernel of ours with the largest share of the step, timed live with CUDA events on
            the launching stream inside the timed region; `kernels` lists every kernel of the path.
 `cpu_baseline`: the oracle (CPU restatement of the reference's algorithm, oracle/step.py) timed on
@@ -336,7 +337,7 @@ def run_b200(args, rank, local_rank, world):
         flow_k = fx.fra(b["flow_k"], b["cid_k"], table, "planar")
         aux = dict(flow_imgs_q=flow_q, flow_imgs_k=flow_k)
         losses = runner(b["imgs_q"], b["imgs_k"], aux, return_loss=True)
-        loss, log_vars = model._parse_losses(losses)        # one all_reduce + the step's device->host read
+        loss, log_vars = model.parse_losses_deferred(losses)  # one all_reduce; the values stay on the device for now
         opt.zero_grad(set_to_none=True)
         loss.backward()
         if graph_state is not None:
@@ -344,12 +345,26 @@ def run_b200(args, rank, local_rank, world):
         if args.torch_optim:
             torch.nn.utils.clip_grad_norm_(params, 40.0)      # config :119
         opt.step()
-        return log_vars
+        return log_vars                  # DeferredLogVars: 23 floats still on the device
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # Every step's log variables are read back to the host (one 92-byte D2H copy per step), but one step late: the
+    # host enqueues step i+1 before it blocks on step i's values, so the device never waits for the host between
+    # steps.  The last step's values are read before the closing event.
+    pending = []
+
+    def collect(deferred):
+        pending.append(deferred)
+        while len(pending) > 1:
+            last["log_vars"] = pending.pop(0).get()
+
+    def flush():
+        while pending:
+            last["log_vars"] = pending.pop(0).get()
 
     def timed(fn, steps):
         sync()
@@ -358,6 +373,7 @@ def run_b200(args, rank, local_rank, world):
         e0.record()
         for i in range(steps):
             fn(i)
+        flush()
         e1.record()
         sync()
         wall = time.perf_counter() - w0
@@ -377,7 +393,7 @@ def run_b200(args, rank, local_rank, world):
     last = {}
 
     def resident_step(i):
-        last["log_vars"] = train_step(resident[i % 2])
+        collect(train_step(resident[i % 2]))
 
     if args.profile_range:
         torch.cuda.synchronize()
@@ -390,12 +406,34 @@ def run_b200(args, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- host-resident inputs through the public API: `e2e` ----
+    # every step's inputs travel from pinned host memory inside the timed region, on a copy stream one step ahead of
+    # the compute stream (what a prefetching loader does); two device slots, guarded by events both ways
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host[0].items()} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[s])                  # the step that last read this slot has finished
+            for k, v in host[i % 2].items():
+                slots[s][k].copy_(v, non_blocking=True)
+            ready[s].record(copy_stream)
+
     def host_step(i):
-        b = {k: v.to(dev, non_blocking=True) for k, v in host[i % 2].items()}
-        last["log_vars"] = train_step(b)
+        cur = torch.cuda.current_stream()
+        if i == 0:
+            prefetch(0)
+        cur.wait_event(ready[i % 2])
+        if i + 1 < args.steps:
+            prefetch(i + 1)                                  # overlaps this step's compute
+        collect(train_step(slots[i % 2]))
+        free[i % 2].record(cur)
 
     for i in range(min(2, args.warmup)):
         host_step(i)
+    flush()
     sec_e2e, wall_e2e = timed(host_step, args.steps)
     d2h_bytes = 4 * len(last["log_vars"])
 

@@ -249,6 +249,11 @@ int mscl_upsample_trilinear_fwd(const float *d_x, float *d_y, int64_t NC, int32_
                                 int32_t Wi, int32_t To, int32_t Ho, int32_t Wo, mscl_stream_t stream);
 int mscl_upsample_trilinear_bwd(const float *d_gy, float *d_gx, int64_t NC, int32_t Ti, int32_t Hi,
                                 int32_t Wi, int32_t To, int32_t Ho, int32_t Wo, mscl_stream_t stream);
+/* The same for channels-last tensors (torch.channels_last_3d): x [N, Ti, Hi, Wi, C] -> y [N, To, Ho, Wo, C], C % 4 == 0. */
+int mscl_upsample_trilinear_ndhwc_fwd(const float *d_x, float *d_y, int64_t N, int32_t C, int32_t Ti, int32_t Hi,
+                                      int32_t Wi, int32_t To, int32_t Ho, int32_t Wo, mscl_stream_t stream);
+int mscl_upsample_trilinear_ndhwc_bwd(const float *d_gy, float *d_gx, int64_t N, int32_t C, int32_t Ti, int32_t Hi,
+                                      int32_t Wi, int32_t To, int32_t Ho, int32_t Wo, mscl_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * K8  flow visualisation + flip.   replaces FlowVisualizer.__call__ / flow_uv_to_colors

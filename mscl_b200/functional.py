@@ -475,34 +475,60 @@ def gather_rows(x, idx):
 # ----------------------------------------------------------------------------------------
 # K7: trilinear up-sampling (TPN neck)
 # ----------------------------------------------------------------------------------------
+def _is_cl3d(t):
+    """Dense channels_last_3d (NDHWC in memory) and not simultaneously row-major (C == 1 or T*H*W == 1 are both)."""
+    return t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d) and not t.is_contiguous()
+
+
 class _UpsampleTrilinear(torch.autograd.Function):
+    """Both dense layouts are served natively: a channels_last_3d input gives a channels_last_3d output (and gradient),
+    so the TPN neck's `y + upsample(...)` stays a same-layout add and no NCDHW <-> NDHWC copy appears on either side."""
+
     @staticmethod
     def forward(ctx, x, size):
         n, c, ti, hi, wi = x.shape
         to, ho, wo = size
-        y = torch.empty(n, c, to, ho, wo, device=x.device)
-        _cabi.call("mscl_upsample_trilinear_fwd", x.data_ptr(), y.data_ptr(), n * c, ti, hi, wi, to, ho, wo, _stream(),
-                   algo_bytes=4 * (x.numel() + y.numel()))
+        cl = _is_cl3d(x) and c % 4 == 0
+        if cl:
+            y = torch.empty((n, c, to, ho, wo), device=x.device, memory_format=torch.channels_last_3d)
+            _cabi.call("mscl_upsample_trilinear_ndhwc_fwd", x.data_ptr(), y.data_ptr(), n, c, ti, hi, wi, to, ho, wo,
+                       _stream(), algo_bytes=4 * (x.numel() + y.numel()))
+        else:
+            x = x.contiguous()
+            y = torch.empty(n, c, to, ho, wo, device=x.device)
+            _cabi.call("mscl_upsample_trilinear_fwd", x.data_ptr(), y.data_ptr(), n * c, ti, hi, wi, to, ho, wo, _stream(),
+                       algo_bytes=4 * (x.numel() + y.numel()))
         ctx.in_shape = tuple(x.shape)
+        ctx.cl = cl
         return y
 
     @staticmethod
     def backward(ctx, gy):
         n, c, ti, hi, wi = ctx.in_shape
-        gy = gy.contiguous()
         to, ho, wo = gy.shape[2:]
-        gx = torch.empty(ctx.in_shape, device=gy.device)
-        _cabi.call("mscl_upsample_trilinear_bwd", gy.data_ptr(), gx.data_ptr(), n * c, ti, hi, wi, to, ho, wo, _stream(),
-                   algo_bytes=4 * (gx.numel() + gy.numel()))
+        if ctx.cl:
+            gy = gy.contiguous(memory_format=torch.channels_last_3d)
+            gx = torch.empty(ctx.in_shape, device=gy.device, memory_format=torch.channels_last_3d)
+            _cabi.call("mscl_upsample_trilinear_ndhwc_bwd", gy.data_ptr(), gx.data_ptr(), n, c, ti, hi, wi, to, ho, wo,
+                       _stream(), algo_bytes=4 * (gx.numel() + gy.numel()))
+        else:
+            gy = gy.contiguous()
+            gx = torch.empty(ctx.in_shape, device=gy.device)
+            _cabi.call("mscl_upsample_trilinear_bwd", gy.data_ptr(), gx.data_ptr(), n * c, ti, hi, wi, to, ho, wo, _stream(),
+                       algo_bytes=4 * (gx.numel() + gy.numel()))
         return gx, None
 
 
 def upsample_trilinear(x, size):
-    """F.interpolate(x, size=size, mode="trilinear") with align_corners=False (necks/sepc.py:126-130) for a
-    contiguous fp32 (N,C,T,H,W) CUDA tensor."""
-    _chk(x, name="x")
+    """F.interpolate(x, size=size, mode="trilinear") with align_corners=False (necks/sepc.py:126-130) for a dense
+    fp32 (N,C,T,H,W) CUDA tensor, row-major or channels_last_3d (any other stride pattern is made row-major first)."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype != torch.float32:
+        raise _cabi.MsclError("upsample_trilinear needs a float32 CUDA tensor (no CPU fallback)")
     if x.dim() != 5 or len(size) != 3:
         raise _cabi.MsclError("upsample_trilinear takes (N,C,T,H,W) and a (T,H,W) size")
+    _cabi.require_device(x.device.index if x.device.index is not None else torch.cuda.current_device())
+    if not (_is_cl3d(x) or x.is_contiguous()):
+        x = x.contiguous()
     return _UpsampleTrilinear.apply(x, tuple(int(v) for v in size))
 
 

@@ -251,6 +251,13 @@ def bench_k789(cfg, N, pk, dev, iters=20):
         us = time_train(lambda i: _cabi.call("mscl_upsample_trilinear_bwd", ys[i % rot].data_ptr(), xs[i % rot].data_ptr(),
                                              N * 128, *shp[2:], *size, _st()), iters)
         out.append(row(cfg, "upsample_trilinear_bwd", f"{size} -> {shp}", us, 4 * (nin + nout), 0, pk))
+        # the channels-last kernels (what the step runs: the encoders are in channels_last_3d); same buffers, NDHWC view
+        us = time_train(lambda i: _cabi.call("mscl_upsample_trilinear_ndhwc_fwd", xs[i % rot].data_ptr(), ys[i % rot].data_ptr(),
+                                             N, 128, *shp[2:], *size, _st()), iters)
+        out.append(row(cfg, "upsample_trilinear_ndhwc_fwd", f"{shp} -> {size}", us, 4 * (nin + nout), 0, pk))
+        us = time_train(lambda i: _cabi.call("mscl_upsample_trilinear_ndhwc_bwd", ys[i % rot].data_ptr(), xs[i % rot].data_ptr(),
+                                             N, 128, *shp[2:], *size, _st()), iters)
+        out.append(row(cfg, "upsample_trilinear_ndhwc_bwd", f"{size} -> {shp}", us, 4 * (nin + nout), 0, pk))
         del xs, ys
     # K8: (N,2,16,112,112) flow -> colour image, K9: (N,3,8,112,112) RGB clips
     T2, HW = 16, 112 * 112

@@ -19,7 +19,7 @@ def _trilinear(x, size):
     The oracle, which re-uses these module classes on the host, replaces the `upsample` attribute of ITS copies
     (oracle/step.py)."""
     from .. import functional as fx
-    return fx.upsample_trilinear(x.contiguous(), size)
+    return fx.upsample_trilinear(x, size)
 
 
 class _Conv(nn.Module):

@@ -17,6 +17,18 @@ from .. import registry as builder
 from ..backbones import ResNetFlow, torchvision_multilevel
 
 
+class DeferredLogVars:
+    """The step's log variables, still on the device as one stacked tensor; `.get()` copies them to the host once."""
+
+    def __init__(self, keys, stacked):
+        self.keys, self.stacked, self._values = keys, stacked, None
+
+    def get(self):
+        if self._values is None:
+            self._values = OrderedDict(zip(self.keys, self.stacked.tolist()))
+        return self._values
+
+
 class BaseMoCoRecognizer(nn.Module):
     def __init__(self, backbone=None, cls_head=None, neck=None, train_cfg=None, test_cfg=None):
         super().__init__()
@@ -83,7 +95,10 @@ class BaseMoCoRecognizer(nn.Module):
 
     # -- loss parsing (recognizers/base.py:275-308) --
     @staticmethod
-    def _parse_losses(losses):
+    def parse_losses_deferred(losses):
+        """`_parse_losses` without its device->host copy: returns (loss, DeferredLogVars).  The caller may enqueue
+        the backward pass and the optimizer before `.get()` reads the step's log variables, so the host never waits
+        for the forward pass in the middle of a step (the reference's `.item()` per variable does, base.py:301-306)."""
         log_vars = OrderedDict()
         for name, value in losses.items():
             if isinstance(value, torch.Tensor):
@@ -98,8 +113,12 @@ class BaseMoCoRecognizer(nn.Module):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             stacked = stacked / dist.get_world_size()
             dist.all_reduce(stacked)
-        values = stacked.tolist()           # the step's single device->host synchronisation
-        return loss, OrderedDict(zip(log_vars.keys(), values))
+        return loss, DeferredLogVars(list(log_vars.keys()), stacked)
+
+    @staticmethod
+    def _parse_losses(losses):
+        loss, deferred = BaseMoCoRecognizer.parse_losses_deferred(losses)
+        return loss, deferred.get()          # the step's single device->host synchronisation
 
     def forward_train(self, imgs, labels, **kwargs):
         raise NotImplementedError("Not support forward_train for BaseMoCoRecognizer")

@@ -51,7 +51,7 @@ def launch_shares(tag):
     T = sum(tot.values())
     mine = sum(v for k, v in tot.items() if any(o in k for o in OURS))
     with open(os.path.join(OUT, f"{tag}_launch_shares.txt"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 2 --warmup 1\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off  python bench.py --steps 2 --warmup 3 --no-graphs --profile-range  (scripts/gpu_profile.sh)\n")
         f.write("# per-launch times are cold-cache and serialised: read the SHARES, not the absolutes\n")
         f.write(f"# {sum(cnt.values())} launches, {T/1e3:.2f} ms summed; this repo's kernels: {mine/1e3:.3f} ms = {100*mine/T:.2f} %\n")
         f.write("#   time_us  share%  launches  kernel\n")

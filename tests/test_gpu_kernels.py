@@ -334,6 +334,32 @@ def test_upsample_trilinear_matches_torch(fx, shape, size):
     np.testing.assert_allclose(y.detach().cpu().numpy(), yc.detach().numpy(), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("shape,size", [((2, 128, 2, 14, 14), (4, 28, 28)), ((3, 128, 1, 7, 7), (2, 14, 14)), ((1, 8, 3, 5, 6), (7, 9, 11)),
+                                        ((2, 4, 4, 6, 6), (4, 6, 6)), ((2, 12, 2, 3, 3), (5, 8, 12))])
+def test_upsample_trilinear_channels_last(fx, shape, size):
+    """The NDHWC kernels: a channels_last_3d input gives a channels_last_3d output and input gradient, same values as
+    F.interpolate; the incoming gradient may arrive in either layout."""
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    cl = torch.channels_last_3d
+    x = torch.randn(shape, generator=g).cuda().contiguous(memory_format=cl).requires_grad_(True)
+    w = torch.randn(shape[:2] + size, generator=g).cuda()
+    y = fx.upsample_trilinear(x, size)
+    assert y.is_contiguous(memory_format=cl) and tuple(y.shape) == shape[:2] + size
+    xr = x.detach().clone().contiguous().requires_grad_(True)
+    yr = F.interpolate(xr, size=size, mode="trilinear")
+    np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+    (yr * w).sum().backward()
+    for wgt in (w, w.contiguous(memory_format=cl)):          # row-major and channels-last incoming gradients
+        x.grad = None
+        (fx.upsample_trilinear(x, size) * wgt).sum().backward()
+        assert x.grad.is_contiguous(memory_format=cl)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), xr.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    # C not a multiple of 4 falls back to the row-major kernels (values unchanged)
+    x3 = torch.randn(2, 6, 2, 4, 4, generator=g).cuda().contiguous(memory_format=cl)
+    np.testing.assert_allclose(fx.upsample_trilinear(x3, (4, 8, 8)).cpu().numpy(),
+                               F.interpolate(x3.contiguous(), size=(4, 8, 8), mode="trilinear").cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
 # ------------------------------------------------------------------ K8 / K9 augmentation front-end
 def _flowvis_close(got, ref):
     """Every op of the visualiser is exactly rounded except atan2 (device vs host libm differ in the last ulp), which can

@@ -174,3 +174,20 @@ def test_whole_train_step_host_logic(cpu_kernels, monkeypatch, kind):
             np.testing.assert_array_equal(rec._cpu_state.count.numpy(), ob.state.count.numpy())
             for pk, po in zip([p for m in (rec.encoder_k, rec.neck_k, rec.mlp_k) for p in m.parameters()], ob.k_params()):
                 np.testing.assert_array_equal(pk.detach().numpy(), po.detach().numpy())
+
+
+def test_parse_losses_deferred_equals_parse_losses():
+    """`parse_losses_deferred` (the log-variable read postponed until `.get()`) returns exactly `_parse_losses`'
+    loss tensor and values (recognizers/base.py:275-308: sum of the `loss*` means, every value averaged)."""
+    from collections import OrderedDict
+    from mscl_b200.recognizers import BaseMoCoRecognizer as B
+    g = torch.Generator().manual_seed(0)
+    losses = OrderedDict(top1_acc=torch.rand((), generator=g), loss_cls=torch.rand(4, generator=g).requires_grad_(True),
+                         loss_list=[torch.rand(2, generator=g), torch.rand(3, generator=g)], top5_acc_pos=torch.rand((), generator=g))
+    loss_a, vars_a = B._parse_losses(losses)
+    loss_b, deferred = B.parse_losses_deferred(losses)
+    assert torch.equal(loss_a, loss_b) and loss_b.requires_grad
+    assert list(vars_a.keys()) == deferred.keys == ["top1_acc", "loss_cls", "loss_list", "top5_acc_pos", "loss"]
+    assert vars_a == deferred.get() and deferred.get() is deferred.get()
+    want = losses["loss_cls"].mean() + losses["loss_list"][0].mean() + losses["loss_list"][1].mean()
+    assert abs(vars_a["loss"] - float(want)) < 1e-6
