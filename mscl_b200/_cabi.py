@@ -58,9 +58,7 @@ _lib = None
 _launches = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
 # how many device kernels one successful call enqueues
 _LAUNCHES_PER_CALL = {"mscl_device_check": 0, "mscl_infonce_num_partials": 0, "mscl_color_pipeline": 2, "mscl_grad_norm_multi": 2,
-                      "mscl_upsample_trilinear_ndhwc_fwd": [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
-    "mscl_upsample_trilinear_ndhwc_bwd": [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
-    "mscl_center_normalize": 3}
+                      "mscl_center_normalize": 3}
 
 
 class MsclError(RuntimeError):

@@ -127,72 +127,79 @@ upsample_trilinear_bwd_kernel(const float *__restrict__ gy, float *__restrict__ 
 // [N, T, H, W, C] with C contiguous.  One thread per (output voxel, 4 channels): the 32 threads of a 128-channel voxel
 // read eight 512-byte input rows (L1/L2: the input is 8x smaller than the output) and write one; no layout copy on
 // either side, and the sum that follows in the neck stays a same-layout vectorised add.
+// One CTA per output row (n, ot, oh): the T/H taps are CTA-uniform, all index arithmetic is 32-bit (the first version
+// spent its time in 64-bit div/mod: 41 us for a 58 MB pass), the Wo * C/4 items of the row are strided over the threads.
 __global__ void __launch_bounds__(256)
-upsample_trilinear_ndhwc_fwd_kernel(const float4 *__restrict__ x, float4 *__restrict__ y, int64_t total, int C4, int Ti,
-                                    int Hi, int Wi, int To, int Ho, int Wo, float st, float sh, float sw) {
-  const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (v >= total) return;
-  const int cg = (int)(v % C4);
-  int64_t r = v / C4;
-  const int ow = (int)(r % Wo);
-  r /= Wo;
-  const int oh = (int)(r % Ho);
-  r /= Ho;
-  const int ot = (int)(r % To);
-  const int64_t n = r / To;
-  const AxisTap at = axis_tap(ot, st, Ti), ah = axis_tap(oh, sh, Hi), aw = axis_tap(ow, sw, Wi);
-  const float4 *p = x + n * (int64_t)Ti * Hi * Wi * C4 + cg;
-  auto at_ = [&](int t, int h, int w) { return __ldg(p + (((int64_t)t * Hi + h) * Wi + w) * C4); };
-  const float4 a000 = at_(at.i0, ah.i0, aw.i0), a001 = at_(at.i0, ah.i0, aw.i1), a010 = at_(at.i0, ah.i1, aw.i0),
-               a011 = at_(at.i0, ah.i1, aw.i1), a100 = at_(at.i1, ah.i0, aw.i0), a101 = at_(at.i1, ah.i0, aw.i1),
-               a110 = at_(at.i1, ah.i1, aw.i0), a111 = at_(at.i1, ah.i1, aw.i1);
-  // same association as ATen's upsample_trilinear3d_out_frame
+upsample_trilinear_ndhwc_fwd_kernel(const float4 *__restrict__ x, float4 *__restrict__ y, int C4, int Ti, int Hi, int Wi,
+                                    int To, int Ho, int Wo, float st, float sh, float sw) {
+  const unsigned row = blockIdx.x;                 // (n * To + ot) * Ho + oh
+  const int oh = (int)(row % (unsigned)Ho);
+  const unsigned r = row / (unsigned)Ho;
+  const int ot = (int)(r % (unsigned)To);
+  const int64_t n = r / (unsigned)To;
+  const AxisTap at = axis_tap(ot, st, Ti), ah = axis_tap(oh, sh, Hi);
+  const float4 *p = x + n * (int64_t)Ti * Hi * Wi * C4;
+  const float4 *r00 = p + (at.i0 * Hi + ah.i0) * Wi * C4, *r01 = p + (at.i0 * Hi + ah.i1) * Wi * C4;
+  const float4 *r10 = p + (at.i1 * Hi + ah.i0) * Wi * C4, *r11 = p + (at.i1 * Hi + ah.i1) * Wi * C4;
+  float4 *dst = y + (int64_t)row * Wo * C4;
+  const int items = Wo * C4;
+  for (int i = threadIdx.x; i < items; i += 256) {
+    const int ow = i / C4, cg = i - ow * C4;
+    const AxisTap aw = axis_tap(ow, sw, Wi);
+    const int o0 = aw.i0 * C4 + cg, o1 = aw.i1 * C4 + cg;
+    const float4 a000 = __ldg(r00 + o0), a001 = __ldg(r00 + o1), a010 = __ldg(r01 + o0), a011 = __ldg(r01 + o1),
+                 a100 = __ldg(r10 + o0), a101 = __ldg(r10 + o1), a110 = __ldg(r11 + o0), a111 = __ldg(r11 + o1);
+    // same association as ATen's upsample_trilinear3d_out_frame
 #define MSCL_TRI(f)                                                                                       \
   (at.l0 * (ah.l0 * (aw.l0 * a000.f + aw.l1 * a001.f) + ah.l1 * (aw.l0 * a010.f + aw.l1 * a011.f)) +    \
    at.l1 * (ah.l0 * (aw.l0 * a100.f + aw.l1 * a101.f) + ah.l1 * (aw.l0 * a110.f + aw.l1 * a111.f)))
-  stg_stream(y + v, make_float4(MSCL_TRI(x), MSCL_TRI(y), MSCL_TRI(z), MSCL_TRI(w)));
+    stg_stream(dst + i, make_float4(MSCL_TRI(x), MSCL_TRI(y), MSCL_TRI(z), MSCL_TRI(w)));
 #undef MSCL_TRI
+  }
 }
 
-// gx [N, Ti, Hi, Wi, C]: gather over the (at most ~4 per axis) outputs that read the voxel; fixed order, no atomics
+// gx [N, Ti, Hi, Wi, C]: one CTA per input row (n, it, ih); gather over the (at most ~4 per axis) outputs that read
+// the voxel, fixed order, no atomics.  The (ot, oh) candidates and their weights are CTA-uniform.
 __global__ void __launch_bounds__(256)
-upsample_trilinear_ndhwc_bwd_kernel(const float4 *__restrict__ gy, float4 *__restrict__ gx, int64_t total, int C4,
-                                    int Ti, int Hi, int Wi, int To, int Ho, int Wo, float st, float sh, float sw) {
-  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (e >= total) return;
-  const int cg = (int)(e % C4);
-  int64_t r = e / C4;
-  const int iw = (int)(r % Wi);
-  r /= Wi;
-  const int ih = (int)(r % Hi);
-  r /= Hi;
-  const int it = (int)(r % Ti);
-  const int64_t n = r / Ti;
-  int t0, t1, h0, h1, w0, w1;
+upsample_trilinear_ndhwc_bwd_kernel(const float4 *__restrict__ gy, float4 *__restrict__ gx, int C4, int Ti, int Hi,
+                                    int Wi, int To, int Ho, int Wo, float st, float sh, float sw) {
+  const unsigned row = blockIdx.x;                 // (n * Ti + it) * Hi + ih
+  const int ih = (int)(row % (unsigned)Hi);
+  const unsigned r = row / (unsigned)Hi;
+  const int it = (int)(r % (unsigned)Ti);
+  const int64_t n = r / (unsigned)Ti;
+  int t0, t1, h0, h1;
   out_range(it, 1.f / st, To, t0, t1);
   out_range(ih, 1.f / sh, Ho, h0, h1);
-  out_range(iw, 1.f / sw, Wo, w0, w1);
-  const float4 *g = gy + n * (int64_t)To * Ho * Wo * C4 + cg;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int ot = t0; ot <= t1; ++ot) {
-    const float wt = tap_weight(axis_tap(ot, st, Ti), it);
-    if (wt == 0.f) continue;
-    for (int oh = h0; oh <= h1; ++oh) {
-      const float wth = wt * tap_weight(axis_tap(oh, sh, Hi), ih);
-      if (wth == 0.f) continue;
-      const float4 *row = g + ((int64_t)ot * Ho + oh) * Wo * C4;
-      for (int ow = w0; ow <= w1; ++ow) {
-        const float wgt = wth * tap_weight(axis_tap(ow, sw, Wi), iw);
-        if (wgt == 0.f) continue;
-        const float4 q = __ldg(row + (int64_t)ow * C4);      // neighbouring voxels of the CTA share taps: keep L1
-        acc.x = fmaf(wgt, q.x, acc.x);
-        acc.y = fmaf(wgt, q.y, acc.y);
-        acc.z = fmaf(wgt, q.z, acc.z);
-        acc.w = fmaf(wgt, q.w, acc.w);
+  const float4 *g = gy + n * (int64_t)To * Ho * Wo * C4;
+  float4 *dst = gx + (int64_t)row * Wi * C4;
+  const int items = Wi * C4;
+  const float inv_sw = 1.f / sw;
+  for (int i = threadIdx.x; i < items; i += 256) {
+    const int iw = i / C4, cg = i - iw * C4;
+    int w0, w1;
+    out_range(iw, inv_sw, Wo, w0, w1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ot = t0; ot <= t1; ++ot) {
+      const float wt = tap_weight(axis_tap(ot, st, Ti), it);
+      if (wt == 0.f) continue;
+      for (int oh = h0; oh <= h1; ++oh) {
+        const float wth = wt * tap_weight(axis_tap(oh, sh, Hi), ih);
+        if (wth == 0.f) continue;
+        const float4 *grow = g + (ot * Ho + oh) * Wo * C4 + cg;
+        for (int ow = w0; ow <= w1; ++ow) {
+          const float wgt = wth * tap_weight(axis_tap(ow, sw, Wi), iw);
+          if (wgt == 0.f) continue;
+          const float4 q = __ldg(grow + ow * C4);      // neighbouring voxels of the CTA share taps: keep L1
+          acc.x = fmaf(wgt, q.x, acc.x);
+          acc.y = fmaf(wgt, q.y, acc.y);
+          acc.z = fmaf(wgt, q.z, acc.z);
+          acc.w = fmaf(wgt, q.w, acc.w);
+        }
       }
     }
+    dst[i] = acc;
   }
-  gx[e] = acc;
 }
 
 }  // namespace mscl
@@ -244,11 +251,11 @@ int mscl_upsample_trilinear_ndhwc_fwd(const float *d_x, float *d_y, int64_t N, i
   if (rc) return rc;
   MSCL_CHECK_ARG(C > 0 && C % 4 == 0, "channels-last form needs C %% 4 == 0 (C=%d)", C);
   const float st = (float)Ti / (float)To, sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
-  const int64_t total = N * To * Ho * Wo * (C / 4);
-  const int64_t blocks = (total + 255) / 256;
-  MSCL_CHECK_ARG(blocks < (1ll << 31), "too many elements");
-  mscl::upsample_trilinear_ndhwc_fwd_kernel<<<(unsigned)blocks, 256, 0, mscl::as_stream(stream)>>>(
-      reinterpret_cast<const float4 *>(d_x), reinterpret_cast<float4 *>(d_y), total, C / 4, Ti, Hi, Wi, To, Ho, Wo, st, sh, sw);
+  const int64_t rows = N * To * Ho;
+  MSCL_CHECK_ARG(rows < (1ll << 31) && (int64_t)Ti * Hi * Wi * (C / 4) < (1ll << 31) && (int64_t)To * Ho * Wo * (C / 4) < (1ll << 31),
+                 "sample too large for 32-bit indexing");
+  mscl::upsample_trilinear_ndhwc_fwd_kernel<<<(unsigned)rows, 256, 0, mscl::as_stream(stream)>>>(
+      reinterpret_cast<const float4 *>(d_x), reinterpret_cast<float4 *>(d_y), C / 4, Ti, Hi, Wi, To, Ho, Wo, st, sh, sw);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }
@@ -259,11 +266,11 @@ int mscl_upsample_trilinear_ndhwc_bwd(const float *d_gy, float *d_gx, int64_t N,
   if (rc) return rc;
   MSCL_CHECK_ARG(C > 0 && C % 4 == 0, "channels-last form needs C %% 4 == 0 (C=%d)", C);
   const float st = (float)Ti / (float)To, sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
-  const int64_t total = N * Ti * Hi * Wi * (C / 4);
-  const int64_t blocks = (total + 255) / 256;
-  MSCL_CHECK_ARG(blocks < (1ll << 31), "too many elements");
-  mscl::upsample_trilinear_ndhwc_bwd_kernel<<<(unsigned)blocks, 256, 0, mscl::as_stream(stream)>>>(
-      reinterpret_cast<const float4 *>(d_gy), reinterpret_cast<float4 *>(d_gx), total, C / 4, Ti, Hi, Wi, To, Ho, Wo, st, sh, sw);
+  const int64_t rows = N * Ti * Hi;
+  MSCL_CHECK_ARG(rows < (1ll << 31) && (int64_t)Ti * Hi * Wi * (C / 4) < (1ll << 31) && (int64_t)To * Ho * Wo * (C / 4) < (1ll << 31),
+                 "sample too large for 32-bit indexing");
+  mscl::upsample_trilinear_ndhwc_bwd_kernel<<<(unsigned)rows, 256, 0, mscl::as_stream(stream)>>>(
+      reinterpret_cast<const float4 *>(d_gy), reinterpret_cast<float4 *>(d_gx), C / 4, Ti, Hi, Wi, To, Ho, Wo, st, sh, sw);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }

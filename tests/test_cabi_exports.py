@@ -63,3 +63,10 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_cabi.MsclError, match="no CPU fallback"):
         _cabi.load()
+
+
+def test_launch_counts_are_integers_for_known_entry_points():
+    """`gpu_launches` of bench.py is summed from this table: every key is a declared entry point, every value an int."""
+    from mscl_b200 import _cabi
+    for name, n in _cabi._LAUNCHES_PER_CALL.items():
+        assert name in _cabi.PROTOTYPES and isinstance(n, int) and 0 <= n <= 4, (name, n)
