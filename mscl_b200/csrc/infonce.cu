@@ -101,7 +101,7 @@ infonce_partial_simt_kernel(const float *__restrict__ qpack, int M,
 #pragma unroll 8
     for (int c = 0; c < kC; ++c) s = fmaf(qrow[c], kr[c], s);
     s *= ds;
-    float p = valid ? exp2f(s - shift2) : 0.f;
+    float p = (valid && !is_dup) ? exp2f(s - shift2) : 0.f;      // the duplicate is handled exactly by finalize
     float cnt = (valid && !is_dup && s > pos2) ? 1.f : 0.f;
     pbuf[tid] = p * ds;
     float ps = warp_sum(p), cs = warp_sum(cnt);
@@ -219,10 +219,18 @@ infonce_finalize_kernel(const float *__restrict__ qpack, const float *__restrict
   }
   const float pos2 = qp[kC], shift2 = qp[kC + 1];
   // A queue entry that IS this row's positive key (enqueued earlier in the step, moco.py:437)
-  // scores pos * 0.99999^age in the reference: above the positive iff pos < 0.  The tensor-core
-  // pass cannot resolve a 1e-5 margin with tf32 operands, so it skips that column's hit test and
-  // the exact comparison happens here.
-  if (__float_as_int(qp[kC + 2]) >= 0 && pos2 * qp[kC + 3] > pos2) cnt += 1.f;
+  // scores pos * 0.99999^age in the reference: above the positive iff pos < 0, and with almost
+  // the positive's own probability -- in the gradient the two nearly cancel against the "- 1" of
+  // the positive, so a tf32-level error on that one column shows up amplified by 1 / (1 - p_pos - p_dup).
+  // The queue pass therefore leaves the column out altogether (no hit test, p = 0), and its exact
+  // fp32 contribution is added here: logit = pos * decay (the entry is a bit-exact copy of kpos).
+  if (__float_as_int(qp[kC + 2]) >= 0) {
+    const float dsc = qp[kC + 3];
+    if (pos2 * dsc > pos2) cnt += 1.f;
+    const float e_dup = exp2f(fmaf(pos2, dsc, -shift2));
+    sum += e_dup;
+    if (with_grad) o = fmaf(e_dup * (dsc * inv_T * kLog2e), kpos[(int64_t)i * kC + c], o);
+  }
   const float e0 = exp2f(pos2 - shift2);
   const float Z = e0 + sum;
   const float inv_Z = 1.0f / Z;

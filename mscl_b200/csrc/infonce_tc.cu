@@ -277,9 +277,9 @@ __device__ __forceinline__ void softmax_half(uint32_t (&v)[32], const float4 *ds
       float p = ex2(fmaf(sv, dd[e], -shift2));
       uint32_t hit = __float_as_uint(fmaf(-sv, dd[e], pos2)) >> 31;    // 1 iff logit > positive logit
       if (!FULL) {  // tail tile (keys beyond K_local) or the tile holding this row's own positive key
-        const bool ok = j < nvalid;
+        const bool ok = j < nvalid && j != dupcol;      // the duplicate of the positive is added exactly by finalize
         p = ok ? p : 0.f;
-        hit = (ok && j != dupcol) ? hit : 0u;
+        hit = ok ? hit : 0u;
       }
       s4[e] += p;
       c4[e] += hit;

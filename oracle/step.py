@@ -82,11 +82,13 @@ class OracleMSCL:
         self.T = model.moco_mx_head.T
         self.t = model.sup_head.labels.shape[1]
         self.mlvl_ids = model.sup_head.mlvl_ids
+        self.trans_rgb = copy.deepcopy(model.sup_head.trans_rgb).cpu()        # Identity unless bkb_channels says otherwise
+        self.trans_flow = copy.deepcopy(model.sup_head.trans_flow).cpu()
         self.weight_aug_flow = model.weight_aug_flow
         self.training = model.training
 
     def parameters(self):
-        return self.rgb.q_params() + self.flow.q_params()
+        return self.rgb.q_params() + self.flow.q_params() + list(self.trans_rgb.parameters()) + list(self.trans_flow.parameters())
 
     def train_step(self, im_q, im_k, flow_q, flow_k):
         """Inputs already augmented: RGB (N,3,T,H,W), flow images (N,3,2T,H,W).  Returns (loss, log_vars).
@@ -106,7 +108,7 @@ class OracleMSCL:
         feats = dict(q=q, k=k, q_f=q_f, k_f=k_f, q_af=q_af, k_af=k_af, q_map=q_mlvl[self.mlvl_ids[0]],
                      qf_map=qf_mlvl[self.mlvl_ids[1]], qaf_map=qaf_mlvl[self.mlvl_ids[1]])
         loss_mx, loss_sup = O.mscl_tail(feats, self.rgb.state.weight, self.flow.state.weight, T, self.t,
-                                        self.weight_aug_flow)
+                                        self.weight_aug_flow, self.trans_rgb, self.trans_flow)
         losses = OrderedDict()
         for d in (loss_img, loss_flow, loss_mx, loss_sup):
             losses.update(d)

@@ -50,12 +50,18 @@ def _fake_enqueue(self, keys):
     self.batch_size = keys.shape[0]
 
 
+def _fake_enqueue_slots(self, n_local, device):
+    return torch.arange(n_local, dtype=torch.int32) + int(self._cpu_state.ptr)
+
+
 @pytest.fixture
 def cpu_kernels(monkeypatch):
     monkeypatch.setattr(MoCoV2, "contrast", _fake_contrast)
     monkeypatch.setattr(MoCoV2, "_dequeue_and_enqueue", _fake_enqueue)
+    monkeypatch.setattr(MoCoV2, "enqueue_slots", _fake_enqueue_slots)
     monkeypatch.setattr(fx, "hw_mean", lambda x: x.mean(dim=(-2, -1)))
     monkeypatch.setattr(fx, "lmcl", _fake_lmcl)
+    monkeypatch.setattr(fx, "upsample_trilinear", lambda x, size: torch.nn.functional.interpolate(x, size=size, mode="trilinear"))
 
 
 def test_sibling_heads_host_logic(cpu_kernels, golden_dir):
@@ -191,3 +197,36 @@ def test_parse_losses_deferred_equals_parse_losses():
     assert vars_a == deferred.get() and deferred.get() is deferred.get()
     want = losses["loss_cls"].mean() + losses["loss_list"][0].mean() + losses["loss_list"][1].mean()
     assert abs(vars_a["loss"] - float(want)) < 1e-6
+
+
+def test_r50_config_whole_step_host_logic(cpu_kernels, monkeypatch):
+    """The r50 config's model (SlowOnly-R50 + TPN with one pyramid convolution, r2d_50 flow branch, LMCL head with a
+    Conv1d(256,128) flow projection; `mscl_r50_cosm_lr3e-2.py`) through MSCLWithAug.train_step against the oracle's
+    step -- shapes, aux-key routing, projection gradients -- on the CPU at a reduced clip size."""
+    from mscl_b200.configs import mscl_r50_model
+    from oracle.step import OracleMSCL
+    monkeypatch.setattr(fx, "EmaTable", _FakeEma)
+    cfg = mscl_r50_model(K=64, aug="IdentityAug")
+    cfg["recognizer"]["max_iters"] = cfg["recognizer_flow"]["max_iters"] = 1000
+    torch.manual_seed(0)
+    model = mscl_b200.build_model(cfg).train()
+    orc = OracleMSCL(model)
+    for rec in (model.recognizer, model.recognizer_flow):
+        _attach_cpu_state(rec)
+    N = 2
+    g = torch.Generator().manual_seed(50)
+    imgs = [torch.rand(N, 3, 8, 64, 64, generator=g) for _ in range(2)]
+    flows = [torch.rand(N, 3, 16, 64, 64, generator=g) for _ in range(2)]
+    torch.manual_seed(100)
+    loss_ref, vars_ref = orc.train_step(imgs[0], imgs[1], flows[0], flows[1])
+    loss_ref.backward()
+    torch.manual_seed(100)
+    out = model.train_step(dict(imgs=imgs, flow_imgs=flows), None)
+    out["loss"].backward()
+    assert list(out["log_vars"].keys()) == list(vars_ref.keys()) and len(vars_ref) == 23
+    for k, v in out["log_vars"].items():
+        assert abs(v - vars_ref[k]) <= 5e-5 * max(1.0, abs(vars_ref[k])), (k, v, vars_ref[k])
+    a, b = model.sup_head.trans_flow.weight.grad, orc.trans_flow.weight.grad
+    assert float((a - b).norm() / b.norm()) < 1e-4
+    for rec, ob in ((model.recognizer, orc.rgb), (model.recognizer_flow, orc.flow)):
+        assert rec._cpu_state.ptr == ob.state.ptr and rec.iters == ob.state.iters
