@@ -240,7 +240,8 @@ def run_reference(args, rank):
 # ----------------------------------------------------------------------------------------------
 # this repo's path
 # ----------------------------------------------------------------------------------------------
-KERNEL_ENTRIES = ["mscl_infonce_partial", "mscl_ema_multi", "mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_fra_fused",
+KERNEL_ENTRIES = ["mscl_infonce_partial", "mscl_ema_multi", "mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_hw_mean_ndhwc_fwd",
+                  "mscl_hw_mean_ndhwc_bwd", "mscl_fra_fused",
                   "mscl_fra_maxrad", "mscl_fra_apply", "mscl_enqueue", "mscl_lmcl", "mscl_infonce_prep", "mscl_infonce_finalize",
                   "mscl_infonce_reduce_scatter", "mscl_flow_visualize", "mscl_color_pipeline", "mscl_grad_norm_multi",
                   "mscl_clip_sgd_multi",
@@ -444,7 +445,8 @@ def run_b200(args, rank, local_rank, world):
     kernels = summarise_kernels(rec, args.steps, pk)
     # `roofline`: the kernel with the largest share of the step among the kernels of the contrastive path proper
     # (K1-K6); the adjacent ones (augmentation K8/K9, optimizer K10) are listed in `kernels`
-    path_entries = ("mscl_infonce_partial", "mscl_ema_multi", "mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_fra_fused",
+    path_entries = ("mscl_infonce_partial", "mscl_ema_multi", "mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_hw_mean_ndhwc_fwd",
+                    "mscl_hw_mean_ndhwc_bwd", "mscl_fra_fused",
                     "mscl_fra_maxrad", "mscl_fra_apply", "mscl_enqueue", "mscl_lmcl", "mscl_gather_rows",
                     "mscl_infonce_reduce_scatter")
     on_path = [k for k in kernels if k["kernel"] in path_entries]

@@ -147,6 +147,10 @@ int mscl_hw_mean_fwd(const float *d_x, float *d_out, int64_t R, int32_t HW,
                      mscl_stream_t stream);
 int mscl_hw_mean_bwd(const float *d_gout, float *d_gx, int64_t R, int32_t HW,
                      mscl_stream_t stream);
+/* The same for a channels-last feature map (torch.channels_last_3d): x [N, T, H*W, C] in memory, C % 32 == 0, N*T <= 65535;
+ * the pooled tensor (and its gradient) stays (N, C, T) row-major. */
+int mscl_hw_mean_ndhwc_fwd(const float *d_x, float *d_out, int64_t N, int32_t C, int32_t T, int32_t HW, mscl_stream_t stream);
+int mscl_hw_mean_ndhwc_bwd(const float *d_gout, float *d_gx, int64_t N, int32_t C, int32_t T, int32_t HW, mscl_stream_t stream);
 int mscl_lmcl(const float *d_xq, const float *d_xf, int32_t N, int32_t C,
               int32_t t, int32_t t2, float inv_T, float *d_out, float *d_gxq,
               float *d_gxf, float *d_part, mscl_stream_t stream);

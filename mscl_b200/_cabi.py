@@ -29,6 +29,8 @@ PROTOTYPES = {
     "mscl_fra_rotate": [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr],
     "mscl_hw_mean_fwd": [c_ptr, c_ptr, c_i64, c_int, c_ptr],
     "mscl_hw_mean_bwd": [c_ptr, c_ptr, c_i64, c_int, c_ptr],
+    "mscl_hw_mean_ndhwc_fwd": [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr],
+    "mscl_hw_mean_ndhwc_bwd": [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr],
     "mscl_lmcl": [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "mscl_infonce_prep": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int,
                           c_ptr],

@@ -112,6 +112,68 @@ hw_mean_bwd_small_kernel(const float *__restrict__ gout, float *__restrict__ gx,
   stg_stream(reinterpret_cast<float4 *>(gx) + v, o);
 }
 
+// ---- channels-last (NDHWC) forms: x is [N, T, H*W, C] in memory (torch.channels_last_3d), the pooled output stays
+// (N, C, T) row-major like the row-major kernels'.  One CTA per (n, t) plane and 32-channel group: 8 lanes (float4) span
+// the 128-byte channel slice of one pixel, 32 pixel groups walk H*W with 4 independent accumulators, a shared-memory
+// tree combines them in a fixed order.  The encoders run channels-last, so this reads the feature map where it lies:
+// the row-major kernels needed a 2 x 51 MB layout copy in front (forward) and behind (backward) at the r18 sizes.
+constexpr int kClGroups = 32;     // pixel groups per CTA (256 threads = 32 groups x 8 lanes)
+__global__ void __launch_bounds__(256)
+hw_mean_ndhwc_fwd_kernel(const float4 *__restrict__ x, float *__restrict__ out, int C, int T, int HW, float inv_hw) {
+  __shared__ float4 red[kClGroups][8];
+  const int lane8 = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  const int c4_per_row = C >> 2;
+  const int cg = blockIdx.x;                       // 32-channel group
+  const int64_t plane = blockIdx.y;                // n * T + t
+  const float4 *p = x + plane * HW * c4_per_row + cg * 8 + lane8;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  int px = grp;
+  for (; px + kClGroups < HW; px += 2 * kClGroups) {
+    const float4 f0 = ldg_stream(p + (int64_t)px * c4_per_row), f1 = ldg_stream(p + (int64_t)(px + kClGroups) * c4_per_row);
+    a0.x += f0.x; a0.y += f0.y; a0.z += f0.z; a0.w += f0.w;
+    a1.x += f1.x; a1.y += f1.y; a1.z += f1.z; a1.w += f1.w;
+  }
+  if (px < HW) {
+    const float4 f0 = ldg_stream(p + (int64_t)px * c4_per_row);
+    a0.x += f0.x; a0.y += f0.y; a0.z += f0.z; a0.w += f0.w;
+  }
+  red[grp][lane8] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+  __syncthreads();
+#pragma unroll
+  for (int half = kClGroups / 2; half > 0; half >>= 1) {
+    if (grp < half) {
+      const float4 o = red[grp + half][lane8];
+      float4 &m = red[grp][lane8];
+      m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+    }
+    __syncthreads();
+  }
+  if (grp == 0) {
+    const float4 m = red[0][lane8];
+    const int64_t n = plane / T;
+    const int t = (int)(plane - n * T);
+    float *o = out + (n * C + cg * 32 + lane8 * 4) * T + t;      // (N, C, T): channel stride T
+    o[0] = m.x * inv_hw;
+    o[T] = m.y * inv_hw;
+    o[2 * T] = m.z * inv_hw;
+    o[3 * T] = m.w * inv_hw;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+hw_mean_ndhwc_bwd_kernel(const float *__restrict__ gout, float4 *__restrict__ gx, int C, int T, int HW, float inv_hw) {
+  const int lane8 = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  const int c4_per_row = C >> 2;
+  const int cg = blockIdx.x;
+  const int64_t plane = blockIdx.y;
+  const int64_t n = plane / T;
+  const int t = (int)(plane - n * T);
+  const float *g = gout + (n * C + cg * 32 + lane8 * 4) * T + t;
+  const float4 v = make_float4(__ldg(g) * inv_hw, __ldg(g + T) * inv_hw, __ldg(g + 2 * T) * inv_hw, __ldg(g + 3 * T) * inv_hw);
+  float4 *p = gx + plane * HW * c4_per_row + cg * 8 + lane8;
+  for (int px = grp; px < HW; px += kClGroups) stg_stream(p + (int64_t)px * c4_per_row, v);
+}
+
 // One CTA (256 threads) per clip.
 // smem floats: y[C*ld] | dy[C*ld] | sim[t*sp] | nrm[tt] | dot[tt] | red[32*3]   with tt = t + t2,
 // ld = tt | 1 and sp = t2 | 1: odd pitches, so the column walks (norms, dy) hit 32 different banks.
@@ -319,6 +381,28 @@ int mscl_hw_mean_bwd(const float *d_gout, float *d_gx, int64_t R, int32_t HW,
   MSCL_CHECK_ARG(blocks < (1ll << 31), "too many rows");
   mscl::hw_mean_bwd_kernel<<<(unsigned)blocks, 256, 0, mscl::as_stream(stream)>>>(
       d_gout, d_gx, R, HW, 1.0f / (float)HW);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+int mscl_hw_mean_ndhwc_fwd(const float *d_x, float *d_out, int64_t N, int32_t C, int32_t T, int32_t HW, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_x && d_out, "null pointer");
+  MSCL_CHECK_ARG(N > 0 && T > 0 && HW > 0 && C > 0 && C % 32 == 0, "bad N=%lld C=%d (multiple of 32) T=%d HW=%d", (long long)N, C, T, HW);
+  MSCL_CHECK_ARG(N * T <= 65535, "N*T=%lld exceeds the grid's y extent", (long long)(N * T));
+  MSCL_CHECK_ARG((((uintptr_t)d_x) & 15) == 0, "x must be 16-byte aligned");
+  mscl::hw_mean_ndhwc_fwd_kernel<<<dim3(C / 32, (unsigned)(N * T)), 256, 0, mscl::as_stream(stream)>>>(
+      reinterpret_cast<const float4 *>(d_x), d_out, C, T, HW, 1.0f / (float)HW);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+int mscl_hw_mean_ndhwc_bwd(const float *d_gout, float *d_gx, int64_t N, int32_t C, int32_t T, int32_t HW, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_gout && d_gx, "null pointer");
+  MSCL_CHECK_ARG(N > 0 && T > 0 && HW > 0 && C > 0 && C % 32 == 0, "bad N=%lld C=%d (multiple of 32) T=%d HW=%d", (long long)N, C, T, HW);
+  MSCL_CHECK_ARG(N * T <= 65535, "N*T=%lld exceeds the grid's y extent", (long long)(N * T));
+  MSCL_CHECK_ARG((((uintptr_t)d_gx) & 15) == 0, "gx must be 16-byte aligned");
+  mscl::hw_mean_ndhwc_bwd_kernel<<<dim3(C / 32, (unsigned)(N * T)), 256, 0, mscl::as_stream(stream)>>>(
+      d_gout, reinterpret_cast<float4 *>(d_gx), C, T, HW, 1.0f / (float)HW);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }

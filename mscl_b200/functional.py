@@ -45,6 +45,11 @@ def _chk_dense(t, name):
     return t
 
 
+def _is_cl3d(t):
+    """Dense channels_last_3d (NDHWC in memory) and not simultaneously row-major (C == 1 or T*H*W == 1 are both)."""
+    return t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d) and not t.is_contiguous()
+
+
 _SM_COUNT = {}
 
 
@@ -283,14 +288,26 @@ def infonce(q, kpos, nq, rows_per_group, T, impl="tc", group=None, dup_slot=None
 # K2: LMCL
 # ----------------------------------------------------------------------------------------
 class _HWMean(torch.autograd.Function):
+    """Mean over (H, W) of a dense (N,C,T,H,W) map -> (N,C,T) row-major.  Both dense layouts are read where they lie:
+    row-major maps by the warp-per-row / staged-rows kernels, channels_last_3d maps (what the encoders produce in the
+    channels-last step) by the NDHWC kernels; the input gradient comes back in the input's layout."""
+
     @staticmethod
     def forward(ctx, x):
         shape = x.shape
         HW = shape[-1] * shape[-2]
         R = x.numel() // HW
         out = torch.empty(shape[:-2], device=x.device)
-        _cabi.call("mscl_hw_mean_fwd", x.data_ptr(), out.data_ptr(), R, HW, _stream(), algo_bytes=4 * R * (HW + 1))
+        cl = x.dim() == 5 and _is_cl3d(x) and shape[1] % 32 == 0 and shape[0] * shape[2] <= 65535
+        if cl:
+            n, c, t = shape[:3]
+            _cabi.call("mscl_hw_mean_ndhwc_fwd", x.data_ptr(), out.data_ptr(), n, c, t, HW, _stream(),
+                       algo_bytes=4 * R * (HW + 1))
+        else:
+            x = x.contiguous()
+            _cabi.call("mscl_hw_mean_fwd", x.data_ptr(), out.data_ptr(), R, HW, _stream(), algo_bytes=4 * R * (HW + 1))
         ctx.shape = shape
+        ctx.cl = cl
         return out
 
     @staticmethod
@@ -298,15 +315,28 @@ class _HWMean(torch.autograd.Function):
         g = g.contiguous()
         shape = ctx.shape
         HW = shape[-1] * shape[-2]
-        gx = torch.empty(shape, device=g.device)
-        _cabi.call("mscl_hw_mean_bwd", g.data_ptr(), gx.data_ptr(), g.numel(), HW, _stream(),
-                   algo_bytes=4 * g.numel() * (HW + 1))
+        if ctx.cl:
+            n, c, t = shape[:3]
+            gx = torch.empty(shape, device=g.device, memory_format=torch.channels_last_3d)
+            _cabi.call("mscl_hw_mean_ndhwc_bwd", g.data_ptr(), gx.data_ptr(), n, c, t, HW, _stream(),
+                       algo_bytes=4 * g.numel() * (HW + 1))
+        else:
+            gx = torch.empty(shape, device=g.device)
+            _cabi.call("mscl_hw_mean_bwd", g.data_ptr(), gx.data_ptr(), g.numel(), HW, _stream(),
+                       algo_bytes=4 * g.numel() * (HW + 1))
         return gx
 
 
 def hw_mean(x):
-    """Mean over the last two dims: AdaptiveAvgPool3d((None,1,1)).view(b,c,t) (local_cl_head.py:61-62)."""
-    _chk(x, name="feature map")
+    """Mean over the last two dims: AdaptiveAvgPool3d((None,1,1)).view(b,c,t) (local_cl_head.py:61-62) for a dense fp32
+    CUDA map, row-major or channels_last_3d (any other stride pattern is made row-major first)."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise _cabi.MsclError("feature map must be a CUDA tensor (the MSCL hot path has no CPU fallback)")
+    if x.dtype != torch.float32:
+        raise _cabi.MsclError(f"feature map must be torch.float32, got {x.dtype}")
+    _cabi.require_device(x.device.index if x.device.index is not None else torch.cuda.current_device())
+    if not (x.is_contiguous() or (x.dim() == 5 and _is_cl3d(x))):
+        x = x.contiguous()
     return _HWMean.apply(x)
 
 
@@ -475,11 +505,6 @@ def gather_rows(x, idx):
 # ----------------------------------------------------------------------------------------
 # K7: trilinear up-sampling (TPN neck)
 # ----------------------------------------------------------------------------------------
-def _is_cl3d(t):
-    """Dense channels_last_3d (NDHWC in memory) and not simultaneously row-major (C == 1 or T*H*W == 1 are both)."""
-    return t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d) and not t.is_contiguous()
-
-
 class _UpsampleTrilinear(torch.autograd.Function):
     """Both dense layouts are served natively: a channels_last_3d input gives a channels_last_3d output (and gradient),
     so the TPN neck's `y + upsample(...)` stays a same-layout add and no NCDHW <-> NDHWC copy appears on either side."""

@@ -38,12 +38,22 @@ class _QSite(nn.Module):
         return (q,) + tuple(q_mlvl)
 
 
+def _static_like(rec, sample):
+    """A static input buffer for `sample` in the layout the encoder's first convolution wants: when the weights are
+    channels_last_3d the per-step `static.copy_(clip)` then does the NCDHW -> NDHWC transposition in the one copy that
+    is needed anyway, instead of a second conversion kernel inside every replayed graph."""
+    w = next(rec.encoder_q.parameters())
+    cl = w.dim() == 5 and w.is_contiguous(memory_format=torch.channels_last_3d) and not w.is_contiguous()
+    fmt = torch.channels_last_3d if (cl and sample.dim() == 5) else torch.contiguous_format
+    return sample.detach().clone(memory_format=fmt)
+
+
 class _KSite:
     """Forward-only graph of a recognizer's key path (no pyramid: MSCLWithAug never reads k_mlvl)."""
 
     def __init__(self, rec, sample):
         self.rec = rec
-        self.static_in = sample.detach().clone(memory_format=torch.preserve_format)
+        self.static_in = _static_like(rec, sample)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
@@ -67,7 +77,7 @@ class GraphedPaths:
         sites = [_QSite(rec) for _ in samples_q]
         for s in sites:
             s.train(rec.training)
-        graphed = torch.cuda.make_graphed_callables(tuple(sites), tuple((x.detach().clone(),) for x in samples_q),
+        graphed = torch.cuda.make_graphed_callables(tuple(sites), tuple((_static_like(rec, x),) for x in samples_q),
                                                     allow_unused_input=True)   # e.g. pyramid convs of a neck whose levels feed nothing
         self.q_sites = list(graphed) if isinstance(graphed, (tuple, list)) else [graphed]
         self.k_sites = [_KSite(rec, x) for x in samples_k]

@@ -45,8 +45,8 @@ class _FrameContrastHead(nn.Module):
 
     def _scores(self, x_q, x_f):
         """(b,c,t,h,w) RGB map and (b,c',t',h',w') flow map -> (FusedScores, labels)."""
-        x_q = self.trans_rgb(fx.hw_mean(x_q.contiguous()))           # (b, 128, t)
-        x_f = self.trans_flow(fx.hw_mean(x_f.contiguous()))          # (b, 128, t')
+        x_q = self.trans_rgb(fx.hw_mean(x_q))           # (b, 128, t); row-major and channels-last maps are read in place
+        x_f = self.trans_flow(fx.hw_mean(x_f))          # (b, 128, t')
         out = fx.lmcl(x_q.contiguous(), x_f.contiguous(), self.T)
         pos_labels = self.labels.repeat((x_q.shape[0], 1)).flatten(0, 1)
         return FusedScores(out, x_q.shape[0] * x_q.shape[2], x_f.shape[2]), pos_labels

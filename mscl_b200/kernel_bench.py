@@ -138,6 +138,12 @@ def bench_k2(cfg, N, t, pk, dev, iters=30):
         out.append(row(cfg, "hw_mean_fwd", f"{name} {shp}", us, 4 * R * (HW + 1), 0, pk))
         us = time_train(lambda i: _cabi.call("mscl_hw_mean_bwd", o.data_ptr(), xs[i % rot].data_ptr(), R, HW, _st()), iters)
         out.append(row(cfg, "hw_mean_bwd", f"{name} {shp}", us, 4 * R * (HW + 1), 0, pk))
+        # channels-last kernels on the same buffers viewed as [N, T, HW, C] (what the channels-last step runs)
+        n_, c_, t_ = shp[:3]
+        us = time_train(lambda i: _cabi.call("mscl_hw_mean_ndhwc_fwd", xs[i % rot].data_ptr(), o.data_ptr(), n_, c_, t_, HW, _st()), iters)
+        out.append(row(cfg, "hw_mean_ndhwc_fwd", f"{name} {shp}", us, 4 * R * (HW + 1), 0, pk))
+        us = time_train(lambda i: _cabi.call("mscl_hw_mean_ndhwc_bwd", o.data_ptr(), xs[i % rot].data_ptr(), n_, c_, t_, HW, _st()), iters)
+        out.append(row(cfg, "hw_mean_ndhwc_bwd", f"{name} {shp}", us, 4 * R * (HW + 1), 0, pk))
         del xs
     xq = torch.randn(N, 128, t, device=dev)
     xf = torch.randn(N, 128, 2 * t, device=dev)

@@ -263,8 +263,10 @@ class MSCLWithAug(BaseMoCoRecognizer):
         rec, recf = self.recognizer, self.recognizer_flow
         if self.cat_flow:
             cat_q, cat_k = aux_info[f"{self.flow_key[0]}_q"], aux_info[f"{self.flow_key[0]}_k"]
-            flow_q, aug_flow_q = (x.contiguous() for x in cat_q.chunk(2, 2))
-            flow_k, aug_flow_k = (x.contiguous() for x in cat_k.chunk(2, 2))
+            # strided views: the encoder's first convolution (or the graphed path's static-input copy) makes the one
+            # dense copy it needs in its own layout; a `.contiguous()` here would be a second 38 MB pass per half
+            flow_q, aug_flow_q = cat_q.chunk(2, 2)
+            flow_k, aug_flow_k = cat_k.chunk(2, 2)
         else:
             flow_q, flow_k = aux_info[f"{self.flow_key[0]}_q"], aux_info[f"{self.flow_key[0]}_k"]
             aug_flow_q, aug_flow_k = aux_info[f"{self.flow_key[1]}_q"], aux_info[f"{self.flow_key[1]}_k"]

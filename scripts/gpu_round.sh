@@ -1,6 +1,8 @@
 #!/bin/bash
-# One GPU-box pass for the round's evidence: parity tests, smoke, full bench line, ncu launch list + full captures.
+# One GPU-box pass for the round's evidence: parity tests, smoke, full bench line, every kernel alone at the shapes of
+# BASELINE configs 2-5, ncu launch list + full captures.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 bash scripts/gpu_check.sh
 cp gpurun_out/bench.log gpurun_out/bench_full.log
+timeout 600 python -m mscl_b200.kernel_bench --configs cfg2,cfg3,cfg4,cfg5 --out gpurun_out/kernel_rooflines.json > gpurun_out/kernel_bench.log 2>&1; echo "kernel_bench rc=$?"
 bash scripts/gpu_profile.sh

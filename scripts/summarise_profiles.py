@@ -27,7 +27,10 @@ ENTRY = {"infonce_tc_kernel": "mscl_infonce_partial", "ema_multi_kernel": "mscl_
          "hw_mean_bwd_small_kernel": "mscl_hw_mean_bwd", "enqueue_kernel": "mscl_enqueue", "lmcl_kernel": "mscl_lmcl", "clip_sgd_multi_kernel": "mscl_clip_sgd_multi",
          "grad_sqnorm_multi_kernel": "mscl_grad_sqnorm_multi", "color_pipeline_fast_kernel": "mscl_color_pipeline",
          "color_pipeline_kernel": "mscl_color_pipeline", "flow_visualize_kernel": "mscl_flow_visualize",
-         "upsample_trilinear_fwd_kernel": "mscl_upsample_trilinear_fwd", "upsample_trilinear_bwd_kernel": "mscl_upsample_trilinear_bwd"}
+         "upsample_trilinear_fwd_kernel": "mscl_upsample_trilinear_fwd", "upsample_trilinear_bwd_kernel": "mscl_upsample_trilinear_bwd",
+         "upsample_trilinear_ndhwc_fwd_kernel": "mscl_upsample_trilinear_ndhwc_fwd",
+         "upsample_trilinear_ndhwc_bwd_kernel": "mscl_upsample_trilinear_ndhwc_bwd",
+         "hw_mean_ndhwc_fwd_kernel": "mscl_hw_mean_ndhwc_fwd", "hw_mean_ndhwc_bwd_kernel": "mscl_hw_mean_ndhwc_bwd"}
 
 
 def launch_shares(tag):

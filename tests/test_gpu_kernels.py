@@ -158,6 +158,26 @@ def test_hw_mean_matches_torch(fx, shape):
     np.testing.assert_allclose(x.grad.cpu().numpy(), want.cpu().numpy(), rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("shape", [(2, 128, 4, 28, 28), (3, 128, 8, 7, 7), (2, 32, 3, 5, 6), (1, 64, 1, 9, 14), (2, 256, 2, 1, 3),
+                                   (2, 48, 2, 4, 4)])
+def test_hw_mean_channels_last(fx, shape):
+    """The NDHWC kernels: a channels_last_3d feature map is pooled where it lies (no layout copy) and its gradient comes
+    back channels_last_3d; C not a multiple of 32 (last case) takes the row-major kernels, values unchanged."""
+    g = torch.Generator().manual_seed(sum(shape) + 3)
+    cl = torch.channels_last_3d
+    x = torch.randn(shape, generator=g).cuda().contiguous(memory_format=cl).requires_grad_(True)
+    w = torch.randn(shape[:3], generator=g).cuda()
+    out = fx.hw_mean(x)
+    assert out.is_contiguous() and tuple(out.shape) == shape[:3]
+    ref = x.detach().double().mean(dim=(-2, -1))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    (out * w).sum().backward()
+    if shape[1] % 32 == 0 and shape[2] * shape[3] * shape[4] > 1:
+        assert x.grad.is_contiguous(memory_format=cl)
+    want = (w / (shape[-1] * shape[-2]))[..., None, None].expand(shape)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), want.cpu().numpy(), rtol=1e-6, atol=0)
+
+
 def _oracle_lmcl(q_map, qf_map, qaf_map, T, t):
     from oracle import mscl_oracle as O
     leaves = [x.clone().requires_grad_(True) for x in (q_map, qf_map, qaf_map)]
