@@ -207,7 +207,8 @@ class MSCLWithAug(BaseMoCoRecognizer):
         use_aug_mx = self.weight_aug_flow[1] > 0
 
         # which decayed queue each cross-modal term reads (heads/moco_head_v2.py:42-47)
-        rf_queue, fr_queue = ("flow_post", "rgb_pre") if self.same_kn else ("rgb_pre", "flow_post")
+        # ... decided by the HEAD's same_kn, as in the reference (the recognizer's own `same_kn` argument is stored, unused)
+        rf_queue, fr_queue = ("flow_post", "rgb_pre") if mx.same_kn else ("rgb_pre", "flow_post")
         terms = {"rgb_pre": [("own", q, k, rec.T)], "flow_pre": [("own_f", q_f, k_f, recf.T)],
                  "flow_post": [("own_af", q_af, k_af, recf.T)]}
         terms[rf_queue].append(("rf", q, k_f, mx.T))

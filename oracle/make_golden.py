@@ -25,18 +25,18 @@ def _flow_recognizer_cfg(K, basename):
                 mlp=True, aux_info=[], aug=dict(type="IdentityAug"))
 
 
-def build_head_level_model(ref, K, t):
+def build_head_level_model(ref, K, t, same_kn=True, update_aug_flow=False, weight_aug_flow=(1.0, 1.0)):
     """A real MSCLWithAug whose encoders are never run: extract_feat is patched per call."""
     cfg = dict(type="MSCLWithAug", recognizer=_flow_recognizer_cfg(K, ""),
                recognizer_flow=_flow_recognizer_cfg(K, "flow"),
-               moco_mx_head=dict(type="MSCLWithAugMxHead", basename="mx", loss_cls=LOSS, same_kn=True, T=0.07),
+               moco_mx_head=dict(type="MSCLWithAugMxHead", basename="mx", loss_cls=LOSS, same_kn=same_kn, T=0.07),
                sup_head=dict(type="MSCLWithAugPosHeadV2", basename="", loss_pos=LOSS,
                              bkb_channels=(None, None), t=t, T=0.07,
                              aux_keys=dict(im_features=dict(q_mlvl="q_mlvl"),
                                            base_flow_features=dict(q_mlvl="q_flow_mlvl"),
                                            aug_flow_features=dict(q_mlvl="q_aug_flow_mlvl"))),
-               im_key="imgs", flow_key="flow_imgs", aux_info=[], update_aug_flow=False,
-               weight_aug_flow=(1.0, 1.0), aug=dict(type="SyncMoCoAugmentV5"), same_kn=True)
+               im_key="imgs", flow_key="flow_imgs", aux_info=[], update_aug_flow=update_aug_flow,
+               weight_aug_flow=weight_aug_flow, aug=dict(type="SyncMoCoAugmentV5"), same_kn=same_kn)
     return ref.builder.build_model(cfg)
 
 
@@ -329,6 +329,55 @@ def golden_retrieval(ref):
     np.savez_compressed(os.path.join(OUT, "retrieval.npz"), **res)
 
 
+MSCL_VARIANTS = {"cross_kn": dict(same_kn=False),
+                 "aug_enqueue": dict(update_aug_flow=True, weight_aug_flow=(0.5, 0.0))}
+
+
+def golden_mscl_variants(ref):
+    """MSCLWithAug with the switches the r18 / r50 configs leave at their defaults (recognizers/mscl.py:225-277,
+    heads/moco_head_v2.py:42-47): `same_kn=False` (rf against the RGB queue, fr against the flow queue) and
+    `update_aug_flow=True, weight_aug_flow=(0.5, 0)` (the FRA-flow call enqueues too, its loss is halved, no *_aug
+    cross-modal terms).  Two consecutive head-level steps each."""
+    kw = dict(seed=4, N=4, C=128, K=256, t=4, hw_rgb=6, hw_flow=3)
+    res = {"kwargs": np.array(repr(kw))}
+    names = ("q", "q_f", "q_af", "q_map", "qf_map", "qaf_map")
+    for vname, opts in MSCL_VARIANTS.items():
+        inp = inputs.head_inputs(**kw)
+        m = build_head_level_model(ref, kw["K"], kw["t"], **opts)
+        m.train()
+        for rec, qn in ((m.recognizer, "queue_rgb"), (m.recognizer_flow, "queue_flow")):
+            rec.queue.copy_(inp[qn])
+            rec.count.copy_(inp["count"])
+            rec.queue_ptr[0] = inp["ptr"]
+        N = kw["N"]
+        dummy = torch.zeros(N, 3, 2, 4, 4)
+        for step in range(2):
+            x = inputs.head_inputs(**dict(kw, seed=kw["seed"] + step))
+            leaves = {n: x[n].clone().requires_grad_(True) for n in names}
+            calls_rgb = [(leaves["q"], [leaves["q_map"]], x["k"], [], {})]
+            calls_flow = [(leaves["q_f"], [leaves["qf_map"]], x["k_f"], [], {}),
+                          (leaves["q_af"], [leaves["qaf_map"]], x["k_af"], [], {})]
+            m.recognizer.extract_feat = lambda a, b: calls_rgb.pop(0)
+            m.recognizer_flow.extract_feat = lambda a, b: calls_flow.pop(0)
+            out = m.train_step(dict(imgs=[dummy, dummy], flow_imgs=[torch.zeros(N, 3, 4, 4, 4)] * 2), None)
+            out["loss"].backward()
+            tag = f"{vname}/step{step}"
+            for k, v in out["log_vars"].items():
+                res[f"{tag}/logvar/{k}"] = np.float64(v)
+            res[f"{tag}/logvar_order"] = np.array(list(out["log_vars"].keys()))
+            for n in ("q", "q_f", "q_af"):
+                res[f"{tag}/grad/{n}"] = leaves[n].grad.numpy()
+            for n in ("q_map", "qf_map", "qaf_map"):
+                res[f"{tag}/gradsum/{n}"] = leaves[n].grad.sum(dim=(-2, -1)).numpy()
+            for br, rec in (("rgb", m.recognizer), ("flow", m.recognizer_flow)):
+                res[f"{tag}/after/{br}/queue"] = rec.queue.numpy().copy()
+                res[f"{tag}/after/{br}/count"] = rec.count.numpy().copy()
+                res[f"{tag}/after/{br}/ptr"] = rec.queue_ptr.numpy().copy()
+                res[f"{tag}/after/{br}/iters"] = np.int64(rec.iters)
+            print(tag, {k: round(float(v), 5) for k, v in out["log_vars"].items()})
+    np.savez_compressed(os.path.join(OUT, "mscl_variants.npz"), **res)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load_reference()
@@ -343,6 +392,7 @@ def main():
     golden_sibling_heads(ref)
     golden_two_branch(ref)
     golden_retrieval(ref)
+    golden_mscl_variants(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

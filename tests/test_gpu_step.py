@@ -23,10 +23,9 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def head_level_model(K, t):
-    """The product's MSCLWithAug with the slim flow encoder on both branches (encoders are not run):
-    the same model dict oracle/make_golden.py hands to the reference."""
-    import mscl_b200
+def head_level_cfg(K, t, same_kn=True, update_aug_flow=False, weight_aug_flow=(1.0, 1.0)):
+    """MSCLWithAug with the slim flow encoder on both branches (encoders are not run): the same model dict
+    oracle/make_golden.py hands to the reference."""
     ce = dict(type="CrossEntropyLoss_torch", ignore_index=-1)
 
     def rec(basename):
@@ -35,15 +34,19 @@ def head_level_model(K, t):
                     dim=128, K=K, m_base=0.994, max_iters=1000, T=0.07, mlp=True, aux_info=[],
                     aug=dict(type="IdentityAug"))
 
-    cfg = dict(type="MSCLWithAug", recognizer=rec(""), recognizer_flow=rec("flow"),
-               moco_mx_head=dict(type="MSCLWithAugMxHead", basename="mx", loss_cls=ce, same_kn=True, T=0.07),
+    return dict(type="MSCLWithAug", recognizer=rec(""), recognizer_flow=rec("flow"),
+               moco_mx_head=dict(type="MSCLWithAugMxHead", basename="mx", loss_cls=ce, same_kn=same_kn, T=0.07),
                sup_head=dict(type="MSCLWithAugPosHeadV2", basename="", loss_pos=ce, bkb_channels=(None, None), t=t,
                              T=0.07, aux_keys=dict(im_features=dict(q_mlvl="q_mlvl"),
                                                    base_flow_features=dict(q_mlvl="q_flow_mlvl"),
                                                    aug_flow_features=dict(q_mlvl="q_aug_flow_mlvl"))),
-               im_key="imgs", flow_key="flow_imgs", aux_info=[], update_aug_flow=False, weight_aug_flow=(1.0, 1.0),
-               aug=dict(type="IdentityAug"), same_kn=True)
-    return mscl_b200.build_model(cfg).cuda()
+               im_key="imgs", flow_key="flow_imgs", aux_info=[], update_aug_flow=update_aug_flow,
+               weight_aug_flow=weight_aug_flow, aug=dict(type="IdentityAug"), same_kn=same_kn)
+
+
+def head_level_model(K, t, **switches):
+    import mscl_b200
+    return mscl_b200.build_model(head_level_cfg(K, t, **switches)).cuda()
 
 
 def run_product_objective(inp, t):
@@ -135,6 +138,44 @@ def test_objective_full_size_vs_oracle(N, K, t):
     from oracle import inputs
     inp = inputs.head_inputs(seed=5, N=N, K=K, t=t, hw_rgb=14, hw_flow=7, b_all=N)
     check_objective(inp, t)
+
+
+@pytest.mark.parametrize("vname", ["cross_kn", "aug_enqueue"])
+def test_objective_switches_vs_reference_golden(vname, golden_dir):
+    """`same_kn=False` (rf against the RGB queue, fr against the post-enqueue flow queue) and `update_aug_flow=True,
+    weight_aug_flow=(0.5, 0)` (third enqueue, halved FRA loss, no *_aug cross-modal terms) over two consecutive steps
+    against the reference's numbers (tests/golden/mscl_variants.npz) and the oracle."""
+    from oracle import inputs
+    from test_oracle_golden import MSCL_VARIANTS, check_mscl_variant_step, run_oracle_mscl_variant
+    g = np.load(os.path.join(golden_dir, "mscl_variants.npz"), allow_pickle=False)
+    kw = eval(str(g["kwargs"]))
+    inp = inputs.head_inputs(**kw)
+    model = head_level_model(kw["K"], kw["t"], **MSCL_VARIANTS[vname]).train()
+    ptr = torch.tensor([inp["ptr"]])
+    model.load_state_dict({"recognizer.queue": inp["queue_rgb"], "recognizer.count": inp["count"], "recognizer.queue_ptr": ptr,
+                           "recognizer_flow.queue": inp["queue_flow"], "recognizer_flow.count": inp["count"],
+                           "recognizer_flow.queue_ptr": ptr}, strict=False)
+    N = kw["N"]
+    names = ("q", "q_f", "q_af", "q_map", "qf_map", "qaf_map")
+    for step, ref_vars, ref_leaves, _, _ in run_oracle_mscl_variant(g, vname):
+        x = inputs.head_inputs(**dict(kw, seed=kw["seed"] + step))
+        leaves = {n: x[n].cuda().requires_grad_(True) for n in names}
+        model.recognizer.note_branch(N, True)
+        model.recognizer_flow.note_branch(N, True)
+        model.recognizer_flow.note_branch(N, model.update_aug_flow)
+        losses = model.objective(dict(q=leaves["q"], q_f=leaves["q_f"], q_af=leaves["q_af"], k=x["k"].cuda(), k_f=x["k_f"].cuda(),
+                                      k_af=x["k_af"].cuda(), q_mlvl=[leaves["q_map"]], q_flow_mlvl=[leaves["qf_map"]],
+                                      q_aug_flow_mlvl=[leaves["qaf_map"]]))
+        loss, log_vars = model._parse_losses(losses)
+        loss.backward()
+        states = {}
+        for br, rec in (("rgb", model.recognizer), ("flow", model.recognizer_flow)):
+            sd = {k: v.cpu() for k, v in rec.state_dict().items() if k in ("queue", "count", "queue_ptr")}
+            states[br] = dict(ptr=int(sd["queue_ptr"]), iters=rec.iters, count=sd["count"].numpy(), queue=sd["queue"].numpy())
+        check_mscl_variant_step(g, f"{vname}/step{step}", log_vars, {n: l.grad.cpu() for n, l in leaves.items()}, states,
+                                rel=REL, rel_grad=REL, rel_map=REL)
+        for n in names:
+            assert _rel(leaves[n].grad, ref_leaves[n].grad) < REL, (vname, step, n)
 
 
 def test_objective_confident_rows():

@@ -230,3 +230,33 @@ def test_r50_config_whole_step_host_logic(cpu_kernels, monkeypatch):
     assert float((a - b).norm() / b.norm()) < 1e-4
     for rec, ob in ((model.recognizer, orc.rgb), (model.recognizer_flow, orc.flow)):
         assert rec._cpu_state.ptr == ob.state.ptr and rec.iters == ob.state.iters
+
+
+@pytest.mark.parametrize("vname", ["cross_kn", "aug_enqueue"])
+def test_mscl_with_aug_switches_host_logic(cpu_kernels, vname, golden_dir):
+    """MSCLWithAug.objective with `same_kn=False` / `update_aug_flow=True, weight_aug_flow=(0.5, 0)`: which queue state
+    each stacked term reads, the extra enqueue, the halved / dropped loss terms -- against the reference's numbers."""
+    from test_gpu_step import head_level_cfg
+    from test_oracle_golden import MSCL_VARIANTS, check_mscl_variant_step
+    g = np.load(os.path.join(golden_dir, "mscl_variants.npz"), allow_pickle=False)
+    kw = eval(str(g["kwargs"]))
+    inp = inputs.head_inputs(**kw)
+    model = mscl_b200.build_model(head_level_cfg(kw["K"], kw["t"], **MSCL_VARIANTS[vname])).train()
+    model.recognizer._cpu_state = O.QueueState(inp["queue_rgb"], inp["count"], inp["ptr"])
+    model.recognizer_flow._cpu_state = O.QueueState(inp["queue_flow"], inp["count"], inp["ptr"])
+    N = kw["N"]
+    names = ("q", "q_f", "q_af", "q_map", "qf_map", "qaf_map")
+    for step in range(2):
+        x = inputs.head_inputs(**dict(kw, seed=kw["seed"] + step))
+        leaves = {n: x[n].clone().requires_grad_(True) for n in names}
+        model.recognizer.note_branch(N, True)                    # what forward_train does after each encoder call
+        model.recognizer_flow.note_branch(N, True)
+        model.recognizer_flow.note_branch(N, model.update_aug_flow)
+        losses = model.objective(dict(q=leaves["q"], q_f=leaves["q_f"], q_af=leaves["q_af"], k=x["k"], k_f=x["k_f"], k_af=x["k_af"],
+                                      q_mlvl=[leaves["q_map"]], q_flow_mlvl=[leaves["qf_map"]], q_aug_flow_mlvl=[leaves["qaf_map"]]))
+        loss, log_vars = model._parse_losses(losses)
+        loss.backward()
+        states = {br: dict(ptr=rec._cpu_state.ptr, iters=rec.iters, count=rec._cpu_state.count.numpy(), queue=rec._cpu_state.queue.numpy())
+                  for br, rec in (("rgb", model.recognizer), ("flow", model.recognizer_flow))}
+        check_mscl_variant_step(g, f"{vname}/step{step}", log_vars, {n: l.grad for n, l in leaves.items()}, states,
+                                rel=2e-6, rel_grad=2e-5, rel_map=1e-4)

@@ -275,3 +275,53 @@ def test_retrieval_oracle_matches_reference(golden_dir):
         rank[~same.any(dim=1)] = sim.shape[1]
         by_rank = [(rank < k).float().mean().item() for k in (1, 5, 10, 20, 50)]
         np.testing.assert_allclose(by_rank, g[f"{name}/acc"], rtol=0, atol=1e-7)
+
+
+MSCL_VARIANTS = {"cross_kn": dict(same_kn=False), "aug_enqueue": dict(update_aug_flow=True, weight_aug_flow=(0.5, 0.0))}
+
+
+def run_oracle_mscl_variant(g, vname):
+    """Two consecutive MSCLWithAug steps with non-default switches through the oracle (shared with the GPU test)."""
+    kw = eval(str(g["kwargs"]))
+    inp = inputs.head_inputs(**kw)
+    rgb = O.QueueState(inp["queue_rgb"], inp["count"], inp["ptr"])
+    flow = O.QueueState(inp["queue_flow"], inp["count"], inp["ptr"])
+    names = ("q", "q_f", "q_af", "q_map", "qf_map", "qaf_map")
+    for step in range(2):
+        x = inputs.head_inputs(**dict(kw, seed=kw["seed"] + step))
+        leaves = {n: x[n].clone().requires_grad_(True) for n in names}
+        feats = dict(k=x["k"], k_f=x["k_f"], k_af=x["k_af"], **leaves)
+        loss, log_vars = O.parse_losses(O.mscl_objective(feats, rgb, flow, T=0.07, t=kw["t"], **MSCL_VARIANTS[vname]))
+        loss.backward()
+        yield step, log_vars, leaves, rgb, flow
+
+
+def check_mscl_variant_step(g, tag, log_vars, grads, states, rel, rel_grad, rel_map, exact_acc=True):
+    """Compare one step's log vars / gradients / queue states with the golden entry `tag`."""
+    assert list(log_vars.keys()) == [str(k) for k in g[f"{tag}/logvar_order"]]
+    for k, v in log_vars.items():
+        ref = float(g[f"{tag}/logvar/{k}"])
+        tol = 1e-6 if ("acc" in k and exact_acc) else rel * max(1.0, abs(ref))
+        assert abs(v - ref) <= tol, (tag, k, v, ref)
+    for n in ("q", "q_f", "q_af"):
+        a, b = grads[n].double(), torch.from_numpy(g[f"{tag}/grad/{n}"]).double()
+        assert float((a - b).norm() / b.norm()) < rel_grad, (tag, n)
+    for n in ("q_map", "qf_map", "qaf_map"):
+        a, b = grads[n].double().sum(dim=(-2, -1)), torch.from_numpy(g[f"{tag}/gradsum/{n}"]).double()
+        assert float((a - b).norm() / b.norm()) < rel_map, (tag, n)
+    for br, st in states.items():
+        assert st["ptr"] == int(g[f"{tag}/after/{br}/ptr"][0]) and st["iters"] == int(g[f"{tag}/after/{br}/iters"]), (tag, br)
+        np.testing.assert_array_equal(st["count"], g[f"{tag}/after/{br}/count"])
+        np.testing.assert_array_equal(st["queue"], g[f"{tag}/after/{br}/queue"])
+
+
+def test_mscl_variants_oracle_matches_reference(golden_dir):
+    """mscl_objective(same_kn=False) and (update_aug_flow=True, weight_aug_flow=(0.5, 0)) vs the reference's MSCLWithAug
+    built with those switches (recognizers/mscl.py:225-277, heads/moco_head_v2.py:42-47)."""
+    g = _load(golden_dir, "mscl_variants.npz")
+    for vname in MSCL_VARIANTS:
+        for step, log_vars, leaves, rgb, flow in run_oracle_mscl_variant(g, vname):
+            states = {br: dict(ptr=st.ptr, iters=st.iters, count=st.count.numpy(), queue=st.queue.numpy())
+                      for br, st in (("rgb", rgb), ("flow", flow))}
+            check_mscl_variant_step(g, f"{vname}/step{step}", log_vars, {n: l.grad for n, l in leaves.items()}, states,
+                                    rel=2e-6, rel_grad=2e-5, rel_map=1e-4)
