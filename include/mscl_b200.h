@@ -258,6 +258,11 @@ int mscl_upsample_trilinear_ndhwc_fwd(const float *d_x, float *d_y, int64_t N, i
                                       int32_t Wi, int32_t To, int32_t Ho, int32_t Wo, mscl_stream_t stream);
 int mscl_upsample_trilinear_ndhwc_bwd(const float *d_gy, float *d_gx, int64_t N, int32_t C, int32_t Ti, int32_t Hi,
                                       int32_t Wi, int32_t To, int32_t Ho, int32_t Wo, mscl_stream_t stream);
+/* One axis of that backward (the trilinear weights factorise): src [outer][out_size][inner4 float4s] ->
+ * dst [outer][in_size][inner4], dst[.., i, ..] = sum over the outputs o that read input index i of w(o, i) * src[.., o, ..].
+ * Three calls (W, H, T) give the channels-last input gradient with every intermediate read once. */
+int mscl_linear_axis_bwd(const float *d_src, float *d_dst, int64_t outer, int32_t in_size, int32_t out_size, int64_t inner4,
+                         mscl_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * K8  flow visualisation + flip.   replaces FlowVisualizer.__call__ / flow_uv_to_colors

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "mscl_upsample_trilinear_bwd": [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
     "mscl_upsample_trilinear_ndhwc_fwd": [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
     "mscl_upsample_trilinear_ndhwc_bwd": [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
+    "mscl_linear_axis_bwd": [c_ptr, c_ptr, c_i64, c_int, c_int, c_i64, c_ptr],
     "mscl_center_normalize": [c_ptr, c_i64, c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr],
     "mscl_retrieval_rank": [c_ptr, c_i64, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr],
 }

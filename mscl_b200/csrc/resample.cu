@@ -202,6 +202,36 @@ upsample_trilinear_ndhwc_bwd_kernel(const float4 *__restrict__ gy, float4 *__res
   }
 }
 
+// Separable backward for channels-last tensors: the trilinear weights factorise, so the gradient of the up-sampling is
+// three 1-D linear-interpolation backward passes (W, then H, then T), each a gather over the <= ~4 outputs that read an
+// input index along that axis.  src [outer][out_size][inner4] -> dst [outer][in_size][inner4] in float4 units; every
+// pass reads its input once, fully coalesced (the direct 3-D gather re-reads each output row for ~4 input rows and
+// is L2-bound: 72 us for a 58 MB pass at the r18 sizes).
+__global__ void __launch_bounds__(256)
+linear_axis_bwd_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, unsigned total, int in_size, int out_size,
+                       int inner4, float scale, float inv_scale) {
+  const unsigned e = blockIdx.x * 256u + threadIdx.x;
+  if (e >= total) return;
+  const unsigned r = e / (unsigned)inner4;
+  const int inner = (int)(e - r * (unsigned)inner4);
+  const unsigned outer = r / (unsigned)in_size;
+  const int i = (int)(r - outer * (unsigned)in_size);
+  int o0, o1;
+  out_range(i, inv_scale, out_size, o0, o1);
+  const float4 *p = src + ((int64_t)outer * out_size) * inner4 + inner;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int o = o0; o <= o1; ++o) {
+    const float w = tap_weight(axis_tap(o, scale, in_size), i);
+    if (w == 0.f) continue;
+    const float4 q = __ldg(p + (int64_t)o * inner4);
+    acc.x = fmaf(w, q.x, acc.x);
+    acc.y = fmaf(w, q.y, acc.y);
+    acc.z = fmaf(w, q.z, acc.z);
+    acc.w = fmaf(w, q.w, acc.w);
+  }
+  dst[e] = acc;
+}
+
 }  // namespace mscl
 
 extern "C" {
@@ -271,6 +301,21 @@ int mscl_upsample_trilinear_ndhwc_bwd(const float *d_gy, float *d_gx, int64_t N,
                  "sample too large for 32-bit indexing");
   mscl::upsample_trilinear_ndhwc_bwd_kernel<<<(unsigned)rows, 256, 0, mscl::as_stream(stream)>>>(
       reinterpret_cast<const float4 *>(d_gy), reinterpret_cast<float4 *>(d_gx), C / 4, Ti, Hi, Wi, To, Ho, Wo, st, sh, sw);
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+int mscl_linear_axis_bwd(const float *d_src, float *d_dst, int64_t outer, int32_t in_size, int32_t out_size, int64_t inner4,
+                         mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_src && d_dst, "null pointer");
+  MSCL_CHECK_ARG(outer > 0 && in_size > 0 && out_size > 0 && inner4 > 0, "bad shape");
+  MSCL_CHECK_ARG((((uintptr_t)d_src | (uintptr_t)d_dst) & 15) == 0, "tensors must be 16-byte aligned");
+  const int64_t total = outer * in_size * inner4;
+  MSCL_CHECK_ARG(total < (1ll << 32) && inner4 < (1ll << 31) && outer * out_size * inner4 < (1ll << 40), "tensor too large");
+  const float scale = (float)in_size / (float)out_size;
+  mscl::linear_axis_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, mscl::as_stream(stream)>>>(
+      reinterpret_cast<const float4 *>(d_src), reinterpret_cast<float4 *>(d_dst), (unsigned)total, in_size, out_size, (int)inner4,
+      scale, 1.f / scale);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }

@@ -532,10 +532,21 @@ class _UpsampleTrilinear(torch.autograd.Function):
         n, c, ti, hi, wi = ctx.in_shape
         to, ho, wo = gy.shape[2:]
         if ctx.cl:
-            gy = gy.contiguous(memory_format=torch.channels_last_3d)
-            gx = torch.empty(ctx.in_shape, device=gy.device, memory_format=torch.channels_last_3d)
-            _cabi.call("mscl_upsample_trilinear_ndhwc_bwd", gy.data_ptr(), gx.data_ptr(), n, c, ti, hi, wi, to, ho, wo,
-                       _stream(), algo_bytes=4 * (gx.numel() + gy.numel()))
+            # separable: one 1-D gather pass per scaled axis (W, H, T), each reading its input once
+            cur = gy.contiguous(memory_format=torch.channels_last_3d)
+            c4 = c // 4
+            dims = [to, ho, wo]                                   # current (T, H, W) extent of `cur`
+            for axis, (n_in, n_out) in ((2, (wi, wo)), (1, (hi, ho)), (0, (ti, to))):
+                if n_in == n_out:
+                    continue
+                outer = n * int(np.prod(dims[:axis], dtype=np.int64))
+                inner4 = int(np.prod(dims[axis + 1:], dtype=np.int64)) * c4
+                dims[axis] = n_in
+                nxt = torch.empty((n, c, dims[0], dims[1], dims[2]), device=gy.device, memory_format=torch.channels_last_3d)
+                _cabi.call("mscl_linear_axis_bwd", cur.data_ptr(), nxt.data_ptr(), outer, n_in, n_out, inner4, _stream(),
+                           algo_bytes=4 * (cur.numel() + nxt.numel()))
+                cur = nxt
+            gx = cur if cur.data_ptr() != gy.data_ptr() else cur.clone()
         else:
             gy = gy.contiguous()
             gx = torch.empty(ctx.in_shape, device=gy.device)

@@ -264,7 +264,24 @@ def bench_k789(cfg, N, pk, dev, iters=20):
         us = time_train(lambda i: _cabi.call("mscl_upsample_trilinear_ndhwc_bwd", ys[i % rot].data_ptr(), xs[i % rot].data_ptr(),
                                              N, 128, *shp[2:], *size, _st()), iters)
         out.append(row(cfg, "upsample_trilinear_ndhwc_bwd", f"{size} -> {shp}", us, 4 * (nin + nout), 0, pk))
-        del xs, ys
+        # what the autograd op runs: the separable backward, one 1-D gather pass per scaled axis (W, H, T)
+        (ti, hi, wi), (to, ho, wo) = shp[2:], size
+        t1 = torch.empty(N * to * ho * wi * 128, device=dev)
+        t2 = torch.empty(N * to * hi * wi * 128, device=dev)
+
+        def separable(i):
+            cur = ys[i % rot].data_ptr()
+            if wi != wo:
+                _cabi.call("mscl_linear_axis_bwd", cur, t1.data_ptr(), N * to * ho, wi, wo, 32, _st())
+                cur = t1.data_ptr()
+            if hi != ho:
+                _cabi.call("mscl_linear_axis_bwd", cur, t2.data_ptr(), N * to, hi, ho, wi * 32, _st())
+                cur = t2.data_ptr()
+            if ti != to:
+                _cabi.call("mscl_linear_axis_bwd", cur, xs[i % rot].data_ptr(), N, ti, to, hi * wi * 32, _st())
+        us = time_train(separable, iters)
+        out.append(row(cfg, "linear_axis_bwd x3 (separable K7 bwd)", f"{size} -> {shp}", us, 4 * (nin + nout), 0, pk))
+        del xs, ys, t1, t2
     # K8: (N,2,16,112,112) flow -> colour image, K9: (N,3,8,112,112) RGB clips
     T2, HW = 16, 112 * 112
     rot = n_rot(20 * N * T2 * HW)

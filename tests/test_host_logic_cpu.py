@@ -260,3 +260,31 @@ def test_mscl_with_aug_switches_host_logic(cpu_kernels, vname, golden_dir):
                   for br, rec in (("rgb", model.recognizer), ("flow", model.recognizer_flow))}
         check_mscl_variant_step(g, f"{vname}/step{step}", log_vars, {n: l.grad for n, l in leaves.items()}, states,
                                 rel=2e-6, rel_grad=2e-5, rel_map=1e-4)
+
+
+def test_eval_mode_step_host_logic(cpu_kernels, monkeypatch):
+    """Validation runs the same train_step (eval_hooks.py:471-478): in eval() the key encoder is
+    still EMA-updated, the permutation still drawn, the keys still enqueued, but `iters` (and so the momentum
+    schedule) stands still (moco.py:504-505) and batch norm uses its running statistics."""
+    from oracle.step import OracleMoCo
+    from test_gpu_siblings import _moco_cfg
+    monkeypatch.setattr(fx, "EmaTable", _FakeEma)
+    torch.manual_seed(0)
+    model = mscl_b200.build_model(_moco_cfg("MoCoV2", 64, m_base=0.99, max_iters=100)).train()
+    orc = OracleMoCo(model)
+    _attach_cpu_state(model)
+    g = torch.Generator().manual_seed(70)
+    batches = [[torch.rand(4, 3, 8, 32, 32, generator=g) for _ in range(2)] for _ in range(3)]
+    for step, mode in enumerate((True, False, True)):          # train, validate, train
+        model.train(mode)
+        orc.branch.train(mode)
+        orc.training = mode
+        torch.manual_seed(100 + step)
+        _, vars_ref = orc.train_step(*batches[step])
+        torch.manual_seed(100 + step)
+        out = model.train_step(dict(imgs=batches[step]), None)
+        for k, v in out["log_vars"].items():
+            assert abs(v - vars_ref[k]) <= 5e-5 * max(1.0, abs(vars_ref[k])), (step, k, v, vars_ref[k])
+        assert model.iters == orc.branch.state.iters == (4, 4, 8)[step]
+        assert model._cpu_state.ptr == orc.branch.state.ptr == 4 * (step + 1)
+        assert abs(model.m - (1 - 0.5 * 0.01 * (np.cos(np.pi * (0, 0.04, 0.04)[step]) + 1))) < 1e-12
