@@ -27,7 +27,7 @@ __device__ __forceinline__ WheelTap wheel_tap(float u, float v) {
   WheelTap w;
   w.rad = __fsqrt_rn(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)));
   const float a = __fdiv_rn(atan2f(-v, -u), 3.14159265358979323846f);
-  const float fk = __fmul_rn(__fdiv_rn(__fadd_rn(a, 1.f), 2.f), 54.f);
+  const float fk = __fmul_rn(__fmul_rn(__fadd_rn(a, 1.f), 0.5f), 54.f);      // x / 2 == x * 0.5 exactly
   const float fl = floorf(fk);
   w.k0 = (int)fl;
   w.k1 = w.k0 + 1;
@@ -38,14 +38,16 @@ __device__ __forceinline__ WheelTap wheel_tap(float u, float v) {
 }
 
 // `wheel`: the shared-memory copy (the lookup index differs per lane: constant memory would serialise it)
-__device__ __forceinline__ float wheel_color(const WheelTap &w, int ch, const double *wheel) {
+// `div255[k]` = float32(k / 255) for k = 0..255, filled once per CTA with the correctly rounded division: the kernel is
+// instruction-bound (~300 per pixel), and three IEEE divisions per pixel were a third of that.
+__device__ __forceinline__ float wheel_color(const WheelTap &w, int ch, const double *wheel, const float *div255) {
   double col = __dadd_rn(__dmul_rn((double)w.omf, wheel[w.k0 * 3 + ch]), __dmul_rn((double)w.f, wheel[w.k1 * 3 + ch]));
   if (w.rad <= 1.f)
     col = __dsub_rn(1.0, __dmul_rn((double)w.rad, __dsub_rn(1.0, col)));
   else
     col = __dmul_rn(col, 0.75);
-  const float q = (float)(unsigned char)floor(__dmul_rn(255.0, col));     // uint8 round trip (ssl_aug.py:121)
-  return __fdiv_rn(q, 255.f);
+  const unsigned char q = (unsigned char)floor(__dmul_rn(255.0, col));     // uint8 round trip (ssl_aug.py:121)
+  return div255[q];
 }
 
 // flow planar [N, 2, T, H, W] -> out [N, 3, T, H, W].  flip: uint8 [N] or null.  norm: float [6] = mean[3], std[3] or null.
@@ -53,16 +55,19 @@ __global__ void __launch_bounds__(256)
 flow_visualize_kernel(const float *__restrict__ flow, const uint8_t *__restrict__ flip, const float *__restrict__ norm,
                       float *__restrict__ out, int T, int H, int W, int64_t total4) {
   __shared__ double s_wheel[55 * 3];
+  __shared__ float s_div255[256];
   if (threadIdx.x < 55 * 3) s_wheel[threadIdx.x] = c_wheel[threadIdx.x];
+  s_div255[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.f);             // blockDim.x == 256
   __syncthreads();
-  const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const unsigned g = blockIdx.x * 256u + threadIdx.x;       // total4 < 2^31 (checked by the launcher): 32-bit div / mod
   if (g >= total4) return;
-  const int w4 = W >> 2;
-  const int wq = (int)(g % w4);
-  int64_t r = g / w4;                       // (n, t, h) row index
+  const unsigned w4 = (unsigned)W >> 2;
+  const unsigned r = g / w4;                                 // (n, t, h) row index
+  const int wq = (int)(g - r * w4);
   const int64_t HW = (int64_t)H * W, THW = (int64_t)T * HW;
-  const int64_t row_in_clip = r % ((int64_t)T * H);
-  const int n = (int)(r / ((int64_t)T * H));
+  const unsigned th = (unsigned)T * (unsigned)H;
+  const int n = (int)(r / th);
+  const int64_t row_in_clip = (int64_t)(r - (unsigned)n * th);
   const bool fl = flip != nullptr && flip[n] != 0;
   const int w_src = fl ? (W - 4 - 4 * wq) : 4 * wq;
   const float *pu = flow + ((int64_t)n * 2 + 0) * THW + row_in_clip * W + w_src;
@@ -80,7 +85,7 @@ flow_visualize_kernel(const float *__restrict__ flow, const uint8_t *__restrict_
     const WheelTap tap = wheel_tap(us[e], vs[e]);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-      float c = wheel_color(tap, ch, s_wheel);
+      float c = wheel_color(tap, ch, s_wheel, s_div255);
       if (norm != nullptr) c = __fdiv_rn(__fsub_rn(c, norm[ch]), norm[3 + ch]);
       o[ch][e] = c;
     }
@@ -399,7 +404,7 @@ int mscl_flow_visualize(const float *d_flow, const uint8_t *d_flip, const float 
   }
   const int64_t total4 = (int64_t)N * T * H * (W / 4);
   const int64_t blocks = (total4 + 255) / 256;
-  MSCL_CHECK_ARG(blocks < (1ll << 31), "too many pixels");
+  MSCL_CHECK_ARG(total4 < (1ll << 31), "too many pixels");
   mscl::flow_visualize_kernel<<<(unsigned)blocks, 256, 0, mscl::as_stream(stream)>>>(d_flow, d_flip, d_norm, d_out, T, H, W,
                                                                                     total4);
   MSCL_LAUNCH_CHECK();

@@ -272,7 +272,6 @@ class MSCLWithAug(BaseMoCoRecognizer):
             flow_q, flow_k = aux_info[f"{self.flow_key[0]}_q"], aux_info[f"{self.flow_key[0]}_k"]
             aug_flow_q, aug_flow_k = aux_info[f"{self.flow_key[1]}_q"], aux_info[f"{self.flow_key[1]}_k"]
         # encoders in the reference's order: each call updates its key encoder by EMA and draws
-        # one shuffle permutation (RGB, base flow, FRA flow)
         # one shuffle permutation (RGB, base flow, FRA flow); `iters` advances after each call so the
         # second flow EMA sees the advanced schedule
         n = im_q.shape[0]
