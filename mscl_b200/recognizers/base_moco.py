@@ -130,6 +130,52 @@ class BaseMoCoRecognizer(nn.Module):
         raise NotImplementedError("Not support forward_gradcam for BaseMoCoRecognizer")
 
 
+class TwoBranchRecognizer(BaseMoCoRecognizer):
+    """What MSCL, MSCLWithAug and MoDist share: an RGB and a flow MoCo recognizer built from config dicts (options in
+    `train_cfg`, e.g. shard_queue, reach both), the `forward` dispatch of the SSL recognizers and their refusals
+    (recognizers/mscl.py:74-83,122-134; modist.py:66-75,120-132)."""
+
+    def _build_branches(self, recognizer, recognizer_flow, train_cfg):
+        if train_cfg:
+            recognizer = dict(recognizer, train_cfg=dict(recognizer.get("train_cfg") or {}, **train_cfg))
+            recognizer_flow = dict(recognizer_flow, train_cfg=dict(recognizer_flow.get("train_cfg") or {}, **train_cfg))
+        self.recognizer = builder.build_recognizer(recognizer)
+        self.recognizer_flow = builder.build_recognizer(recognizer_flow)
+
+    def _collect_aux(self, data_batch):
+        aux_info = {}
+        for item in self.aux_info:
+            assert item in data_batch
+            aux_info[item] = data_batch[item]
+        return aux_info
+
+    def _finish_step(self, losses, n):
+        loss, log_vars = self._parse_losses(losses)
+        return dict(num_samples=n, loss=loss, log_vars=log_vars)
+
+    def forward(self, *inputs, return_loss=True, **kwargs):
+        if kwargs.pop("gradcam", False):
+            return self.forward_gradcam(*inputs, **kwargs)
+        if return_loss:
+            return self.forward_train(*inputs, **kwargs)
+        raise NotImplementedError("MoCo doesnt support test mode")
+
+    def forward_test(self, imgs):
+        raise NotImplementedError("Not support for ssl recognizer !!!")
+
+    def forward_gradcam(self, *inputs, **kwargs):
+        raise NotImplementedError("Not support for ssl recognizer !!!")
+
+    def extract_global_feat(self):
+        raise NotImplementedError("Not support for ssl recognizer !!!")
+
+    def extract_feat(self, im_q, im_k):
+        pass
+
+    def visualize(self, data_batch):
+        pass
+
+
 def warn_once(msg, _seen=set()):
     if msg not in _seen:
         _seen.add(msg)

@@ -8,21 +8,17 @@ read it stacked (`mscl.two_branch_rows`), then both enqueues run; loss keys, the
 """
 from collections import OrderedDict
 
-from ..registry import RECOGNIZERS, build_recognizer, build_ssl_aug
-from .base_moco import BaseMoCoRecognizer
+from ..registry import RECOGNIZERS, build_ssl_aug
+from .base_moco import TwoBranchRecognizer
 from .mscl import two_branch_rows
 
 
 @RECOGNIZERS.register_module()
-class MoDist(BaseMoCoRecognizer):
+class MoDist(TwoBranchRecognizer):
     def __init__(self, recognizer, recognizer_flow, moco_head, im_key="imgs", flow_key="flow_imgs", aux_info=[],
                  aug=dict(dtype="MoCoAugmentV3", moco_aug=(112, 112), t=8), same_kn=True, train_cfg=None, test_cfg=None):
         super().__init__(train_cfg=train_cfg, test_cfg=test_cfg)
-        if train_cfg:
-            recognizer = dict(recognizer, train_cfg=dict(recognizer.get("train_cfg") or {}, **train_cfg))
-            recognizer_flow = dict(recognizer_flow, train_cfg=dict(recognizer_flow.get("train_cfg") or {}, **train_cfg))
-        self.recognizer = build_recognizer(recognizer)
-        self.recognizer_flow = build_recognizer(recognizer_flow)
+        self._build_branches(recognizer, recognizer_flow, train_cfg)
         self.T = self.recognizer.T
         self.im_key = im_key
         self.flow_key = flow_key
@@ -38,21 +34,8 @@ class MoDist(BaseMoCoRecognizer):
     def train_step(self, data_batch, optimizer, **kwargs):
         im_q, im_k = data_batch[self.im_key][0], data_batch[self.im_key][1]
         flow_q, flow_k = data_batch[self.flow_key][0], data_batch[self.flow_key][1]
-        aux_info = {}
-        for item in self.aux_info:
-            assert item in data_batch
-            aux_info[item] = data_batch[item]
-        losses = self(im_q, im_k, flow_q, flow_k, aux_info, return_loss=True)
-        loss, log_vars = self._parse_losses(losses)
-        return dict(num_samples=im_q.shape[0], loss=loss, log_vars=log_vars)
-
-    def forward(self, im_q, im_k, flow_q, flow_k, aux_info, return_loss=True, **kwargs):
-        if kwargs.get("gradcam", False):
-            del kwargs["gradcam"]
-            return self.forward_gradcam(im_q, im_k, flow_q, flow_k, aux_info, **kwargs)
-        if return_loss:
-            return self.forward_train(im_q, im_k, flow_q, flow_k, aux_info, **kwargs)
-        raise NotImplementedError("MoCo doesnt support test mode")
+        losses = self(im_q, im_k, flow_q, flow_k, self._collect_aux(data_batch), return_loss=True)
+        return self._finish_step(losses, im_q.shape[0])
 
     def objective(self, q, k, q_f, k_f):
         """modist.py:84-118 from the encoder outputs on; losses in the reference's order (rf, fr, RGB, flow)."""
@@ -78,17 +61,3 @@ class MoDist(BaseMoCoRecognizer):
         recf.note_branch(n, True)
         return self.objective(q, k, q_f, k_f)
 
-    def forward_test(self, imgs):
-        raise NotImplementedError("Not support for ssl recognizer !!!")
-
-    def forward_gradcam(self, imgs):
-        raise NotImplementedError("Not support for ssl recognizer !!!")
-
-    def extract_global_feat(self):
-        raise NotImplementedError("Not support for ssl recognizer !!!")
-
-    def extract_feat(self, im_q, im_k):
-        pass
-
-    def visualize(self, data_batch):
-        pass

@@ -18,8 +18,8 @@ from collections import OrderedDict
 
 import torch
 
-from ..registry import RECOGNIZERS, build_recognizer, build_ssl_aug
-from .base_moco import BaseMoCoRecognizer
+from ..registry import RECOGNIZERS, build_ssl_aug
+from .base_moco import TwoBranchRecognizer
 
 
 def two_branch_rows(rec, recf, q, k, q_f, k_f, same_kn, T_mx):
@@ -54,7 +54,7 @@ def _wants(head, name):
 
 
 @RECOGNIZERS.register_module()
-class MSCL(BaseMoCoRecognizer):
+class MSCL(TwoBranchRecognizer):
     """RGB MoCo + flow MoCo + cross-modal InfoNCE (`moco_mx_head`) + a frame-level head (`sup_head`, e.g.
     MoDistv2PosHead) on the base flow only (recognizers/mscl.py:9-134)."""
 
@@ -62,11 +62,7 @@ class MSCL(BaseMoCoRecognizer):
                  flow_img_key="flow_imgs", aux_info=[], aug=dict(dtype="MoCoAugmentV3", moco_aug=(112, 112), t=8),
                  same_kn=True, update_aug_flow=False, weight_aug_flow=(1.0, 1.0), train_cfg=None, test_cfg=None):
         super().__init__(train_cfg=train_cfg, test_cfg=test_cfg)
-        if train_cfg:
-            recognizer = dict(recognizer, train_cfg=dict(recognizer.get("train_cfg") or {}, **train_cfg))
-            recognizer_flow = dict(recognizer_flow, train_cfg=dict(recognizer_flow.get("train_cfg") or {}, **train_cfg))
-        self.recognizer = build_recognizer(recognizer)
-        self.recognizer_flow = build_recognizer(recognizer_flow)
+        self._build_branches(recognizer, recognizer_flow, train_cfg)
         self.im_key = im_key
         self.same_kn = same_kn
         self.update_aug_flow = update_aug_flow        # stored, unused (as the reference)
@@ -82,20 +78,8 @@ class MSCL(BaseMoCoRecognizer):
         im_q = data_batch[self.im_key][0]
         im_k = data_batch[self.im_key][1]
         aux_info = {f"{self.flow_key}_q": data_batch[self.flow_key][0], f"{self.flow_key}_k": data_batch[self.flow_key][1]}
-        for item in self.aux_info:
-            assert item in data_batch
-            aux_info[item] = data_batch[item]
-        losses = self(im_q, im_k, aux_info, return_loss=True)
-        loss, log_vars = self._parse_losses(losses)
-        return dict(num_samples=im_q.shape[0], loss=loss, log_vars=log_vars)
-
-    def forward(self, im_q, im_k, aux_info, return_loss=True, **kwargs):
-        if kwargs.get("gradcam", False):
-            del kwargs["gradcam"]
-            return self.forward_gradcam(im_q, im_k, aux_info, **kwargs)
-        if return_loss:
-            return self.forward_train(im_q, im_k, aux_info, **kwargs)
-        raise NotImplementedError("MoCo doesnt support test mode")
+        aux_info.update(self._collect_aux(data_batch))
+        return self._finish_step(self(im_q, im_k, aux_info, return_loss=True), im_q.shape[0])
 
     def objective(self, feats):
         """Everything after the encoders (mscl.py:92-120).  feats: q, k, q_f, k_f (N,128) and the feature dicts
@@ -129,33 +113,15 @@ class MSCL(BaseMoCoRecognizer):
                                    im_features=dict(q=q, q_mlvl=q_mlvl, k=k, k_mlvl=k_mlvl, q_neg=None),
                                    flow_features=dict(q=q_f, q_mlvl=qf_mlvl, k=k_f, k_mlvl=kf_mlvl, q_neg=None)))
 
-    def forward_test(self, imgs):
-        raise NotImplementedError("Not support for ssl recognizer !!!")
-
-    def forward_gradcam(self, imgs):
-        raise NotImplementedError("Not support for ssl recognizer !!!")
-
-    def extract_global_feat(self):
-        raise NotImplementedError("Not support for ssl recognizer !!!")
-
-    def extract_feat(self, im_q, im_k):
-        pass
-
-    def visualize(self, data_batch):
-        pass
 
 
 @RECOGNIZERS.register_module()
-class MSCLWithAug(BaseMoCoRecognizer):
+class MSCLWithAug(TwoBranchRecognizer):
     def __init__(self, recognizer, recognizer_flow, moco_mx_head, sup_head, im_key="imgs", flow_key="flow_imgs",
                  aux_info=[], aug=dict(dtype="MoCoAugmentV3", moco_aug=(112, 112), t=8), same_kn=True,
                  update_aug_flow=False, weight_aug_flow=(1.0, 1.0), train_cfg=None, test_cfg=None):
         super().__init__(train_cfg=train_cfg, test_cfg=test_cfg)
-        if train_cfg:   # options such as shard_queue reach both branches
-            recognizer = dict(recognizer, train_cfg=dict(recognizer.get("train_cfg") or {}, **train_cfg))
-            recognizer_flow = dict(recognizer_flow, train_cfg=dict(recognizer_flow.get("train_cfg") or {}, **train_cfg))
-        self.recognizer = build_recognizer(recognizer)
-        self.recognizer_flow = build_recognizer(recognizer_flow)
+        self._build_branches(recognizer, recognizer_flow, train_cfg)       # options such as shard_queue reach both
         self.im_key = im_key
         self.same_kn = same_kn
         self.update_aug_flow = update_aug_flow
@@ -178,20 +144,8 @@ class MSCLWithAug(BaseMoCoRecognizer):
         for flow_key in self.flow_key:
             aux_info[f"{flow_key}_q"] = data_batch[flow_key][0]
             aux_info[f"{flow_key}_k"] = data_batch[flow_key][1]
-        for item in self.aux_info:
-            assert item in data_batch
-            aux_info[item] = data_batch[item]
-        losses = self(im_q, im_k, aux_info, return_loss=True)
-        loss, log_vars = self._parse_losses(losses)
-        return dict(num_samples=im_q.shape[0], loss=loss, log_vars=log_vars)
-
-    def forward(self, im_q, im_k, aux_info, return_loss=True, **kwargs):
-        if kwargs.get("gradcam", False):
-            del kwargs["gradcam"]
-            return self.forward_gradcam(im_q, im_k, aux_info, **kwargs)
-        if return_loss:
-            return self.forward_train(im_q, im_k, aux_info, **kwargs)
-        raise NotImplementedError("MoCo doesnt support test mode")
+        aux_info.update(self._collect_aux(data_batch))
+        return self._finish_step(self(im_q, im_k, aux_info, return_loss=True), im_q.shape[0])
 
     def objective(self, feats):
         """Everything after the encoders (mscl.py:228-277 + moco.py:481-510), fused.
@@ -284,17 +238,3 @@ class MSCLWithAug(BaseMoCoRecognizer):
         return self.objective(dict(q=q, k=k, q_f=q_f, k_f=k_f, q_af=q_af, k_af=k_af, q_mlvl=q_mlvl,
                                    q_flow_mlvl=qf_mlvl, q_aug_flow_mlvl=qaf_mlvl))
 
-    def forward_test(self, imgs):
-        raise NotImplementedError("Not support for ssl recognizer !!!")
-
-    def forward_gradcam(self, imgs):
-        raise NotImplementedError("Not support for ssl recognizer !!!")
-
-    def extract_global_feat(self):
-        raise NotImplementedError("Not support for ssl recognizer !!!")
-
-    def extract_feat(self, im_q, im_k):
-        pass
-
-    def visualize(self, data_batch):
-        pass
