@@ -217,3 +217,45 @@ def test_two_branch_full_step_matches_reference(kind):
             assert int(rec.queue_ptr) == st.ptr and rec.iters == st.iters and rec.batch_size == st.batch_size
             np.testing.assert_array_equal(rec.count.numpy(), st.count.numpy())
             np.testing.assert_allclose(rec.queue.numpy(), st.queue.numpy(), rtol=0, atol=2e-6)
+
+
+def test_r50_config_full_step_matches_reference():
+    """`mscl_r50_cosm_lr3e-2.py`'s model dict (SlowOnly-R50 + TPN with one pyramid convolution, r2d_50 flow branch, LMCL
+    head with a Conv1d(256,128) flow projection) built by the unmodified reference and by this repo: identical
+    state_dict keys, and the oracle's step (oracle/step.py, host copies of this repo's modules) reproduces the
+    reference's train_step at a reduced clip size."""
+    import mscl_b200
+    from mscl_b200.configs import mscl_r50_model
+    from oracle.step import OracleMSCL
+    ref = ref_shim.load_reference()
+    ref_shim.load_slowonly()                       # registers ResNet3dSlowOnly into the reference's BACKBONES
+    ref_shim.ensure_process_group()
+    cfg = mscl_r50_model(K=64, aug="IdentityAug")
+    cfg["recognizer"]["max_iters"] = cfg["recognizer_flow"]["max_iters"] = 1000
+    torch.manual_seed(0)
+    ref_model = ref.builder.build_model(dict(cfg, aug=dict(type="SyncMoCoAugmentV5")))
+    mine = mscl_b200.build_model(cfg)
+    sd_ref = ref_model.state_dict()
+    assert set(sd_ref) == set(mine.state_dict())
+    mine.load_state_dict(sd_ref, strict=True)
+    ref_model.train(), mine.train()
+    orc = OracleMSCL(mine)
+    g = torch.Generator().manual_seed(8)
+    N = 2
+    data = dict(imgs=[torch.rand(N, 3, 8, 64, 64, generator=g) for _ in range(2)],
+                flow_imgs=[torch.rand(N, 3, 16, 64, 64, generator=g) for _ in range(2)])
+    torch.manual_seed(100)
+    out = ref_model.train_step(data, None)
+    out["loss"].backward()
+    torch.manual_seed(100)
+    loss, log_vars = orc.train_step(data["imgs"][0], data["imgs"][1], data["flow_imgs"][0], data["flow_imgs"][1])
+    loss.backward()
+    assert list(log_vars) == list(out["log_vars"]) and len(log_vars) == 23
+    for k, v in out["log_vars"].items():
+        assert abs(log_vars[k] - v) <= 5e-5 * max(1.0, abs(v)), (k, log_vars[k], v)
+    for rec, st in ((ref_model.recognizer, orc.rgb.state), (ref_model.recognizer_flow, orc.flow.state)):
+        assert int(rec.queue_ptr) == st.ptr and rec.iters == st.iters and rec.batch_size == st.batch_size
+        np.testing.assert_array_equal(rec.count.numpy(), st.count.numpy())
+    gr = dict(ref_model.named_parameters())
+    a, b = orc.trans_flow.weight.grad, gr["sup_head.trans_flow.weight"].grad
+    assert float((a - b).norm() / b.norm()) < 2e-4
