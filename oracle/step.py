@@ -75,6 +75,35 @@ class OracleBranch:
         return q, q_mlvl, k
 
 
+def extract_feat_ranks(branch, im_qs, im_ks):
+    """moco.py:517-547 for G ranks emulated in ONE process (data-parallel semantics of the reference): every rank
+    encodes its own queries; the key batch of all ranks is gathered rank-major (:564-567), permuted by rank 0's
+    `torch.randperm` (:160-163), each rank's key encoder sees ITS slice of the permuted batch (so batch-norm statistics
+    are per rank, per shuffled subset), and the keys are gathered again and un-permuted (:174-191).
+    Returns ([(q_r, q_mlvl_r)], [k_r], k_all) with k_all in rank-major order (what the enqueue receives)."""
+    G, n = len(im_qs), im_qs[0].shape[0]
+    outs_q = []
+    for r in range(G):
+        q_mlvl = branch.encoder_q(im_qs[r])
+        (q_emb, q_mlvl), _ = branch.neck_q(q_mlvl)
+        outs_q.append((F.normalize(branch.mlp_q(q_emb), dim=1), q_mlvl))
+    with torch.no_grad():
+        m = branch.fixed_m if branch.fixed_m is not None else O.momentum(branch.state.iters, branch.max_iters, branch.m_base)
+        for pk, new in zip(branch.k_params(), O.ema_update([p.data for p in branch.k_params()],
+                                                           [p.data for p in branch.q_params()], m)):
+            pk.data = new
+        idx = torch.randperm(n * G)
+        x_all = torch.cat(im_ks)
+        ks = []
+        for r in range(G):
+            sub, _ = O.batch_shuffle(x_all, idx, r, G)
+            k_mlvl = branch.encoder_k(sub)
+            (k_emb, _), _ = branch.neck_k(k_mlvl)
+            ks.append(F.normalize(branch.mlp_k(k_emb), dim=1))
+        k_all = torch.cat(ks)[torch.argsort(idx)]
+    return outs_q, [k_all[r * n:(r + 1) * n] for r in range(G)], k_all
+
+
 class OracleMSCL:
     def __init__(self, model):
         self.rgb = OracleBranch(model.recognizer)
@@ -131,6 +160,26 @@ class OracleMoCo:
         q, _, k = self.branch.extract_feat(im_q, im_k)
         losses = self.branch.state.branch(q, k, self.branch.T, self.basename, True, self.training)
         return O.parse_losses(losses)
+
+    def train_step_ranks(self, im_qs, im_ks):
+        """The same step on G data-parallel ranks emulated in one process: every rank's logits against the SAME
+        pre-enqueue snapshot, ONE enqueue of the rank-major gathered keys, iters += the global batch, log variables
+        averaged over ranks (recognizers/base.py:301-306).  Returns ([loss_r], averaged log_vars)."""
+        outs_q, ks, k_all = extract_feat_ranks(self.branch, im_qs, im_ks)
+        st = self.branch.state
+        st.weight = O.decayed_weight(st.queue, st.count)
+        per_rank = []
+        for (q, _), k in zip(outs_q, ks):
+            logits = O.infonce_logits(q, k, st.weight, self.branch.T)
+            labels = torch.zeros(logits.shape[0], dtype=torch.long)
+            per_rank.append(O.parse_losses(O.head_loss(logits, labels, self.basename)))
+        st.ptr = O.enqueue(st.queue, st.count, st.ptr, k_all)
+        st.batch_size = k_all.shape[0]
+        if self.training:
+            st.iters += st.batch_size
+        keys = list(per_rank[0][1].keys())
+        avg = {k: sum(lv[k] for _, lv in per_rank) / len(per_rank) for k in keys}
+        return [loss for loss, _ in per_rank], avg
 
 
 class OracleTwoBranch:

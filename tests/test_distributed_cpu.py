@@ -171,3 +171,68 @@ def test_parse_losses_one_collective():
         assert r["log_vars"]["top1_acc"] == pytest.approx(0.375)
         assert r["log_vars"]["loss_cls"] == pytest.approx(2.5)
         assert r["log_vars"]["loss"] == pytest.approx(3.0)
+
+
+# ---------------------------------------------------------------- a whole recognizer step on two ranks
+def _whole_step_job(rank):
+    """MoCoV2.train_step on 2 ranks (different clips per rank): rank 0's permutation wins, the key batch is exchanged
+    by the all-to-all plan, keys are gathered rank-major for ONE enqueue, iters advance by the GLOBAL batch, log
+    variables are averaged over ranks -- against the oracle's in-process emulation of both ranks.  The four kernel
+    entry points are replaced by oracle arithmetic as in tests/test_host_logic_cpu.py (test infrastructure)."""
+    import mscl_b200
+    from mscl_b200 import functional as fx
+    from mscl_b200.recognizers.moco import MoCoV2, concat_all_gather
+    from oracle import mscl_oracle as O
+    from oracle.step import OracleMoCo
+    import test_host_logic_cpu as H
+
+    def fake_enqueue(self, keys):
+        keys = concat_all_gather(keys.contiguous())                      # rank-major (moco.py:558-568)
+        st = self._cpu_state
+        st.ptr = O.enqueue(st.queue, st.count, st.ptr, keys.detach())
+        self.batch_size = keys.shape[0]
+
+    MoCoV2.contrast = H._fake_contrast
+    MoCoV2._dequeue_and_enqueue = fake_enqueue
+    fx.EmaTable = H._FakeEma
+    fx.gather_rows = lambda x, idx: x[idx]
+    cfg = dict(type="MoCoV2", backbone=dict(type="resnet_flow.r2d_18"), neck=dict(type="BaseMoCo"),
+               moco_head=dict(type="MoCoHead", basename="", loss_cls=dict(type="CrossEntropyLoss_torch", ignore_index=-1)),
+               im_key="imgs", dim_in=128, dim=128, K=64, m_base=0.99, max_iters=100, T=0.07, mlp=True, aux_info=[],
+               aug=dict(type="IdentityAug"))
+    torch.manual_seed(0)                                                  # same weights and queue on both ranks
+    model = mscl_b200.build_model(cfg).train()
+    orc = OracleMoCo(model)
+    H._attach_cpu_state(model)
+    n = 4
+    ok, msgs = True, []
+    for step in range(2):
+        batches = [[torch.rand(n, 3, 8, 32, 32, generator=torch.Generator().manual_seed(1000 * step + 10 * r + v)) for v in range(2)]
+                   for r in range(WORLD)]
+        torch.manual_seed(200 + step)
+        _, vars_ref = orc.train_step_ranks([b[0] for b in batches], [b[1] for b in batches])
+        torch.manual_seed(200 + step + 7 * rank)                          # ranks draw DIFFERENT permutations; rank 0's must win
+        if rank == 0:
+            torch.manual_seed(200 + step)
+        out = model.train_step(dict(imgs=batches[rank]), None)
+        for k, v in out["log_vars"].items():
+            if abs(v - vars_ref[k]) > 5e-5 * max(1.0, abs(vars_ref[k])):
+                ok = False
+                msgs.append((step, k, v, vars_ref[k]))
+        st, ref = model._cpu_state, orc.branch.state
+        if not (st.ptr == ref.ptr == (n * WORLD * (step + 1)) % 64 and model.iters == ref.iters == n * WORLD * (step + 1)
+                and model.batch_size == n * WORLD and torch.equal(st.count, ref.count)
+                and torch.allclose(st.queue, ref.queue, rtol=0, atol=1e-6)):
+            ok = False
+            msgs.append((step, "queue state", st.ptr, ref.ptr, model.iters, ref.iters))
+        for pk, po in zip([p for m in (model.encoder_k, model.neck_k, model.mlp_k) for p in m.parameters()], orc.branch.k_params()):
+            if not torch.equal(pk.detach(), po.detach()):
+                ok = False
+                msgs.append((step, "ema"))
+                break
+    return dict(ok=ok, msgs=msgs)
+
+
+def test_whole_step_on_two_ranks_matches_the_oracle():
+    for r in _run(_whole_step_job):
+        assert r["ok"], r["msgs"]
