@@ -259,3 +259,32 @@ def test_r50_config_full_step_matches_reference():
     gr = dict(ref_model.named_parameters())
     a, b = orc.trans_flow.weight.grad, gr["sup_head.trans_flow.weight"].grad
     assert float((a - b).norm() / b.norm()) < 2e-4
+
+
+def test_moco_head_v2_materialised_form_matches_reference():
+    """MoCoHeadV2 (heads/moco_head_v3.py:15-85; its line 8 imports a package that does not exist and is skipped): the
+    materialised `forward(q, k, weight)` + `loss(cls_score, ssl_label)` of this repo's class against the reference's,
+    on host tensors (plain PyTorch on both sides; the fused path is checked on the GPU against this same form)."""
+    import sys
+    import mscl_b200
+    ref = ref_shim.load_reference()
+    if "mmaction.models.heads.moco_head_v3" not in sys.modules:
+        ref_shim._load("mmaction.models.heads.moco_head_v3", "mmaction/models/heads/moco_head_v3.py", strip_lines=(8,))
+    RefHead = sys.modules["mmaction.models.heads.moco_head_v3"].MoCoHeadV2
+    loss_cfg = dict(type="CrossEntropyLoss_torch", ignore_index=-1)
+    rh = RefHead(basename="v2", loss_cls=loss_cfg, T=0.2)
+    mh = mscl_b200.build_head(dict(type="MoCoHeadV2", basename="v2", loss_cls=loss_cfg, T=0.2))
+    g = torch.Generator().manual_seed(0)
+    q = torch.nn.functional.normalize(torch.randn(16, 128, generator=g), dim=1)
+    k = torch.nn.functional.normalize(q + 0.5 * torch.randn(16, 128, generator=g), dim=1)
+    w = torch.nn.functional.normalize(torch.randn(128, 512, generator=g), dim=0) * 0.9
+    qa, qb = q.clone().requires_grad_(True), q.clone().requires_grad_(True)
+    ra, rb = rh(qa, k, w), mh(qb, k, w)
+    assert torch.equal(ra["ssl_label"], rb["ssl_label"])
+    np.testing.assert_allclose(rb["cls_score"].detach().numpy(), ra["cls_score"].detach().numpy(), rtol=1e-6, atol=1e-6)
+    la, lb = rh.loss(**ra), mh.loss(**rb)
+    assert list(la.keys()) == list(lb.keys()) == ["top1_acc_v2", "top5_acc_v2", "loss_cls_v2"]
+    for key in la:
+        assert abs(float(la[key]) - float(lb[key])) <= 1e-6 * max(1.0, abs(float(la[key]))), key
+    la["loss_cls_v2"].backward(), lb["loss_cls_v2"].backward()
+    np.testing.assert_allclose(qb.grad.numpy(), qa.grad.numpy(), rtol=1e-5, atol=1e-7)
