@@ -288,3 +288,37 @@ def test_moco_head_v2_materialised_form_matches_reference():
         assert abs(float(la[key]) - float(lb[key])) <= 1e-6 * max(1.0, abs(float(la[key]))), key
     la["loss_cls_v2"].backward(), lb["loss_cls_v2"].backward()
     np.testing.assert_allclose(qb.grad.numpy(), qa.grad.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_materialised_head_forms_match_reference(pair):
+    """The reference-signature paths the fused recognizers bypass but callers holding logits may still use:
+    MoCoHead.loss(cls_score, labels), MSCLWithAugMxHead._forward_moco_mx / .loss, and the on-device top-k
+    (`#scores above the label < k`) against the reference's NumPy argsort top_k_accuracy."""
+    import mscl_b200
+    from mscl_b200.heads.moco_head import topk_hits_on_device
+    ref = pair[0]
+    loss_cfg = dict(type="CrossEntropyLoss_torch", ignore_index=-1)
+    g = torch.Generator().manual_seed(1)
+    q, k, qf, kf = (torch.nn.functional.normalize(torch.randn(12, 128, generator=g), dim=1) for _ in range(4))
+    w, wf = (torch.nn.functional.normalize(torch.randn(128, 300, generator=g), dim=0) for _ in range(2))
+    for same_kn in (True, False):
+        rh = ref.MSCLWithAugMxHead(basename="mx", loss_cls=loss_cfg, same_kn=same_kn, T=0.07)
+        mh = mscl_b200.build_head(dict(type="MSCLWithAugMxHead", basename="mx", loss_cls=loss_cfg, same_kn=same_kn, T=0.07))
+        ra, rb = rh._forward_moco_mx(q, k, qf, kf, w, wf), mh._forward_moco_mx(q, k, qf, kf, w, wf)
+        for a, b in zip(ra, rb):
+            np.testing.assert_allclose(b.numpy(), a.numpy(), rtol=1e-6, atol=1e-6)
+        la, lb = rh.loss(*ra, suffix="_aug"), mh.loss(*rb, suffix="_aug")
+        assert list(la.keys()) == list(lb.keys())
+        for key in la:
+            assert abs(float(la[key]) - float(lb[key])) <= 1e-6 * max(1.0, abs(float(la[key]))), (same_kn, key)
+    logits = torch.randn(64, 257, generator=g)
+    labels = torch.randint(0, 257, (64,), generator=g)
+    rhd = ref.MoCoHead(basename="x", loss_cls=loss_cfg)
+    mhd = mscl_b200.build_head(dict(type="MoCoHead", basename="x", loss_cls=loss_cfg))
+    la, lb = rhd.loss(logits, labels), mhd.loss(logits, labels)
+    assert list(la.keys()) == list(lb.keys())
+    for key in la:
+        assert abs(float(la[key]) - float(lb[key])) <= 1e-6 * max(1.0, abs(float(la[key]))), key
+    want = ref.top_k_accuracy(logits.numpy(), labels.numpy(), (1, 5))
+    got = [float(v) for v in topk_hits_on_device(logits, labels)]
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-7)
