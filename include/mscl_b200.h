@@ -170,7 +170,8 @@ int mscl_lmcl(const float *d_xq, const float *d_xf, int32_t N, int32_t C,
  *              pos2_i   = (q_i . kpos_i) / T * log2(e)
  *              shift2_i = |q_i| * key_norm_bound / T * log2(e)   (>= every logit)
  *              dscale_j = 0.99999^(n_enq - birth_j) / T * log2(e);  d_dscale holds
- *              ceil(K_local/128)*128 floats, the pad is written as 0
+ *              ceil(K_local/128)*128 floats, the pad is written as 0 (d_dscale may be NULL when
+ *              mscl_infonce_pass follows: it derives the scale from birth[] itself)
  *              d_dup_slot (int32 [M] or NULL): GLOBAL queue slot that holds a copy of
  *              row i's positive key (the cross-modal rf term reads the flow queue right
  *              after k_flow was enqueued into it, mscl.py:239-248), -1 for none; dup_age
@@ -233,6 +234,34 @@ int mscl_infonce_finalize(const float *d_qpack, const float *d_kpos,
                           float *d_group_out, mscl_stream_t stream);
 int mscl_infonce_bwd(const float *d_dq_unit, const float *d_gout, int32_t M,
                      int32_t rows_per_group, float *d_dq, mscl_stream_t stream);
+
+/* K1, single-launch form (csrc/infonce_fused.cu): prep + pass + cross-CTA reduction + finalize of the block above in ONE
+ * kernel.  Same replaced reference lines (moco.py:481-498, heads/moco_head.py:38-77, heads/moco_head_v2.py:38-100,
+ * losses/cross_entropy_loss.py:134-138, core/evaluation/accuracy.py:130-149) and the same formulas; the differences:
+ *  - q / kpos are the raw fp32 rows [M, 128] (no qpack): pos2, shift2 and the tf32 rounding of q happen in the kernel;
+ *  - the per-key scale 0.99999^(n_enq - birth_j) / T * log2(e) is computed from d_birth / d_qstate tile by tile (no dscale);
+ *  - every CTA adds its partial rows into ONE accumulator with a TMA reduce-add (fp32 adds performed in L2, order not
+ *    fixed: reproducible to rounding, not bit for bit -- the slab form above is); the last CTA to finish turns the
+ *    accumulator into d_row_loss / d_dq_unit / d_group_out (same meaning as mscl_infonce_finalize).
+ * d_ws: float [M*132 + 4] workspace (accumulator + CTA counter).  It must be ZERO before the first call; the kernel
+ * leaves it zero.  One workspace per stream: two calls that may run concurrently must not share it.
+ * n_part: CTAs along the keys (x ceil(M/128) row blocks), from mscl_infonce_fused_parts.
+ * flags: MSCL_INFONCE_EARLY_PREFETCH -- the queue was NOT written by the launch immediately preceding this one on the
+ * stream, so its tiles may be requested before the programmatic-dependent-launch wait.
+ */
+#define MSCL_INFONCE_EARLY_PREFETCH 1
+int mscl_infonce_fused(const float *d_q, const float *d_kpos, int32_t M, const float *d_queue_tf32,
+                       const int32_t *d_birth, const int64_t *d_qstate, int64_t K_local, float inv_T,
+                       float key_norm_bound, const int32_t *d_dup_slot, int32_t dup_age, float *d_ws,
+                       int32_t n_part, int32_t rows_per_group, int32_t with_grad, int32_t flags,
+                       float *d_row_loss, float *d_dq_unit, float *d_group_out, mscl_stream_t stream);
+/* The pass alone in the same form, for the sharded queue: d_qpack [M, 132] is the gathered table mscl_infonce_prep fills
+ * on every rank, d_acc float [M, 132] receives the sums (O | sum-exp | count) by reduce-add and must be ZERO on entry;
+ * mscl_infonce_reduce_scatter (n_part = 1) and mscl_infonce_finalize follow as before. */
+int mscl_infonce_pass(const float *d_qpack, int32_t M, const float *d_queue_tf32, const int32_t *d_birth,
+                      const int64_t *d_qstate, int64_t K_local, int64_t shard_begin, float inv_T, float *d_acc,
+                      int32_t n_part, int32_t with_grad, int32_t flags, mscl_stream_t stream);
+int mscl_infonce_fused_parts(int32_t M, int64_t K_local, int32_t num_sms);
 
 /* ---------------------------------------------------------------------------
  * K6  shuffle-BN row gather.   replaces x_gather[idx_this] in

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmscl_b200.so")
-SOURCES = ["abi.cu", "enqueue.cu", "ema.cu", "fra.cu", "lmcl.cu", "infonce.cu", "infonce_tc.cu", "resample.cu", "augment.cu", "optim.cu", "retrieval.cu"]
+SOURCES = ["abi.cu", "enqueue.cu", "ema.cu", "fra.cu", "lmcl.cu", "infonce.cu", "infonce_tc.cu", "infonce_fused.cu", "resample.cu", "augment.cu", "optim.cu", "retrieval.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

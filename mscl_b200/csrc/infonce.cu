@@ -18,8 +18,11 @@ infonce_prep_kernel(const float *__restrict__ q, const float *__restrict__ kpos,
                     float *__restrict__ qpack, float *__restrict__ dscale,
                     const int32_t *__restrict__ dup_slot, int dup_age,
                     float *const *__restrict__ peer_qpack, int n_peers, int row_offset) {
-  pdl_trigger();   // the tcgen05 pass may launch now and prefetch queue tiles; it waits for this grid before reading qpack / dscale
-  pdl_wait();      // this grid itself may have been launched early behind a finalize (back-to-back objectives)
+  // Wait first, trigger second: the tcgen05 pass launched behind this grid prefetches queue tiles BEFORE its own
+  // dependency wait, so it may only start once everything older than this grid (an enqueue into that queue, say)
+  // has completed -- which is what this grid's wait establishes.
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * 8;
   const float sc = inv_T * kLog2e;
@@ -47,6 +50,7 @@ infonce_prep_kernel(const float *__restrict__ q, const float *__restrict__ kpos,
       if (lane == 0) reinterpret_cast<float4 *>(pd)[32] = tail;
     }
   }
+  if (dscale == nullptr) return;      // the single-launch pass derives the per-key scale from birth[] itself
   const int64_t n_enq = qstate[1];
   const int64_t tid = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * 256;
@@ -292,13 +296,13 @@ int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
                       float inv_T, float key_norm_bound, float *d_qpack, float *d_dscale,
                       const int32_t *d_dup_slot, int32_t dup_age, float *const *d_peer_qpack,
                       int32_t n_peers, int32_t row_offset, mscl_stream_t stream) {
-  MSCL_CHECK_ARG(d_q && d_kpos && d_birth && d_qstate && d_qpack && d_dscale, "null pointer");
+  MSCL_CHECK_ARG(d_q && d_kpos && d_birth && d_qstate && d_qpack, "null pointer");
   MSCL_CHECK_ARG(M > 0 && K_local > 0, "bad M=%d K_local=%lld", M, (long long)K_local);
   MSCL_CHECK_ARG(inv_T > 0.f && key_norm_bound > 0.f, "bad inv_T / key_norm_bound");
   MSCL_CHECK_ARG((n_peers == 0) || (d_peer_qpack != nullptr && n_peers > 0 && row_offset >= 0), "bad peer table");
   MSCL_CHECK_ARG((((uintptr_t)d_q | (uintptr_t)d_kpos | (uintptr_t)d_qpack) & 15) == 0,
                  "q/kpos/qpack must be 16-byte aligned");
-  int64_t want = (K_local + 255) / 256;
+  int64_t want = d_dscale ? (K_local + 255) / 256 : 1;
   if ((M + 7) / 8 > want) want = (M + 7) / 8;
   if (want > 1184) want = 1184;
   MSCL_CUDA(mscl::launch_pdl(mscl::infonce_prep_kernel, dim3((unsigned)want), dim3(256), 0, mscl::as_stream(stream), d_q,

@@ -1,0 +1,829 @@
+// K1, single-launch form: the whole InfoNCE term -- per-row positive logit and shift, per-key age decay, the
+// tensor-core pass over the queue, the cross-CTA reduction and the loss / top-k / d loss/d q epilogue -- in ONE
+// kernel (infonce_tc.cu + infonce.cu need three launches and a 148-slab round trip through L2 for the same result).
+// replaces moco.py:481-498, heads/moco_head.py:38-77, heads/moco_head_v2.py:38-100, losses/cross_entropy_loss.py:134-138,
+// core/evaluation/accuracy.py:130-149.  sm_100a only.
+//
+// Mathematics as in infonce_tc.cu:  S = Q W^T (scaled per key by dscale_j), P = 2^(S - shift), O = P (dscale . W).
+//
+// What is different from the slab form, and why (profiles/r01_tc_timeline.txt, VERDICT r01 "weak" 1):
+//  * work unit = 64 keys.  A CTA owns a contiguous range of units; it processes them as 128-key PAIR tiles (a tf32
+//    tcgen05 dispatch never costs less than ~61 cycles, so N = 128 keys per MMA1 dispatch is the efficient shape) plus,
+//    when its unit count is odd, one 64-key HALF tile that is requested first, lands first and starts the pipeline
+//    early.  1024 units over 148 CTAs is 6.92 per CTA (max 7): the 128-key split was 3.46 (max 4), i.e. the slowest CTA
+//    streamed 14 % more than the average.
+//  * ring 1 = two pair slots + one dedicated half-tile slot: 160 KB of a CTA's <= 224 KB are requested before anything
+//    else happens (was 128 of <= 256 KB).  Ring 2 (the MN-major copy for the second GEMM, L2 hits) has two 64-key slots.
+//  * no prep launch: the softmax warps compute pos2 / shift2 from q and kpos (warp per row, coalesced), round q to tf32
+//    on its way into TMEM, and a 12th warp turns birth[] into the per-key scale 0.99999^age / T * log2(e) tile by tile.
+//  * no slabs, no finalize launch: each CTA adds its [rows x 132] partial (O | sum-exp | count) into ONE accumulator
+//    with a single TMA reduce-add (cp.reduce.async.bulk.tensor, fp32 add performed in L2); the last CTA to finish
+//    (device counter) turns the accumulator into losses, top-k flags and dq, and leaves accumulator and counter zeroed
+//    for the next call.  The order of the fp32 adds in L2 is not fixed: results are reproducible to rounding only
+//    (the slab form stays available where bit-reproducibility matters).
+//
+// CTA = 384 threads, one CTA per SM:
+//   warp 0      ring-1 TMA producer (queue tiles from HBM, the Q tile)
+//   warp 1      tcgen05.mma issuer
+//   warps 2..9  softmax / epilogue (thread <-> query row == TMEM lane; two warps per lane quarter, 64 keys each)
+//   warp 10     ring-2 TMA producer
+//   warp 11     per-key scale (birth -> dscale) into a 2-deep shared-memory ring
+// TMEM (512 columns): O [0,128) | S/P double buffer [128,384) | Q [384,512).
+#include "tc_common.cuh"
+
+namespace mscl {
+namespace tcf {
+using namespace mscl::tc;
+
+constexpr int kUnit = 64;             // keys per work unit / ring-2 slot / half tile
+constexpr int kTile = 128;            // keys per pair tile
+constexpr int kStages2 = 2;           // ring 2 slots (64 keys each)
+constexpr int kCb = 4;                // channel blocks of 32 fp32 (one 128-byte swizzle row)
+constexpr int kSoftmaxWarps = 8;
+constexpr int kWarps = 4 + kSoftmaxWarps;
+constexpr int kThreads = kWarps * 32;                  // 384
+
+constexpr uint32_t kPairBytes = kTile * kC * 4;        // 65536
+constexpr uint32_t kPairSlab = kTile * 128;            // bytes per channel block of a pair tile
+constexpr uint32_t kUnitBytes = kUnit * kC * 4;        // 32768
+constexpr uint32_t kUnitSlab = kUnit * 128;
+constexpr uint32_t kQBytes = kRows * kC * 4;           // 65536
+constexpr uint32_t kQSlab = kRows * 128;
+
+// shared memory map (the dynamic segment is 1024-byte aligned: checked at kernel entry)
+constexpr uint32_t kOffPair = 0;                               // 2 x 64 KB pair slots; the [128][132] output tile at the end
+constexpr uint32_t kOffSingle = kOffPair + 2 * kPairBytes;     // 32 KB: the half tile
+constexpr uint32_t kOffW2 = kOffSingle + kUnitBytes;           // ring 2: 2 x 32 KB; the Q tile before the first ring-2 load
+constexpr uint32_t kOffBar = kOffW2 + kStages2 * kUnitBytes;
+constexpr uint32_t kNumBars = 2 + 2 + 1 + 2 * kStages2 + 1 + 2 + 2 + 1 + 1 + 1 + 2 + 2;
+constexpr uint32_t kOffTmemPtr = kOffBar + 8 * kNumBars;
+constexpr uint32_t kOffFlag = kOffTmemPtr + 8;
+constexpr uint32_t kOffDs = kOffBar + 256;                     // [2][128] floats: per-key scales of the tile in flight
+constexpr uint32_t kOffRow = kOffDs + 2 * kTile * 4;           // [128] float2 (pos2, shift2); later [2][128] sum / count
+constexpr uint32_t kSmemBytes = kOffRow + kRows * 8;
+static_assert(kOffFlag + 8 <= kOffDs, "barrier block overflows");
+static_assert(kQBytes <= kStages2 * kUnitBytes, "the Q tile is staged through ring 2");
+static_assert(kRows * kLd * 4 <= 2 * kPairBytes, "the output tile is staged through the pair slots");
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColO = 0;
+constexpr uint32_t kColS = 128;
+constexpr uint32_t kColQ = 384;
+
+constexpr uint32_t kIdescBase = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kRows >> 4) << 24);
+constexpr uint32_t kIdesc1 = kIdescBase | ((uint32_t)(kTile >> 3) << 17);               // N = 128 keys
+constexpr uint32_t kIdesc1H = kIdescBase | ((uint32_t)(kUnit >> 3) << 17);              // N = 64 keys (half tile)
+constexpr uint32_t kIdesc2 = kIdescBase | (1u << 16) | ((uint32_t)(kC >> 3) << 17);     // N = 128 channels, B MN-major
+
+enum : int { kFlagEarlyPrefetch = 1 };
+
+struct Params {
+  const float *q;            // FUSED: raw q [M][128];  else qpack [M][132] (rows already tf32, row info at [128..131])
+  const float *kpos;         // FUSED: positives [M][128]
+  const int32_t *birth;      // [K_local]
+  const int64_t *qstate;     // {ptr, n_enq, ..}
+  const int32_t *dup_slot;   // FUSED: [M] or null
+  float *acc;                // [M][132] accumulator (+ the CTA counter right behind it when FUSED)
+  float *row_loss;           // FUSED outputs
+  float *dq_unit;
+  float *group_out;
+  int64_t K_local;
+  int64_t shard_begin;
+  int M;
+  int rows_per_group;
+  int dup_age;
+  int flags;
+  float inv_T;
+  float key_norm_bound;
+};
+
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+#ifdef MSCL_TC_TIMELINE
+__device__ unsigned long long g_timeline_f[148 * 2 * 32];
+__device__ __forceinline__ unsigned long long gtime_f() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TLF(slot) g_timeline_f[(blockIdx.y * gridDim.x + blockIdx.x) * 32 + (slot)] = gtime_f()
+#else
+#define TLF(slot)
+#endif
+
+// 32 keys of one tile for one query row, on registers (see infonce_tc.cu::softmax_half); the 32 per-key scales come
+// from shared memory (warp-uniform addresses: broadcast reads).
+template <bool GRAD, bool FULL>
+__device__ __forceinline__ void softmax_chunk(uint32_t (&v)[32], const float4 *ds, float shift2, float pos2, int nvalid,
+                                              int dupcol, float &sum, int &cnt) {
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t c4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 d4 = ds[j4];
+    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = j4 * 4 + e;
+      const float sv = __uint_as_float(v[j]);
+      float p = ex2(fmaf(sv, dd[e], -shift2));
+      uint32_t hit = __float_as_uint(fmaf(-sv, dd[e], pos2)) >> 31;    // 1 iff logit > positive logit
+      if (!FULL) {
+        const bool ok = j < nvalid && j != dupcol;      // the duplicate of the positive is added exactly by the epilogue
+        p = ok ? p : 0.f;
+        hit = ok ? hit : 0u;
+      }
+      s4[e] += p;
+      c4[e] += hit;
+      v[j] = GRAD ? __float_as_uint(p * dd[e]) + 0x1000u : 0u;    // P' = p * scale, rounded to nearest tf32
+    }
+  }
+  sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  cnt += (int)((c4[0] + c4[1]) + (c4[2] + c4[3]));
+}
+
+// The last CTA: accumulator -> per-row loss / top-k count / dq, per-group means; accumulator and counter left zero.
+// (formulas: infonce.cu::infonce_finalize_kernel)
+template <bool GRAD>
+__device__ __forceinline__ void finalize_rows(const Params &p, unsigned *counter) {
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float sc = p.inv_T * kLog2e;
+  const float inv_rows = 1.0f / (float)p.rows_per_group;
+  const float dsc = exp2f((float)p.dup_age * kLog2Decay);
+  constexpr int kU = 4;
+  for (int r0 = wid; r0 < p.M; r0 += kWarps * kU) {
+    float4 o[kU], st[kU], a[kU], kk[kU];
+    int dup[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int row = r0 + u * kWarps;
+      dup[u] = -1;
+      if (row < p.M) {
+        const float4 *arow = reinterpret_cast<const float4 *>(p.acc + (int64_t)row * kLd);
+        o[u] = __ldcg(arow + lane);
+        st[u] = __ldcg(arow + 32);
+        a[u] = __ldg(reinterpret_cast<const float4 *>(p.q + (int64_t)row * kC) + lane);
+        kk[u] = __ldg(reinterpret_cast<const float4 *>(p.kpos + (int64_t)row * kC) + lane);
+        if (p.dup_slot != nullptr) dup[u] = __ldg(p.dup_slot + row);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int row = r0 + u * kWarps;
+      if (row >= p.M) continue;                      // warp-uniform
+      float4 *arow = reinterpret_cast<float4 *>(p.acc + (int64_t)row * kLd);
+      __stcg(arow + lane, make_float4(0.f, 0.f, 0.f, 0.f));
+      if (lane == 0) __stcg(arow + 32, make_float4(0.f, 0.f, 0.f, 0.f));
+      float d = a[u].x * kk[u].x + a[u].y * kk[u].y + a[u].z * kk[u].z + a[u].w * kk[u].w;
+      float ss = a[u].x * a[u].x + a[u].y * a[u].y + a[u].z * a[u].z + a[u].w * a[u].w;
+      d = warp_sum(d);
+      ss = warp_sum(ss);
+      const float pos2 = d * sc, shift2 = sqrtf(ss) * p.key_norm_bound * sc;
+      float sum = st[u].x, cnt = st[u].y;
+      float4 ov = o[u];
+      if (dup[u] >= 0) {      // the queue entry that IS this row's positive: exact fp32 terms (see infonce.cu)
+        if (pos2 * dsc > pos2) cnt += 1.f;
+        const float e_dup = exp2f(fmaf(pos2, dsc, -shift2));
+        sum += e_dup;
+        const float w = e_dup * (dsc * p.inv_T * kLog2e);
+        ov.x = fmaf(w, kk[u].x, ov.x);
+        ov.y = fmaf(w, kk[u].y, ov.y);
+        ov.z = fmaf(w, kk[u].z, ov.z);
+        ov.w = fmaf(w, kk[u].w, ov.w);
+      }
+      const float e0 = exp2f(pos2 - shift2);
+      const float Z = e0 + sum;
+      const float inv_Z = 1.0f / Z;
+      const float p0 = e0 * inv_Z;
+      if (GRAD) {
+        float4 g;
+        g.x = ((p0 - 1.0f) * kk[u].x * p.inv_T + ov.x * inv_Z * kLn2) * inv_rows;
+        g.y = ((p0 - 1.0f) * kk[u].y * p.inv_T + ov.y * inv_Z * kLn2) * inv_rows;
+        g.z = ((p0 - 1.0f) * kk[u].z * p.inv_T + ov.z * inv_Z * kLn2) * inv_rows;
+        g.w = ((p0 - 1.0f) * kk[u].w * p.inv_T + ov.w * inv_Z * kLn2) * inv_rows;
+        reinterpret_cast<float4 *>(p.dq_unit + (int64_t)row * kC)[lane] = g;
+      }
+      if (lane == 0) {
+        p.row_loss[row] = (shift2 + log2f(Z) - pos2) * kLn2;
+        p.row_loss[p.M + row] = cnt;
+      }
+    }
+  }
+  __syncthreads();
+  const int n_groups = p.M / p.rows_per_group;
+  for (int g = wid; g < n_groups; g += kWarps) {
+    float sl = 0.f, s1 = 0.f, s5 = 0.f;
+    for (int r = lane; r < p.rows_per_group; r += 32) {
+      const int row = g * p.rows_per_group + r;
+      sl += __ldcg(p.row_loss + row);
+      const float k = __ldcg(p.row_loss + p.M + row);
+      s1 += (k < 1.f) ? 1.f : 0.f;
+      s5 += (k < 5.f) ? 1.f : 0.f;
+    }
+    sl = warp_sum(sl);
+    s1 = warp_sum(s1);
+    s5 = warp_sum(s5);
+    if (lane == 0)
+      *reinterpret_cast<float4 *>(p.group_out + g * 4) = make_float4(sl * inv_rows, s1 * inv_rows, s5 * inv_rows, 0.f);
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+template <bool GRAD, bool FUSED>
+__global__ void __launch_bounds__(kThreads, 1)
+infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_wh,
+                     const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_q,
+                     const __grid_constant__ CUtensorMap tmap_acc, const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *gbase = smem_raw;
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) asm volatile("trap;");      // the swizzled tile layouts need a 1024-byte aligned base
+  const uint32_t sPair = base + kOffPair;
+  const uint32_t sSingle = base + kOffSingle;
+  const uint32_t sW2 = base + kOffW2;
+  const uint32_t sQ = sW2;
+  const uint32_t bar0 = base + kOffBar;
+  auto bar_full1 = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty1 = [&](int s) { return bar0 + 8u * (2 + s); };
+  const uint32_t bar_fullH = bar0 + 8u * 4;
+  auto bar_full2 = [&](int s) { return bar0 + 8u * (5 + s); };
+  auto bar_empty2 = [&](int s) { return bar0 + 8u * (5 + kStages2 + s); };
+  constexpr int kB = 5 + 2 * kStages2;
+  const uint32_t bar_q = bar0 + 8u * kB;
+  auto bar_sfull = [&](int b) { return bar0 + 8u * (kB + 1 + b); };
+  auto bar_pfull = [&](int b) { return bar0 + 8u * (kB + 3 + b); };
+  const uint32_t bar_ofull = bar0 + 8u * (kB + 5);
+  const uint32_t bar_qload = bar0 + 8u * (kB + 6);
+  const uint32_t bar_qfree = bar0 + 8u * (kB + 7);
+  auto bar_dfull = [&](int b) { return bar0 + 8u * (kB + 8 + b); };
+  auto bar_dfree = [&](int b) { return bar0 + 8u * (kB + 10 + b); };
+  static_assert(kB + 12 == kNumBars, "barrier count");
+  volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(gbase + kOffTmemPtr);
+  volatile int *last_flag = reinterpret_cast<volatile int *>(gbase + kOffFlag);
+  float *ds_smem = reinterpret_cast<float *>(gbase + kOffDs);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+
+  // this CTA's schedule: units [u_begin, u_end) of 64 keys -> an optional half tile (first) + pair tiles
+  const int64_t n_units = (p.K_local + kUnit - 1) / kUnit;
+  const int64_t u_begin = n_units * blockIdx.x / gridDim.x;
+  const int64_t u_end = n_units * (blockIdx.x + 1) / gridDim.x;
+  const int nu = (int)(u_end - u_begin);
+  const int hasH = nu & 1;
+  const int np = nu >> 1;
+  const int nt = np + hasH;                         // processing steps
+  const int64_t key_begin = u_begin * kUnit;
+  const int64_t key_end = u_end * kUnit < p.K_local ? u_end * kUnit : p.K_local;
+  const int row0 = blockIdx.y * kRows;
+  // step i covers keys [key0(i), key0(i) + (half tile ? 64 : 128))
+  auto step_key0 = [&](int i) { return key_begin + (i == 0 ? 0 : (int64_t)i * kTile - hasH * kUnit); };
+
+  if (warp == 0 && lane == 0) {
+    TLF(0);
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_wh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
+    if (GRAD) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_acc) : "memory");
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_full1(s), 1);
+      mbar_init(bar_empty1(s), 1);
+    }
+    mbar_init(bar_fullH, 1);
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(bar_full2(s), 1);
+      mbar_init(bar_empty2(s), 1);
+    }
+    mbar_init(bar_q, kSoftmaxWarps);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_sfull(b), 1);
+      mbar_init(bar_pfull(b), kSoftmaxWarps);
+      mbar_init(bar_dfull(b), 1);
+      mbar_init(bar_dfree(b), kSoftmaxWarps);
+    }
+    mbar_init(bar_ofull, 1);
+    mbar_init(bar_qload, 1);
+    mbar_init(bar_qfree, kSoftmaxWarps);
+    *last_flag = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + kOffTmemPtr),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+
+  if (warp == 0) {
+    // ===================== ring-1 producer =====================
+    if (elect_one()) {
+      TLF(1);
+      auto load_pair = [&](int pi) {
+        const int s = pi & 1;
+        mbar_wait(bar_empty1(s), ((uint32_t)(pi >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar_full1(s), kPairBytes);
+        tma_load_3d(sPair + s * kPairBytes, &tmap_w, bar_full1(s), 0, (int)(key_begin + hasH * kUnit + (int64_t)pi * kTile), 0);
+      };
+      auto load_first = [&]() {
+        if (hasH) {
+          mbar_arrive_expect_tx(bar_fullH, kUnitBytes);
+          tma_load_3d(sSingle, &tmap_wh, bar_fullH, 0, (int)key_begin, 0);
+        }
+        for (int pi = 0; pi < 2 && pi < np; ++pi) load_pair(pi);
+      };
+      auto load_q = [&]() {   // rows >= M are zero-filled by the TMA unit
+        mbar_arrive_expect_tx(bar_qload, kQBytes);
+        tma_load_3d(sQ, &tmap_q, bar_qload, 0, row0, 0);
+      };
+      // kFlagEarlyPrefetch: the caller guarantees the queue was not written by the launch this grid may overlap with
+      // (programmatic dependent launch), so its tiles may be requested before the dependency wait.
+      if (p.flags & kFlagEarlyPrefetch) {
+        load_first();
+        pdl_wait();
+        pdl_trigger();       // only after the wait: a dependent of THIS grid may then assume this grid's predecessors are done
+        load_q();
+      } else {
+        pdl_wait();
+        pdl_trigger();
+        load_q();
+        load_first();
+      }
+      for (int pi = 2; pi < np; ++pi) load_pair(pi);
+      TLF(4);
+    }
+    __syncwarp();
+  } else if (warp == 2 + kSoftmaxWarps) {
+    // ===================== ring-2 producer: the MN-major copy of every unit (the same bytes again: L2 hits) ======
+    if (GRAD && elect_one()) {
+      if (!(p.flags & kFlagEarlyPrefetch)) pdl_wait();
+      mbar_wait(bar_qfree, 0);                      // ring 2 held the Q tile
+      for (int u = 0; u < nu; ++u) {
+        const int s = u % kStages2;
+        mbar_wait(bar_empty2(s), ((uint32_t)(u / kStages2) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar_full2(s), kUnitBytes);
+        tma_load_3d(sW2 + s * kUnitBytes, &tmap_w2, bar_full2(s), 0, (int)(key_begin + (int64_t)u * kUnit), 0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3 + kSoftmaxWarps) {
+    // ===================== per-key scale: 0.99999^(n_enq - birth_j) / T * log2(e), 0 for keys outside the tile ======
+    pdl_wait();
+    const int64_t n_enq = p.qstate[1];
+    const float sc = p.inv_T * kLog2e;
+    for (int i = 0; i < nt; ++i) {
+      const int b = i & 1;
+      mbar_wait(bar_dfree(b), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      const int64_t k0 = step_key0(i) + 4 * lane;
+      const int64_t tile_end = (hasH && i == 0) ? key_begin + kUnit : step_key0(i) + kTile;
+      const int64_t lim = tile_end < key_end ? tile_end : key_end;
+      int bi[4] = {0, 0, 0, 0};
+      if (k0 + 3 < lim) {
+        const int4 t = __ldg(reinterpret_cast<const int4 *>(p.birth + k0));
+        bi[0] = t.x; bi[1] = t.y; bi[2] = t.z; bi[3] = t.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (k0 + e < lim) bi[e] = __ldg(p.birth + k0 + e);
+      }
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        v[e] = (k0 + e < lim) ? exp2f((float)(n_enq - (int64_t)bi[e]) * kLog2Decay) * sc : 0.f;
+      reinterpret_cast<float4 *>(ds_smem + b * kTile)[lane] = make_float4(v[0], v[1], v[2], v[3]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dfull(b));
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t kHi1 = (1024u >> 4) | (1u << 14) | (2u << 29);      // K-major, SWIZZLE_128B, SBO 1024
+    constexpr uint32_t kHi2 = (512u >> 4) | (1u << 14) | (1u << 29);       // MN-major, SWIZZLE_128B_BASE32B, SBO 512
+    const uint32_t lo1_pair = ((sPair & 0x3FFFFu) >> 4) | ((16u >> 4) << 16);
+    const uint32_t lo1_single = ((sSingle & 0x3FFFFu) >> 4) | ((16u >> 4) << 16);
+    const uint32_t lo2_base = ((sW2 & 0x3FFFFu) >> 4) | ((kUnitSlab >> 4) << 16);
+    if (elect_one()) {
+      auto issue_mma1 = [&](int i) {
+        const uint32_t d = tmem + kColS + (uint32_t)(i & 1) * kTile;
+        if (hasH && i == 0) {
+          mbar_wait(bar_fullH, 0);
+          tc_fence_after();
+#pragma unroll
+          for (int cb = 0; cb < kCb; ++cb) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_ts_lh(d, tmem + kColQ + cb * 32 + ks * 8, lo1_single + ((cb * kUnitSlab + ks * 32) >> 4), kHi1, kIdesc1H,
+                        (cb | ks) ? 1u : 0u);
+          }
+          tc_commit(bar_sfull(i & 1));
+        } else {
+          const int pi = i - hasH;
+          const int s = pi & 1;
+          mbar_wait(bar_full1(s), (uint32_t)(pi >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t lo = lo1_pair + (uint32_t)s * (kPairBytes >> 4);
+#pragma unroll
+          for (int cb = 0; cb < kCb; ++cb) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_ts_lh(d, tmem + kColQ + cb * 32 + ks * 8, lo + ((cb * kPairSlab + ks * 32) >> 4), kHi1, kIdesc1,
+                        (cb | ks) ? 1u : 0u);
+          }
+          tc_commit(bar_sfull(i & 1));
+          tc_commit(bar_empty1(s));      // the pair slot is free once MMA1 has read it
+        }
+      };
+      mbar_wait(bar_q, 0);
+      tc_fence_after();
+      if (nt > 0) issue_mma1(0);
+      for (int i = 0; i < nt; ++i) {
+        if (i + 1 < nt) issue_mma1(i + 1);
+        mbar_wait(bar_pfull(i & 1), (uint32_t)(i >> 1) & 1u);
+        tc_fence_after();
+        if (GRAD) {
+          const int n_un = (hasH && i == 0) ? 1 : 2;
+          const int u0 = i == 0 ? 0 : 2 * i - hasH;
+          for (int h = 0; h < n_un; ++h) {
+            const int u = u0 + h;
+            const int s = u % kStages2;
+            mbar_wait(bar_full2(s), (uint32_t)(u / kStages2) & 1u);
+            tc_fence_after();
+            const uint32_t a = tmem + kColS + (uint32_t)(i & 1) * kTile + h * kUnit;
+            const uint32_t lo = lo2_base + (uint32_t)s * (kUnitBytes >> 4);
+            // B = the ring-2 copy read MN-major (SWIZZLE_128B_BASE32B): 8 keys per step = two 4-row atoms
+            // 512 bytes apart (SBO); channel blocks kUnitSlab bytes apart (LBO)
+            if (u == 0) {
+#pragma unroll
+              for (int j = 0; j < kUnit / 8; ++j)
+                mma_ts_lh(tmem + kColO, a + j * 8, lo + ((j * 1024) >> 4), kHi2, kIdesc2, j ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int j = 0; j < kUnit / 8; ++j)
+                mma_ts_lh(tmem + kColO, a + j * 8, lo + ((j * 1024) >> 4), kHi2, kIdesc2, 1u);
+            }
+            tc_commit(bar_empty2(s));
+          }
+        }
+      }
+      if (GRAD) tc_commit(bar_ofull);
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax / epilogue warps (8: two per TMEM lane quarter) =====================
+    const int sw = warp - 2;                      // 0..7
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = sw >> 2;                     // which 64 of a pair tile's 128 keys (and which half of Q / O)
+    const int r = quarter * 32 + lane;            // row within the CTA's block == TMEM lane
+    const int row = row0 + r;
+    const bool row_ok = row < p.M;
+    const bool warp_ok = (row0 + quarter * 32) < p.M;
+    float shift2 = 0.f, pos2 = INFINITY;
+    int64_t dup_local = -1;
+    pdl_wait();
+    if (FUSED) {
+      // pos2 = q.k / T * log2e, shift2 = |q| * bound / T * log2e: one warp per row, 128-bit coalesced loads
+      float2 *rowinfo = reinterpret_cast<float2 *>(gbase + kOffRow);
+      const float sc = p.inv_T * kLog2e;
+#pragma unroll
+      for (int g = 0; g < kRows / kSoftmaxWarps / 4; ++g) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rr = row0 + sw + (g * 4 + u) * kSoftmaxWarps;
+          a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rr < p.M) {
+            a[u] = __ldg(reinterpret_cast<const float4 *>(p.q + (int64_t)rr * kC) + lane);
+            b[u] = __ldg(reinterpret_cast<const float4 *>(p.kpos + (int64_t)rr * kC) + lane);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rl = sw + (g * 4 + u) * kSoftmaxWarps;
+          float d = a[u].x * b[u].x + a[u].y * b[u].y + a[u].z * b[u].z + a[u].w * b[u].w;
+          float ss = a[u].x * a[u].x + a[u].y * a[u].y + a[u].z * a[u].z + a[u].w * a[u].w;
+          d = warp_sum(d);
+          ss = warp_sum(ss);
+          if (lane == 0) rowinfo[rl] = make_float2(d * sc, sqrtf(ss) * p.key_norm_bound * sc);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
+      if (row_ok) {
+        const float2 ri = rowinfo[r];
+        pos2 = ri.x;
+        shift2 = ri.y;
+        if (p.dup_slot != nullptr) {
+          const int dup = __ldg(p.dup_slot + row);
+          if (dup >= 0) dup_local = (int64_t)dup - p.shard_begin;
+        }
+      }
+    } else if (row_ok) {
+      const float4 x = __ldg(reinterpret_cast<const float4 *>(p.q + (int64_t)row * kLd + kC));
+      shift2 = x.y;
+      pos2 = x.x;
+      const int dup = __float_as_int(x.z);
+      if (dup >= 0) dup_local = (int64_t)dup - p.shard_begin;
+    }
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    {   // this row of Q: smem (TMA, swizzled) -> tf32 -> TMEM columns [kColQ + 64*half, +64): the A operand of every MMA1
+      mbar_wait(bar_qload, 0);
+      const uint8_t *qs = gbase + kOffW2;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cb = half * 2 + hh;
+        const uint8_t *rowp = qs + cb * kQSlab + r * 128;
+        uint32_t v[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 f = *reinterpret_cast<const float4 *>(rowp + ((c ^ (r & 7)) << 4));
+          if (FUSED) f = to_tf32_rn(f);
+          v[c * 4 + 0] = __float_as_uint(f.x);
+          v[c * 4 + 1] = __float_as_uint(f.y);
+          v[c * 4 + 2] = __float_as_uint(f.z);
+          v[c * 4 + 3] = __float_as_uint(f.w);
+        }
+        TC_ST32(lane_base + kColQ + cb * 32, v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_qfree);
+        mbar_arrive(bar_q);
+      }
+      if (threadIdx.x == 64) TLF(2);
+    }
+    float sum = 0.f;
+    int cnt = 0;
+    for (int i = 0; i < nt; ++i) {
+      const int b = i & 1;
+      const bool is_h = hasH && i == 0;
+      const int64_t key0 = step_key0(i) + half * kUnit;
+      const bool active = warp_ok && !(is_h && half == 1);
+      mbar_wait(bar_dfull(b), (uint32_t)(i >> 1) & 1u);
+      mbar_wait(bar_sfull(b), (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+#ifdef MSCL_TC_TIMELINE
+      if (threadIdx.x == 64 && i < 8) TLF(8 + i);
+#endif
+      if (active) {
+        const uint32_t taddr = lane_base + kColS + (uint32_t)b * kTile + half * kUnit;
+        const float4 *ds = reinterpret_cast<const float4 *>(ds_smem + b * kTile + half * kUnit);
+        uint32_t v0[32], v1[32];
+        TC_LD32(taddr, v0);
+        TC_LD32(taddr + 32, v1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int64_t k0 = key0 + ch * 32;
+          const int64_t left = key_end - k0;
+          const int nvalid = left < 32 ? (left < 0 ? 0 : (int)left) : 32;
+          const int64_t dcol = dup_local - k0;
+          const bool has_dup = dcol >= 0 && dcol < 32;
+          uint32_t(&v)[32] = ch ? v1 : v0;
+          // warp-uniform choice (tcgen05.ld/st are .sync.aligned): slow path if any row of the warp needs it
+          if (nvalid == 32 && !__any_sync(0xffffffffu, has_dup))
+            softmax_chunk<GRAD, true>(v, ds + ch * 8, shift2, pos2, 32, -1, sum, cnt);
+          else
+            softmax_chunk<GRAD, false>(v, ds + ch * 8, shift2, pos2, nvalid, has_dup ? (int)dcol : -1, sum, cnt);
+          if (GRAD) TC_ST32(taddr + ch * 32, v);
+        }
+        if (GRAD) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_pfull(b));
+        mbar_arrive(bar_dfree(b));
+      }
+#ifdef MSCL_TC_TIMELINE
+      if (threadIdx.x == 64 && i < 8) TLF(20 + i);
+#endif
+    }
+    if (threadIdx.x == 64) TLF(5);
+    // combine the two key halves of each row (the row-info array is dead: every thread holds its pos2 / shift2)
+    float *red = reinterpret_cast<float *>(gbase + kOffRow);
+    asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
+    if (half == 1) {
+      red[r] = sum;
+      red[kRows + r] = (float)cnt;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
+    if (half == 0) {
+      sum += red[r];
+      cnt += (int)red[kRows + r];
+    }
+    if (GRAD) {
+      // [128][132] output tile (O | sum | count | 0 | 0) in the pair slots (every tile is consumed once o_full fires),
+      // then ONE TMA reduce-add into the accumulator; rows >= M are clipped by the TMA unit.
+      float *tile = reinterpret_cast<float *>(gbase + kOffPair);
+      if (nt > 0) {
+        mbar_wait(bar_ofull, 0);
+        tc_fence_after();
+      }
+      if (threadIdx.x == 64) TLF(6);
+      if (warp_ok && nt > 0) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cb = half * 2 + hh;
+          uint32_t v[32];
+          TC_LD32(lane_base + kColO + cb * 32, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float4 *dst = reinterpret_cast<float4 *>(tile + r * kLd + cb * 32);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            dst[c] = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                                 __uint_as_float(v[4 * c + 3]));
+        }
+        if (half == 0) *reinterpret_cast<float4 *>(tile + r * kLd + kC) = make_float4(sum, (float)cnt, 0.f, 0.f);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
+      if (threadIdx.x == 64 && nt > 0) {
+        tma_reduce_add_2d(&tmap_acc, sPair, 0, row0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // the adds have been performed
+      }
+    } else {
+      if (half == 0 && row_ok && nt > 0) {
+        atomicAdd(p.acc + (int64_t)row * kLd + kC, sum);
+        atomicAdd(p.acc + (int64_t)row * kLd + kC + 1, (float)cnt);
+      }
+      if (FUSED) {
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
+      }
+    }
+    if (FUSED && threadIdx.x == 64) {
+      // release this CTA's adds, then count it; the last CTA finalises
+      __threadfence();
+      unsigned *counter = reinterpret_cast<unsigned *>(p.acc + (int64_t)p.M * kLd);
+      const unsigned done = atomicAdd(counter, 1u);
+      *last_flag = (done == gridDim.x * gridDim.y - 1u) ? 1 : 0;
+    }
+  }
+
+  if (threadIdx.x == 64) TLF(7);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+  if (FUSED && *last_flag) {
+    __threadfence();
+    finalize_rows<GRAD>(p, reinterpret_cast<unsigned *>(p.acc + (int64_t)p.M * kLd));
+  }
+  if (threadIdx.x == 0) TLF(3);
+}
+
+// acc [M][132] viewed as {132, M}: one box = one CTA's [128][132] output tile
+static int make_map_acc(CUtensorMap *map, float *ptr, int M) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_err(MSCL_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)kLd, (cuuint64_t)M};
+  cuuint64_t strides[1] = {(cuuint64_t)kLd * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kLd, (cuuint32_t)kRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(MSCL_ECUDA, "cuTensorMapEncodeTiled(acc) failed with CUresult %d (M=%d)", (int)r, M);
+  return MSCL_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of the function: set it once on every device
+// this process launches on.
+template <typename F>
+static int ensure_smem(F func, int which) {
+  static bool done[4][64] = {};
+  int dev = 0;
+  MSCL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !done[which][dev]) {
+    MSCL_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    if (dev >= 0 && dev < 64) done[which][dev] = true;
+  }
+  return MSCL_OK;
+}
+
+static int launch(bool fused, bool grad, const Params &p, const float *d_queue, int n_part, cudaStream_t s) {
+  const int64_t n_units = (p.K_local + kUnit - 1) / kUnit;
+  MSCL_CHECK_ARG(n_part > 0 && n_part <= n_units, "n_part=%d must be in [1, %lld] (one 64-key unit per CTA at least)", n_part,
+                 (long long)n_units);
+  CUtensorMap tw, twh, tw2, tq, ta;
+  int rc = make_map(&tw, d_queue, p.K_local, kC, kTile);
+  if (rc) return rc;
+  rc = make_map(&twh, d_queue, p.K_local, kC, kUnit);
+  if (rc) return rc;
+  rc = make_map(&tw2, d_queue, p.K_local, kC, kUnit, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  rc = make_map(&tq, p.q, p.M, fused ? kC : kLd, kRows);
+  if (rc) return rc;
+  rc = make_map_acc(&ta, p.acc, p.M);
+  if (rc) return rc;
+  const int row_blocks = (p.M + kRows - 1) / kRows;
+  dim3 grid((unsigned)n_part, (unsigned)row_blocks);
+#define MSCL_FUSED_LAUNCH(G, F, W)                                                                                   \
+  do {                                                                                                               \
+    rc = ensure_smem(infonce_fused_kernel<G, F>, W);                                                                 \
+    if (rc) return rc;                                                                                               \
+    MSCL_CUDA(mscl::launch_pdl(infonce_fused_kernel<G, F>, grid, dim3(kThreads), kSmemBytes, s, tw, twh, tw2, tq, ta, p)); \
+  } while (0)
+  if (fused && grad) MSCL_FUSED_LAUNCH(true, true, 0);
+  else if (fused) MSCL_FUSED_LAUNCH(false, true, 1);
+  else if (grad) MSCL_FUSED_LAUNCH(true, false, 2);
+  else MSCL_FUSED_LAUNCH(false, false, 3);
+#undef MSCL_FUSED_LAUNCH
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
+
+}  // namespace tcf
+}  // namespace mscl
+
+extern "C" int mscl_infonce_fused(const float *d_q, const float *d_kpos, int32_t M, const float *d_queue,
+                                  const int32_t *d_birth, const int64_t *d_qstate, int64_t K_local, float inv_T,
+                                  float key_norm_bound, const int32_t *d_dup_slot, int32_t dup_age, float *d_ws,
+                                  int32_t n_part, int32_t rows_per_group, int32_t with_grad, int32_t flags,
+                                  float *d_row_loss, float *d_dq_unit, float *d_group_out, mscl_stream_t stream) {
+  using namespace mscl::tcf;
+  MSCL_CHECK_ARG(d_q && d_kpos && d_queue && d_birth && d_qstate && d_ws && d_row_loss && d_dq_unit && d_group_out,
+                 "null pointer");
+  MSCL_CHECK_ARG(M > 0 && K_local > 0, "bad M=%d K_local=%lld", M, (long long)K_local);
+  MSCL_CHECK_ARG(K_local < (1ll << 31), "K_local too large for a TMA coordinate");
+  MSCL_CHECK_ARG(rows_per_group > 0 && M % rows_per_group == 0, "M=%d must be a multiple of rows_per_group=%d", M,
+                 rows_per_group);
+  MSCL_CHECK_ARG(inv_T > 0.f && key_norm_bound > 0.f, "bad inv_T / key_norm_bound");
+  MSCL_CHECK_ARG((((uintptr_t)d_q | (uintptr_t)d_kpos | (uintptr_t)d_queue | (uintptr_t)d_birth | (uintptr_t)d_ws |
+                   (uintptr_t)d_dq_unit | (uintptr_t)d_group_out) & 15) == 0,
+                 "q/kpos/queue/birth/ws/dq_unit/group_out must be 16-byte aligned");
+  Params p = {};
+  p.q = d_q;
+  p.kpos = d_kpos;
+  p.birth = d_birth;
+  p.qstate = d_qstate;
+  p.dup_slot = d_dup_slot;
+  p.acc = d_ws;
+  p.row_loss = d_row_loss;
+  p.dq_unit = d_dq_unit;
+  p.group_out = d_group_out;
+  p.K_local = K_local;
+  p.shard_begin = 0;
+  p.M = M;
+  p.rows_per_group = rows_per_group;
+  p.dup_age = dup_age;
+  p.flags = flags;
+  p.inv_T = inv_T;
+  p.key_norm_bound = key_norm_bound;
+  return launch(true, with_grad != 0, p, d_queue, n_part, mscl::as_stream(stream));
+}
+
+extern "C" int mscl_infonce_pass(const float *d_qpack, int32_t M, const float *d_queue, const int32_t *d_birth,
+                                 const int64_t *d_qstate, int64_t K_local, int64_t shard_begin, float inv_T,
+                                 float *d_acc, int32_t n_part, int32_t with_grad, int32_t flags, mscl_stream_t stream) {
+  using namespace mscl::tcf;
+  MSCL_CHECK_ARG(d_qpack && d_queue && d_birth && d_qstate && d_acc, "null pointer");
+  MSCL_CHECK_ARG(M > 0 && K_local > 0, "bad M=%d K_local=%lld", M, (long long)K_local);
+  MSCL_CHECK_ARG(K_local < (1ll << 31), "K_local too large for a TMA coordinate");
+  MSCL_CHECK_ARG(inv_T > 0.f, "bad inv_T");
+  MSCL_CHECK_ARG((((uintptr_t)d_qpack | (uintptr_t)d_queue | (uintptr_t)d_birth | (uintptr_t)d_acc) & 15) == 0,
+                 "qpack/queue/birth/acc must be 16-byte aligned");
+  Params p = {};
+  p.q = d_qpack;
+  p.birth = d_birth;
+  p.qstate = d_qstate;
+  p.acc = d_acc;
+  p.K_local = K_local;
+  p.shard_begin = shard_begin;
+  p.M = M;
+  p.rows_per_group = 1;
+  p.flags = flags;
+  p.inv_T = inv_T;
+  p.key_norm_bound = 1.f;
+  return launch(false, with_grad != 0, p, d_queue, n_part, mscl::as_stream(stream));
+}
+
+// How many CTAs along the keys mscl_infonce_fused / mscl_infonce_pass should be given.
+extern "C" int mscl_infonce_fused_parts(int32_t M, int64_t K_local, int32_t num_sms) {
+  using namespace mscl::tcf;
+  if (M <= 0 || K_local <= 0 || num_sms <= 0) return mscl::set_err(MSCL_EINVAL, "bad M / K_local / num_sms");
+  const int64_t n_units = (K_local + kUnit - 1) / kUnit;
+  const int row_blocks = (M + kRows - 1) / kRows;
+  int64_t gx = num_sms / row_blocks;
+  if (gx < 1) gx = 1;
+  if (gx > n_units) gx = n_units;
+  return (int)gx;
+}
+
+#ifdef MSCL_TC_TIMELINE
+extern "C" int mscl_debug_timeline_fused(unsigned long long *host_out, int n) {
+  MSCL_CUDA(cudaMemcpyFromSymbol(host_out, mscl::tcf::g_timeline_f, sizeof(unsigned long long) * n));
+  return MSCL_OK;
+}
+#endif

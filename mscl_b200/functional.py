@@ -91,6 +91,7 @@ class NegativeQueue:
         self.ptr = 0          # host mirrors (deterministic, never read back from the device)
         self.n_enq = 0
         self.max_key_norm = 1.0
+        self._fresh = True    # written since the last pass over it (see _prefetch_flag)
 
     # -- reference-layout import / export (state_dict compatibility) --
     def load(self, queue_ck, count, ptr):
@@ -107,6 +108,7 @@ class NegativeQueue:
         _cabi.call("mscl_queue_import", self.queue.data_ptr(), self.queue_tf32.data_ptr(), self.birth.data_ptr(),
                    self.qstate.data_ptr(),
                    q_loc.data_ptr(), c_loc.data_ptr(), self.C, self.K_local, _stream())
+        self._fresh = True
         # keep the staging tensors alive until the kernel has consumed them
         torch.cuda.current_stream().synchronize()
 
@@ -140,6 +142,7 @@ class NegativeQueue:
                    algo_bytes=2 * b * self.C * 4)
         self.ptr = (self.ptr + b) % self.K
         self.n_enq += 1
+        self._fresh = True
 
 
 # ----------------------------------------------------------------------------------------
@@ -183,6 +186,27 @@ def peer_workspace(nq, group, rows):
 EXCHANGE = "peer"      # "peer": NVLink peer stores from the kernels + device barriers; "nccl": all_gather / reduce_scatter
 
 
+_FUSED_WS = {}
+
+
+def _fused_workspace(dev, M):
+    """Zero-initialised accumulator + CTA counter of the single-launch InfoNCE op (mscl_infonce_fused leaves it zero).
+    One per (device, stream, M): two launches that may overlap must not share it."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(), int(M))
+    ws = _FUSED_WS.get(key)
+    if ws is None:
+        ws = _FUSED_WS[key] = torch.zeros(M * PACK_LD + 4, device=dev)
+    return ws
+
+
+def _prefetch_flag(nq):
+    """MSCL_INFONCE_EARLY_PREFETCH unless the queue was (re)written since the last pass over it: a pass launched as a
+    programmatic dependent of the launch before it may only prefetch queue tiles early when that launch did not write them."""
+    early = 0 if getattr(nq, "_fresh", True) else 1
+    nq._fresh = False
+    return early
+
+
 class _InfoNCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, kpos, nq, rows_per_group, inv_T, impl, group, need_grad, dup_slot, dup_age):
@@ -191,13 +215,33 @@ class _InfoNCE(torch.autograd.Function):
         st = _stream()
         world = dist.get_world_size(group) if (group is not None and nq.world > 1) else 1
         M_all = M * world
+        n_groups = M // rows_per_group
+        row_loss = torch.empty(2 * M, device=dev)
+        dq_unit = torch.empty(M, DIM, device=dev)
+        group_out = torch.empty(n_groups, 4, device=dev)
+        if impl == "fused" and world == 1:
+            # ONE launch: prep + tcgen05 pass + reduce-add into one accumulator + finalize by the last CTA
+            n_part = _cabi.query("mscl_infonce_fused_parts", M, nq.K_local, sm_count(dev))
+            ws = _fused_workspace(dev, M)
+            _cabi.call("mscl_infonce_fused", q.data_ptr(), kpos.data_ptr(), M, nq.queue_tf32.data_ptr(), nq.birth.data_ptr(),
+                       nq.qstate.data_ptr(), nq.K_local, inv_T, nq.max_key_norm,
+                       dup_slot.data_ptr() if dup_slot is not None else None, dup_age, ws.data_ptr(), n_part, rows_per_group,
+                       int(need_grad), _prefetch_flag(nq), row_loss.data_ptr(), dq_unit.data_ptr(), group_out.data_ptr(), st,
+                       algo_bytes=infonce_algo_bytes(M, nq.K_local), algo_flops=(4 if need_grad else 2) * M * nq.K_local * DIM)
+            ctx.save_for_backward(dq_unit)
+            ctx.rows_per_group = rows_per_group
+            ctx.mark_non_differentiable(row_loss)
+            return group_out, row_loss
         qpack = torch.empty(M, PACK_LD, device=dev)
-        k_pad = (nq.K_local + 127) // 128 * 128
-        dscale = torch.empty(k_pad, device=dev)
+        fused_pass = impl in ("fused", "fused_pass")      # "fused_pass": the sharded-queue launch sequence on one rank (tests)
+        dscale = None
+        if not fused_pass:
+            k_pad = (nq.K_local + 127) // 128 * 128
+            dscale = torch.empty(k_pad, device=dev)
         peer = world > 1 and EXCHANGE == "peer" and impl != "simt"
         ws = peer_workspace(nq, group, M) if peer else None
         _cabi.call("mscl_infonce_prep", q.data_ptr(), kpos.data_ptr(), M, nq.birth.data_ptr(), nq.qstate.data_ptr(),
-                   nq.K_local, inv_T, nq.max_key_norm, qpack.data_ptr(), dscale.data_ptr(),
+                   nq.K_local, inv_T, nq.max_key_norm, qpack.data_ptr(), dscale.data_ptr() if dscale is not None else None,
                    dup_slot.data_ptr() if dup_slot is not None else None, dup_age,
                    ws.qp_ptrs.data_ptr() if peer else None, world if peer else 0, ws.rank * M if peer else 0, st)
         if peer:                # every rank's rows were stored into every rank's table: wait for all of them
@@ -213,6 +257,14 @@ class _InfoNCE(torch.autograd.Function):
             part = torch.zeros(1, M_all, PACK_LD, device=dev)
             _cabi.call("mscl_infonce_partial_simt", qpack_all.data_ptr(), M_all, nq.queue_tf32.data_ptr(), dscale.data_ptr(),
                        nq.K_local, nq.shard_begin, part.data_ptr(), int(need_grad), st)
+        elif fused_pass:        # the pass in its single-launch form: all CTAs reduce-add into ONE zeroed slab
+            n_part = 1
+            part = torch.zeros(1, M_all, PACK_LD, device=dev)
+            _cabi.call("mscl_infonce_pass", qpack_all.data_ptr(), M_all, nq.queue_tf32.data_ptr(), nq.birth.data_ptr(),
+                       nq.qstate.data_ptr(), nq.K_local, nq.shard_begin, inv_T, part.data_ptr(),
+                       _cabi.query("mscl_infonce_fused_parts", M_all, nq.K_local, sm_count(dev)), int(need_grad),
+                       _prefetch_flag(nq), st, algo_bytes=infonce_algo_bytes(M_all, nq.K_local),
+                       algo_flops=(4 if need_grad else 2) * M_all * nq.K_local * DIM)
         else:
             n_part = _cabi.query("mscl_infonce_num_partials", M_all, nq.K_local, sm_count(dev))
             part = torch.empty(n_part, M_all, PACK_LD, device=dev)
@@ -228,15 +280,14 @@ class _InfoNCE(torch.autograd.Function):
             ws.barrier()
             part, n_part = ws.acc, world
         elif world > 1:         # local slabs -> one slab, summed across ranks, each rank keeps its own rows
-            acc = torch.empty(M_all, PACK_LD, device=dev)
-            _cabi.call("mscl_infonce_reduce", part.data_ptr(), n_part, M_all, acc.data_ptr(), st)
+            if n_part > 1:
+                acc = torch.empty(M_all, PACK_LD, device=dev)
+                _cabi.call("mscl_infonce_reduce", part.data_ptr(), n_part, M_all, acc.data_ptr(), st)
+            else:
+                acc = part.view(M_all, PACK_LD)
             part = torch.empty(1, M, PACK_LD, device=dev)
             dist.reduce_scatter_tensor(part.view(M, PACK_LD), acc, op=dist.ReduceOp.SUM, group=group)
             n_part = 1
-        n_groups = M // rows_per_group
-        row_loss = torch.empty(2 * M, device=dev)
-        dq_unit = torch.empty(M, DIM, device=dev)
-        group_out = torch.empty(n_groups, 4, device=dev)
         _cabi.call("mscl_infonce_finalize", qpack.data_ptr(), kpos.data_ptr(), part.data_ptr(), n_part, M, rows_per_group,
                    inv_T, int(need_grad), row_loss.data_ptr(), dq_unit.data_ptr(), group_out.data_ptr(), st)
         ctx.save_for_backward(dq_unit)
@@ -260,13 +311,15 @@ def infonce_algo_bytes(M, K_local):
     return K_local * DIM * 4 + K_local * 4 + 2 * M * PACK_LD * 4
 
 
-def infonce(q, kpos, nq, rows_per_group, T, impl="tc", group=None, dup_slot=None, dup_age=1):
+def infonce(q, kpos, nq, rows_per_group, T, impl="fused", group=None, dup_slot=None, dup_age=1):
     """Fused InfoNCE over the queue `nq`.
 
     q, kpos: (M, 128) stacked query rows and the positive key of each row; consecutive
     blocks of rows_per_group rows form one loss term (one "head call" of the reference).
     dup_slot: optional int32 (M,) GLOBAL queue slot that currently holds a copy of the row's own
     positive key (-1: none), dup_age its age -- see include/mscl_b200.h (K1, prep).
+    impl: "fused" (default) -- one launch (csrc/infonce_fused.cu; with a sharded queue: its pass between the peer
+    exchange kernels); "tc" -- the three-launch slab form (csrc/infonce_tc.cu, bit-reproducible); "simt" -- CUDA-core twin.
     Returns (group_out (M/rows_per_group, 4) = [loss, top1, top5, 0], row_stats (2M,)).
     Gradient flows to q only (keys and queue are detached in the reference, moco.py:486,532).
     """

@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--Ks", default="16384,65536,262144,1048576")
     ap.add_argument("--Ms", default="32,64,96,128,192,384")
     ap.add_argument("--iters", type=int, default=40)
+    ap.add_argument("--flags", type=int, default=1, help="mscl_infonce_fused flags (1 = early queue prefetch)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -112,11 +113,31 @@ def main():
             res["op_gbs"] = res["algo_bytes"] / us / 1e3
             res["op_frac"] = res["op_gbs"] / pk
             res["loss"] = float(gout[0, 0])
+
+            # the single-launch form: prep + pass + reduce-add + finalize in one kernel (csrc/infonce_fused.cu)
+            n_fp = _cabi.query("mscl_infonce_fused_parts", M, K, sms)
+            ws = torch.zeros(M * fx.PACK_LD + 4, device=dev)
+            for grad in (1, 0):
+                def fused(i, grad=grad):
+                    nq = queues[i % n_rot]
+                    _cabi.call("mscl_infonce_fused", q.data_ptr(), k.data_ptr(), M, nq.queue_tf32.data_ptr(), nq.birth.data_ptr(),
+                               nq.qstate.data_ptr(), K, 1 / 0.07, 1.0, None, 1, ws.data_ptr(), n_fp, M, grad, args.flags,
+                               row_loss.data_ptr(), dq.data_ptr(), gout.data_ptr(), st)
+                for i in range(5):
+                    fused(i)
+                us = time_train(fused, args.iters)
+                tag = "fused" if grad else "fused_nograd"
+                res[f"{tag}_us"] = us
+                res[f"{tag}_frac"] = res["algo_bytes"] / us / 1e3 / pk
+            res["fused_loss"] = float(gout[0, 0])
+            us = res["op_us"]
             rows.append(res)
             print(f"K={K:8d} M={M:4d} parts={n_part:3d}  partial(grad) {res['partial_grad_us']:8.1f} us "
                   f"{res['partial_grad_gbs']:7.0f} GB/s {100 * res['partial_grad_frac']:5.1f}%  {res['partial_grad_tflops']:6.1f} TF | "
                   f"nograd {res['partial_nograd_us']:8.1f} us {100 * res['partial_nograd_frac']:5.1f}% | "
-                  f"prep+partial+finalize {us:8.1f} us {100 * res['op_frac']:5.1f}%  loss {res['loss']:.4f}", flush=True)
+                  f"prep+partial+finalize {us:8.1f} us {100 * res['op_frac']:5.1f}%  loss {res['loss']:.4f} | "
+                  f"FUSED op {res['fused_us']:8.1f} us {100 * res['fused_frac']:5.1f}% (nograd {res['fused_nograd_us']:.1f} us) "
+                  f"loss {res['fused_loss']:.4f}", flush=True)
         del queues
         torch.cuda.empty_cache()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)

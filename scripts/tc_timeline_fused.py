@@ -1,0 +1,40 @@
+"""GPU debug: per-CTA phase timeline of the single-launch InfoNCE kernel (needs a MSCL_TIMELINE=1 build)."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from mscl_b200 import functional as fx, _cabi
+
+M, K = int(sys.argv[1]) if len(sys.argv) > 1 else 96, int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+FLUSH = int(sys.argv[3]) if len(sys.argv) > 3 else 1      # 1: dirty the L2 before each launch, 0: back-to-back launches
+g = torch.Generator().manual_seed(0)
+q = torch.nn.functional.normalize(torch.randn(M, 128, generator=g), dim=1).cuda()
+kp = torch.nn.functional.normalize(torch.randn(M, 128, generator=g), dim=1).cuda()
+nqs = []
+for s in range(6):
+    nq = fx.NegativeQueue(K)
+    nq.load(torch.nn.functional.normalize(torch.randn(128, K, generator=g), dim=0), torch.ones(K, dtype=torch.long), 0)
+    nqs.append(nq)
+flush = torch.empty(64 * 1024 * 1024, device="cuda")
+lib = _cabi.load()
+for it in range(4):
+    if FLUSH:
+        flush.fill_(it)
+    _cabi.start_timing(["mscl_infonce_fused"])
+    for j in range(1 if FLUSH else 6):
+        nqs[j]._fresh = False
+        qd = q.clone().requires_grad_(True)
+        out, _ = fx.infonce(qd, kp, nqs[j], M, 0.07)
+    rec = _cabi.stop_timing()
+    buf = (ctypes.c_ulonglong * (148 * 32))()
+    assert lib.mscl_debug_timeline_fused(buf, 148 * 32) == 0
+    t = np.array(buf, dtype=np.int64).reshape(148, 32)
+    base = t[:, 0].min()
+    rel = (t - base) / 1e3
+    names = {0: "entry", 1: "setup done", 2: "Q staged", 8: "S0", 9: "S1", 10: "S2", 11: "S3", 12: "S4", 20: "P0", 21: "P1", 22: "P2", 23: "P3",
+             24: "P4", 4: "TMA issued", 5: "softmax done", 6: "O full", 7: "epilogue done", 3: "exit"}
+    print(f"iter {it}: event {rec['mscl_infonce_fused'][-1][0]*1e3:.1f} us; kernel span {(t[:, 3].max() - base)/1e3:.2f} us")
+    for k in sorted(names, key=lambda k: np.median(rel[:, k])):
+        col = rel[:, k][t[:, k] > 0]
+        if col.size:
+            print(f"   {names[k]:>16}: min {col.min():6.2f}  median {np.median(col):6.2f}  max {col.max():6.2f} us  ({col.size} CTAs)")

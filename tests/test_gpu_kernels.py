@@ -237,7 +237,7 @@ CASES = [  # M, K, rows_per_group, b_all
 ]
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("impl", ["simt", "tc", "fused", "fused_pass"])
 @pytest.mark.parametrize("M,K,rpg,b_all", CASES)
 def test_infonce_vs_oracle(fx, impl, M, K, rpg, b_all):
     q, kpos, queue, count = _make_case(M + K, M, K, b_all)
@@ -266,15 +266,59 @@ def test_infonce_vs_oracle(fx, impl, M, K, rpg, b_all):
     assert _rel(qd.grad.cpu(), gref) < tol, _rel(qd.grad.cpu(), gref)
 
 
-def test_infonce_tc_matches_simt_no_grad(fx):
+@pytest.mark.parametrize("impl", ["tc", "fused", "fused_pass"])
+def test_infonce_tc_matches_simt_no_grad(fx, impl):
     M, K = 64, 32768
     q, kpos, queue, count = _make_case(9, M, K, 64)
     nq = fx.NegativeQueue(K)
     nq.load(queue, count, 0)
     with torch.no_grad():
-        a, _ = fx.infonce(q.cuda(), kpos.cuda(), nq, 32, 0.07, impl="tc")
-        b, _ = fx.infonce(q.cuda(), kpos.cuda(), nq, 32, 0.07, impl="simt")
+        a, ra = fx.infonce(q.cuda(), kpos.cuda(), nq, 32, 0.07, impl=impl)
+        b, rb = fx.infonce(q.cuda(), kpos.cuda(), nq, 32, 0.07, impl="simt")
     assert _rel(a[:, 0].cpu(), b[:, 0].cpu()) < 1e-3
+    assert float((ra[M:] - rb[M:]).abs().max()) <= 2            # hit counts: tf32 tensor-core vs fp32 products of the same operands
+
+
+@pytest.mark.parametrize("impl", ["tc", "fused"])
+@pytest.mark.parametrize("K", [262144, 1048576])
+def test_infonce_large_queue_vs_oracle(fx, impl, K):
+    """The far end of BASELINE configs[2] (queue sweep to 1 Mi negatives) against the CPU oracle: loss, hit counts, dq."""
+    M, rpg = 64, 32
+    q, kpos, queue, count = _make_case(K // 1024, M, K, 256)
+    ref, gref, logits = _oracle_infonce(q, kpos, queue, count, 0.07, rpg)
+    nq = fx.NegativeQueue(K)
+    nq.load(queue, count, (5 * 256) % K)
+    qd = q.cuda().requires_grad_(True)
+    out, rows = fx.infonce(qd, kpos.cuda(), nq, rpg, 0.07, impl=impl)
+    out[:, 0].sum().backward()
+    for gi, (loss, _, _) in enumerate(ref):
+        assert abs(float(out[gi, 0]) - float(loss)) <= 1e-3 * abs(float(loss))
+    neg, pos = logits[:, 1:], logits[:, :1]
+    close_call = ((neg - pos).abs() < 0.02).sum(1)
+    assert bool(((rows[M:].cpu() - (neg > pos).sum(1).float()).abs() <= close_call).all())
+    assert _rel(qd.grad.cpu(), gref) < 1e-3
+
+
+def test_infonce_fused_workspace_stays_zero_and_repeats(fx):
+    """mscl_infonce_fused accumulates into a zero workspace and must leave it zero (accumulator AND CTA counter), so
+    back-to-back calls agree to rounding (the fp32 adds in L2 are unordered) and never see stale sums."""
+    M, K = 96, 65536
+    q, kpos, queue, count = _make_case(3, M, K, 128)
+    nq = fx.NegativeQueue(K)
+    nq.load(queue, count, 0)
+    outs = []
+    for _ in range(4):
+        qd = q.cuda().requires_grad_(True)
+        out, rows = fx.infonce(qd, kpos.cuda(), nq, 32, 0.07, impl="fused")
+        out[:, 0].sum().backward()
+        outs.append((out.detach().clone(), rows.clone(), qd.grad.clone()))
+    ws = fx._fused_workspace(q.cuda().device, M)
+    torch.cuda.synchronize()
+    assert int(torch.count_nonzero(ws)) == 0
+    for o, r, g in outs[1:]:
+        assert _rel(o[:, 0], outs[0][0][:, 0]) < 1e-6
+        assert torch.equal(r[M:], outs[0][1][M:])                # hit counts are integers: exact whatever the add order
+        assert _rel(g, outs[0][2]) < 1e-5
 
 
 def test_infonce_fresh_queue_and_after_enqueue(fx):
@@ -297,7 +341,7 @@ def test_infonce_fresh_queue_and_after_enqueue(fx):
         nq.enqueue(keys.cuda())
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("impl", ["simt", "tc", "fused", "fused_pass"])
 def test_infonce_positive_key_present_in_queue(fx, impl):
     """The rf term of MSCLWithAug reads the flow queue right after k_flow was enqueued (mscl.py:239-248):
     every row finds its own positive key among the negatives, scored pos*0.99999.  The reference ranks it
