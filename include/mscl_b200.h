@@ -235,16 +235,20 @@ int mscl_infonce_finalize(const float *d_qpack, const float *d_kpos,
 int mscl_infonce_bwd(const float *d_dq_unit, const float *d_gout, int32_t M,
                      int32_t rows_per_group, float *d_dq, mscl_stream_t stream);
 
-/* K1, single-launch form (csrc/infonce_fused.cu): prep + pass + cross-CTA reduction + finalize of the block above in ONE
+/* K1, single-launch form (csrc/infonce_fused.cu): prep + pass + statistics reduction + finalize of the block above in ONE
  * kernel.  Same replaced reference lines (moco.py:481-498, heads/moco_head.py:38-77, heads/moco_head_v2.py:38-100,
  * losses/cross_entropy_loss.py:134-138, core/evaluation/accuracy.py:130-149) and the same formulas; the differences:
  *  - q / kpos are the raw fp32 rows [M, 128] (no qpack): pos2, shift2 and the tf32 rounding of q happen in the kernel;
  *  - the per-key scale 0.99999^(n_enq - birth_j) / T * log2(e) is computed from d_birth / d_qstate tile by tile (no dscale);
- *  - every CTA adds its partial rows into ONE accumulator with a TMA reduce-add (fp32 adds performed in L2, order not
- *    fixed: reproducible to rounding, not bit for bit -- the slab form above is); the last CTA to finish turns the
- *    accumulator into d_row_loss / d_dq_unit / d_group_out (same meaning as mscl_infonce_finalize).
- * d_ws: float [M*132 + 4] workspace (accumulator + CTA counter).  It must be ZERO before the first call; the kernel
- * leaves it zero.  One workspace per stream: two calls that may run concurrently must not share it.
+ *  - the row statistics (sum-exp, hit count) of all CTAs are added into d_ws with red.global.add (the float sum-exp in no
+ *    fixed order: the loss is reproducible to rounding, the hit counts exactly); the last CTA to finish turns them into
+ *    d_row_loss / d_group_out (same meaning as mscl_infonce_finalize) and d_rowaux;
+ *  - the O partials stay per-CTA slabs d_part [n_part, M, 132] (written only when with_grad); mscl_infonce_bwd_slabs sums
+ *    them in a fixed order when autograd asks for the gradient:
+ *        d_dq[i] = d_gout[group(i)] * ( ck_i * kpos_i + co_i * sum_p part[p][i][0:128] ),   (ck_i, co_i) = d_rowaux[i][2:4].
+ * d_ws: float [16*M*4 + 4] workspace (16 copies of the statistics accumulator + CTA counter).  It must be ZERO before the first call; the
+ * kernel leaves it zero.  One workspace per stream: two calls that may run concurrently must not share it.
+ * d_rowaux: float [M, 4] = pos2, shift2, ck, co per row.
  * n_part: CTAs along the keys (x ceil(M/128) row blocks), from mscl_infonce_fused_parts.
  * flags: MSCL_INFONCE_EARLY_PREFETCH -- the queue was NOT written by the launch immediately preceding this one on the
  * stream, so its tiles may be requested before the programmatic-dependent-launch wait.
@@ -253,13 +257,15 @@ int mscl_infonce_bwd(const float *d_dq_unit, const float *d_gout, int32_t M,
 int mscl_infonce_fused(const float *d_q, const float *d_kpos, int32_t M, const float *d_queue_tf32,
                        const int32_t *d_birth, const int64_t *d_qstate, int64_t K_local, float inv_T,
                        float key_norm_bound, const int32_t *d_dup_slot, int32_t dup_age, float *d_ws,
-                       int32_t n_part, int32_t rows_per_group, int32_t with_grad, int32_t flags,
-                       float *d_row_loss, float *d_dq_unit, float *d_group_out, mscl_stream_t stream);
+                       float *d_part, int32_t n_part, int32_t rows_per_group, int32_t with_grad, int32_t flags,
+                       float *d_row_loss, float *d_rowaux, float *d_group_out, mscl_stream_t stream);
+int mscl_infonce_bwd_slabs(const float *d_part, int32_t n_part, int32_t M, const float *d_kpos, const float *d_rowaux,
+                           const float *d_gout, int32_t rows_per_group, float *d_dq, mscl_stream_t stream);
 /* The pass alone in the same form, for the sharded queue: d_qpack [M, 132] is the gathered table mscl_infonce_prep fills
- * on every rank, d_acc float [M, 132] receives the sums (O | sum-exp | count) by reduce-add and must be ZERO on entry;
- * mscl_infonce_reduce_scatter (n_part = 1) and mscl_infonce_finalize follow as before. */
+ * on every rank; d_part float [n_part, M, 132] receives the per-CTA slabs exactly as mscl_infonce_partial writes them
+ * (mscl_infonce_reduce_scatter / mscl_infonce_finalize follow as before), n_part from mscl_infonce_fused_parts. */
 int mscl_infonce_pass(const float *d_qpack, int32_t M, const float *d_queue_tf32, const int32_t *d_birth,
-                      const int64_t *d_qstate, int64_t K_local, int64_t shard_begin, float inv_T, float *d_acc,
+                      const int64_t *d_qstate, int64_t K_local, int64_t shard_begin, float inv_T, float *d_part,
                       int32_t n_part, int32_t with_grad, int32_t flags, mscl_stream_t stream);
 int mscl_infonce_fused_parts(int32_t M, int64_t K_local, int32_t num_sms);
 

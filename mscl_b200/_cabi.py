@@ -41,8 +41,9 @@ PROTOTYPES = {
     "mscl_infonce_reduce": [c_ptr, c_int, c_int, c_ptr, c_ptr],
     "mscl_infonce_finalize": [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_f32, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "mscl_infonce_bwd": [c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr],
-    "mscl_infonce_fused": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_int, c_ptr, c_int, c_int, c_int,
-                           c_int, c_ptr, c_ptr, c_ptr, c_ptr],
+    "mscl_infonce_fused": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_int, c_ptr, c_ptr, c_int, c_int,
+                           c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
+    "mscl_infonce_bwd_slabs": [c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr],
     "mscl_infonce_pass": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_ptr, c_int, c_int, c_int, c_ptr],
     "mscl_infonce_fused_parts": [c_int, c_i64, c_int],
     "mscl_gather_rows": [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr],

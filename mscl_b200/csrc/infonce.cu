@@ -287,9 +287,55 @@ infonce_bwd_kernel(const float *__restrict__ dq_unit, const float *__restrict__ 
   dq[(int64_t)i * kC + c] = dq_unit[(int64_t)i * kC + c] * __ldg(gout + i / rows_per_group);
 }
 
+// Backward of the single-launch form: dq_i = gout[group(i)] * (ck_i kpos_i + co_i sum_p part[p][i][0:128]).
+// One CTA per query row, kFinGroups groups of 128 threads (thread <-> channel): group g sums the slabs p = g, g+G, ...
+// with all its loads in flight at once, the groups are combined through shared memory in a fixed order
+// (bit-reproducible given the slabs).
+__global__ void __launch_bounds__(128 * kFinGroups)
+infonce_bwd_slabs_kernel(const float *__restrict__ part, int n_part, int M, const float *__restrict__ kpos,
+                         const float *__restrict__ rowaux, const float *__restrict__ gout, int rows_per_group,
+                         float *__restrict__ dq) {
+  const int i = blockIdx.x, c = threadIdx.x & 127, g = threadIdx.x >> 7;
+  const int64_t slab = (int64_t)M * kLd;
+  const float *src = part + (int64_t)i * kLd;
+  __shared__ float s_o[kFinGroups][128];
+  float o = 0.f;
+  pdl_wait();      // may have been launched early behind the forward kernel (back-to-back in benchmarks)
+  pdl_trigger();
+  for (int p0 = g; p0 < n_part; p0 += kFinGroups * kFinMaxPer) {
+    float v[kFinMaxPer];
+#pragma unroll
+    for (int u = 0; u < kFinMaxPer; ++u) {
+      const int p = p0 + u * kFinGroups;
+      v[u] = p < n_part ? __ldg(src + p * slab + c) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kFinMaxPer; ++u) o += v[u];
+  }
+  s_o[g][c] = o;
+  __syncthreads();
+  if (g != 0) return;
+  o = 0.f;
+#pragma unroll
+  for (int k = 0; k < kFinGroups; ++k) o += s_o[k][c];
+  const float4 ra = __ldg(reinterpret_cast<const float4 *>(rowaux) + i);
+  dq[(int64_t)i * kC + c] = __ldg(gout + i / rows_per_group) * fmaf(ra.z, kpos[(int64_t)i * kC + c], ra.w * o);
+}
+
 }  // namespace mscl
 
 extern "C" {
+
+int mscl_infonce_bwd_slabs(const float *d_part, int32_t n_part, int32_t M, const float *d_kpos, const float *d_rowaux,
+                           const float *d_gout, int32_t rows_per_group, float *d_dq, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_part && d_kpos && d_rowaux && d_gout && d_dq, "null pointer");
+  MSCL_CHECK_ARG(M > 0 && n_part > 0 && rows_per_group > 0 && M % rows_per_group == 0,
+                 "M=%d must be a multiple of rows_per_group=%d (n_part=%d)", M, rows_per_group, n_part);
+  MSCL_CHECK_ARG(((uintptr_t)d_rowaux & 15) == 0, "rowaux must be 16-byte aligned");
+  MSCL_CUDA(mscl::launch_pdl(mscl::infonce_bwd_slabs_kernel, dim3(M), dim3(128 * mscl::kFinGroups), 0, mscl::as_stream(stream),
+                             d_part, n_part, M, d_kpos, d_rowaux, d_gout, rows_per_group, d_dq));
+  return MSCL_OK;
+}
 
 int mscl_infonce_prep(const float *d_q, const float *d_kpos, int32_t M,
                       const int32_t *d_birth, const int64_t *d_qstate, int64_t K_local,

@@ -16,11 +16,14 @@
 //    else happens (was 128 of <= 256 KB).  Ring 2 (the MN-major copy for the second GEMM, L2 hits) has two 64-key slots.
 //  * no prep launch: the softmax warps compute pos2 / shift2 from q and kpos (warp per row, coalesced), round q to tf32
 //    on its way into TMEM, and a 12th warp turns birth[] into the per-key scale 0.99999^age / T * log2(e) tile by tile.
-//  * no slabs, no finalize launch: each CTA adds its [rows x 132] partial (O | sum-exp | count) into ONE accumulator
-//    with a single TMA reduce-add (cp.reduce.async.bulk.tensor, fp32 add performed in L2); the last CTA to finish
-//    (device counter) turns the accumulator into losses, top-k flags and dq, and leaves accumulator and counter zeroed
-//    for the next call.  The order of the fp32 adds in L2 is not fixed: results are reproducible to rounding only
-//    (the slab form stays available where bit-reproducibility matters).
+//  * no finalize launch: the row statistics (sum-exp, hit count: 8 bytes per row and CTA) are added into one small
+//    accumulator with red.global.add, and the last CTA to finish (device counter) turns them into losses, top-k flags,
+//    group means and the two per-row gradient coefficients -- on the four warps that are idle by then, while the
+//    softmax warps of the same CTA are still storing O.  The O partials (48 KB per CTA) are NOT reduced in the forward
+//    launch: a first version added them into one accumulator with a TMA reduce-add and measured ~1 TB/s of fp32 adds
+//    in L2, i.e. 7 us for the 7.5 MB of K = 65536 / M = 96 (profiles/r02_k1_fused_v0_timeline.txt).  They are stored
+//    as per-CTA slabs (one TMA store each, off the critical path) and summed in a fixed order by the backward kernel
+//    (mscl_infonce_bwd_slabs), which needs them only when autograd asks for dq.
 //
 // CTA = 384 threads, one CTA per SM:
 //   warp 0      ring-1 TMA producer (queue tiles from HBM, the Q tile)
@@ -29,6 +32,8 @@
 //   warp 10     ring-2 TMA producer
 //   warp 11     per-key scale (birth -> dscale) into a 2-deep shared-memory ring
 // TMEM (512 columns): O [0,128) | S/P double buffer [128,384) | Q [384,512).
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace mscl {
@@ -47,22 +52,21 @@ constexpr uint32_t kPairBytes = kTile * kC * 4;        // 65536
 constexpr uint32_t kPairSlab = kTile * 128;            // bytes per channel block of a pair tile
 constexpr uint32_t kUnitBytes = kUnit * kC * 4;        // 32768
 constexpr uint32_t kUnitSlab = kUnit * 128;
-constexpr uint32_t kQBytes = kRows * kC * 4;           // 65536
-constexpr uint32_t kQSlab = kRows * 128;
 
 // shared memory map (the dynamic segment is 1024-byte aligned: checked at kernel entry)
 constexpr uint32_t kOffPair = 0;                               // 2 x 64 KB pair slots; the [128][132] output tile at the end
 constexpr uint32_t kOffSingle = kOffPair + 2 * kPairBytes;     // 32 KB: the half tile
 constexpr uint32_t kOffW2 = kOffSingle + kUnitBytes;           // ring 2: 2 x 32 KB; the Q tile before the first ring-2 load
 constexpr uint32_t kOffBar = kOffW2 + kStages2 * kUnitBytes;
-constexpr uint32_t kNumBars = 2 + 2 + 1 + 2 * kStages2 + 1 + 2 + 2 + 1 + 1 + 1 + 2 + 2;
+constexpr uint32_t kNumBars = 2 + 2 + 1 + 2 * kStages2 + 1 + 2 + 2 + 1 + 1 + 1 + 2 + 2;   // (the q_load slot is now "prologue loads issued")
+constexpr int kStatCopies = 16;       // the row statistics are spread over this many accumulator copies (see the epilogue)
 constexpr uint32_t kOffTmemPtr = kOffBar + 8 * kNumBars;
 constexpr uint32_t kOffFlag = kOffTmemPtr + 8;
 constexpr uint32_t kOffDs = kOffBar + 256;                     // [2][128] floats: per-key scales of the tile in flight
 constexpr uint32_t kOffRow = kOffDs + 2 * kTile * 4;           // [128] float2 (pos2, shift2); later [2][128] sum / count
 constexpr uint32_t kSmemBytes = kOffRow + kRows * 8;
 static_assert(kOffFlag + 8 <= kOffDs, "barrier block overflows");
-static_assert(kQBytes <= kStages2 * kUnitBytes, "the Q tile is staged through ring 2");
+static_assert(kRows * 512 <= kStages2 * kUnitBytes, "the Q tile is staged through ring 2");
 static_assert(kRows * kLd * 4 <= 2 * kPairBytes, "the output tile is staged through the pair slots");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 
@@ -84,9 +88,10 @@ struct Params {
   const int32_t *birth;      // [K_local]
   const int64_t *qstate;     // {ptr, n_enq, ..}
   const int32_t *dup_slot;   // FUSED: [M] or null
-  float *acc;                // [M][132] accumulator (+ the CTA counter right behind it when FUSED)
-  float *row_loss;           // FUSED outputs
-  float *dq_unit;
+  float *ws;                 // FUSED: [kStatCopies][M][4] (sum-exp, count, 0, 0) accumulators + the CTA counter behind them
+  float *part;               // [n_part][M][132] per-CTA slabs: O | sum-exp | count | 0 | 0 (null when FUSED && !GRAD)
+  float *row_loss;           // FUSED outputs: [2M] loss_i, then #{negatives above the positive}
+  float *rowaux;             // FUSED: [M][4] pos2, shift2, ck, co  (dq_i = gout * (ck k_i + co sum_slabs O_i))
   float *group_out;
   int64_t K_local;
   int64_t shard_begin;
@@ -98,9 +103,20 @@ struct Params {
   float key_norm_bound;
 };
 
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
-               "r"(src), "r"(c0), "r"(c1)
+// A coherent (not .nc) volatile load: neither the compiler nor ptxas moves it across a barrier, so it is issued where
+// it is written (the read-only path's loads are sunk to their first use, microseconds later under load).
+__device__ __forceinline__ float4 ld_now(const float4 *p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 
@@ -147,81 +163,59 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[32], const float4 *d
   cnt += (int)((c4[0] + c4[1]) + (c4[2] + c4[3]));
 }
 
-// The last CTA: accumulator -> per-row loss / top-k count / dq, per-group means; accumulator and counter left zero.
-// (formulas: infonce.cu::infonce_finalize_kernel)
-template <bool GRAD>
-__device__ __forceinline__ void finalize_rows(const Params &p, unsigned *counter) {
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float sc = p.inv_T * kLog2e;
+// The last CTA, on its four idle warps (128 threads): row statistics -> per-row loss / top-k count / gradient
+// coefficients, per-group means; accumulator and counter left zero.  (formulas: infonce.cu::infonce_finalize_kernel)
+//   d loss_i / d q_i = gout * [ ((p0 - 1)/T + w_dup inv_Z ln2) k_i + inv_Z ln2 sum_slabs O_i ] / rows_per_group
+__device__ __forceinline__ void finalize_stats(const Params &p, int tid, unsigned *counter, float *sm_rows, int sm_cap) {
   const float inv_rows = 1.0f / (float)p.rows_per_group;
   const float dsc = exp2f((float)p.dup_age * kLog2Decay);
-  constexpr int kU = 4;
-  for (int r0 = wid; r0 < p.M; r0 += kWarps * kU) {
-    float4 o[kU], st[kU], a[kU], kk[kU];
-    int dup[kU];
+  for (int row = tid; row < p.M; row += 128) {
+    float4 *arow = reinterpret_cast<float4 *>(p.rowaux) + row;
+    float4 st[kStatCopies];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int row = r0 + u * kWarps;
-      dup[u] = -1;
-      if (row < p.M) {
-        const float4 *arow = reinterpret_cast<const float4 *>(p.acc + (int64_t)row * kLd);
-        o[u] = __ldcg(arow + lane);
-        st[u] = __ldcg(arow + 32);
-        a[u] = __ldg(reinterpret_cast<const float4 *>(p.q + (int64_t)row * kC) + lane);
-        kk[u] = __ldg(reinterpret_cast<const float4 *>(p.kpos + (int64_t)row * kC) + lane);
-        if (p.dup_slot != nullptr) dup[u] = __ldg(p.dup_slot + row);
-      }
+    for (int c = 0; c < kStatCopies; ++c) st[c] = __ldcg(reinterpret_cast<float4 *>(p.ws) + (int64_t)c * p.M + row);
+    const float4 ra = __ldcg(arow);
+    const int dup = p.dup_slot != nullptr ? __ldg(p.dup_slot + row) : -1;
+    float sum = 0.f, cnt = 0.f, w = 0.f;
+#pragma unroll
+    for (int c = 0; c < kStatCopies; ++c) {
+      __stcg(reinterpret_cast<float4 *>(p.ws) + (int64_t)c * p.M + row, make_float4(0.f, 0.f, 0.f, 0.f));
+      sum += st[c].x;
+      cnt += st[c].y;
     }
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int row = r0 + u * kWarps;
-      if (row >= p.M) continue;                      // warp-uniform
-      float4 *arow = reinterpret_cast<float4 *>(p.acc + (int64_t)row * kLd);
-      __stcg(arow + lane, make_float4(0.f, 0.f, 0.f, 0.f));
-      if (lane == 0) __stcg(arow + 32, make_float4(0.f, 0.f, 0.f, 0.f));
-      float d = a[u].x * kk[u].x + a[u].y * kk[u].y + a[u].z * kk[u].z + a[u].w * kk[u].w;
-      float ss = a[u].x * a[u].x + a[u].y * a[u].y + a[u].z * a[u].z + a[u].w * a[u].w;
-      d = warp_sum(d);
-      ss = warp_sum(ss);
-      const float pos2 = d * sc, shift2 = sqrtf(ss) * p.key_norm_bound * sc;
-      float sum = st[u].x, cnt = st[u].y;
-      float4 ov = o[u];
-      if (dup[u] >= 0) {      // the queue entry that IS this row's positive: exact fp32 terms (see infonce.cu)
-        if (pos2 * dsc > pos2) cnt += 1.f;
-        const float e_dup = exp2f(fmaf(pos2, dsc, -shift2));
-        sum += e_dup;
-        const float w = e_dup * (dsc * p.inv_T * kLog2e);
-        ov.x = fmaf(w, kk[u].x, ov.x);
-        ov.y = fmaf(w, kk[u].y, ov.y);
-        ov.z = fmaf(w, kk[u].z, ov.z);
-        ov.w = fmaf(w, kk[u].w, ov.w);
-      }
-      const float e0 = exp2f(pos2 - shift2);
-      const float Z = e0 + sum;
-      const float inv_Z = 1.0f / Z;
-      const float p0 = e0 * inv_Z;
-      if (GRAD) {
-        float4 g;
-        g.x = ((p0 - 1.0f) * kk[u].x * p.inv_T + ov.x * inv_Z * kLn2) * inv_rows;
-        g.y = ((p0 - 1.0f) * kk[u].y * p.inv_T + ov.y * inv_Z * kLn2) * inv_rows;
-        g.z = ((p0 - 1.0f) * kk[u].z * p.inv_T + ov.z * inv_Z * kLn2) * inv_rows;
-        g.w = ((p0 - 1.0f) * kk[u].w * p.inv_T + ov.w * inv_Z * kLn2) * inv_rows;
-        reinterpret_cast<float4 *>(p.dq_unit + (int64_t)row * kC)[lane] = g;
-      }
-      if (lane == 0) {
-        p.row_loss[row] = (shift2 + log2f(Z) - pos2) * kLn2;
-        p.row_loss[p.M + row] = cnt;
-      }
+    const float pos2 = ra.x, shift2 = ra.y;
+    if (dup >= 0) {      // the queue entry that IS this row's positive: exact fp32 terms (see infonce.cu)
+      if (pos2 * dsc > pos2) cnt += 1.f;
+      const float e_dup = exp2f(fmaf(pos2, dsc, -shift2));
+      sum += e_dup;
+      w = e_dup * (dsc * p.inv_T * kLog2e);
+    }
+    const float e0 = exp2f(pos2 - shift2);
+    const float Z = e0 + sum;
+    const float inv_Z = 1.0f / Z;
+    const float p0 = e0 * inv_Z;
+    const float co = inv_Z * kLn2 * inv_rows;
+    const float ck = (p0 - 1.0f) * p.inv_T * inv_rows + w * co;
+    __stcg(arow, make_float4(pos2, shift2, ck, co));
+    const float loss = (shift2 + log2f(Z) - pos2) * kLn2;
+    p.row_loss[row] = loss;
+    p.row_loss[p.M + row] = cnt;
+    if (2 * p.M <= sm_cap) {        // the group stage reads them back from shared memory (no second L2 round trip)
+      sm_rows[row] = loss;
+      sm_rows[p.M + row] = cnt;
     }
   }
-  __syncthreads();
+  __threadfence_block();
+  asm volatile("bar.sync 2, 128;" ::: "memory");
+  const bool from_smem = 2 * p.M <= sm_cap;
+  const int wid = tid >> 5, lane = tid & 31;
   const int n_groups = p.M / p.rows_per_group;
-  for (int g = wid; g < n_groups; g += kWarps) {
+  for (int g = wid; g < n_groups; g += 4) {
     float sl = 0.f, s1 = 0.f, s5 = 0.f;
     for (int r = lane; r < p.rows_per_group; r += 32) {
       const int row = g * p.rows_per_group + r;
-      sl += __ldcg(p.row_loss + row);
-      const float k = __ldcg(p.row_loss + p.M + row);
+      sl += from_smem ? sm_rows[row] : __ldcg(p.row_loss + row);
+      const float k = from_smem ? sm_rows[p.M + row] : __ldcg(p.row_loss + p.M + row);
       s1 += (k < 1.f) ? 1.f : 0.f;
       s5 += (k < 5.f) ? 1.f : 0.f;
     }
@@ -231,14 +225,14 @@ __device__ __forceinline__ void finalize_rows(const Params &p, unsigned *counter
     if (lane == 0)
       *reinterpret_cast<float4 *>(p.group_out + g * 4) = make_float4(sl * inv_rows, s1 * inv_rows, s5 * inv_rows, 0.f);
   }
-  if (threadIdx.x == 0) *counter = 0u;
+  if (tid == 0) *counter = 0u;
 }
 
 template <bool GRAD, bool FUSED>
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_wh,
-                     const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_q,
-                     const __grid_constant__ CUtensorMap tmap_acc, const __grid_constant__ Params p) {
+                     const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_part,
+                     const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *gbase = smem_raw;
   const uint32_t base = smem_u32(smem_raw);
@@ -246,7 +240,6 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
   const uint32_t sPair = base + kOffPair;
   const uint32_t sSingle = base + kOffSingle;
   const uint32_t sW2 = base + kOffW2;
-  const uint32_t sQ = sW2;
   const uint32_t bar0 = base + kOffBar;
   auto bar_full1 = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty1 = [&](int s) { return bar0 + 8u * (2 + s); };
@@ -288,9 +281,8 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     TLF(0);
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_wh) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
-    if (GRAD) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_acc) : "memory");
+    if (GRAD) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_part) : "memory");
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_full1(s), 1);
       mbar_init(bar_empty1(s), 1);
@@ -308,7 +300,7 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       mbar_init(bar_dfree(b), kSoftmaxWarps);
     }
     mbar_init(bar_ofull, 1);
-    mbar_init(bar_qload, 1);
+    mbar_init(bar_qload, kSoftmaxWarps);
     mbar_init(bar_qfree, kSoftmaxWarps);
     *last_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -334,30 +326,31 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         mbar_arrive_expect_tx(bar_full1(s), kPairBytes);
         tma_load_3d(sPair + s * kPairBytes, &tmap_w, bar_full1(s), 0, (int)(key_begin + hasH * kUnit + (int64_t)pi * kTile), 0);
       };
-      auto load_first = [&]() {
+      auto load_first = [&](int n_pairs) {
         if (hasH) {
           mbar_arrive_expect_tx(bar_fullH, kUnitBytes);
           tma_load_3d(sSingle, &tmap_wh, bar_fullH, 0, (int)key_begin, 0);
         }
-        for (int pi = 0; pi < 2 && pi < np; ++pi) load_pair(pi);
-      };
-      auto load_q = [&]() {   // rows >= M are zero-filled by the TMA unit
-        mbar_arrive_expect_tx(bar_qload, kQBytes);
-        tma_load_3d(sQ, &tmap_q, bar_qload, 0, row0, 0);
+        for (int pi = 0; pi < n_pairs && pi < np; ++pi) load_pair(pi);
       };
       // kFlagEarlyPrefetch: the caller guarantees the queue was not written by the launch this grid may overlap with
       // (programmatic dependent launch), so its tiles may be requested before the dependency wait.
+      // The 96 KB of q / kpos rows every CTA needs come through the same L2 -> SM path as the queue tiles and were
+      // measured to take ~4 us when issued behind 160 KB of tile requests: the bulk of the tile requests is held back
+      // until the softmax warps have issued those loads (bar_qload).
       if (p.flags & kFlagEarlyPrefetch) {
-        load_first();
+        load_first(0);       // the half tile only
         pdl_wait();
         pdl_trigger();       // only after the wait: a dependent of THIS grid may then assume this grid's predecessors are done
-        load_q();
+        mbar_wait(bar_qload, 0);
+        for (int pi = 0; pi < 2 && pi < np; ++pi) load_pair(pi);
       } else {
         pdl_wait();
         pdl_trigger();
-        load_q();
-        load_first();
+        mbar_wait(bar_qload, 0);
+        load_first(2);
       }
+      TLF(18);
       for (int pi = 2; pi < np; ++pi) load_pair(pi);
       TLF(4);
     }
@@ -374,6 +367,12 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         tma_load_3d(sW2 + s * kUnitBytes, &tmap_w2, bar_full2(s), 0, (int)(key_begin + (int64_t)u * kUnit), 0);
       }
     }
+#ifdef MSCL_TC_TIMELINE
+    else if (lane == 31 && nt > 0) {      // an idle lane watches the first MMA1 complete
+      mbar_wait(bar_sfull(0), 0);
+      TLF(15);
+    }
+#endif
     __syncwarp();
   } else if (warp == 3 + kSoftmaxWarps) {
     // ===================== per-key scale: 0.99999^(n_enq - birth_j) / T * log2(e), 0 for keys outside the tile ======
@@ -402,6 +401,9 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       reinterpret_cast<float4 *>(ds_smem + b * kTile)[lane] = make_float4(v[0], v[1], v[2], v[3]);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dfull(b));
+#ifdef MSCL_TC_TIMELINE
+      if (lane == 0 && i == 0) TLF(19);
+#endif
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -443,9 +445,14 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       };
       mbar_wait(bar_q, 0);
       tc_fence_after();
+      TLF(28);
       if (nt > 0) issue_mma1(0);
+      TLF(29);
       for (int i = 0; i < nt; ++i) {
         if (i + 1 < nt) issue_mma1(i + 1);
+#ifdef MSCL_TC_TIMELINE
+        if (i < 2) TLF(30 + i);
+#endif
         mbar_wait(bar_pfull(i & 1), (uint32_t)(i >> 1) & 1u);
         tc_fence_after();
         if (GRAD) {
@@ -488,32 +495,104 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     float shift2 = 0.f, pos2 = INFINITY;
     int64_t dup_local = -1;
     pdl_wait();
+    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    float2 *rowinfo = reinterpret_cast<float2 *>(gbase + kOffRow);
+    const float sc = p.inv_T * kLog2e;
+    // ---- Q tile: global -> shared (warp per row: rows sw, sw+8, ..., one coalesced 512-byte load each) -> TMEM (thread per
+    // row).  Staged in the ring-2 area, dense 512-byte rows whose 16-byte chunks are XOR-swizzled with the row index, so
+    // that both the row-wise writes and the thread-per-row reads are free of bank conflicts.  (A TMA load of this tile
+    // queues behind the queue tiles in the SM's TMA unit and lands microseconds late.)
+    uint8_t *qs = gbase + kOffW2;
+    const int q_ld = FUSED ? kC : kLd;
+    // Every global load of the prologue is issued NOW, before the queue tiles flood the memory system (a load issued
+    // 2 us later was measured to take ~3 us): q rows by cp.async straight into shared memory, positives into registers.
+    constexpr int kRW = kRows / kSoftmaxWarps;     // 16 rows per warp
+#pragma unroll
+    for (int u = 0; u < kRW; ++u) {
+      const int rl = sw + u * kSoftmaxWarps;
+      const uint32_t dst = smem_u32(qs + rl * 512 + ((lane ^ (rl & 31)) << 4));
+      if (row0 + rl < p.M) {
+        const float *src = p.q + (int64_t)(row0 + rl) * q_ld + lane * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      } else {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "f"(0.f) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    float4 rb[kRW];
     if (FUSED) {
-      // pos2 = q.k / T * log2e, shift2 = |q| * bound / T * log2e: one warp per row, 128-bit coalesced loads
-      float2 *rowinfo = reinterpret_cast<float2 *>(gbase + kOffRow);
-      const float sc = p.inv_T * kLog2e;
 #pragma unroll
-      for (int g = 0; g < kRows / kSoftmaxWarps / 4; ++g) {
-        float4 a[4], b[4];
+      for (int u = 0; u < kRW; ++u) {
+        const int rr = row0 + sw + u * kSoftmaxWarps;
+        rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rr < p.M) rb[u] = ld_now(reinterpret_cast<const float4 *>(p.kpos + (int64_t)rr * kC) + lane);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_qload);         // this warp's prologue loads are in flight: the tile requests may follow
+    // pos2 = q.k / T * log2e and shift2 = |q| * bound / T * log2e, one warp per row
+    auto rowinfo_reduce = [&]() {
+      // vals[u] = this lane's part of q.k of row slot u, vals[16 + u] = of |q|^2
+      float vals[2 * kRW];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int rr = row0 + sw + (g * 4 + u) * kSoftmaxWarps;
-          a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rr < p.M) {
-            a[u] = __ldg(reinterpret_cast<const float4 *>(p.q + (int64_t)rr * kC) + lane);
-            b[u] = __ldg(reinterpret_cast<const float4 *>(p.kpos + (int64_t)rr * kC) + lane);
-          }
-        }
+      for (int u = 0; u < kRW; ++u) {
+        const int rl = sw + u * kSoftmaxWarps;
+        const float4 a = *reinterpret_cast<const float4 *>(qs + rl * 512 + ((lane ^ (rl & 31)) << 4));
+        vals[u] = a.x * rb[u].x + a.y * rb[u].y + a.z * rb[u].z + a.w * rb[u].w;
+        vals[kRW + u] = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+      }
+      if (threadIdx.x == 64) TLF(12);
+      // transpose-reduce: 32 values x 32 lanes -> lane l ends up with the warp total of value l, in 31 shuffles (a
+      // butterfly per value would be 160); at each level a lane hands over the half of its values its partner keeps
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int rl = sw + (g * 4 + u) * kSoftmaxWarps;
-          float d = a[u].x * b[u].x + a[u].y * b[u].y + a[u].z * b[u].z + a[u].w * b[u].w;
-          float ss = a[u].x * a[u].x + a[u].y * a[u].y + a[u].z * a[u].z + a[u].w * a[u].w;
-          d = warp_sum(d);
-          ss = warp_sum(ss);
-          if (lane == 0) rowinfo[rl] = make_float2(d * sc, sqrtf(ss) * p.key_norm_bound * sc);
+      for (int s = 16; s > 0; s >>= 1) {
+        const bool up = lane & s;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+          const float lo = vals[i], hi = vals[i + s];
+          const float recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, s);
+          vals[i] = (up ? hi : lo) + recv;
         }
       }
+      // lane u < 16 holds q.k of row slot u, lane 16 + u its |q|^2
+      const float ss = __shfl_down_sync(0xffffffffu, vals[0], 16);
+      const int rl = sw + lane * kSoftmaxWarps;
+      if (lane < kRW && row0 + rl < p.M) {
+        const float2 ri = make_float2(vals[0] * sc, sqrtf(ss) * p.key_norm_bound * sc);
+        rowinfo[rl] = ri;
+        // one CTA per row block publishes the pair for the finalising CTA
+        if (blockIdx.x == 0) *reinterpret_cast<float2 *>(p.rowaux + (int64_t)(row0 + rl) * 4) = ri;
+      }
+    };
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
+    {   // this row of Q: smem -> tf32 -> TMEM columns [kColQ + 64*half, +64): the A operand of every MMA1
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cb = half * 2 + hh;
+        uint32_t v[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 f = *reinterpret_cast<const float4 *>(qs + r * 512 + (((cb * 8 + c) ^ (r & 31)) << 4));
+          if (FUSED) f = to_tf32_rn(f);
+          v[c * 4 + 0] = __float_as_uint(f.x);
+          v[c * 4 + 1] = __float_as_uint(f.y);
+          v[c * 4 + 2] = __float_as_uint(f.z);
+          v[c * 4 + 3] = __float_as_uint(f.w);
+        }
+        TC_ST32(lane_base + kColQ + cb * 32, v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_q);
+      if (threadIdx.x == 64) TLF(2);
+    }
+    if (FUSED) rowinfo_reduce();
+    if (threadIdx.x == 64) TLF(13);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_qfree);         // the staging area goes back to ring 2
+    if (FUSED) {
       asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
       if (row_ok) {
         const float2 ri = rowinfo[r];
@@ -531,42 +610,17 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       const int dup = __float_as_int(x.z);
       if (dup >= 0) dup_local = (int64_t)dup - p.shard_begin;
     }
-    const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-    {   // this row of Q: smem (TMA, swizzled) -> tf32 -> TMEM columns [kColQ + 64*half, +64): the A operand of every MMA1
-      mbar_wait(bar_qload, 0);
-      const uint8_t *qs = gbase + kOffW2;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int cb = half * 2 + hh;
-        const uint8_t *rowp = qs + cb * kQSlab + r * 128;
-        uint32_t v[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 f = *reinterpret_cast<const float4 *>(rowp + ((c ^ (r & 7)) << 4));
-          if (FUSED) f = to_tf32_rn(f);
-          v[c * 4 + 0] = __float_as_uint(f.x);
-          v[c * 4 + 1] = __float_as_uint(f.y);
-          v[c * 4 + 2] = __float_as_uint(f.z);
-          v[c * 4 + 3] = __float_as_uint(f.w);
-        }
-        TC_ST32(lane_base + kColQ + cb * 32, v);
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar_qfree);
-        mbar_arrive(bar_q);
-      }
-      if (threadIdx.x == 64) TLF(2);
-    }
     float sum = 0.f;
     int cnt = 0;
+    if (threadIdx.x == 64) TLF(14);
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
       const bool is_h = hasH && i == 0;
-      const int64_t key0 = step_key0(i) + half * kUnit;
-      const bool active = warp_ok && !(is_h && half == 1);
+      // a pair tile: this warp's 64 keys as two 32-key chunks; the half tile: one 32-key chunk per warp
+      const int koff = is_h ? half * 32 : half * kUnit;
+      const int nch = is_h ? 1 : 2;
+      const int64_t key0 = step_key0(i) + koff;
+      const bool active = warp_ok;
       mbar_wait(bar_dfull(b), (uint32_t)(i >> 1) & 1u);
       mbar_wait(bar_sfull(b), (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
@@ -574,14 +628,15 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       if (threadIdx.x == 64 && i < 8) TLF(8 + i);
 #endif
       if (active) {
-        const uint32_t taddr = lane_base + kColS + (uint32_t)b * kTile + half * kUnit;
-        const float4 *ds = reinterpret_cast<const float4 *>(ds_smem + b * kTile + half * kUnit);
+        const uint32_t taddr = lane_base + kColS + (uint32_t)b * kTile + koff;
+        const float4 *ds = reinterpret_cast<const float4 *>(ds_smem + b * kTile + koff);
         uint32_t v0[32], v1[32];
         TC_LD32(taddr, v0);
-        TC_LD32(taddr + 32, v1);
+        if (nch == 2) TC_LD32(taddr + 32, v1);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
+          if (ch >= nch) break;                    // warp-uniform
           const int64_t k0 = key0 + ch * 32;
           const int64_t left = key_end - k0;
           const int nvalid = left < 32 ? (left < 0 ? 0 : (int)left) : 32;
@@ -620,22 +675,38 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       sum += red[r];
       cnt += (int)red[kRows + r];
     }
+    if (FUSED) {
+      // hand the row statistics to the scale warp (idle by now): it adds them into the accumulator, takes this CTA's
+      // ticket and finalises if it is the last -- none of which the O epilogue below has to wait for
+      if (half == 0) {
+        red[r] = sum;
+        red[kRows + r] = (float)cnt;
+      }
+      asm volatile("bar.arrive 3, %0;" ::"r"(kSoftmaxWarps * 32 + 32) : "memory");
+    }
     if (GRAD) {
-      // [128][132] output tile (O | sum | count | 0 | 0) in the pair slots (every tile is consumed once o_full fires),
-      // then ONE TMA reduce-add into the accumulator; rows >= M are clipped by the TMA unit.
+      // [128][132] output tile (O | sum | count | 0 | 0) in the pair slots (every tile is consumed once o_full fires):
+      // thread <-> row out of TMEM, then warp <-> row out to this CTA's slab, 512 contiguous bytes per store instruction
+      // (16-byte stores straight from the row-per-thread registers are 3072 separate L2 requests per CTA: 2 us;
+      //  one TMA store of the tile: 1.5 us at the ~85 GB/s one SM's TMA unit moves)
       float *tile = reinterpret_cast<float *>(gbase + kOffPair);
       if (nt > 0) {
         mbar_wait(bar_ofull, 0);
         tc_fence_after();
       }
       if (threadIdx.x == 64) TLF(6);
-      if (warp_ok && nt > 0) {
+      if (warp_ok) {
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int cb = half * 2 + hh;
           uint32_t v[32];
-          TC_LD32(lane_base + kColO + cb * 32, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (nt > 0) {
+            TC_LD32(lane_base + kColO + cb * 32, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = 0u;
+          }
           float4 *dst = reinterpret_cast<float4 *>(tile + r * kLd + cb * 32);
 #pragma unroll
           for (int c = 0; c < 8; ++c)
@@ -644,57 +715,84 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         }
         if (half == 0) *reinterpret_cast<float4 *>(tile + r * kLd + kC) = make_float4(sum, (float)cnt, 0.f, 0.f);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
-      if (threadIdx.x == 64 && nt > 0) {
-        tma_reduce_add_2d(&tmap_acc, sPair, 0, row0);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // the adds have been performed
+      const int n_rows = p.M - row0 < kRows ? p.M - row0 : kRows;
+      float *slab = p.part + ((int64_t)blockIdx.x * p.M + row0) * kLd;
+      for (int rl = sw; rl < n_rows; rl += kSoftmaxWarps) {
+        const float4 *src = reinterpret_cast<const float4 *>(tile + rl * kLd);
+        float4 *dst = reinterpret_cast<float4 *>(slab + (int64_t)rl * kLd);
+        stg_stream(dst + lane, src[lane]);
+        if (lane == 0) stg_stream(dst + 32, src[32]);
       }
-    } else {
-      if (half == 0 && row_ok && nt > 0) {
-        atomicAdd(p.acc + (int64_t)row * kLd + kC, sum);
-        atomicAdd(p.acc + (int64_t)row * kLd + kC + 1, (float)cnt);
-      }
-      if (FUSED) {
-        __threadfence();
-        asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
+    } else if (!FUSED) {
+      float *prow = p.part + ((int64_t)blockIdx.x * p.M + row) * kLd;
+      if (half == 0 && row_ok) *reinterpret_cast<float4 *>(prow + kC) = make_float4(sum, (float)cnt, 0.f, 0.f);
+    }
+    if (threadIdx.x == 64) TLF(16);
+  }
+
+  if (FUSED && warp == 3 + kSoftmaxWarps) {
+    // row statistics -> one of kStatCopies small accumulators (148 same-address atomics serialise in L2 at ~13 ns each:
+    // 2 us when every CTA hits the same 2 floats per row; 16 copies make it ~10 adds per address), then this CTA's ticket
+    const float *red = reinterpret_cast<const float *>(gbase + kOffRow);
+    asm volatile("bar.sync 3, %0;" ::"r"(kSoftmaxWarps * 32 + 32) : "memory");
+    if (nt > 0) {
+#pragma unroll
+      for (int u = 0; u < kRows / 32; ++u) {
+        const int rl = lane + 32 * u;
+        if (row0 + rl < p.M) {
+          float *wrow = p.ws + ((int64_t)(blockIdx.x % kStatCopies) * p.M + row0 + rl) * 4;
+          atomicAdd(wrow, red[rl]);
+          atomicAdd(wrow + 1, red[kRows + rl]);
+        }
       }
     }
-    if (FUSED && threadIdx.x == 64) {
-      // release this CTA's adds, then count it; the last CTA finalises
-      __threadfence();
-      unsigned *counter = reinterpret_cast<unsigned *>(p.acc + (int64_t)p.M * kLd);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");      // the adds above are performed before the ticket below
+    __syncwarp();
+    if (lane == 0) {
+      unsigned *counter = reinterpret_cast<unsigned *>(p.ws + (int64_t)kStatCopies * p.M * 4);
       const unsigned done = atomicAdd(counter, 1u);
-      *last_flag = (done == gridDim.x * gridDim.y - 1u) ? 1 : 0;
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      *last_flag = (done == gridDim.x * gridDim.y - 1u) ? 2 : 1;
+      TLF(7);
+    }
+  }
+  if (FUSED && (warp < 2 || warp >= 2 + kSoftmaxWarps)) {
+    // the four warps that are idle once their role is done: wait for this CTA's ticket; the last CTA finalises here,
+    // concurrently with its softmax warps storing O
+    int f;
+    while ((f = *last_flag) == 0) __nanosleep(64);
+    if (f == 2) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      const int tid = (warp < 2 ? warp : warp - kSoftmaxWarps) * 32 + lane;
+      // scratch for the row losses: the half-tile slot (consumed long ago; the softmax warps stage O in the pair slots)
+      finalize_stats(p, tid, reinterpret_cast<unsigned *>(p.ws + (int64_t)kStatCopies * p.M * 4),
+                     reinterpret_cast<float *>(gbase + kOffSingle), (int)(kUnitBytes / 4));
+      if (tid == 0) TLF(17);
     }
   }
 
-  if (threadIdx.x == 64) TLF(7);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
   }
-  if (FUSED && *last_flag) {
-    __threadfence();
-    finalize_rows<GRAD>(p, reinterpret_cast<unsigned *>(p.acc + (int64_t)p.M * kLd));
-  }
   if (threadIdx.x == 0) TLF(3);
 }
 
-// acc [M][132] viewed as {132, M}: one box = one CTA's [128][132] output tile
-static int make_map_acc(CUtensorMap *map, float *ptr, int M) {
+// part [n_part][M][132] viewed as {132, M, n_part}: one box = one CTA's [128][132] output tile (rows >= M clipped)
+static int make_map_slab(CUtensorMap *map, float *ptr, int M, int n_part) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_err(MSCL_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[2] = {(cuuint64_t)kLd, (cuuint64_t)M};
-  cuuint64_t strides[1] = {(cuuint64_t)kLd * 4};
-  cuuint32_t box[2] = {(cuuint32_t)kLd, (cuuint32_t)kRows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  cuuint64_t dims[3] = {(cuuint64_t)kLd, (cuuint64_t)M, (cuuint64_t)n_part};
+  cuuint64_t strides[2] = {(cuuint64_t)kLd * 4, (cuuint64_t)M * kLd * 4};
+  cuuint32_t box[3] = {(cuuint32_t)kLd, (cuuint32_t)kRows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_err(MSCL_ECUDA, "cuTensorMapEncodeTiled(acc) failed with CUresult %d (M=%d)", (int)r, M);
+  if (r != CUDA_SUCCESS)
+    return set_err(MSCL_ECUDA, "cuTensorMapEncodeTiled(slab) failed with CUresult %d (M=%d n_part=%d)", (int)r, M, n_part);
   return MSCL_OK;
 }
 
@@ -716,24 +814,25 @@ static int launch(bool fused, bool grad, const Params &p, const float *d_queue, 
   const int64_t n_units = (p.K_local + kUnit - 1) / kUnit;
   MSCL_CHECK_ARG(n_part > 0 && n_part <= n_units, "n_part=%d must be in [1, %lld] (one 64-key unit per CTA at least)", n_part,
                  (long long)n_units);
-  CUtensorMap tw, twh, tw2, tq, ta;
+  CUtensorMap tw, twh, tw2, ta;
   int rc = make_map(&tw, d_queue, p.K_local, kC, kTile);
   if (rc) return rc;
   rc = make_map(&twh, d_queue, p.K_local, kC, kUnit);
   if (rc) return rc;
   rc = make_map(&tw2, d_queue, p.K_local, kC, kUnit, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
-  rc = make_map(&tq, p.q, p.M, fused ? kC : kLd, kRows);
-  if (rc) return rc;
-  rc = make_map_acc(&ta, p.acc, p.M);
-  if (rc) return rc;
+  memset(&ta, 0, sizeof(ta));
+  if (p.part != nullptr) {
+    rc = make_map_slab(&ta, p.part, p.M, n_part);
+    if (rc) return rc;
+  }
   const int row_blocks = (p.M + kRows - 1) / kRows;
   dim3 grid((unsigned)n_part, (unsigned)row_blocks);
 #define MSCL_FUSED_LAUNCH(G, F, W)                                                                                   \
   do {                                                                                                               \
     rc = ensure_smem(infonce_fused_kernel<G, F>, W);                                                                 \
     if (rc) return rc;                                                                                               \
-    MSCL_CUDA(mscl::launch_pdl(infonce_fused_kernel<G, F>, grid, dim3(kThreads), kSmemBytes, s, tw, twh, tw2, tq, ta, p)); \
+    MSCL_CUDA(mscl::launch_pdl(infonce_fused_kernel<G, F>, grid, dim3(kThreads), kSmemBytes, s, tw, twh, tw2, ta, p)); \
   } while (0)
   if (fused && grad) MSCL_FUSED_LAUNCH(true, true, 0);
   else if (fused) MSCL_FUSED_LAUNCH(false, true, 1);
@@ -750,28 +849,30 @@ static int launch(bool fused, bool grad, const Params &p, const float *d_queue, 
 extern "C" int mscl_infonce_fused(const float *d_q, const float *d_kpos, int32_t M, const float *d_queue,
                                   const int32_t *d_birth, const int64_t *d_qstate, int64_t K_local, float inv_T,
                                   float key_norm_bound, const int32_t *d_dup_slot, int32_t dup_age, float *d_ws,
-                                  int32_t n_part, int32_t rows_per_group, int32_t with_grad, int32_t flags,
-                                  float *d_row_loss, float *d_dq_unit, float *d_group_out, mscl_stream_t stream) {
+                                  float *d_part, int32_t n_part, int32_t rows_per_group, int32_t with_grad, int32_t flags,
+                                  float *d_row_loss, float *d_rowaux, float *d_group_out, mscl_stream_t stream) {
   using namespace mscl::tcf;
-  MSCL_CHECK_ARG(d_q && d_kpos && d_queue && d_birth && d_qstate && d_ws && d_row_loss && d_dq_unit && d_group_out,
+  MSCL_CHECK_ARG(d_q && d_kpos && d_queue && d_birth && d_qstate && d_ws && d_row_loss && d_rowaux && d_group_out,
                  "null pointer");
+  MSCL_CHECK_ARG(!with_grad || d_part, "with_grad needs the slab buffer d_part");
   MSCL_CHECK_ARG(M > 0 && K_local > 0, "bad M=%d K_local=%lld", M, (long long)K_local);
   MSCL_CHECK_ARG(K_local < (1ll << 31), "K_local too large for a TMA coordinate");
   MSCL_CHECK_ARG(rows_per_group > 0 && M % rows_per_group == 0, "M=%d must be a multiple of rows_per_group=%d", M,
                  rows_per_group);
   MSCL_CHECK_ARG(inv_T > 0.f && key_norm_bound > 0.f, "bad inv_T / key_norm_bound");
   MSCL_CHECK_ARG((((uintptr_t)d_q | (uintptr_t)d_kpos | (uintptr_t)d_queue | (uintptr_t)d_birth | (uintptr_t)d_ws |
-                   (uintptr_t)d_dq_unit | (uintptr_t)d_group_out) & 15) == 0,
-                 "q/kpos/queue/birth/ws/dq_unit/group_out must be 16-byte aligned");
+                   (uintptr_t)d_part | (uintptr_t)d_rowaux | (uintptr_t)d_group_out) & 15) == 0,
+                 "q/kpos/queue/birth/ws/part/rowaux/group_out must be 16-byte aligned");
   Params p = {};
   p.q = d_q;
   p.kpos = d_kpos;
   p.birth = d_birth;
   p.qstate = d_qstate;
   p.dup_slot = d_dup_slot;
-  p.acc = d_ws;
+  p.ws = d_ws;
+  p.part = with_grad ? d_part : nullptr;
   p.row_loss = d_row_loss;
-  p.dq_unit = d_dq_unit;
+  p.rowaux = d_rowaux;
   p.group_out = d_group_out;
   p.K_local = K_local;
   p.shard_begin = 0;
@@ -786,19 +887,19 @@ extern "C" int mscl_infonce_fused(const float *d_q, const float *d_kpos, int32_t
 
 extern "C" int mscl_infonce_pass(const float *d_qpack, int32_t M, const float *d_queue, const int32_t *d_birth,
                                  const int64_t *d_qstate, int64_t K_local, int64_t shard_begin, float inv_T,
-                                 float *d_acc, int32_t n_part, int32_t with_grad, int32_t flags, mscl_stream_t stream) {
+                                 float *d_part, int32_t n_part, int32_t with_grad, int32_t flags, mscl_stream_t stream) {
   using namespace mscl::tcf;
-  MSCL_CHECK_ARG(d_qpack && d_queue && d_birth && d_qstate && d_acc, "null pointer");
+  MSCL_CHECK_ARG(d_qpack && d_queue && d_birth && d_qstate && d_part, "null pointer");
   MSCL_CHECK_ARG(M > 0 && K_local > 0, "bad M=%d K_local=%lld", M, (long long)K_local);
   MSCL_CHECK_ARG(K_local < (1ll << 31), "K_local too large for a TMA coordinate");
   MSCL_CHECK_ARG(inv_T > 0.f, "bad inv_T");
-  MSCL_CHECK_ARG((((uintptr_t)d_qpack | (uintptr_t)d_queue | (uintptr_t)d_birth | (uintptr_t)d_acc) & 15) == 0,
-                 "qpack/queue/birth/acc must be 16-byte aligned");
+  MSCL_CHECK_ARG((((uintptr_t)d_qpack | (uintptr_t)d_queue | (uintptr_t)d_birth | (uintptr_t)d_part) & 15) == 0,
+                 "qpack/queue/birth/part must be 16-byte aligned");
   Params p = {};
   p.q = d_qpack;
   p.birth = d_birth;
   p.qstate = d_qstate;
-  p.acc = d_acc;
+  p.part = d_part;
   p.K_local = K_local;
   p.shard_begin = shard_begin;
   p.M = M;

@@ -190,12 +190,12 @@ _FUSED_WS = {}
 
 
 def _fused_workspace(dev, M):
-    """Zero-initialised accumulator + CTA counter of the single-launch InfoNCE op (mscl_infonce_fused leaves it zero).
-    One per (device, stream, M): two launches that may overlap must not share it."""
+    """Zero-initialised statistics accumulator + CTA counter of the single-launch InfoNCE op (mscl_infonce_fused leaves it
+    zero).  One per (device, stream, M): two launches that may overlap must not share it."""
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(), int(M))
     ws = _FUSED_WS.get(key)
     if ws is None:
-        ws = _FUSED_WS[key] = torch.zeros(M * PACK_LD + 4, device=dev)
+        ws = _FUSED_WS[key] = torch.zeros(16 * M * 4 + 4, device=dev)
     return ws
 
 
@@ -217,21 +217,27 @@ class _InfoNCE(torch.autograd.Function):
         M_all = M * world
         n_groups = M // rows_per_group
         row_loss = torch.empty(2 * M, device=dev)
-        dq_unit = torch.empty(M, DIM, device=dev)
         group_out = torch.empty(n_groups, 4, device=dev)
-        if impl == "fused" and world == 1:
-            # ONE launch: prep + tcgen05 pass + reduce-add into one accumulator + finalize by the last CTA
+        ctx.fused = impl == "fused" and world == 1
+        if ctx.fused:
+            # ONE launch: prep + tcgen05 pass + statistics reduction + finalize by the last CTA; the O slabs are summed
+            # by the backward kernel
             n_part = _cabi.query("mscl_infonce_fused_parts", M, nq.K_local, sm_count(dev))
             ws = _fused_workspace(dev, M)
+            part = torch.empty(n_part, M, PACK_LD, device=dev) if need_grad else None
+            rowaux = torch.empty(M, 4, device=dev)
             _cabi.call("mscl_infonce_fused", q.data_ptr(), kpos.data_ptr(), M, nq.queue_tf32.data_ptr(), nq.birth.data_ptr(),
                        nq.qstate.data_ptr(), nq.K_local, inv_T, nq.max_key_norm,
-                       dup_slot.data_ptr() if dup_slot is not None else None, dup_age, ws.data_ptr(), n_part, rows_per_group,
-                       int(need_grad), _prefetch_flag(nq), row_loss.data_ptr(), dq_unit.data_ptr(), group_out.data_ptr(), st,
+                       dup_slot.data_ptr() if dup_slot is not None else None, dup_age, ws.data_ptr(),
+                       part.data_ptr() if need_grad else None, n_part, rows_per_group,
+                       int(need_grad), _prefetch_flag(nq), row_loss.data_ptr(), rowaux.data_ptr(), group_out.data_ptr(), st,
                        algo_bytes=infonce_algo_bytes(M, nq.K_local), algo_flops=(4 if need_grad else 2) * M * nq.K_local * DIM)
-            ctx.save_for_backward(dq_unit)
+            if need_grad:
+                ctx.save_for_backward(part, rowaux, kpos)
             ctx.rows_per_group = rows_per_group
             ctx.mark_non_differentiable(row_loss)
             return group_out, row_loss
+        dq_unit = torch.empty(M, DIM, device=dev)
         qpack = torch.empty(M, PACK_LD, device=dev)
         fused_pass = impl in ("fused", "fused_pass")      # "fused_pass": the sharded-queue launch sequence on one rank (tests)
         dscale = None
@@ -257,12 +263,11 @@ class _InfoNCE(torch.autograd.Function):
             part = torch.zeros(1, M_all, PACK_LD, device=dev)
             _cabi.call("mscl_infonce_partial_simt", qpack_all.data_ptr(), M_all, nq.queue_tf32.data_ptr(), dscale.data_ptr(),
                        nq.K_local, nq.shard_begin, part.data_ptr(), int(need_grad), st)
-        elif fused_pass:        # the pass in its single-launch form: all CTAs reduce-add into ONE zeroed slab
-            n_part = 1
-            part = torch.zeros(1, M_all, PACK_LD, device=dev)
+        elif fused_pass:        # the pass of the single-launch form (64-key units, in-kernel decay scale), slabs out
+            n_part = _cabi.query("mscl_infonce_fused_parts", M_all, nq.K_local, sm_count(dev))
+            part = torch.empty(n_part, M_all, PACK_LD, device=dev)
             _cabi.call("mscl_infonce_pass", qpack_all.data_ptr(), M_all, nq.queue_tf32.data_ptr(), nq.birth.data_ptr(),
-                       nq.qstate.data_ptr(), nq.K_local, nq.shard_begin, inv_T, part.data_ptr(),
-                       _cabi.query("mscl_infonce_fused_parts", M_all, nq.K_local, sm_count(dev)), int(need_grad),
+                       nq.qstate.data_ptr(), nq.K_local, nq.shard_begin, inv_T, part.data_ptr(), n_part, int(need_grad),
                        _prefetch_flag(nq), st, algo_bytes=infonce_algo_bytes(M_all, nq.K_local),
                        algo_flops=(4 if need_grad else 2) * M_all * nq.K_local * DIM)
         else:
@@ -280,11 +285,8 @@ class _InfoNCE(torch.autograd.Function):
             ws.barrier()
             part, n_part = ws.acc, world
         elif world > 1:         # local slabs -> one slab, summed across ranks, each rank keeps its own rows
-            if n_part > 1:
-                acc = torch.empty(M_all, PACK_LD, device=dev)
-                _cabi.call("mscl_infonce_reduce", part.data_ptr(), n_part, M_all, acc.data_ptr(), st)
-            else:
-                acc = part.view(M_all, PACK_LD)
+            acc = torch.empty(M_all, PACK_LD, device=dev)
+            _cabi.call("mscl_infonce_reduce", part.data_ptr(), n_part, M_all, acc.data_ptr(), st)
             part = torch.empty(1, M, PACK_LD, device=dev)
             dist.reduce_scatter_tensor(part.view(M, PACK_LD), acc, op=dist.ReduceOp.SUM, group=group)
             n_part = 1
@@ -297,9 +299,16 @@ class _InfoNCE(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_group, _g_rows):
+        gout = g_group[:, 0].contiguous()
+        if ctx.fused:
+            part, rowaux, kpos = ctx.saved_tensors
+            n_part, M = part.shape[0], part.shape[1]
+            dq = torch.empty(M, DIM, device=part.device)
+            _cabi.call("mscl_infonce_bwd_slabs", part.data_ptr(), n_part, M, kpos.data_ptr(), rowaux.data_ptr(), gout.data_ptr(),
+                       ctx.rows_per_group, dq.data_ptr(), _stream(), algo_bytes=4 * M * (n_part * DIM + 2 * DIM + 4))
+            return dq, None, None, None, None, None, None, None, None, None
         (dq_unit,) = ctx.saved_tensors
         M = dq_unit.shape[0]
-        gout = g_group[:, 0].contiguous()
         dq = torch.empty_like(dq_unit)
         _cabi.call("mscl_infonce_bwd", dq_unit.data_ptr(), gout.data_ptr(), M, ctx.rows_per_group, dq.data_ptr(), _stream())
         return dq, None, None, None, None, None, None, None, None, None

@@ -116,13 +116,16 @@ def main():
 
             # the single-launch form: prep + pass + reduce-add + finalize in one kernel (csrc/infonce_fused.cu)
             n_fp = _cabi.query("mscl_infonce_fused_parts", M, K, sms)
-            ws = torch.zeros(M * fx.PACK_LD + 4, device=dev)
+            ws = torch.zeros(16 * M * 4 + 4, device=dev)
+            fpart = torch.empty(n_fp, M, fx.PACK_LD, device=dev)
+            rowaux = torch.empty(M, 4, device=dev)
+            gone = torch.ones(1, device=dev)
             for grad in (1, 0):
                 def fused(i, grad=grad):
                     nq = queues[i % n_rot]
                     _cabi.call("mscl_infonce_fused", q.data_ptr(), k.data_ptr(), M, nq.queue_tf32.data_ptr(), nq.birth.data_ptr(),
-                               nq.qstate.data_ptr(), K, 1 / 0.07, 1.0, None, 1, ws.data_ptr(), n_fp, M, grad, args.flags,
-                               row_loss.data_ptr(), dq.data_ptr(), gout.data_ptr(), st)
+                               nq.qstate.data_ptr(), K, 1 / 0.07, 1.0, None, 1, ws.data_ptr(), fpart.data_ptr(), n_fp, M, grad, args.flags,
+                               row_loss.data_ptr(), rowaux.data_ptr(), gout.data_ptr(), st)
                 for i in range(5):
                     fused(i)
                 us = time_train(fused, args.iters)
@@ -130,13 +133,23 @@ def main():
                 res[f"{tag}_us"] = us
                 res[f"{tag}_frac"] = res["algo_bytes"] / us / 1e3 / pk
             res["fused_loss"] = float(gout[0, 0])
+
+            def fused_fb(i):          # forward launch + the backward kernel that sums the O slabs
+                fused(i, 1)
+                _cabi.call("mscl_infonce_bwd_slabs", fpart.data_ptr(), n_fp, M, k.data_ptr(), rowaux.data_ptr(), gone.data_ptr(), M,
+                           dq.data_ptr(), st)
+            for i in range(3):
+                fused_fb(i)
+            res["fused_fwd_bwd_us"] = time_train(fused_fb, args.iters)
+            res["fused_fwd_bwd_frac"] = res["algo_bytes"] / res["fused_fwd_bwd_us"] / 1e3 / pk
             us = res["op_us"]
             rows.append(res)
             print(f"K={K:8d} M={M:4d} parts={n_part:3d}  partial(grad) {res['partial_grad_us']:8.1f} us "
                   f"{res['partial_grad_gbs']:7.0f} GB/s {100 * res['partial_grad_frac']:5.1f}%  {res['partial_grad_tflops']:6.1f} TF | "
                   f"nograd {res['partial_nograd_us']:8.1f} us {100 * res['partial_nograd_frac']:5.1f}% | "
                   f"prep+partial+finalize {us:8.1f} us {100 * res['op_frac']:5.1f}%  loss {res['loss']:.4f} | "
-                  f"FUSED op {res['fused_us']:8.1f} us {100 * res['fused_frac']:5.1f}% (nograd {res['fused_nograd_us']:.1f} us) "
+                  f"FUSED op {res['fused_us']:8.1f} us {100 * res['fused_frac']:5.1f}% (nograd {res['fused_nograd_us']:.1f} us, "
+                  f"fwd+bwd {res['fused_fwd_bwd_us']:.1f} us {100 * res['fused_fwd_bwd_frac']:.1f}%) "
                   f"loss {res['fused_loss']:.4f}", flush=True)
         del queues
         torch.cuda.empty_cache()

@@ -6,7 +6,7 @@ import torch
 from mscl_b200 import functional as fx, _cabi
 
 M, K = int(sys.argv[1]) if len(sys.argv) > 1 else 96, int(sys.argv[2]) if len(sys.argv) > 2 else 65536
-FLUSH = int(sys.argv[3]) if len(sys.argv) > 3 else 1      # 1: dirty the L2 before each launch, 0: back-to-back launches
+FLUSH = int(sys.argv[3]) if len(sys.argv) > 3 else 1      # 1: dirty the L2 before each launch, 0: back-to-back launches, 2: one launch after a device sync
 g = torch.Generator().manual_seed(0)
 q = torch.nn.functional.normalize(torch.randn(M, 128, generator=g), dim=1).cuda()
 kp = torch.nn.functional.normalize(torch.randn(M, 128, generator=g), dim=1).cuda()
@@ -18,8 +18,10 @@ for s in range(6):
 flush = torch.empty(64 * 1024 * 1024, device="cuda")
 lib = _cabi.load()
 for it in range(4):
-    if FLUSH:
+    if FLUSH == 1:
         flush.fill_(it)
+    if FLUSH == 2:
+        torch.cuda.synchronize()
     _cabi.start_timing(["mscl_infonce_fused"])
     for j in range(1 if FLUSH else 6):
         nqs[j]._fresh = False
@@ -32,9 +34,11 @@ for it in range(4):
     base = t[:, 0].min()
     rel = (t - base) / 1e3
     names = {0: "entry", 1: "setup done", 2: "Q staged", 8: "S0", 9: "S1", 10: "S2", 11: "S3", 12: "S4", 20: "P0", 21: "P1", 22: "P2", 23: "P3",
-             24: "P4", 4: "TMA issued", 5: "softmax done", 6: "O full", 7: "epilogue done", 3: "exit"}
+             24: "P4", 4: "TMA issued", 5: "softmax done", 6: "O full", 7: "ticket taken", 16: "epilogue done", 17: "finalize done", 3: "exit",
+             12: "positives landed (thread 64)", 13: "row info reduced (thread 64)", 14: "softmax warps enter the tile loop", 15: "MMA1(0) complete (s_full[0] fires)", 18: "producer: dependency wait over", 19: "scales of tile 0 ready", 28: "mma: Q in TMEM seen", 29: "mma: tile 0 landed, MMA1(0) issued",
+             30: "mma: tile 1 landed, MMA1(1) issued", 31: "mma: tile 2 landed, MMA1(2) issued"}
     print(f"iter {it}: event {rec['mscl_infonce_fused'][-1][0]*1e3:.1f} us; kernel span {(t[:, 3].max() - base)/1e3:.2f} us")
     for k in sorted(names, key=lambda k: np.median(rel[:, k])):
         col = rel[:, k][t[:, k] > 0]
         if col.size:
-            print(f"   {names[k]:>16}: min {col.min():6.2f}  median {np.median(col):6.2f}  max {col.max():6.2f} us  ({col.size} CTAs)")
+            print(f"   {names[k]:>36}: min {col.min():6.2f}  median {np.median(col):6.2f}  max {col.max():6.2f} us  ({col.size} CTAs)")

@@ -300,8 +300,8 @@ def test_infonce_large_queue_vs_oracle(fx, impl, K):
 
 
 def test_infonce_fused_workspace_stays_zero_and_repeats(fx):
-    """mscl_infonce_fused accumulates into a zero workspace and must leave it zero (accumulator AND CTA counter), so
-    back-to-back calls agree to rounding (the fp32 adds in L2 are unordered) and never see stale sums."""
+    """mscl_infonce_fused accumulates the row statistics into a zero workspace and must leave it zero (accumulator AND
+    CTA counter), so back-to-back calls agree to rounding (the float adds are unordered) and never see stale sums."""
     M, K = 96, 65536
     q, kpos, queue, count = _make_case(3, M, K, 128)
     nq = fx.NegativeQueue(K)
@@ -318,7 +318,7 @@ def test_infonce_fused_workspace_stays_zero_and_repeats(fx):
     for o, r, g in outs[1:]:
         assert _rel(o[:, 0], outs[0][0][:, 0]) < 1e-6
         assert torch.equal(r[M:], outs[0][1][M:])                # hit counts are integers: exact whatever the add order
-        assert _rel(g, outs[0][2]) < 1e-5
+        assert _rel(g, outs[0][2]) < 1e-6                        # the slabs are summed in a fixed order
 
 
 def test_infonce_fresh_queue_and_after_enqueue(fx):
