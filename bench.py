@@ -240,16 +240,33 @@ def run_reference(args, rank):
 # ----------------------------------------------------------------------------------------------
 # this repo's path
 # ----------------------------------------------------------------------------------------------
-KERNEL_ENTRIES = ["mscl_infonce_partial", "mscl_ema_multi", "mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_hw_mean_ndhwc_fwd",
-                  "mscl_hw_mean_ndhwc_bwd", "mscl_fra_fused",
-                  "mscl_fra_maxrad", "mscl_fra_apply", "mscl_enqueue", "mscl_lmcl", "mscl_infonce_prep", "mscl_infonce_finalize",
-                  "mscl_infonce_reduce_scatter", "mscl_flow_visualize", "mscl_color_pipeline", "mscl_grad_norm_multi",
-                  "mscl_clip_sgd_multi",
-                  "mscl_gather_rows"]
+# The ops of the contrastive path (SURVEY.md section 8a / DESIGN.md section 4).  `primary` entry points carry the op's
+# algorithmic bytes (one per op instance); `aux` entry points are further launches of the SAME op instance (its backward
+# kernel, the exchange kernels of the sharded queue, ...): their time is added, their bytes are not.
+OPS = [
+    ("K1 InfoNCE (op)", "8a1-a3", ("mscl_infonce_fused", "mscl_infonce_partial", "mscl_infonce_pass"),
+     ("mscl_infonce_bwd_slabs", "mscl_infonce_prep", "mscl_infonce_finalize", "mscl_infonce_bwd", "mscl_infonce_reduce",
+      "mscl_infonce_reduce_scatter")),
+    ("K2 LMCL pooling + loss (op)", "8a4", ("mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_hw_mean_ndhwc_fwd", "mscl_hw_mean_ndhwc_bwd",
+                                             "mscl_lmcl"), ()),
+    ("K3 FRA (op)", "8a9", ("mscl_fra_fused", "mscl_fra_apply"), ("mscl_fra_maxrad",)),
+    ("K4 momentum EMA (op)", "8a5", ("mscl_ema_multi",), ()),
+    ("K5 enqueue (op)", "8a6", ("mscl_enqueue",), ()),
+    ("K6 shuffle row gather (op)", "8a7", ("mscl_gather_rows",), ()),
+    ("K7 trilinear up-sampling (op, adjacent)", "f", ("mscl_upsample_trilinear_fwd", "mscl_upsample_trilinear_bwd",
+                                                       "mscl_upsample_trilinear_ndhwc_fwd", "mscl_upsample_trilinear_ndhwc_bwd",
+                                                       "mscl_linear_axis_bwd"), ()),
+    ("K8 flow visualiser (op, adjacent)", "f-1", ("mscl_flow_visualize",), ()),
+    ("K9 colour pipeline (op, adjacent)", "f-1", ("mscl_color_pipeline",), ()),
+    ("K10 clip + SGD (op, adjacent)", "f-3", ("mscl_clip_sgd_multi",), ("mscl_grad_norm_multi",)),
+]
+KERNEL_ENTRIES = sorted({e for _, _, prim, aux in OPS for e in prim + aux})
+PATH_OPS = ("K1 InfoNCE (op)", "K2 LMCL pooling + loss (op)", "K3 FRA (op)", "K4 momentum EMA (op)", "K5 enqueue (op)",
+            "K6 shuffle row gather (op)")
 
 
 def summarise_kernels(rec, steps, pk):
-    """Group the event-timed launches by (entry point, algorithmic bytes): one row per launch class."""
+    """One row per (entry point, algorithmic bytes) launch class: what each launch costs inside the step."""
     rows = []
     for name, launches in rec.items():
         groups = {}
@@ -265,6 +282,31 @@ def summarise_kernels(rec, steps, pk):
             if flops and avg > 0:
                 row["tflops"] = flops / (avg * 1e-3) / 1e12
             rows.append(row)
+    rows.sort(key=lambda r: -r["step_share_ms"])
+    return rows
+
+
+def summarise_ops(rec, steps, pk):
+    """One row per OP: every launch of the op summed (forward, backward, exchange kernels), algorithmic bytes counted once
+    per op instance -- so that a kernel split into several launches is not ranked below a single-launch one."""
+    rows = []
+    for name, sect, prim, aux in OPS:
+        ms = sum(m for e in prim + aux for m, _, _ in rec.get(e, []))
+        n_inst = sum(len(rec.get(e, [])) for e in prim)
+        n_launch = sum(len(rec.get(e, [])) for e in prim + aux)
+        nbytes = sum(b for e in prim for _, b, _ in rec.get(e, []))
+        flops = sum(f for e in prim for _, _, f in rec.get(e, []))
+        if n_launch == 0:
+            continue
+        row = dict(op=name, survey_row=sect, instances_per_step=n_inst / steps, launches_per_step=n_launch / steps,
+                   step_share_ms=ms / steps, us_per_instance=ms * 1e3 / max(n_inst, 1), algo_bytes_per_step=nbytes / steps,
+                   entry_points=[e for e in prim + aux if rec.get(e)])
+        if nbytes and ms > 0:
+            row["gbs"] = nbytes / (ms * 1e-3) / 1e9
+            row["frac_hbm"] = row["gbs"] / pk["hbm"]
+        if flops and ms > 0:
+            row["tflops"] = flops / (ms * 1e-3) / 1e12
+        rows.append(row)
     rows.sort(key=lambda r: -r["step_share_ms"])
     return rows
 
@@ -443,24 +485,27 @@ def run_b200(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
     kernels = summarise_kernels(rec, args.steps, pk)
-    # `roofline`: the kernel with the largest share of the step among the kernels of the contrastive path proper
-    # (K1-K6); the adjacent ones (augmentation K8/K9, optimizer K10) are listed in `kernels`
-    path_entries = ("mscl_infonce_partial", "mscl_ema_multi", "mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_hw_mean_ndhwc_fwd",
-                    "mscl_hw_mean_ndhwc_bwd", "mscl_fra_fused",
-                    "mscl_fra_maxrad", "mscl_fra_apply", "mscl_enqueue", "mscl_lmcl", "mscl_gather_rows",
-                    "mscl_infonce_reduce_scatter")
-    on_path = [k for k in kernels if k["kernel"] in path_entries]
-    top = on_path[0] if on_path else (kernels[0] if kernels else None)
+    ops = summarise_ops(rec, args.steps, pk)
+    # `roofline`: the OP with the largest share of the step among the ops of the contrastive path proper (SURVEY.md
+    # section 8a: K1-K6), all its launches summed; the adjacent ones (K7-K10) are in `roofline_all` / `kernels`.
+    on_path = [o for o in ops if o["op"] in PATH_OPS]
+    top = on_path[0] if on_path else (ops[0] if ops else None)
     roofline = None
+    traffic = {}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):       # dram bytes per launch read from an ncu --set full capture (profiles/)
+        with open(traffic_file) as f:
+            traffic = json.load(f)
     if top is not None:
-        roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top.get("gbs"), "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": top.get("frac_hbm"), "traffic": None, "avg_us": top["avg_us"], "algo_bytes": top["algo_bytes"],
-                    "peak_source": pk["src"] + " (burst copy figure)",
-                    "selection": "largest step share among the section-8a path kernels (K1-K6)"}
-        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(traffic_file):       # dram bytes per launch read from an ncu --set full capture (profiles/)
-            with open(traffic_file) as f:
-                roofline["traffic"] = json.load(f).get(top["kernel"])
+        roofline = {"bound": "hbm", "kernel": top["op"].replace("K1 InfoNCE (op)", "mscl_infonce (op)"), "op": top["op"],
+                    "achieved": top.get("gbs"), "peak": pk["hbm"], "unit": "GB/s", "frac": top.get("frac_hbm"),
+                    "traffic": traffic.get(top["op"]), "us_per_instance": top["us_per_instance"],
+                    "launches_per_step": top["launches_per_step"], "algo_bytes_per_step": top["algo_bytes_per_step"],
+                    "entry_points": top["entry_points"], "peak_source": pk["src"] + " (burst copy figure)",
+                    "timing": "in-step: CUDA events around every launch of the op inside the timed region (each pair includes the "
+                              "launch gap); frac_standalone = the same op alone, launch trains over L2-cold buffers "
+                              "(kernel_rooflines)",
+                    "selection": "largest step share among the section-8a path ops (K1-K6), all launches of an op summed"}
     clips = N * world
     line = {"metric": METRIC, "value": clips / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -474,6 +519,7 @@ def run_b200(args, rank, local_rank, world):
                     "pipeline": "every step's inputs copied from pinned host memory on a copy stream one step ahead (2 device "
                                 "slots); every step's log variables read back one step late, the last before the closing event"},
             "wall_ms_per_step": wall * 1e3, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "roofline_all": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in o.items()} for o in ops],
             "kernels": kernels, "loss": last["log_vars"].get("loss")}
     if world == 1 and not args.no_kernel_rooflines:
         # every kernel of the path alone, at this workload's shapes (cfg2) and at the queue sweep's (cfg3): graph-replayed
@@ -481,9 +527,17 @@ def run_b200(args, rank, local_rank, world):
         from mscl_b200 import kernel_bench
         del resident
         torch.cuda.empty_cache()
-        kr = kernel_bench.run(("cfg2", "cfg3"), device=local_rank, verbose=False)
+        kr = kernel_bench.run(("cfg2", "cfg3", "cfg4", "cfg5"), device=local_rank, verbose=False)
         line["kernel_rooflines"] = dict(timing=kr["timing"], hbm_peak_gbs=kr["hbm_peak_gbs"], rows=[
             {k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items() if k != "note"} for r in kr["rows"]])
+        if roofline is not None and roofline["op"] == "K1 InfoNCE (op)":
+            for r in kr["rows"]:        # the same op alone at the step's largest shape (forward launch + backward kernel)
+                if r["config"] == "cfg2" and r["shape"] == f"M={3 * N} K={args.K}" and r["kernel"].startswith("K1 op + backward"):
+                    roofline["frac_standalone"] = r["frac_hbm"]
+                    roofline["us_standalone"] = r["us"]
+                if r["config"] == "cfg2" and r["shape"] == f"M={3 * N} K={args.K}" and r["kernel"].startswith("K1 op = infonce_fused"):
+                    roofline["frac_standalone_forward_launch"] = r["frac_hbm"]
+                    roofline["us_standalone_forward_launch"] = r["us"]
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         step, desc = cpu_step_factory(args.K, args.ref_clips, threads)

@@ -314,13 +314,17 @@ int mscl_flow_visualize(const float *d_flow, const uint8_t *d_flip, const float 
  * K9  RGB colour pipeline of SyncMoCoAugmentV5 (common/ssl_aug_v2.py:31-48,66-68, common/ssl_aug.py:138-174):
  *     flip -> ColorJitter(brightness, contrast, saturation, hue) -> grayscale -> separable Gaussian blur
  *     (reflect border) -> Normalize, decisions and parameters per clip, drawn by the caller.
- * x [N, 3, T, H, W] in [0,1] -> out same shape.  d_params float [N][16]: flip, jitter?, brightness, contrast,
- * saturation, hue matrix[9] (row major, RGB -> RGB), gray?, blur?.  d_taps float[n_taps] (odd, <= 31) the 1-D blur
- * kernel; d_norm float[6] = mean[3], std[3]; d_gray_partial float [N][n_chunks] scratch for the clip luminance sums.
+ * x [N, 3, T, H, W] in [0,1] -> out same shape.  d_params float [U][16]: flip, jitter?, brightness, contrast,
+ * saturation, hue matrix[9] (row major, RGB -> RGB), gray?, blur?, with U = N rows (per_frame = 0: one set per clip, the
+ * reference's 'params' sync level, toConsistentAug, ssl_aug.py:62-66) or U = N*T rows (per_frame = 1: one set per frame,
+ * row n*T + t -- the 'batch' sync level, toVideoAug, :56-60, shares only the apply decisions between the frames of a
+ * clip; the caller repeats those); the contrast step is taken about the mean luminance of the clip / of the frame.
+ * d_taps float[n_taps] (odd, <= 31) the 1-D blur kernel; d_norm float[6] = mean[3], std[3]; d_gray_partial float
+ * [U][n_chunks] scratch for the luminance sums.
  */
 int mscl_color_pipeline(const float *d_x, const float *d_params, const float *d_taps, int32_t n_taps,
                         const float *d_norm, float *d_gray_partial, int32_t n_chunks, float *d_out,
-                        int32_t N, int32_t T, int32_t H, int32_t W, mscl_stream_t stream);
+                        int32_t N, int32_t T, int32_t H, int32_t W, int32_t per_frame, mscl_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * K10  gradient-norm clip + SGD-momentum step, multi-tensor.   replaces torch.nn.utils.clip_grad_norm_(max_norm=40)

@@ -48,7 +48,7 @@ PROTOTYPES = {
     "mscl_infonce_fused_parts": [c_int, c_i64, c_int],
     "mscl_gather_rows": [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr],
     "mscl_flow_visualize": [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
-    "mscl_color_pipeline": [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_int, c_ptr],
+    "mscl_color_pipeline": [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr],
     "mscl_grad_norm_multi": [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr],
     "mscl_clip_sgd_multi": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_f32, c_f32, c_f32, c_int, c_ptr],
     "mscl_upsample_trilinear_fwd": [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr],
@@ -120,6 +120,27 @@ def stop_timing():
     return {n: [(a.elapsed_time(b), nbytes, flops) for a, b, nbytes, flops in evs] for n, evs in (rec or {}).items()}
 
 
+# NVTX: every entry-point call is a named range (nsys / ncu --nvtx timelines show the hot path's ops by name, the
+# reference's tracing hook being mmcv's logger only).  MSCL_NVTX=0 turns the ranges off.
+_nvtx = None
+
+
+def _nvtx_api():
+    global _nvtx
+    if _nvtx is None:
+        _nvtx = False
+        if os.environ.get("MSCL_NVTX", "1") != "0":
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    torch.cuda.nvtx.range_push("mscl_b200")
+                    torch.cuda.nvtx.range_pop()
+                    _nvtx = torch.cuda.nvtx
+            except Exception:
+                _nvtx = False
+    return _nvtx
+
+
 def call(name, *args, algo_bytes=0, algo_flops=0):
     """Invoke an entry point; raise MsclError carrying mscl_last_error() on failure.
     algo_bytes / algo_flops: algorithmic work of this launch, only filed
@@ -131,7 +152,14 @@ def call(name, *args, algo_bytes=0, algo_flops=0):
         import torch
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    rc = getattr(lib, name)(*args)
+    nvtx = _nvtx_api()
+    if nvtx:
+        nvtx.range_push(name)
+    try:
+        rc = getattr(lib, name)(*args)
+    finally:
+        if nvtx:
+            nvtx.range_pop()
     if rc != 0:
         msg = lib.mscl_last_error()
         raise MsclError(f"{name} failed ({rc}): {msg.decode() if msg else ''}")

@@ -144,16 +144,21 @@ def ResNetFlow(name, pretrained=False, disable_clf=False, **kwargs):
     return net
 
 
+def _multilevel_forward(self, x):
+    x = self.stem(x)
+    outs = []
+    for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+        x = layer(x)
+        outs.append(x)
+    return outs
+
+
 def torchvision_multilevel(net):
     """Make a torchvision VideoResNet return [layer1..layer4] outputs; parameter names are
-    untouched (the reference monkey-patches `.forward` the same way, moco.py:374-376)."""
-    def forward(x, _net=net):
-        x = _net.stem(x)
-        outs = []
-        for layer in (_net.layer1, _net.layer2, _net.layer3, _net.layer4):
-            x = layer(x)
-            outs.append(x)
-        return outs
-
-    net.forward = forward
+    untouched (the reference monkey-patches `.forward` the same way, moco.py:374-376).
+    The patch is a BOUND METHOD, not a closure: copy.deepcopy re-binds it to the copied module (a closure over `net`
+    would keep running the original's layers from inside the copy, as functools.partial(forward, encoder) in the
+    reference does not)."""
+    import types
+    net.forward = types.MethodType(_multilevel_forward, net)
     return net

@@ -81,6 +81,9 @@ class SyncMoCoAugmentV5:
         if isinstance(sync_level, str):
             sync_level = (sync_level, sync_level)
         assert all(v in ("batch", "params") for v in sync_level)
+        # per view (query, key): 'batch' = toVideoAug (ssl_aug.py:56-60): the frames of a clip share the APPLY decisions
+        # only, the jitter factors are drawn per frame; 'params' = toConsistentAug (:62-66): they share the factors too
+        self.sync_level = tuple(sync_level)
         self.mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1, 1)
         self.std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1, 1)
         self.visualize = bool(visualize)
@@ -119,13 +122,17 @@ class SyncMoCoAugmentV5:
                     aux_info[k] = img
         return clips, aux_info, mask
 
-    def _color_params(self, n, dev):
-        """One draw of every decision / parameter of the colour pipeline for n clips ('batch' sync level: shared by
-        the frames of a clip): ColorJitter(0.4,0.4,0.4,0.1) p=.8, grayscale p=.2, blur p=.5, one sigma per call."""
-        rnd = lambda lo, hi: torch.empty(n, device=dev).uniform_(lo, hi)
-        prm = dict(jit=torch.rand(n, device=dev) < 0.8, brightness=rnd(0.6, 1.4), contrast=rnd(0.6, 1.4),
-                   saturation=rnd(0.6, 1.4), hue=rnd(-0.1, 0.1), gray=torch.rand(n, device=dev) < 0.2,
-                   blur=torch.rand(n, device=dev) < 0.5, sigma=float(torch.empty(1).uniform_(0.1, 2.0)))
+    def _color_params(self, n, dev, frames=1):
+        """One draw of every decision / parameter of the colour pipeline for n clips: ColorJitter(0.4,0.4,0.4,0.1) p=.8,
+        grayscale p=.2, blur p=.5, one sigma per call.  The apply decisions are per clip.  frames = 1: one set of jitter
+        factors per clip ('params' sync level); frames = T: one set per frame ('batch' sync level), every tensor then
+        has n*T entries in (clip, frame) order, the decisions repeated over the frames of a clip."""
+        nf = n * frames
+        rnd = lambda lo, hi: torch.empty(nf, device=dev).uniform_(lo, hi)
+        dec = lambda p: (torch.rand(n, device=dev) < p).repeat_interleave(frames)
+        prm = dict(jit=dec(0.8), brightness=rnd(0.6, 1.4), contrast=rnd(0.6, 1.4),
+                   saturation=rnd(0.6, 1.4), hue=rnd(-0.1, 0.1), gray=dec(0.2),
+                   blur=dec(0.5), sigma=float(torch.empty(1).uniform_(0.1, 2.0)))
         r = self.blur_radius
         ax = torch.arange(r, device=dev, dtype=torch.float32) - r // 2
         k1 = torch.exp(-ax ** 2 / (2 * prm["sigma"] ** 2))
@@ -149,9 +156,11 @@ class SyncMoCoAugmentV5:
             raise MsclError(f"{type(self).__name__} runs on CUDA tensors only (no CPU fallback)")
         from .. import functional as fx      # K9: flip + colour + blur + normalise in one pass over the clip
         clips, aux_info, mask = self.forward_flip(clips, aux_info, suffix, flip_clips=False)
-        prm = self._color_params(clips.shape[0], clips.device)
+        frames = clips.shape[2] if self.sync_level[0 if suffix == "_q" else 1] == "batch" else 1
+        prm = self._color_params(clips.shape[0], clips.device, frames)
         norm = torch.cat([self.mean.view(-1), self.std.view(-1)]).to(clips.device)
-        out = fx.color_pipeline(clips.contiguous().float(), self._pack_params(prm, mask, weak), prm["taps"].contiguous(), norm)
+        out = fx.color_pipeline(clips.contiguous().float(), self._pack_params(prm, mask.repeat_interleave(frames), weak),
+                                prm["taps"].contiguous(), norm)
         if flow is not None:
             flow = self.flip(flow, mask)
         return out, aux_info, flow
@@ -171,7 +180,7 @@ class SyncMoCoAugmentV2(SyncMoCoAugmentV5):
 
     def __init__(self, crop_size, flip_transform=dict(p=0.5, same_on_batch=False), sync_level="batch", t=None,
                  with_flow=False, img_width=112):
-        assert sync_level in ("batch", "params")
+        assert sync_level in ("batch", "params")      # 'batch' -> toVideoAug, 'params' -> toConsistentAug (ssl_aug.py:259-262)
         super().__init__(crop_size, flip_transform=flip_transform, sync_level=sync_level, t=t, flow_suffix=None,
                          img_width=img_width, visualize=False, weak_aug=(False, False), normalize_flow=False)
         self.with_flow = with_flow

@@ -101,12 +101,14 @@ __device__ __forceinline__ float gray_of(float r, float g, float b) {
   return 0.299f * r + 0.587f * g + 0.114f * b;
 }
 
-// partial[n][chunk] = sum over this chunk of the clip's pixels of gray(x); grid (chunks, N)
+// partial[u][chunk] = sum over this chunk of unit u's pixels of gray(x); grid (chunks, units).  A unit is a clip
+// (frames_per_unit = T: `count` = T*H*W pixels) or one frame of it (frames_per_unit = 1: `count` = H*W pixels).
 __global__ void __launch_bounds__(256)
-clip_gray_sum_kernel(const float *__restrict__ x, float *__restrict__ partial, int64_t THW) {
-  const int n = blockIdx.y;
-  const float *pr = x + (int64_t)n * 3 * THW, *pg = pr + THW, *pb = pg + THW;
-  const int64_t n4 = THW >> 2;
+clip_gray_sum_kernel(const float *__restrict__ x, float *__restrict__ partial, int64_t THW, int64_t count, int units_per_clip) {
+  const int u = blockIdx.y;
+  const int n = u / units_per_clip, f = u - n * units_per_clip;
+  const float *pr = x + (int64_t)n * 3 * THW + (int64_t)f * count, *pg = pr + THW, *pb = pg + THW;
+  const int64_t n4 = count >> 2;
   float acc = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
     const float4 r = ldg_stream(reinterpret_cast<const float4 *>(pr) + i);
@@ -122,11 +124,12 @@ clip_gray_sum_kernel(const float *__restrict__ x, float *__restrict__ partial, i
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += s[w];
-    partial[n * gridDim.x + blockIdx.x] = t;
+    partial[u * gridDim.x + blockIdx.x] = t;
   }
 }
 
-// Per-clip parameters, float [N][kColorParams]:
+// Parameters, float [N][kColorParams] (per clip) or [N*T][kColorParams] (per frame: the reference's 'batch' sync level draws
+// the jitter factors per image, ssl_aug.py:33-60; the contrast step then uses the frame's own mean luminance):
 //  0 flip  1 jitter?  2 brightness  3 contrast  4 saturation  5..13 hue matrix (row major)  14 gray?  15 blur?
 constexpr int kColorParams = 16;
 constexpr int kMaxTaps = 31;
@@ -135,14 +138,15 @@ constexpr int kMaxTaps = 31;
 __global__ void __launch_bounds__(512)
 color_pipeline_kernel(const float *__restrict__ x, const float *__restrict__ params, const float *__restrict__ gray_partial,
                       int n_chunks, const float *__restrict__ taps, int n_taps, const float *__restrict__ norm,
-                      float *__restrict__ out, int T, int H, int W) {
+                      float *__restrict__ out, int T, int H, int W, int per_frame) {
   extern __shared__ float sm[];
   const int HW = H * W;
   float *a = sm, *b = sm + HW;
   __shared__ float s_taps[kMaxTaps];
   const int frame = blockIdx.x;
   const int n = frame / T, t = frame - n * T;
-  const float *p = params + n * kColorParams;
+  const int unit = per_frame ? frame : n;
+  const float *p = params + unit * kColorParams;
   const bool flip = p[0] != 0.f, jit = p[1] != 0.f, to_gray = p[14] != 0.f, blur = p[15] != 0.f;
   const float br = p[2], ct = p[3], sat = p[4];
   float hm[9];
@@ -151,8 +155,8 @@ color_pipeline_kernel(const float *__restrict__ x, const float *__restrict__ par
   const int64_t THW = (int64_t)T * HW;
   // clip mean of gray(x * brightness): the partial sums in a fixed order
   float gsum = 0.f;
-  for (int c = 0; c < n_chunks; ++c) gsum += __ldg(gray_partial + n * n_chunks + c);
-  const float m = br * (gsum / (float)THW);     // mean over (1, T, H, W) of the luminance
+  for (int c = 0; c < n_chunks; ++c) gsum += __ldg(gray_partial + unit * n_chunks + c);
+  const float m = br * (gsum / (per_frame ? (float)HW : (float)THW));     // mean luminance of the clip / of the frame
   if (threadIdx.x < n_taps) s_taps[threadIdx.x] = taps[threadIdx.x];
   const float *pr = x + (int64_t)n * 3 * THW + (int64_t)t * HW, *pg = pr + THW, *pb = pg + THW;
   float *po = out + (int64_t)n * 3 * THW + (int64_t)t * HW;
@@ -230,15 +234,16 @@ template <int TAPS>
 __global__ void __launch_bounds__(512)
 color_pipeline_fast_kernel(const float *__restrict__ x, const float *__restrict__ params, const float *__restrict__ gray_partial,
                            int n_chunks, const float *__restrict__ taps, const float *__restrict__ norm,
-                           float *__restrict__ out, int T, int H, int W, int band_rows) {
+                           float *__restrict__ out, int T, int H, int W, int band_rows, int per_frame) {
   extern __shared__ float sm[];
   constexpr int HALF = TAPS / 2;
   const int HW = H * W;
   const int frame = blockIdx.x;
   const int n = frame / T, t = frame - n * T;
+  const int unit = per_frame ? frame : n;
   const int r0 = blockIdx.y * band_rows, r1 = min(r0 + band_rows, H);        // output rows of this band
   if (r0 >= H) return;
-  const float *p = params + n * kColorParams;
+  const float *p = params + unit * kColorParams;
   const bool flip = p[0] != 0.f, jit = p[1] != 0.f, to_gray = p[14] != 0.f, blur = p[15] != 0.f;
   const int s0 = blur ? max(r0 - HALF, 0) : r0, s1 = blur ? min(r1 + HALF, H) : r1;   // staged rows
   const int SR = s1 - s0, SP = SR * W;                                         // rows / floats per staged plane
@@ -251,8 +256,8 @@ color_pipeline_fast_kernel(const float *__restrict__ x, const float *__restrict_
   for (int k = 0; k < TAPS; ++k) tp[k] = __ldg(taps + k);
   const int64_t THW = (int64_t)T * HW;
   float gsum = 0.f;
-  for (int c = 0; c < n_chunks; ++c) gsum += __ldg(gray_partial + n * n_chunks + c);
-  const float m = br * (gsum / (float)THW);
+  for (int c = 0; c < n_chunks; ++c) gsum += __ldg(gray_partial + unit * n_chunks + c);
+  const float m = br * (gsum / (per_frame ? (float)HW : (float)THW));
   const float *pr = x + (int64_t)n * 3 * THW + (int64_t)t * HW;
   float *po = out + (int64_t)n * 3 * THW + (int64_t)t * HW;
   const float n0 = norm[0], n1 = norm[1], n2 = norm[2];
@@ -413,7 +418,7 @@ int mscl_flow_visualize(const float *d_flow, const uint8_t *d_flip, const float 
 
 int mscl_color_pipeline(const float *d_x, const float *d_params, const float *d_taps, int32_t n_taps, const float *d_norm,
                         float *d_gray_partial, int32_t n_chunks, float *d_out, int32_t N, int32_t T, int32_t H, int32_t W,
-                        mscl_stream_t stream) {
+                        int32_t per_frame, mscl_stream_t stream) {
   MSCL_CHECK_ARG(d_x && d_params && d_taps && d_norm && d_gray_partial && d_out, "null pointer");
   MSCL_CHECK_ARG(N > 0 && T > 0 && H > 0 && W > 0, "bad shape");
   MSCL_CHECK_ARG(n_taps >= 1 && n_taps <= mscl::kMaxTaps && (n_taps & 1), "n_taps=%d must be odd and <= %d", n_taps,
@@ -425,7 +430,12 @@ int mscl_color_pipeline(const float *d_x, const float *d_params, const float *d_
   const size_t smem = (size_t)2 * H * W * sizeof(float);
   MSCL_CHECK_ARG(smem <= 200 * 1024, "frame of %dx%d does not fit in shared memory", H, W);
   cudaStream_t s = mscl::as_stream(stream);
-  mscl::clip_gray_sum_kernel<<<dim3(n_chunks, N), 256, 0, s>>>(d_x, d_gray_partial, THW);
+  MSCL_CHECK_ARG(!per_frame || ((int64_t)H * W) % 4 == 0, "H*W must be a multiple of 4 for per-frame parameters");
+  MSCL_CHECK_ARG((int64_t)N * (per_frame ? T : 1) <= 65535, "too many clips / frames for one launch");
+  if (per_frame)
+    mscl::clip_gray_sum_kernel<<<dim3(n_chunks, N * T), 256, 0, s>>>(d_x, d_gray_partial, THW, (int64_t)H * W, T);
+  else
+    mscl::clip_gray_sum_kernel<<<dim3(n_chunks, N), 256, 0, s>>>(d_x, d_gray_partial, THW, THW, 1);
   MSCL_LAUNCH_CHECK();
   if (n_taps == 11 && W <= 128 && W > 10 && H > 10 && W % 4 == 0) {     // the config's case: 11 taps, 112x112 crops
     // bands of rows sized for ~3 CTAs per SM (<= 72 KB of staged rows incl. the 5 + 5 halo rows)
@@ -434,25 +444,16 @@ int mscl_color_pipeline(const float *d_x, const float *d_params, const float *d_
     const int band_rows = (H + bands - 1) / bands;
     const size_t smem_fast = (size_t)3 * (band_rows + 10) * W * sizeof(float);
     if (band_rows >= 6 && smem_fast <= 200 * 1024) {
-      static size_t configured_fast = 48 * 1024;
-      if (smem_fast > configured_fast) {
-        MSCL_CUDA(cudaFuncSetAttribute(mscl::color_pipeline_fast_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_fast));
-        configured_fast = smem_fast;
-      }
+      MSCL_CUDA(mscl::ensure_dyn_smem(mscl::color_pipeline_fast_kernel<11>, smem_fast));
       mscl::color_pipeline_fast_kernel<11><<<dim3(N * T, bands), 512, smem_fast, s>>>(d_x, d_params, d_gray_partial, n_chunks,
-                                                                                      d_taps, d_norm, d_out, T, H, W, band_rows);
+                                                                                      d_taps, d_norm, d_out, T, H, W, band_rows, per_frame);
       MSCL_LAUNCH_CHECK();
       return MSCL_OK;
     }
   }
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    MSCL_CUDA(cudaFuncSetAttribute(mscl::color_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  MSCL_CUDA(mscl::ensure_dyn_smem(mscl::color_pipeline_kernel, smem));
   mscl::color_pipeline_kernel<<<N * T, 512, smem, s>>>(d_x, d_params, d_gray_partial, n_chunks, d_taps, n_taps, d_norm, d_out,
-                                                       T, H, W);
+                                                       T, H, W, per_frame);
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }

@@ -35,6 +35,14 @@ int set_err(int code, const char *fmt, ...);
 
 static inline cudaStream_t as_stream(mscl_stream_t s) { return (cudaStream_t)s; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is an attribute of (function, DEVICE): raise it to `bytes` on the current
+// device unless this process already did so there (thread-safe; defined in abi.cu).  Returns a cudaError_t.
+cudaError_t ensure_dyn_smem_impl(const void *func, size_t bytes);
+template <typename F>
+static inline cudaError_t ensure_dyn_smem(F func, size_t bytes) {
+  return ensure_dyn_smem_impl(reinterpret_cast<const void *>(func), bytes);
+}
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 // The reference hard-codes the decay base 0.99999 (moco.py:484) and evaluates

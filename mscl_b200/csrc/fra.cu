@@ -352,14 +352,10 @@ int mscl_fra_fused(const float *d_flow, const int32_t *d_cid, const float *d_cs,
   MSCL_CHECK_ARG(smem <= 200 * 1024, "frame of %d pixels does not fit a cluster's shared memory: use maxrad + apply", HW);
   int threads = chunk / 4 >= 512 ? 512 : 256;
   if (env_threads > 0) threads = env_threads;
-  static size_t configured[2] = {48 * 1024, 48 * 1024};
-  if (smem > configured[layout]) {
-    if (layout == 0)
-      MSCL_CUDA(cudaFuncSetAttribute(mscl::fra_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-      MSCL_CUDA(cudaFuncSetAttribute(mscl::fra_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[layout] = smem;
-  }
+  if (layout == 0)
+    MSCL_CUDA(mscl::ensure_dyn_smem(mscl::fra_fused_kernel<0>, smem));
+  else
+    MSCL_CUDA(mscl::ensure_dyn_smem(mscl::fra_fused_kernel<1>, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cluster, N * T);
   cfg.blockDim = dim3(threads);

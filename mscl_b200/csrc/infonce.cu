@@ -363,8 +363,7 @@ int mscl_infonce_partial_simt(const float *d_qpack, int32_t M, const float *d_qu
   MSCL_CHECK_ARG(d_qpack && d_queue && d_dscale && d_acc, "null pointer");
   MSCL_CHECK_ARG(M > 0 && K_local > 0, "bad M=%d K_local=%lld", M, (long long)K_local);
   const size_t smem = sizeof(float) * (mscl::kSimtKeys * 129 + mscl::kC + mscl::kSimtKeys + 8);
-  MSCL_CUDA(cudaFuncSetAttribute(mscl::infonce_partial_simt_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MSCL_CUDA(mscl::ensure_dyn_smem(mscl::infonce_partial_simt_kernel, smem));
   const int64_t blocks = (K_local + mscl::kSimtKeys - 1) / mscl::kSimtKeys;
   mscl::infonce_partial_simt_kernel<<<(unsigned)blocks, 128, smem, mscl::as_stream(stream)>>>(
       d_qpack, M, d_queue, d_dscale, K_local, shard_begin, d_acc, with_grad);

@@ -796,20 +796,6 @@ static int make_map_slab(CUtensorMap *map, float *ptr, int M, int n_part) {
   return MSCL_OK;
 }
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of the function: set it once on every device
-// this process launches on.
-template <typename F>
-static int ensure_smem(F func, int which) {
-  static bool done[4][64] = {};
-  int dev = 0;
-  MSCL_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !done[which][dev]) {
-    MSCL_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    if (dev >= 0 && dev < 64) done[which][dev] = true;
-  }
-  return MSCL_OK;
-}
-
 static int launch(bool fused, bool grad, const Params &p, const float *d_queue, int n_part, cudaStream_t s) {
   const int64_t n_units = (p.K_local + kUnit - 1) / kUnit;
   MSCL_CHECK_ARG(n_part > 0 && n_part <= n_units, "n_part=%d must be in [1, %lld] (one 64-key unit per CTA at least)", n_part,
@@ -830,8 +816,7 @@ static int launch(bool fused, bool grad, const Params &p, const float *d_queue, 
   dim3 grid((unsigned)n_part, (unsigned)row_blocks);
 #define MSCL_FUSED_LAUNCH(G, F, W)                                                                                   \
   do {                                                                                                               \
-    rc = ensure_smem(infonce_fused_kernel<G, F>, W);                                                                 \
-    if (rc) return rc;                                                                                               \
+    MSCL_CUDA(mscl::ensure_dyn_smem(infonce_fused_kernel<G, F>, kSmemBytes));                                        \
     MSCL_CUDA(mscl::launch_pdl(infonce_fused_kernel<G, F>, grid, dim3(kThreads), kSmemBytes, s, tw, twh, tw2, ta, p)); \
   } while (0)
   if (fused && grad) MSCL_FUSED_LAUNCH(true, true, 0);

@@ -508,12 +508,8 @@ extern "C" int mscl_infonce_partial(const float *d_qpack, int32_t M, const float
   const int row_blocks = (M + kRows - 1) / kRows;
   dim3 grid((unsigned)n_part, (unsigned)row_blocks);
   cudaStream_t s = mscl::as_stream(stream);
-  static bool configured = false;      // once per process (idempotent, so a race between threads is harmless)
-  if (!configured) {
-    MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    MSCL_CUDA(cudaFuncSetAttribute(infonce_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    configured = true;
-  }
+  MSCL_CUDA(mscl::ensure_dyn_smem(infonce_tc_kernel<true>, kSmemBytes));      // per device ("weak" 9)
+  MSCL_CUDA(mscl::ensure_dyn_smem(infonce_tc_kernel<false>, kSmemBytes));
   if (with_grad) {
     MSCL_CUDA(mscl::launch_pdl(infonce_tc_kernel<true>, grid, dim3(kThreads), kSmemBytes, s, tw, tw2, tq, tp, d_qpack, M,
                                d_dscale, K_local, shard_begin, d_part));

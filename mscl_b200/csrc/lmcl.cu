@@ -416,12 +416,7 @@ int mscl_lmcl(const float *d_xq, const float *d_xf, int32_t N, int32_t C, int32_
   const size_t smem = sizeof(float) * ((size_t)2 * C * (tt | 1) + (size_t)t * (t2 | 1) + 2 * tt + 96);
   MSCL_CHECK_ARG(smem <= 200 * 1024, "C*(t+t2) too large for one CTA (%zu B of shared memory)",
                  smem);
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    MSCL_CUDA(cudaFuncSetAttribute(mscl::lmcl_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  MSCL_CUDA(mscl::ensure_dyn_smem(mscl::lmcl_kernel, smem));
   const int threads = (C * tt >= 4096) ? 1024 : ((C * tt >= 2048) ? 512 : 256);     // one thread per ~6 staged elements
   mscl::lmcl_kernel<<<N, threads, smem, mscl::as_stream(stream)>>>(d_xq, d_xf, N, C, t, t2, inv_T,
                                                               d_out, d_gxq, d_gxf, d_part);

@@ -70,7 +70,12 @@ class NegativeQueue:
     (mmaction/models/recognizers/moco.py:390-396) on the hot path.  Layout: key-major
     fp32 [K_local, C]; ages as int32 `birth` with count = n_enq - birth; `qstate`
     int64[4] = {ptr, n_enq, counter, 0} lives on the device so no call ever syncs.
-    With world_size G > 1 and shard=True each rank owns K/G consecutive slots.
+    With world_size G > 1 and shard=True each rank owns K/G consecutive slots: that is what the
+    tensor-core pass streams.  Every rank ALSO keeps the bit-exact fp32 master of the WHOLE queue
+    (`full_queue`, `full_birth`; 32 MB at K = 65536 -- the gathered keys every rank already holds
+    are written into it by a second enqueue launch), so that state_dict() / `.queue` / `.count`
+    never need a collective: mmcv saves checkpoints from rank 0 only (`@master_only`), where a
+    gather of the shards would hang.
     """
 
     def __init__(self, K, C=DIM, device="cuda", rank=0, world=1, shard=False):
@@ -88,6 +93,10 @@ class NegativeQueue:
         self.queue_tf32 = torch.zeros(self.K_local, C, device=self.device)   # RN-rounded operand copy
         self.birth = torch.zeros(self.K_local, dtype=torch.int32, device=self.device)
         self.qstate = torch.zeros(4, dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            self.full_queue = torch.zeros(self.K, C, device=self.device)
+            self.full_birth = torch.zeros(self.K, dtype=torch.int32, device=self.device)
+            self.full_qstate = torch.zeros(4, dtype=torch.int64, device=self.device)
         self.ptr = 0          # host mirrors (deterministic, never read back from the device)
         self.n_enq = 0
         self.max_key_norm = 1.0
@@ -108,9 +117,24 @@ class NegativeQueue:
         _cabi.call("mscl_queue_import", self.queue.data_ptr(), self.queue_tf32.data_ptr(), self.birth.data_ptr(),
                    self.qstate.data_ptr(),
                    q_loc.data_ptr(), c_loc.data_ptr(), self.C, self.K_local, _stream())
+        if self.world > 1:
+            self.full_qstate.copy_(self.qstate)
+            q_all = queue_ck.contiguous()
+            _cabi.call("mscl_queue_import", self.full_queue.data_ptr(), None, self.full_birth.data_ptr(),
+                       self.full_qstate.data_ptr(), q_all.data_ptr(), count.data_ptr(), self.C, self.K, _stream())
         self._fresh = True
         # keep the staging tensors alive until the kernel has consumed them
         torch.cuda.current_stream().synchronize()
+
+    def export_full(self):
+        """Return (queue_ck (C,K), count (K,) int64) of the WHOLE queue without a collective."""
+        if self.world == 1:
+            return self.export()
+        q = torch.empty(self.C, self.K, device=self.device)
+        c = torch.empty(self.K, dtype=torch.int64, device=self.device)
+        _cabi.call("mscl_queue_export", self.full_queue.data_ptr(), self.full_birth.data_ptr(), self.full_qstate.data_ptr(),
+                   q.data_ptr(), c.data_ptr(), self.C, self.K, _stream())
+        return q, c
 
     def export(self):
         """Return (queue_ck (C,K_local), count (K_local,) int64) of this shard."""
@@ -140,6 +164,9 @@ class NegativeQueue:
                    self.qstate.data_ptr(),
                    keys_all.data_ptr(), b, self.C, self.K, self.shard_begin, self.K_local, None, None, _stream(),
                    algo_bytes=2 * b * self.C * 4)
+        if self.world > 1:      # the whole-queue fp32 master every rank keeps for a collective-free state_dict()
+            _cabi.call("mscl_enqueue", self.full_queue.data_ptr(), None, self.full_birth.data_ptr(), self.full_qstate.data_ptr(),
+                       keys_all.data_ptr(), b, self.C, self.K, 0, self.K, None, None, _stream())
         self.ptr = (self.ptr + b) % self.K
         self.n_enq += 1
         self._fresh = True
@@ -658,14 +685,19 @@ _GRAY_CHUNKS = 16
 
 @torch.no_grad()
 def color_pipeline(x, params, taps, norm):
-    """Fused flip / colour jitter / grayscale / Gaussian blur / normalise of RGB clips (N,3,T,H,W); params (N,16)
-    as described in include/mscl_b200.h (K9), taps the odd-length 1-D blur kernel, norm = [mean3, std3]."""
+    """Fused flip / colour jitter / grayscale / Gaussian blur / normalise of RGB clips (N,3,T,H,W); params (N,16): one
+    set per clip, or (N*T,16): one set per frame (row n*T + t), as described in include/mscl_b200.h (K9); taps the
+    odd-length 1-D blur kernel, norm = [mean3, std3]."""
     _chk(x, name="clips"), _chk(params, name="params"), _chk(taps, name="taps"), _chk(norm, name="norm")
-    if x.dim() != 5 or x.shape[1] != 3 or tuple(params.shape) != (x.shape[0], COLOR_PARAMS):
-        raise _cabi.MsclError("clips must be (N,3,T,H,W) and params (N,16)")
+    if x.dim() != 5 or x.shape[1] != 3 or params.dim() != 2 or params.shape[1] != COLOR_PARAMS:
+        raise _cabi.MsclError("clips must be (N,3,T,H,W) and params (N,16) or (N*T,16)")
     N, _, T, H, W = x.shape
+    if params.shape[0] not in (N, N * T):
+        raise _cabi.MsclError(f"params must have {N} (per clip) or {N * T} (per frame) rows, got {params.shape[0]}")
+    per_frame = int(params.shape[0] == N * T and T > 1)
     out = torch.empty_like(x)
-    scratch = torch.empty(N, _GRAY_CHUNKS, device=x.device)
+    chunks = 1 if per_frame else _GRAY_CHUNKS
+    scratch = torch.empty(params.shape[0], chunks, device=x.device)
     _cabi.call("mscl_color_pipeline", x.data_ptr(), params.data_ptr(), taps.data_ptr(), taps.numel(), norm.data_ptr(),
-               scratch.data_ptr(), _GRAY_CHUNKS, out.data_ptr(), N, T, H, W, _stream(), algo_bytes=36 * N * T * H * W)
+               scratch.data_ptr(), chunks, out.data_ptr(), N, T, H, W, per_frame, _stream(), algo_bytes=36 * N * T * H * W)
     return out

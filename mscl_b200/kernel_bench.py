@@ -117,9 +117,34 @@ def bench_k1(cfg, M, K, pk, dev, iters=30):
     ab = fx.infonce_algo_bytes(M, K)
     fl = 4 * M * K * 128
     shape = f"M={M} K={K}"
-    out = [row(cfg, "infonce_tc_kernel<grad> (K1 pass)", shape, time_train(partial, iters), ab, fl, pk,
+    out = [row(cfg, "infonce_tc_kernel<grad> (K1 pass, slab form)", shape, time_train(partial, iters), ab, fl, pk,
                note=f"{n_part} CTAs along the keys; queue ring of {rot}"),
-           row(cfg, "K1 op = prep + pass + finalize", shape, time_train(whole, iters), ab, fl, pk)]
+           row(cfg, "K1 op, slab form = prep + pass + finalize (3 launches)", shape, time_train(whole, iters), ab, fl, pk)]
+    # the single-launch form (csrc/infonce_fused.cu): what functional.infonce runs
+    n_fp = _cabi.query("mscl_infonce_fused_parts", M, K, fx.sm_count(dev))
+    ws = torch.zeros(16 * M * 4 + 4, device=dev)
+    fpart = torch.empty(n_fp, M, fx.PACK_LD, device=dev)
+    rowaux = torch.empty(M, 4, device=dev)
+    gone = torch.ones(1, device=dev)
+
+    def fused(i, grad=1):
+        nq = queues[i % rot]
+        _cabi.call("mscl_infonce_fused", q.data_ptr(), k.data_ptr(), M, nq.queue_tf32.data_ptr(), nq.birth.data_ptr(),
+                   nq.qstate.data_ptr(), K, 1 / 0.07, 1.0, None, 1, ws.data_ptr(), fpart.data_ptr(), n_fp, M, grad, 1,
+                   row_loss.data_ptr(), rowaux.data_ptr(), gout.data_ptr(), _st())
+
+    def bwd(i):
+        _cabi.call("mscl_infonce_bwd_slabs", fpart.data_ptr(), n_fp, M, k.data_ptr(), rowaux.data_ptr(), gone.data_ptr(), M,
+                   dq.data_ptr(), _st())
+
+    def fused_fb(i):
+        fused(i), bwd(i)
+
+    out += [row(cfg, "K1 op = infonce_fused_kernel<grad> (1 launch: prep + pass + loss / top-k)", shape, time_train(fused, iters),
+                ab, fl, pk, note=f"{n_fp} CTAs along the keys; the O slabs are summed by the backward kernel"),
+            row(cfg, "K1 op + backward = infonce_fused_kernel + infonce_bwd_slabs (2 launches)", shape, time_train(fused_fb, iters),
+                ab, fl, pk),
+            row(cfg, "K1 op, forward only (no grad)", shape, time_train(lambda i: fused(i, 0), iters), ab, 2 * M * K * 128, pk)]
     del queues
     return out
 
@@ -310,7 +335,7 @@ def bench_k789(cfg, N, pk, dev, iters=20):
         taps = prm["taps"].contiguous()
         us = time_train(lambda i: _cabi.call("mscl_color_pipeline", xs[i % rot].data_ptr(), params.data_ptr(), taps.data_ptr(),
                                              taps.numel(), norm.data_ptr(), scratch.data_ptr(), fx._GRAY_CHUNKS,
-                                             ys[i % rot].data_ptr(), N, T, 112, 112, _st()), iters)
+                                             ys[i % rot].data_ptr(), N, T, 112, 112, 0, _st()), iters)
         out.append(row(cfg, "clip_gray_sum + color_pipeline", f"({N},3,{T},112,112) {name}", us, 36 * N * T * HW, 0, pk))
     return out
 
@@ -327,7 +352,7 @@ def run(configs=("cfg2", "cfg3", "cfg4", "cfg5"), device=0, verbose=True):
         if verbose:
             for r in rs:
                 frac = f"{100 * r['frac_hbm']:5.1f}% of HBM peak" if "frac_hbm" in r else ""
-                print(f"[{r['config']}] {r['kernel']:<34} {r['shape']:<44} {r['us']:8.1f} us  "
+                print(f"[{r['config']}] {r['kernel']:<78} {r['shape']:<44} {r['us']:8.1f} us  "
                       f"{r.get('gbs', 0):7.0f} GB/s  {frac}", flush=True)
         torch.cuda.empty_cache()
 

@@ -110,22 +110,29 @@ class MoCoV2(BaseMoCoRecognizer):
         rank = dist.get_rank() if _dist_on() else 0
         world = dist.get_world_size() if _dist_on() else 1
         nq = fx.NegativeQueue(self.K, self.dim, device, rank, world, shard=self.shard_queue and world > 1)
+        if world > 1:
+            # The reference registers queue / count / queue_ptr as buffers, so DDP's initial module-state sync makes every
+            # rank start from rank 0's random queue (moco.py:390-396); here they are plain state staged on the host and
+            # drawn per rank, so rank 0's copy is broadcast on first use (a collective: every rank's first forward).
+            st = self._staged
+            q0 = st["queue"].to(device, torch.float32).contiguous()
+            c0 = st["count"].to(device, torch.int64).contiguous()
+            p0 = torch.tensor([int(st["ptr"])], dtype=torch.int64, device=device)
+            for t in (q0, c0, p0):
+                dist.broadcast(t, src=0)
+            self._staged = dict(queue=q0, count=c0, ptr=int(p0.item()))
         with torch.cuda.device(device):
             nq.load(self._staged["queue"], self._staged["count"], self._staged["ptr"])
         self._nq, self._staged = nq, None
         return nq
 
     def _gathered_state(self):
-        """Reference-layout state (queue (C,K), count (K,), ptr).  Collective when the queue is sharded."""
+        """Reference-layout state (queue (C,K), count (K,), ptr).  NOT a collective, sharded queue or not: every rank
+        keeps the fp32 master of the whole queue (functional.NegativeQueue), so `state_dict()` may be called from one
+        rank alone -- mmcv's checkpoint hook runs under `@master_only`."""
         if self._nq is None:
             return self._staged
-        q, c = self._nq.export()
-        if self._nq.world > 1:
-            qs = [torch.empty_like(q) for _ in range(self._nq.world)]
-            cs = [torch.empty_like(c) for _ in range(self._nq.world)]
-            dist.all_gather(qs, q)
-            dist.all_gather(cs, c)
-            q, c = torch.cat(qs, dim=1), torch.cat(cs)
+        q, c = self._nq.export_full()
         return dict(queue=q, count=c, ptr=self._nq.ptr)
 
     @property

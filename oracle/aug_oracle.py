@@ -42,14 +42,28 @@ def normalize(x, mean, std):
 
 def color_pipeline(x, prm, blur_radius):
     """Brightness -> contrast -> saturation -> hue (applied where prm['jit']), grayscale where prm['gray'],
-    separable Gaussian blur with reflect padding where prm['blur']; x (N,3,T,H,W), one decision per clip."""
-    v = lambda t: t.view(-1, 1, 1, 1, 1)
+    separable Gaussian blur with reflect padding where prm['blur']; x (N,3,T,H,W).  The entries of prm have N values
+    (one set per clip: the 'params' sync level) or N*T values in (clip, frame) order (one set per frame: the 'batch'
+    sync level, whose apply decisions the caller repeats over the frames of a clip); the contrast step is taken about
+    the mean luminance of the clip / of the frame respectively."""
+    n, _, t = x.shape[:3]
+    per_frame = prm["brightness"].numel() == n * t and t > 1
+    if per_frame:
+        v = lambda p: p.view(n, 1, t, 1, 1)
+        mean_dims = (1, 3, 4)
+    else:
+        v = lambda p: p.view(-1, 1, 1, 1, 1)
+        mean_dims = (1, 2, 3, 4)
     y = x * v(prm["brightness"])
-    m = rgb_to_gray(y).mean(dim=(1, 2, 3, 4), keepdim=True)
+    m = rgb_to_gray(y).mean(dim=mean_dims, keepdim=True)
     y = (y - m) * v(prm["contrast"]) + m
     g = rgb_to_gray(y)
     y = (y - g) * v(prm["saturation"]) + g
-    y = torch.einsum("nij,njthw->nithw", hue_matrix(prm["hue"]), y)
+    hm = hue_matrix(prm["hue"])
+    if per_frame:
+        y = torch.einsum("ntij,njthw->nithw", hm.view(n, t, 3, 3), y)
+    else:
+        y = torch.einsum("nij,njthw->nithw", hm, y)
     x = torch.where(v(prm["jit"]), y.clamp(0, 1), x)
     x = torch.where(v(prm["gray"]), rgb_to_gray(x).expand_as(x), x)
     r = blur_radius
@@ -72,7 +86,8 @@ def augment_view(aug, clips, aux_info, suffix, weak):
                 img = flip(O.flow_visualize(aux_info[k]) if aug.visualize else aux_info[k], mask)
                 aux_info[k] = normalize(img, aug.mean.view(-1), aug.std.view(-1)) if aug.normalize_flow else img
     if not weak:
-        clips = color_pipeline(clips, aug._color_params(clips.shape[0], clips.device), aug.blur_radius)
+        frames = clips.shape[2] if aug.sync_level[0 if suffix == "_q" else 1] == "batch" else 1
+        clips = color_pipeline(clips, aug._color_params(clips.shape[0], clips.device, frames), aug.blur_radius)
     return normalize(clips, aug.mean.view(-1), aug.std.view(-1)), aux_info
 
 

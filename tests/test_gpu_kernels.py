@@ -452,12 +452,15 @@ def test_flow_visualize_golden_and_oracle(fx, golden_dir):
     assert d.max() <= (1.0 / 255) / 0.224 + 1e-5 and (d > 1e-6).mean() <= 5e-3
 
 
+@pytest.mark.parametrize("per_frame", [False, True])
 @pytest.mark.parametrize("shape,crop", [((6, 3, 4, 32, 48), 112), ((3, 3, 8, 112, 112), 112), ((6, 3, 2, 24, 36), 64),
                                         ((2, 3, 2, 130, 132), 112)])
-def test_color_pipeline_matches_torch_ops(fx, shape, crop):
+def test_color_pipeline_matches_torch_ops(fx, shape, crop, per_frame):
     """K9 against the same pipeline written as PyTorch ops (oracle/aug_oracle.py): every
     combination of jitter / grayscale / blur / flip decisions, given parameters.  crop 112 -> 11 taps (frames up to 128
-    wide take the in-place shared-memory kernel, wider ones the generic one), crop 64 -> 7 taps (generic kernel)."""
+    wide take the in-place shared-memory kernel, wider ones the generic one), crop 64 -> 7 taps (generic kernel).
+    per_frame: the jitter factors differ between the frames of a clip ('batch' sync level, ssl_aug.py:56-60) and the
+    contrast step uses each frame's own mean luminance; otherwise one set per clip ('params' level, :62-66)."""
     from mscl_b200.common.ssl_aug import SyncMoCoAugmentV5
     from oracle import aug_oracle as A
     aug = SyncMoCoAugmentV5(crop_size=crop, sync_level=("batch", "batch"), t=(8, 8), flow_suffix="flow_imgs")
@@ -466,19 +469,23 @@ def test_color_pipeline_matches_torch_ops(fx, shape, crop):
     gen = torch.Generator().manual_seed(n)
     x = torch.rand(shape, generator=gen)
     torch.manual_seed(5)
-    prm = aug._color_params(n, torch.device("cpu"))
+    frames = shape[2] if per_frame else 1
+    prm = aug._color_params(n, torch.device("cpu"), frames)
+    assert prm["brightness"].numel() == n * frames
     combos = [(1, 1, 1), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (0, 0, 0)]
-    prm["jit"] = torch.tensor([combos[i % 6][0] for i in range(n)], dtype=torch.bool)
-    prm["gray"] = torch.tensor([combos[i % 6][1] for i in range(n)], dtype=torch.bool)
-    prm["blur"] = torch.tensor([combos[i % 6][2] for i in range(n)], dtype=torch.bool)
+    rep = lambda j: torch.tensor([combos[i % 6][j] for i in range(n)], dtype=torch.bool).repeat_interleave(frames)
+    prm["jit"], prm["gray"], prm["blur"] = rep(0), rep(1), rep(2)
     flip = torch.tensor([i % 2 == 0 for i in range(n)])
     want = A.normalize(A.color_pipeline(A.flip(x, flip), prm, aug.blur_radius), mean, std)
     dev = torch.device("cuda")
     prm_d = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in prm.items()}
     norm = torch.cat([aug.mean.view(-1), aug.std.view(-1)]).to(dev)
-    got = fx.color_pipeline(x.to(dev), aug._pack_params(prm_d, flip.to(dev), False), prm_d["taps"].contiguous(), norm)
+    flip_u = flip.repeat_interleave(frames).to(dev)
+    got = fx.color_pipeline(x.to(dev), aug._pack_params(prm_d, flip_u, False), prm_d["taps"].contiguous(), norm)
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-5, atol=2e-5)
-    weak = fx.color_pipeline(x.to(dev), aug._pack_params(prm_d, flip.to(dev), True), prm_d["taps"].contiguous(), norm)
+    if per_frame and shape[2] > 1:      # the frames of a jittered clip really got different factors
+        assert prm["brightness"].view(n, frames).std(dim=1).min() > 0
+    weak = fx.color_pipeline(x.to(dev), aug._pack_params(prm_d, flip_u, True), prm_d["taps"].contiguous(), norm)
     np.testing.assert_allclose(weak.cpu().numpy(), A.normalize(A.flip(x, flip), mean, std).numpy(), rtol=1e-6, atol=1e-6)
 
 
