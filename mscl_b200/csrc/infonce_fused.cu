@@ -58,7 +58,7 @@ constexpr uint32_t kOffPair = 0;                               // 2 x 64 KB pair
 constexpr uint32_t kOffSingle = kOffPair + 2 * kPairBytes;     // 32 KB: the half tile
 constexpr uint32_t kOffW2 = kOffSingle + kUnitBytes;           // ring 2: 2 x 32 KB; the Q tile before the first ring-2 load
 constexpr uint32_t kOffBar = kOffW2 + kStages2 * kUnitBytes;
-constexpr uint32_t kNumBars = 2 + 2 + 1 + 2 * kStages2 + 1 + 2 + 2 + 1 + 1 + 1 + 2 + 2;   // (the q_load slot is now "prologue loads issued")
+constexpr uint32_t kNumBars = 2 + 2 + 1 + 2 * kStages2 + 1 + 2 + 2 + 1 + 1 + 1 + 2 + 2 + 1;   // (the q_load slot is now "prologue loads issued")
 constexpr int kStatCopies = 16;       // the row statistics are spread over this many accumulator copies (see the epilogue)
 constexpr uint32_t kOffTmemPtr = kOffBar + 8 * kNumBars;
 constexpr uint32_t kOffFlag = kOffTmemPtr + 8;
@@ -255,7 +255,8 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
   const uint32_t bar_qfree = bar0 + 8u * (kB + 7);
   auto bar_dfull = [&](int b) { return bar0 + 8u * (kB + 8 + b); };
   auto bar_dfree = [&](int b) { return bar0 + 8u * (kB + 10 + b); };
-  static_assert(kB + 12 == kNumBars, "barrier count");
+  const uint32_t bar_ticket = bar0 + 8u * (kB + 12);           // this CTA's ticket (last or not) is in last_flag
+  static_assert(kB + 13 == kNumBars, "barrier count");
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(gbase + kOffTmemPtr);
   volatile int *last_flag = reinterpret_cast<volatile int *>(gbase + kOffFlag);
   float *ds_smem = reinterpret_cast<float *>(gbase + kOffDs);
@@ -302,6 +303,7 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     mbar_init(bar_ofull, 1);
     mbar_init(bar_qload, kSoftmaxWarps);
     mbar_init(bar_qfree, kSoftmaxWarps);
+    mbar_init(bar_ticket, 1);
     *last_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -754,14 +756,15 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       const unsigned done = atomicAdd(counter, 1u);
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
       *last_flag = (done == gridDim.x * gridDim.y - 1u) ? 2 : 1;
+      mbar_arrive(bar_ticket);                   // release: the flag is visible to whoever completes the wait below
       TLF(7);
     }
   }
   if (FUSED && (warp < 2 || warp >= 2 + kSoftmaxWarps)) {
     // the four warps that are idle once their role is done: wait for this CTA's ticket; the last CTA finalises here,
     // concurrently with its softmax warps storing O
-    int f;
-    while ((f = *last_flag) == 0) __nanosleep(64);
+    mbar_wait(bar_ticket, 0);
+    const int f = *last_flag;
     if (f == 2) {
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
       const int tid = (warp < 2 ? warp : warp - kSoftmaxWarps) * 32 + lane;

@@ -490,8 +490,11 @@ class EmaTable:
         dev = self.params_k[0].device
         for pk, pq in zip(self.params_k, self.params_q):
             _chk_dense(pk.data, "param_k"), _chk_dense(pq.data, "param_q")
-            if pk.shape != pq.shape or pk.stride() != pq.stride():
-                raise _cabi.MsclError("key/query parameter shapes or strides differ")
+            # same memory ORDER is what the element-wise walk needs: literal strides may differ where an extent is 1
+            # (a [32,16,1,1,1] weight is row-major with strides (16,1,1,1,1) and with (16,1,16,16,16) alike)
+            same_order = pk.stride() == pq.stride() or (pk.is_contiguous() and pq.is_contiguous())
+            if pk.shape != pq.shape or not same_order:
+                raise _cabi.MsclError("key/query parameter shapes or memory layouts differ")
         sizes = [p.numel() for p in self.params_k]
         blk_t, blk_s = [], []
         for i, n in enumerate(sizes):

@@ -20,12 +20,15 @@ from . import mscl_oracle as O
 
 
 class OracleBranch:
-    """One MoCoV2: q/k encoder, neck, MLP on the CPU + reference-layout queue state."""
+    """One MoCoV2: q/k encoder, neck, MLP on the CPU + reference-layout queue state.
+    device: where the copies live.  "cpu" for every checker use; bench.py's `gpu_eager_baseline` passes the GPU to time the
+    reference's operation sequence as eager PyTorch on the same B200 (the GPU-vs-GPU bar)."""
 
-    def __init__(self, rec, state=None):
-        self.encoder_q, self.encoder_k = copy.deepcopy(rec.encoder_q).cpu(), copy.deepcopy(rec.encoder_k).cpu()
-        self.neck_q, self.neck_k = copy.deepcopy(rec.neck_q).cpu(), copy.deepcopy(rec.neck_k).cpu()
-        self.mlp_q, self.mlp_k = copy.deepcopy(rec.mlp_q).cpu(), copy.deepcopy(rec.mlp_k).cpu()
+    def __init__(self, rec, state=None, device="cpu"):
+        dev = torch.device(device)
+        self.encoder_q, self.encoder_k = copy.deepcopy(rec.encoder_q).to(dev), copy.deepcopy(rec.encoder_k).to(dev)
+        self.neck_q, self.neck_k = copy.deepcopy(rec.neck_q).to(dev), copy.deepcopy(rec.neck_k).to(dev)
+        self.mlp_q, self.mlp_k = copy.deepcopy(rec.mlp_q).to(dev), copy.deepcopy(rec.mlp_k).to(dev)
         # torchvision backbones carry the multi-level forward as an instance attribute bound to the
         # ORIGINAL module; rebind it to the copy
         from mscl_b200.backbones import torchvision_multilevel
@@ -39,7 +42,7 @@ class OracleBranch:
                 if hasattr(mod, "upsample"):
                     mod.upsample = lambda x, size: F.interpolate(x, size=size, mode="trilinear")
         st = state or rec._gathered_state()
-        self.state = O.QueueState(st["queue"].cpu().float(), st["count"].cpu().long(), int(st["ptr"]))
+        self.state = O.QueueState(st["queue"].to(dev).float(), st["count"].to(dev).long(), int(st["ptr"]))
         self.state.iters, self.state.batch_size = rec.iters, rec.batch_size
         self.m_base, self.max_iters, self.T = rec.m_base, rec.max_iters, rec.T
         # the first MoCo recognizer keeps a constant momentum (moco.py:114-124); MoCoV2 anneals it (:413-415)
@@ -105,14 +108,14 @@ def extract_feat_ranks(branch, im_qs, im_ks):
 
 
 class OracleMSCL:
-    def __init__(self, model):
-        self.rgb = OracleBranch(model.recognizer)
-        self.flow = OracleBranch(model.recognizer_flow)
+    def __init__(self, model, device="cpu"):
+        self.rgb = OracleBranch(model.recognizer, device=device)
+        self.flow = OracleBranch(model.recognizer_flow, device=device)
         self.T = model.moco_mx_head.T
         self.t = model.sup_head.labels.shape[1]
         self.mlvl_ids = model.sup_head.mlvl_ids
-        self.trans_rgb = copy.deepcopy(model.sup_head.trans_rgb).cpu()        # Identity unless bkb_channels says otherwise
-        self.trans_flow = copy.deepcopy(model.sup_head.trans_flow).cpu()
+        self.trans_rgb = copy.deepcopy(model.sup_head.trans_rgb).to(device)   # Identity unless bkb_channels says otherwise
+        self.trans_flow = copy.deepcopy(model.sup_head.trans_flow).to(device)
         self.weight_aug_flow = model.weight_aug_flow
         self.training = model.training
 

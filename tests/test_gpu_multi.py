@@ -42,19 +42,22 @@ def _run(fn, world):
     return [out[r] for r in range(world)]
 
 
-def _world():
+def _need(world):
     n = torch.cuda.device_count() if torch.cuda.is_available() else 0
-    if n < 2:
-        pytest.skip("needs at least 2 GPUs")
-    return 2 if n < 4 else 4
+    if n < world:
+        pytest.skip(f"needs at least {world} GPUs, this box has {n}")
+    return world
 
 
-def _objective_job(rank, world):
+WORLDS = [2, 4, 8]
+
+
+def _objective_job(rank, world, N=8, K=4096):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from test_gpu_step import head_level_model
     from oracle import inputs, mscl_oracle as O
-    N, K, t = 8, 4096, 4
+    t = 4
     inp = inputs.head_inputs(seed=11, N=N * world, K=K, t=t, hw_rgb=6, hw_flow=3, b_all=N * world)
     sl = slice(rank * N, (rank + 1) * N)
     # product: this rank's rows, sharded queue
@@ -109,9 +112,21 @@ def _objective_job(rank, world):
     return res
 
 
-def test_sharded_objective_matches_replicated_oracle():
-    world = _world()
-    for r in _run(_objective_job, world):
+@pytest.mark.parametrize("world", WORLDS)
+def test_sharded_objective_matches_replicated_oracle(world):
+    for r in _run(_objective_job, _need(world)):
+        assert r["ok"], r["msgs"]
+
+
+def _objective_job_cfg2(rank, world):
+    return _objective_job(rank, world, N=32, K=65536)
+
+
+@pytest.mark.parametrize("world", WORLDS)
+def test_sharded_objective_at_the_config_size(world):
+    """The north star's configuration: 32 clips per GPU, K = 65536 negatives sharded K/G (8192 keys per GPU at G = 8),
+    every rank's 23 log variables, gradients and the gathered queue state against the replicated-queue oracle."""
+    for r in _run(_objective_job_cfg2, _need(world)):
         assert r["ok"], r["msgs"]
 
 
@@ -133,7 +148,40 @@ def _shuffle_job(rank, world):
                 perm_ok=bool(torch.equal(idx, torch.randperm(n * world))))
 
 
-def test_device_shuffle_exchange():
-    world = _world()
-    for r in _run(_shuffle_job, world):
+@pytest.mark.parametrize("world", WORLDS)
+def test_device_shuffle_exchange(world):
+    for r in _run(_shuffle_job, _need(world)):
         assert r["ok"] and r["perm_ok"], r
+
+
+def _state_dict_one_rank_job(rank, world):
+    """state_dict() of a model with sharded queues called on rank 0 ONLY (mmcv's checkpoint hook runs under
+    @master_only): must return the whole queue without a collective -- every rank keeps the fp32 master."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_gpu_step import head_level_model
+    from oracle import inputs, mscl_oracle as O
+    K, N = 1024, 4
+    inp = inputs.head_inputs(seed=3, N=N * world, K=K, t=4, hw_rgb=6, hw_flow=3, b_all=N * world)
+    model = head_level_model(K, 4)
+    model.recognizer.shard_queue = True
+    model.train()
+    model.load_state_dict({"recognizer.queue": inp["queue_rgb"], "recognizer.count": inp["count"],
+                           "recognizer.queue_ptr": torch.tensor([inp["ptr"]])}, strict=False)
+    rec = model.recognizer
+    keys = inp["k"].cuda()                       # the gathered keys, identical on every rank
+    rec.negative_queue().enqueue(keys)
+    ok = True
+    if rank == 0:                                # no other rank enters state_dict(): a collective in there would hang
+        sd = rec.state_dict()
+        st = O.QueueState(inp["queue_rgb"], inp["count"], inp["ptr"])
+        st.ptr = O.enqueue(st.queue, st.count, st.ptr, inp["k"])
+        ok = bool(torch.equal(sd["queue"].cpu(), st.queue)) and bool(torch.equal(sd["count"].cpu(), st.count)) \
+            and int(sd["queue_ptr"]) == st.ptr
+    dist.barrier()
+    return dict(ok=ok, sharded=rec.negative_queue().K_local == K // world)
+
+
+def test_state_dict_from_one_rank_with_a_sharded_queue():
+    for r in _run(_state_dict_one_rank_job, _need(2)):
+        assert r["ok"] and r["sharded"], r
