@@ -399,7 +399,9 @@ def test_upsample_trilinear_matches_torch(fx, shape, size):
 
 
 @pytest.mark.parametrize("shape,size", [((2, 128, 2, 14, 14), (4, 28, 28)), ((3, 128, 1, 7, 7), (2, 14, 14)), ((1, 8, 3, 5, 6), (7, 9, 11)),
-                                        ((2, 4, 4, 6, 6), (4, 6, 6)), ((2, 12, 2, 3, 3), (5, 8, 12))])
+                                        ((2, 4, 4, 6, 6), (4, 6, 6)), ((2, 12, 2, 3, 3), (5, 8, 12)),
+                                        # C % 16 == 0: the one-pass backward, at non-integer scales and with an unscaled axis
+                                        ((1, 16, 3, 5, 6), (7, 9, 11)), ((2, 32, 4, 6, 6), (4, 6, 6)), ((2, 48, 2, 3, 3), (5, 8, 12))])
 def test_upsample_trilinear_channels_last(fx, shape, size):
     """The NDHWC kernels: a channels_last_3d input gives a channels_last_3d output and input gradient, same values as
     F.interpolate; the incoming gradient may arrive in either layout."""
