@@ -4,7 +4,6 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 bash scripts/gpu_check.sh
 cp gpurun_out/bench.log gpurun_out/bench_full.log
-timeout 600 python -m mscl_b200.kernel_bench --configs cfg2,cfg3,cfg4,cfg5 --out gpurun_out/kernel_rooflines.json > gpurun_out/kernel_bench.log 2>&1; echo "kernel_bench rc=$?"
 # the reference's op sequence per block: on the box's host cores and as eager PyTorch on the GPU
 timeout 600 python scripts/ref_blocks.py --device cpu > gpurun_out/ref_blocks_cpu.jsonl 2> gpurun_out/ref_blocks.err; echo "ref_blocks cpu rc=$?"
 timeout 300 python scripts/ref_blocks.py --device cuda > gpurun_out/ref_blocks_cuda.jsonl 2>> gpurun_out/ref_blocks.err; echo "ref_blocks cuda rc=$?"

@@ -21,7 +21,8 @@ GP = os.path.join(ROOT, "gpurun_out")
 OURS = ("infonce", "ema_multi", "fra_", "hw_mean", "enqueue_kernel", "lmcl_kernel", "queue_transpose", "gather_rows",
         "clip_sgd_multi", "grad_sqnorm_multi", "grad_norm_finish", "color_pipeline", "clip_gray_sum", "flow_visualize",
         "upsample_trilinear")
-ENTRY = {"infonce_tc_kernel": "mscl_infonce_partial", "ema_multi_kernel": "mscl_ema_multi", "fra_maxrad_kernel": "mscl_fra_maxrad",
+ENTRY = {"infonce_fused_kernel": "mscl_infonce_fused", "infonce_bwd_slabs_kernel": "mscl_infonce_bwd_slabs",
+         "infonce_tc_kernel": "mscl_infonce_partial", "ema_multi_kernel": "mscl_ema_multi", "fra_maxrad_kernel": "mscl_fra_maxrad",
          "fra_apply_kernel": "mscl_fra_apply", "fra_fused_kernel": "mscl_fra_fused", "hw_mean_fwd_kernel": "mscl_hw_mean_fwd",
          "hw_mean_bwd_kernel": "mscl_hw_mean_bwd", "hw_mean_fwd_small_kernel": "mscl_hw_mean_fwd",
          "hw_mean_bwd_small_kernel": "mscl_hw_mean_bwd", "enqueue_kernel": "mscl_enqueue", "lmcl_kernel": "mscl_lmcl", "clip_sgd_multi_kernel": "mscl_clip_sgd_multi",
@@ -105,6 +106,13 @@ def kernel_metrics(tag):
     for entry, by_grid in traffic.items():
         best = max(by_grid.values(), key=lambda v: sum(v) / len(v))
         out[entry] = sum(best) / len(best)
+    # per OP (what bench.py's roofline reports): one instance of the K1 op = its forward launch + the backward kernel
+    if "mscl_infonce_fused" in out:
+        out["K1 InfoNCE (op)"] = out["mscl_infonce_fused"] + out.get("mscl_infonce_bwd_slabs", 0.0)
+    for op, entry in (("K4 momentum EMA (op)", "mscl_ema_multi"), ("K3 FRA (op)", "mscl_fra_fused"), ("K5 enqueue (op)", "mscl_enqueue"),
+                      ("K8 flow visualiser (op, adjacent)", "mscl_flow_visualize"), ("K9 colour pipeline (op, adjacent)", "mscl_color_pipeline")):
+        if entry in out:
+            out[op] = out[entry]
     with open(os.path.join(OUT, "traffic.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(out)
