@@ -259,6 +259,18 @@ int mscl_infonce_fused(const float *d_q, const float *d_kpos, int32_t M, const f
                        float key_norm_bound, const int32_t *d_dup_slot, int32_t dup_age, float *d_ws,
                        float *d_part, int32_t n_part, int32_t rows_per_group, int32_t with_grad, int32_t flags,
                        float *d_row_loss, float *d_rowaux, float *d_group_out, mscl_stream_t stream);
+/* Several independent terms ("jobs": own queries, queue, workspace and outputs) in ONE launch: blockIdx.y runs over the row
+ * blocks of all jobs, so they occupy disjoint SMs and pay the launch's ramp / drain / finalize once.  Every argument of
+ * mscl_infonce_fused becomes a HOST array of n_jobs (<= 4) entries (d_dup_slot[j] / d_part[j] may be NULL as there);
+ * n_part from mscl_infonce_fused_parts_multi, with_grad common to all jobs, one distinct workspace per job. */
+int mscl_infonce_fused_multi(int32_t n_jobs, const float *const *d_q, const float *const *d_kpos, const int32_t *M,
+                             const float *const *d_queue_tf32, const int32_t *const *d_birth,
+                             const int64_t *const *d_qstate, const int64_t *K_local, const float *inv_T,
+                             const float *key_norm_bound, const int32_t *const *d_dup_slot, const int32_t *dup_age,
+                             float *const *d_ws, float *const *d_part, int32_t n_part, const int32_t *rows_per_group,
+                             int32_t with_grad, const int32_t *flags, float *const *d_row_loss, float *const *d_rowaux,
+                             float *const *d_group_out, mscl_stream_t stream);
+int mscl_infonce_fused_parts_multi(int32_t n_jobs, const int32_t *M, const int64_t *K_local, int32_t num_sms);
 int mscl_infonce_bwd_slabs(const float *d_part, int32_t n_part, int32_t M, const float *d_kpos, const float *d_rowaux,
                            const float *d_gout, int32_t rows_per_group, float *d_dq, mscl_stream_t stream);
 /* The pass alone in the same form, for the sharded queue: d_qpack [M, 132] is the gathered table mscl_infonce_prep fills

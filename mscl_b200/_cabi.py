@@ -43,6 +43,8 @@ PROTOTYPES = {
     "mscl_infonce_bwd": [c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr],
     "mscl_infonce_fused": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_int, c_ptr, c_ptr, c_int, c_int,
                            c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
+    "mscl_infonce_fused_multi": [c_int] + [c_ptr] * 13 + [c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "mscl_infonce_fused_parts_multi": [c_int, c_ptr, c_ptr, c_int],
     "mscl_infonce_bwd_slabs": [c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr],
     "mscl_infonce_pass": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_ptr, c_int, c_int, c_int, c_ptr],
     "mscl_infonce_fused_parts": [c_int, c_i64, c_int],
@@ -65,7 +67,7 @@ _lock = threading.Lock()
 _lib = None
 _launches = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
 # how many device kernels one successful call enqueues
-_LAUNCHES_PER_CALL = {"mscl_device_check": 0, "mscl_infonce_num_partials": 0, "mscl_infonce_fused_parts": 0, "mscl_color_pipeline": 2, "mscl_grad_norm_multi": 2,
+_LAUNCHES_PER_CALL = {"mscl_device_check": 0, "mscl_infonce_num_partials": 0, "mscl_infonce_fused_parts": 0, "mscl_infonce_fused_parts_multi": 0, "mscl_color_pipeline": 2, "mscl_grad_norm_multi": 2,
                       "mscl_center_normalize": 3}
 
 

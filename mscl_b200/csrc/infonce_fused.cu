@@ -114,6 +114,21 @@ __device__ __forceinline__ float4 ld_now(const float4 *p) {
   return r;
 }
 
+// Several independent InfoNCE terms ("jobs": their own queries, queue and outputs) in ONE launch.  blockIdx.y runs over
+// the row blocks of all jobs, blockIdx.x over the key ranges of a job, so the jobs occupy disjoint sets of SMs and the
+// fixed costs of a launch -- ramp (first bytes 2-3 us after launch), drain, finalize, launch gap: ~9 of the 15 us a
+// single K = 65536 term takes -- are paid once for all of them.  MSCLWithAug.objective runs its two independent
+// pre-enqueue passes (W_rgb: 96 rows, W_flow: 32 rows, recognizers/mscl.py:247-269 of the reference) this way.
+constexpr int kMaxJobs = 4;
+struct alignas(64) JobTable {
+  CUtensorMap tmap_w[kMaxJobs];     // queue [K_local][128] fp32: 128-key box, 128B swizzle (pair tiles, K-major)
+  CUtensorMap tmap_wh[kMaxJobs];    // the same, 64-key box (half tile)
+  CUtensorMap tmap_w2[kMaxJobs];    // 64-key box, 32-byte-atom 128B swizzle (MN-major copy)
+  Params p[kMaxJobs];
+  int n_jobs;
+  int rb_begin[kMaxJobs + 1];       // first blockIdx.y of each job (row blocks of 128 query rows)
+};
+
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
                "r"(c0), "r"(c1), "r"(c2)
@@ -230,9 +245,12 @@ __device__ __forceinline__ void finalize_stats(const Params &p, int tid, unsigne
 
 template <bool GRAD, bool FUSED>
 __global__ void __launch_bounds__(kThreads, 1)
-infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_wh,
-                     const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_part,
-                     const __grid_constant__ Params p) {
+infonce_fused_kernel(const __grid_constant__ JobTable jt) {
+  int job = 0;
+  while (job + 1 < jt.n_jobs && (int)blockIdx.y >= jt.rb_begin[job + 1]) ++job;
+  const Params &p = jt.p[job];
+  const CUtensorMap &tmap_w = jt.tmap_w[job], &tmap_wh = jt.tmap_wh[job], &tmap_w2 = jt.tmap_w2[job];
+  const unsigned n_ctas_job = gridDim.x * (unsigned)(jt.rb_begin[job + 1] - jt.rb_begin[job]);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *gbase = smem_raw;
   const uint32_t base = smem_u32(smem_raw);
@@ -274,7 +292,7 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
   const int nt = np + hasH;                         // processing steps
   const int64_t key_begin = u_begin * kUnit;
   const int64_t key_end = u_end * kUnit < p.K_local ? u_end * kUnit : p.K_local;
-  const int row0 = blockIdx.y * kRows;
+  const int row0 = ((int)blockIdx.y - jt.rb_begin[job]) * kRows;
   // step i covers keys [key0(i), key0(i) + (half tile ? 64 : 128))
   auto step_key0 = [&](int i) { return key_begin + (i == 0 ? 0 : (int64_t)i * kTile - hasH * kUnit); };
 
@@ -283,7 +301,6 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_wh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
-    if (GRAD) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_part) : "memory");
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_full1(s), 1);
       mbar_init(bar_empty1(s), 1);
@@ -755,7 +772,7 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
       unsigned *counter = reinterpret_cast<unsigned *>(p.ws + (int64_t)kStatCopies * p.M * 4);
       const unsigned done = atomicAdd(counter, 1u);
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      *last_flag = (done == gridDim.x * gridDim.y - 1u) ? 2 : 1;
+      *last_flag = (done == n_ctas_job - 1u) ? 2 : 1;
       mbar_arrive(bar_ticket);                   // release: the flag is visible to whoever completes the wait below
       TLF(7);
     }
@@ -784,62 +801,49 @@ infonce_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
   if (threadIdx.x == 0) TLF(3);
 }
 
-// part [n_part][M][132] viewed as {132, M, n_part}: one box = one CTA's [128][132] output tile (rows >= M clipped)
-static int make_map_slab(CUtensorMap *map, float *ptr, int M, int n_part) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return set_err(MSCL_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[3] = {(cuuint64_t)kLd, (cuuint64_t)M, (cuuint64_t)n_part};
-  cuuint64_t strides[2] = {(cuuint64_t)kLd * 4, (cuuint64_t)M * kLd * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kLd, (cuuint32_t)kRows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return set_err(MSCL_ECUDA, "cuTensorMapEncodeTiled(slab) failed with CUresult %d (M=%d n_part=%d)", (int)r, M, n_part);
-  return MSCL_OK;
-}
-
-static int launch(bool fused, bool grad, const Params &p, const float *d_queue, int n_part, cudaStream_t s) {
-  const int64_t n_units = (p.K_local + kUnit - 1) / kUnit;
-  MSCL_CHECK_ARG(n_part > 0 && n_part <= n_units, "n_part=%d must be in [1, %lld] (one 64-key unit per CTA at least)", n_part,
-                 (long long)n_units);
-  CUtensorMap tw, twh, tw2, ta;
-  int rc = make_map(&tw, d_queue, p.K_local, kC, kTile);
-  if (rc) return rc;
-  rc = make_map(&twh, d_queue, p.K_local, kC, kUnit);
-  if (rc) return rc;
-  rc = make_map(&tw2, d_queue, p.K_local, kC, kUnit, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  if (rc) return rc;
-  memset(&ta, 0, sizeof(ta));
-  if (p.part != nullptr) {
-    rc = make_map_slab(&ta, p.part, p.M, n_part);
+static int launch(bool fused, bool grad, int n_jobs, const Params *ps, const float *const *queues, int n_part, cudaStream_t s) {
+  MSCL_CHECK_ARG(n_jobs >= 1 && n_jobs <= kMaxJobs, "n_jobs=%d must be in [1, %d]", n_jobs, kMaxJobs);
+  MSCL_CHECK_ARG(n_part > 0, "n_part=%d must be positive", n_part);
+  JobTable jt;
+  memset(&jt, 0, sizeof(jt));
+  jt.n_jobs = n_jobs;
+  int64_t max_units = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    const Params &p = ps[j];
+    const int64_t n_units = (p.K_local + kUnit - 1) / kUnit;
+    max_units = n_units > max_units ? n_units : max_units;
+    int rc = make_map(&jt.tmap_w[j], queues[j], p.K_local, kC, kTile);
     if (rc) return rc;
+    rc = make_map(&jt.tmap_wh[j], queues[j], p.K_local, kC, kUnit);
+    if (rc) return rc;
+    rc = make_map(&jt.tmap_w2[j], queues[j], p.K_local, kC, kUnit, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    jt.p[j] = p;
+    jt.rb_begin[j + 1] = jt.rb_begin[j] + (p.M + kRows - 1) / kRows;
   }
-  const int row_blocks = (p.M + kRows - 1) / kRows;
-  dim3 grid((unsigned)n_part, (unsigned)row_blocks);
-#define MSCL_FUSED_LAUNCH(G, F, W)                                                                                   \
-  do {                                                                                                               \
-    MSCL_CUDA(mscl::ensure_dyn_smem(infonce_fused_kernel<G, F>, kSmemBytes));                                        \
-    MSCL_CUDA(mscl::launch_pdl(infonce_fused_kernel<G, F>, grid, dim3(kThreads), kSmemBytes, s, tw, twh, tw2, ta, p)); \
+  for (int j = n_jobs; j < kMaxJobs; ++j) jt.rb_begin[j + 1] = jt.rb_begin[n_jobs];
+  MSCL_CHECK_ARG(n_part <= max_units, "n_part=%d exceeds the %lld 64-key units of the largest queue", n_part, (long long)max_units);
+  MSCL_CHECK_ARG(jt.rb_begin[n_jobs] <= 65535, "too many row blocks");
+  dim3 grid((unsigned)n_part, (unsigned)jt.rb_begin[n_jobs]);
+#define MSCL_FUSED_LAUNCH(G, F)                                                                                \
+  do {                                                                                                         \
+    MSCL_CUDA(mscl::ensure_dyn_smem(infonce_fused_kernel<G, F>, kSmemBytes));                                  \
+    MSCL_CUDA(mscl::launch_pdl(infonce_fused_kernel<G, F>, grid, dim3(kThreads), kSmemBytes, s, jt));          \
   } while (0)
-  if (fused && grad) MSCL_FUSED_LAUNCH(true, true, 0);
-  else if (fused) MSCL_FUSED_LAUNCH(false, true, 1);
-  else if (grad) MSCL_FUSED_LAUNCH(true, false, 2);
-  else MSCL_FUSED_LAUNCH(false, false, 3);
+  if (fused && grad) MSCL_FUSED_LAUNCH(true, true);
+  else if (fused) MSCL_FUSED_LAUNCH(false, true);
+  else if (grad) MSCL_FUSED_LAUNCH(true, false);
+  else MSCL_FUSED_LAUNCH(false, false);
 #undef MSCL_FUSED_LAUNCH
   MSCL_LAUNCH_CHECK();
   return MSCL_OK;
 }
 
-}  // namespace tcf
-}  // namespace mscl
-
-extern "C" int mscl_infonce_fused(const float *d_q, const float *d_kpos, int32_t M, const float *d_queue,
-                                  const int32_t *d_birth, const int64_t *d_qstate, int64_t K_local, float inv_T,
-                                  float key_norm_bound, const int32_t *d_dup_slot, int32_t dup_age, float *d_ws,
-                                  float *d_part, int32_t n_part, int32_t rows_per_group, int32_t with_grad, int32_t flags,
-                                  float *d_row_loss, float *d_rowaux, float *d_group_out, mscl_stream_t stream) {
-  using namespace mscl::tcf;
+// argument checks + Params of one fused job
+static int fused_job(Params &p, const float *d_q, const float *d_kpos, int32_t M, const float *d_queue, const int32_t *d_birth,
+                     const int64_t *d_qstate, int64_t K_local, float inv_T, float key_norm_bound, const int32_t *d_dup_slot,
+                     int32_t dup_age, float *d_ws, float *d_part, int32_t rows_per_group, int32_t with_grad, int32_t flags,
+                     float *d_row_loss, float *d_rowaux, float *d_group_out) {
   MSCL_CHECK_ARG(d_q && d_kpos && d_queue && d_birth && d_qstate && d_ws && d_row_loss && d_rowaux && d_group_out,
                  "null pointer");
   MSCL_CHECK_ARG(!with_grad || d_part, "with_grad needs the slab buffer d_part");
@@ -851,7 +855,7 @@ extern "C" int mscl_infonce_fused(const float *d_q, const float *d_kpos, int32_t
   MSCL_CHECK_ARG((((uintptr_t)d_q | (uintptr_t)d_kpos | (uintptr_t)d_queue | (uintptr_t)d_birth | (uintptr_t)d_ws |
                    (uintptr_t)d_part | (uintptr_t)d_rowaux | (uintptr_t)d_group_out) & 15) == 0,
                  "q/kpos/queue/birth/ws/part/rowaux/group_out must be 16-byte aligned");
-  Params p = {};
+  p = Params();
   p.q = d_q;
   p.kpos = d_kpos;
   p.birth = d_birth;
@@ -870,7 +874,48 @@ extern "C" int mscl_infonce_fused(const float *d_q, const float *d_kpos, int32_t
   p.flags = flags;
   p.inv_T = inv_T;
   p.key_norm_bound = key_norm_bound;
-  return launch(true, with_grad != 0, p, d_queue, n_part, mscl::as_stream(stream));
+  return MSCL_OK;
+}
+
+}  // namespace tcf
+}  // namespace mscl
+
+extern "C" int mscl_infonce_fused(const float *d_q, const float *d_kpos, int32_t M, const float *d_queue,
+                                  const int32_t *d_birth, const int64_t *d_qstate, int64_t K_local, float inv_T,
+                                  float key_norm_bound, const int32_t *d_dup_slot, int32_t dup_age, float *d_ws,
+                                  float *d_part, int32_t n_part, int32_t rows_per_group, int32_t with_grad, int32_t flags,
+                                  float *d_row_loss, float *d_rowaux, float *d_group_out, mscl_stream_t stream) {
+  using namespace mscl::tcf;
+  Params p;
+  int rc = fused_job(p, d_q, d_kpos, M, d_queue, d_birth, d_qstate, K_local, inv_T, key_norm_bound, d_dup_slot, dup_age, d_ws,
+                     d_part, rows_per_group, with_grad, flags, d_row_loss, d_rowaux, d_group_out);
+  if (rc) return rc;
+  return launch(true, with_grad != 0, 1, &p, &d_queue, n_part, mscl::as_stream(stream));
+}
+
+extern "C" int mscl_infonce_fused_multi(int32_t n_jobs, const float *const *d_q, const float *const *d_kpos, const int32_t *M,
+                                        const float *const *d_queue, const int32_t *const *d_birth,
+                                        const int64_t *const *d_qstate, const int64_t *K_local, const float *inv_T,
+                                        const float *key_norm_bound, const int32_t *const *d_dup_slot, const int32_t *dup_age,
+                                        float *const *d_ws, float *const *d_part, int32_t n_part,
+                                        const int32_t *rows_per_group, int32_t with_grad, const int32_t *flags,
+                                        float *const *d_row_loss, float *const *d_rowaux, float *const *d_group_out,
+                                        mscl_stream_t stream) {
+  using namespace mscl::tcf;
+  MSCL_CHECK_ARG(n_jobs >= 1 && n_jobs <= kMaxJobs, "n_jobs=%d must be in [1, %d]", n_jobs, kMaxJobs);
+  MSCL_CHECK_ARG(d_q && d_kpos && M && d_queue && d_birth && d_qstate && K_local && inv_T && key_norm_bound && d_dup_slot &&
+                     dup_age && d_ws && d_part && rows_per_group && flags && d_row_loss && d_rowaux && d_group_out,
+                 "null table");
+  Params ps[kMaxJobs];
+  for (int j = 0; j < n_jobs; ++j) {
+    int rc = fused_job(ps[j], d_q[j], d_kpos[j], M[j], d_queue[j], d_birth[j], d_qstate[j], K_local[j], inv_T[j],
+                       key_norm_bound[j], d_dup_slot[j], dup_age[j], d_ws[j], d_part[j], rows_per_group[j], with_grad, flags[j],
+                       d_row_loss[j], d_rowaux[j], d_group_out[j]);
+    if (rc) return rc;
+    for (int i = 0; i < j; ++i)
+      MSCL_CHECK_ARG(d_ws[i] != d_ws[j], "jobs %d and %d share a workspace", i, j);
+  }
+  return launch(true, with_grad != 0, n_jobs, ps, d_queue, n_part, mscl::as_stream(stream));
 }
 
 extern "C" int mscl_infonce_pass(const float *d_qpack, int32_t M, const float *d_queue, const int32_t *d_birth,
@@ -895,7 +940,7 @@ extern "C" int mscl_infonce_pass(const float *d_qpack, int32_t M, const float *d
   p.flags = flags;
   p.inv_T = inv_T;
   p.key_norm_bound = 1.f;
-  return launch(false, with_grad != 0, p, d_queue, n_part, mscl::as_stream(stream));
+  return launch(false, with_grad != 0, 1, &p, &d_queue, n_part, mscl::as_stream(stream));
 }
 
 // How many CTAs along the keys mscl_infonce_fused / mscl_infonce_pass should be given.
@@ -907,6 +952,23 @@ extern "C" int mscl_infonce_fused_parts(int32_t M, int64_t K_local, int32_t num_
   int64_t gx = num_sms / row_blocks;
   if (gx < 1) gx = 1;
   if (gx > n_units) gx = n_units;
+  return (int)gx;
+}
+
+// The same for several jobs in one launch: the SMs are divided over all row blocks of all jobs.
+extern "C" int mscl_infonce_fused_parts_multi(int32_t n_jobs, const int32_t *M, const int64_t *K_local, int32_t num_sms) {
+  using namespace mscl::tcf;
+  if (n_jobs < 1 || n_jobs > kMaxJobs || !M || !K_local || num_sms <= 0) return mscl::set_err(MSCL_EINVAL, "bad job table / num_sms");
+  int64_t rbs = 0, max_units = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    if (M[j] <= 0 || K_local[j] <= 0) return mscl::set_err(MSCL_EINVAL, "bad M / K_local of job %d", j);
+    rbs += (M[j] + kRows - 1) / kRows;
+    const int64_t u = (K_local[j] + kUnit - 1) / kUnit;
+    max_units = u > max_units ? u : max_units;
+  }
+  int64_t gx = num_sms / rbs;
+  if (gx < 1) gx = 1;
+  if (gx > max_units) gx = max_units;
   return (int)gx;
 }
 

@@ -216,10 +216,11 @@ EXCHANGE = "peer"      # "peer": NVLink peer stores from the kernels + device ba
 _FUSED_WS = {}
 
 
-def _fused_workspace(dev, M):
+def _fused_workspace(dev, M, slot=0):
     """Zero-initialised statistics accumulator + CTA counter of the single-launch InfoNCE op (mscl_infonce_fused leaves it
-    zero).  One per (device, stream, M): two launches that may overlap must not share it."""
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(), int(M))
+    zero).  One per (device, stream, M, slot): two launches that may overlap -- or two jobs of one launch (slot) -- must
+    not share it."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(), int(M), int(slot))
     ws = _FUSED_WS.get(key)
     if ws is None:
         ws = _FUSED_WS[key] = torch.zeros(16 * M * 4 + 4, device=dev)
@@ -339,6 +340,92 @@ class _InfoNCE(torch.autograd.Function):
         dq = torch.empty_like(dq_unit)
         _cabi.call("mscl_infonce_bwd", dq_unit.data_ptr(), gout.data_ptr(), M, ctx.rows_per_group, dq.data_ptr(), _stream())
         return dq, None, None, None, None, None, None, None, None, None
+
+
+class _InfoNCEMulti(torch.autograd.Function):
+    """Several independent fused InfoNCE terms in one launch (mscl_infonce_fused_multi); one backward kernel per job."""
+
+    @staticmethod
+    def forward(ctx, jobs, need_grad, *qs):
+        import ctypes
+        n = len(jobs)
+        dev = qs[0].device
+        st = _stream()
+        Ms = [int(q.shape[0]) for q in qs]
+        Ks = [int(j["nq"].K_local) for j in jobs]
+        arr_i32 = lambda v: (ctypes.c_int32 * n)(*v)
+        arr_i64 = lambda v: (ctypes.c_int64 * n)(*v)
+        arr_f32 = lambda v: (ctypes.c_float * n)(*v)
+        arr_ptr = lambda ts: (ctypes.c_void_p * n)(*[(t.data_ptr() if t is not None else None) for t in ts])
+        n_part = _cabi.query("mscl_infonce_fused_parts_multi", n, arr_i32(Ms), arr_i64(Ks), sm_count(dev))
+        ws = [_fused_workspace(dev, M, slot=i) for i, M in enumerate(Ms)]
+        parts = [torch.empty(n_part, M, PACK_LD, device=dev) if need_grad else None for M in Ms]
+        rowaux = [torch.empty(M, 4, device=dev) for M in Ms]
+        row_loss = [torch.empty(2 * M, device=dev) for M in Ms]
+        group_out = [torch.empty(M // j["rows_per_group"], 4, device=dev) for M, j in zip(Ms, jobs)]
+        nbytes = sum(infonce_algo_bytes(M, K) for M, K in zip(Ms, Ks))
+        flops = sum((4 if need_grad else 2) * M * K * DIM for M, K in zip(Ms, Ks))
+        _cabi.call("mscl_infonce_fused_multi", n, arr_ptr(qs), arr_ptr([j["kpos"] for j in jobs]), arr_i32(Ms),
+                   arr_ptr([j["nq"].queue_tf32 for j in jobs]), arr_ptr([j["nq"].birth for j in jobs]),
+                   arr_ptr([j["nq"].qstate for j in jobs]), arr_i64(Ks), arr_f32([j["inv_T"] for j in jobs]),
+                   arr_f32([j["nq"].max_key_norm for j in jobs]), arr_ptr([j["dup_slot"] for j in jobs]),
+                   arr_i32([j["dup_age"] for j in jobs]), arr_ptr(ws), arr_ptr(parts), n_part,
+                   arr_i32([j["rows_per_group"] for j in jobs]), int(need_grad), arr_i32([_prefetch_flag(j["nq"]) for j in jobs]),
+                   arr_ptr(row_loss), arr_ptr(rowaux), arr_ptr(group_out), st, algo_bytes=nbytes, algo_flops=flops)
+        ctx.n = n
+        ctx.need_grad = need_grad
+        ctx.rpg = [j["rows_per_group"] for j in jobs]
+        if need_grad:
+            ctx.save_for_backward(*parts, *rowaux, *[j["kpos"] for j in jobs])
+        ctx.mark_non_differentiable(*row_loss)
+        out = []
+        for g, r in zip(group_out, row_loss):
+            out += [g, r]
+        return tuple(out)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        parts, rowaux, kpos = saved[:n], saved[n:2 * n], saved[2 * n:]
+        dqs = []
+        for i in range(n):
+            g = grads[2 * i]
+            if g is None:
+                dqs.append(None)
+                continue
+            gout = g[:, 0].contiguous()
+            n_part, M = parts[i].shape[0], parts[i].shape[1]
+            dq = torch.empty(M, DIM, device=parts[i].device)
+            _cabi.call("mscl_infonce_bwd_slabs", parts[i].data_ptr(), n_part, M, kpos[i].data_ptr(), rowaux[i].data_ptr(),
+                       gout.data_ptr(), ctx.rpg[i], dq.data_ptr(), _stream(), algo_bytes=4 * M * (n_part * DIM + 2 * DIM + 4))
+            dqs.append(dq)
+        return (None, None, *dqs)
+
+
+def infonce_multi(jobs):
+    """Several independent fused InfoNCE terms in ONE launch.  jobs: list (<= 4) of dicts with q, kpos (M,128), nq
+    (an unsharded NegativeQueue), rows_per_group, T and optionally dup_slot / dup_age, as for `infonce`.  Returns a list
+    of (group_out, row_stats) pairs.  The jobs occupy disjoint SMs and share the launch's fixed costs."""
+    if not 1 <= len(jobs) <= 4:
+        raise _cabi.MsclError("infonce_multi takes 1 to 4 jobs")
+    prepared, qs = [], []
+    for j in jobs:
+        q, kpos, nq = j["q"], j["kpos"].detach(), j["nq"]
+        _chk(q, name="q"), _chk(kpos, name="kpos")
+        if q.dim() != 2 or q.shape[1] != DIM or kpos.shape != q.shape or q.shape[0] % j["rows_per_group"]:
+            raise _cabi.MsclError("bad job shapes")
+        if nq.world != 1:
+            raise _cabi.MsclError("infonce_multi needs unsharded queues")
+        dup = j.get("dup_slot")
+        if dup is not None:
+            _chk(dup, torch.int32, "dup_slot")
+        prepared.append(dict(kpos=kpos, nq=nq, rows_per_group=int(j["rows_per_group"]), inv_T=float(1.0 / j["T"]),
+                             dup_slot=dup, dup_age=int(j.get("dup_age", 1))))
+        qs.append(q)
+    need_grad = bool(torch.is_grad_enabled() and any(q.requires_grad for q in qs))
+    flat = _InfoNCEMulti.apply(prepared, need_grad, *qs)
+    return [(flat[2 * i], flat[2 * i + 1]) for i in range(len(jobs))]
 
 
 def infonce_algo_bytes(M, K_local):

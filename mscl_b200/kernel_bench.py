@@ -149,6 +149,64 @@ def bench_k1(cfg, M, K, pk, dev, iters=30):
     return out
 
 
+def bench_k1_pair(cfg, Ms, K, pk, dev, iters=30):
+    """What MSCLWithAug.objective launches for its two independent pre-enqueue passes: len(Ms) jobs over different queues
+    in ONE mscl_infonce_fused_multi launch (disjoint SMs, shared ramp / drain / finalize)."""
+    import ctypes
+    n = len(Ms)
+    rot = n_rot(n * K * 512)
+    g = torch.Generator().manual_seed(K + sum(Ms))
+    rings = []
+    for s in range(rot):
+        qs = []
+        for _ in range(n):
+            nq = fx.NegativeQueue(K, 128, dev)
+            nq.load(F.normalize(torch.randn(128, K, generator=g), dim=0), torch.randint(0, 2000, (K,), generator=g), 0)
+            qs.append(nq)
+        rings.append(qs)
+    q = [F.normalize(torch.randn(M, 128, generator=g), dim=1).to(dev) for M in Ms]
+    k = [F.normalize(torch.randn(M, 128, generator=g), dim=1).to(dev) for M in Ms]
+    arr_i32 = lambda v: (ctypes.c_int32 * n)(*v)
+    arr_i64 = lambda v: (ctypes.c_int64 * n)(*v)
+    arr_f32 = lambda v: (ctypes.c_float * n)(*v)
+    arr_ptr = lambda ts: (ctypes.c_void_p * n)(*[(t.data_ptr() if t is not None else None) for t in ts])
+    n_part = _cabi.query("mscl_infonce_fused_parts_multi", n, arr_i32(Ms), arr_i64([K] * n), fx.sm_count(dev))
+    ws = [torch.zeros(16 * M * 4 + 4, device=dev) for M in Ms]
+    part = [torch.empty(n_part, M, fx.PACK_LD, device=dev) for M in Ms]
+    rowaux = [torch.empty(M, 4, device=dev) for M in Ms]
+    row_loss = [torch.empty(2 * M, device=dev) for M in Ms]
+    gout = [torch.empty(1, 4, device=dev) for _ in Ms]
+    dq = [torch.empty(M, 128, device=dev) for M in Ms]
+    gone = torch.ones(1, device=dev)
+    # every table is built once: the launches of the train only differ in the queue ring slot
+    tabs = [dict(queue=arr_ptr([nq.queue_tf32 for nq in qs]), birth=arr_ptr([nq.birth for nq in qs]),
+                 qstate=arr_ptr([nq.qstate for nq in qs])) for qs in rings]
+    fixed = dict(q=arr_ptr(q), k=arr_ptr(k), M=arr_i32(Ms), K=arr_i64([K] * n), invT=arr_f32([1 / 0.07] * n), bound=arr_f32([1.0] * n),
+                 dup=arr_ptr([None] * n), age=arr_i32([1] * n), ws=arr_ptr(ws), part=arr_ptr(part), rpg=arr_i32(Ms),
+                 flags=arr_i32([1] * n), rl=arr_ptr(row_loss), ra=arr_ptr(rowaux), go=arr_ptr(gout))
+
+    def fwd(i):
+        t = tabs[i % rot]
+        _cabi.call("mscl_infonce_fused_multi", n, fixed["q"], fixed["k"], fixed["M"], t["queue"], t["birth"], t["qstate"], fixed["K"],
+                   fixed["invT"], fixed["bound"], fixed["dup"], fixed["age"], fixed["ws"], fixed["part"], n_part, fixed["rpg"], 1,
+                   fixed["flags"], fixed["rl"], fixed["ra"], fixed["go"], _st())
+
+    def fwd_bwd(i):
+        fwd(i)
+        for j in range(n):
+            _cabi.call("mscl_infonce_bwd_slabs", part[j].data_ptr(), n_part, Ms[j], k[j].data_ptr(), rowaux[j].data_ptr(),
+                       gone.data_ptr(), Ms[j], dq[j].data_ptr(), _st())
+
+    ab = sum(fx.infonce_algo_bytes(M, K) for M in Ms)
+    fl = sum(4 * M * K * 128 for M in Ms)
+    shape = "M=" + "+".join(str(M) for M in Ms) + f" K={K} x{n} queues"
+    out = [row(cfg, f"K1 x{n} ops in one launch = infonce_fused_kernel<grad>, {n} jobs (what the step runs)", shape,
+               time_train(fwd, iters), ab, fl, pk, note=f"{n_part} CTAs per job"),
+           row(cfg, f"K1 x{n} ops in one launch + their backward kernels", shape, time_train(fwd_bwd, iters), ab, fl, pk)]
+    del rings
+    return out
+
+
 # ------------------------------------------------------------------------------------------ K2
 def bench_k2(cfg, N, t, pk, dev, iters=30):
     out = []
@@ -359,6 +417,7 @@ def run(configs=("cfg2", "cfg3", "cfg4", "cfg5"), device=0, verbose=True):
     if "cfg2" in configs:      # the r18 pre-training step, 32 clips/GPU, K = 65536
         for M in (96, 32):
             add(bench_k1("cfg2", M, 65536, pk, dev))
+        add(bench_k1_pair("cfg2", (96, 32), 65536, pk, dev))
         add(bench_k2("cfg2", 32, 4, pk, dev))
         add(bench_k3("cfg2", 32, 8, pk, dev))
         add(bench_k4("cfg2", "r18 RGB key side", r3d18_key_sizes(), pk, dev))

@@ -278,11 +278,8 @@ class MoCoV2(BaseMoCoRecognizer):
         nq = self._nq
         return dist.group.WORLD if (nq is not None and nq.world > 1) else None
 
-    def contrast(self, terms, T=None):
-        """Fused InfoNCE of several (q, k_pos[, dup_slot]) row sets against the CURRENT queue state in
-        one pass.  dup_slot: int32 (n,) global slots holding copies of the term's own positive keys
-        (a term whose keys were enqueued before the pass), or None.
-        Returns a (len(terms), 4) tensor of [loss, top1, top5, 0] rows."""
+    def _stack_terms(self, terms):
+        """(q, k_pos[, dup_slot]) row sets -> stacked q, k_pos, dup_slot (or None) and the rows per term."""
         n = terms[0][0].shape[0]
         q = torch.cat([t[0] for t in terms], dim=0).contiguous()
         kp = torch.cat([t[1].detach() for t in terms], dim=0).contiguous()
@@ -291,9 +288,32 @@ class MoCoV2(BaseMoCoRecognizer):
         if any(d is not None for d in dups):
             none = torch.full((n,), -1, dtype=torch.int32, device=q.device)
             dup = torch.cat([none if d is None else d for d in dups]).contiguous()
+        return q, kp, dup, n
+
+    def contrast(self, terms, T=None):
+        """Fused InfoNCE of several (q, k_pos[, dup_slot]) row sets against the CURRENT queue state in
+        one pass.  dup_slot: int32 (n,) global slots holding copies of the term's own positive keys
+        (a term whose keys were enqueued before the pass), or None.
+        Returns a (len(terms), 4) tensor of [loss, top1, top5, 0] rows."""
+        q, kp, dup, n = self._stack_terms(terms)
         nq = self.negative_queue(q.device)
         out, _ = fx.infonce(q, kp, nq, n, self.T if T is None else T, group=self._group(), dup_slot=dup)
         return out
+
+    @staticmethod
+    def contrast_many(calls):
+        """Several `contrast` calls on DIFFERENT recognizers (queues) that do not depend on each other, as ONE launch
+        when none of the queues is sharded (functional.infonce_multi: the jobs share the launch's fixed costs);
+        otherwise one after the other.  calls: list of (recognizer, terms, T).  Returns the list of their results."""
+        if len(calls) < 2 or not all(terms[0][0].is_cuda for _, terms, _ in calls):
+            return [rec.contrast(terms, T) for rec, terms, T in calls]      # (contrast refuses host tensors itself)
+        stacked = [(rec,) + rec._stack_terms(terms) + (T,) for rec, terms, T in calls]
+        queues = [rec.negative_queue(q.device) for rec, q, _, _, _, _ in stacked]
+        if len(calls) < 2 or len(calls) > 4 or any(nq.world != 1 for nq in queues) or len({id(nq) for nq in queues}) != len(queues):
+            return [rec.contrast(terms, T) for rec, terms, T in calls]
+        jobs = [dict(q=q, kpos=kp, nq=nq, rows_per_group=n, T=rec.T if T is None else T, dup_slot=dup)
+                for (rec, q, kp, dup, n, T), nq in zip(stacked, queues)]
+        return [out for out, _ in fx.infonce_multi(jobs)]
 
     def enqueue_slots(self, n_local, device):
         """Global queue slots the NEXT enqueue writes this rank's n_local keys to (rank-major gather

@@ -176,21 +176,30 @@ class MSCLWithAug(TwoBranchRecognizer):
         # the queue (`rf` with same_kn=True): the kernel needs the slot to rank it exactly.
         kf_slots = recf.enqueue_slots(k_f.shape[0], k_f.device)
 
-        def run(phase, owner):
+        def passes(phase):
             by_T = OrderedDict()          # one pass per distinct temperature (one, in the configs)
             for name, qq, kk, T in terms[phase]:
                 dup = kf_slots if (phase == "flow_post" and kk is k_f) else None
                 by_T.setdefault(T, []).append((name, qq, kk, dup))
-            for T, items in by_T.items():
-                out = owner.contrast([(qq, kk, dup) for _, qq, kk, dup in items], T)
-                for i, item in enumerate(items):
-                    rows[item[0]] = out[i]
+            return list(by_T.items())
 
-        run("rgb_pre", rec)                        # W_rgb before this step's enqueue
-        run("flow_pre", recf)                      # W_flow before the base-flow enqueue
+        def run(*phase_owner):
+            """The passes of the given (phase, recognizer) pairs; passes over different queues that do not depend on
+            each other go out as ONE launch (MoCoV2.contrast_many)."""
+            calls, names = [], []
+            for phase, owner in phase_owner:
+                for T, items in passes(phase):
+                    calls.append((owner, [(qq, kk, dup) for _, qq, kk, dup in items], T))
+                    names.append([item[0] for item in items])
+            for out, nm in zip(type(rec).contrast_many(calls), names):
+                for i, name in enumerate(nm):
+                    rows[name] = out[i]
+
+        # W_rgb before this step's enqueue and W_flow before the base-flow enqueue: two independent passes, one launch
+        run(("rgb_pre", rec), ("flow_pre", recf))
         rec._dequeue_and_enqueue(k)                # RGB call's enqueue (deferred past its consumers)
         recf._dequeue_and_enqueue(k_f)             # base-flow call's enqueue
-        run("flow_post", recf)                     # W_flow containing this step's base-flow keys
+        run(("flow_post", recf))                   # W_flow containing this step's base-flow keys
         if self.update_aug_flow:
             recf._dequeue_and_enqueue(k_af)
 

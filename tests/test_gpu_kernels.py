@@ -299,6 +299,47 @@ def test_infonce_large_queue_vs_oracle(fx, impl, K):
     assert _rel(qd.grad.cpu(), gref) < 1e-3
 
 
+def test_infonce_multi_jobs_match_single_launches_and_oracle(fx):
+    """mscl_infonce_fused_multi: independent terms over different queues in ONE launch (what MSCLWithAug.objective does
+    with its two pre-enqueue passes) -- every job's loss / hit counts / dq against the oracle and against the same job
+    launched alone; jobs of different sizes, one with a positive key present in its queue."""
+    specs = [(96, 65536, 32, 128, 0.07), (32, 65536, 32, 128, 0.07), (24, 1000, 8, 8, 0.2)]
+    cases, jobs, qds = [], [], []
+    for i, (M, K, rpg, b_all, T) in enumerate(specs):
+        q, kpos, queue, count = _make_case(100 + i, M, K, b_all)
+        dup = None
+        if i == 1:      # rows 0..M-1 find their own positive at slots 5*b_all .. (the rf term of MSCLWithAug)
+            ptr = 5 * b_all
+            queue[:, ptr:ptr + M] = kpos.t()
+            count = count + 1
+            count[ptr:ptr + M] = 1
+            dup = (torch.arange(M, dtype=torch.int32) + ptr).cuda()
+        nq = fx.NegativeQueue(K)
+        nq.load(queue, count, 0)
+        qd = q.cuda().requires_grad_(True)
+        cases.append((q, kpos, queue, count, T, rpg, M))
+        qds.append(qd)
+        jobs.append(dict(q=qd, kpos=kpos.cuda(), nq=nq, rows_per_group=rpg, T=T, dup_slot=dup, dup_age=1))
+    outs = fx.infonce_multi(jobs)
+    sum(o[:, 0].sum() for o, _ in outs).backward()
+    for (q, kpos, queue, count, T, rpg, M), job, qd, (out, rows) in zip(cases, jobs, qds, outs):
+        ref, gref, logits = _oracle_infonce(q, kpos, queue, count, T, rpg)
+        for gi, (loss, _, _) in enumerate(ref):
+            assert abs(float(out[gi, 0]) - float(loss)) <= 1e-3 * abs(float(loss))
+        neg, pos = logits[:, 1:].clone(), logits[:, :1]
+        if job["dup_slot"] is not None:
+            neg[torch.arange(M), job["dup_slot"].cpu().long()] = 1e9
+        close_call = ((neg - pos).abs() < 0.02 * (0.07 / T) + 1e-3).sum(1)
+        cnt_ref = (logits[:, 1:] > logits[:, :1]).sum(1).float()
+        assert bool(((rows[M:].cpu() - cnt_ref).abs() <= close_call).all())
+        assert _rel(qd.grad.cpu(), gref) < 1e-3
+        # the same job alone
+        q1 = q.cuda().requires_grad_(True)
+        o1, r1 = fx.infonce(q1, job["kpos"], job["nq"], rpg, T, impl="fused", dup_slot=job["dup_slot"], dup_age=1)
+        o1[:, 0].sum().backward()
+        assert _rel(o1[:, 0], out[:, 0]) < 1e-6 and torch.equal(r1[M:], rows[M:]) and _rel(q1.grad, qd.grad) < 1e-5
+
+
 def test_infonce_fused_workspace_stays_zero_and_repeats(fx):
     """mscl_infonce_fused accumulates the row statistics into a zero workspace and must leave it zero (accumulator AND
     CTA counter), so back-to-back calls agree to rounding (the float adds are unordered) and never see stale sums."""
