@@ -402,8 +402,13 @@ def write_timeline(path, step_fn, flush, sync, rank, world, n=3):
         flush()
         torch.cuda.synchronize()
     sync()
+    # device kernels only: torch.profiler also files GPU-side user annotations ("nccl:all_reduce", "DistributedDataParallel.forward",
+    # "GraphedBackward", ...) under the CUDA device type; their spans would count as compute and hide every collective inside
+    skip = ("nccl:", "DistributedDataParallel", "Graphed", "autograd::", "Optimizer", "ProfilerStep")
     kern = [e for e in prof.events() if getattr(e, "device_type", None) is not None and "CUDA" in str(e.device_type)
-            and e.time_range is not None and e.time_range.end > e.time_range.start]
+            and e.time_range is not None and e.time_range.end > e.time_range.start
+            and not getattr(e, "is_user_annotation", False) and not e.name.startswith(skip) and "Memcpy" not in e.name
+            and "Memset" not in e.name]
     is_comm = lambda e: "nccl" in e.name.lower() or "symm" in e.name.lower() or "barrier" in e.name.lower()
     comp = sorted((e.time_range.start, e.time_range.end) for e in kern if not is_comm(e))
     merged = []

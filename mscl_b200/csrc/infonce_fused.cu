@@ -9,13 +9,14 @@
 // What is different from the slab form, and why (profiles/r01_tc_timeline.txt, VERDICT r01 "weak" 1):
 //  * work unit = 64 keys.  A CTA owns a contiguous range of units; it processes them as 128-key PAIR tiles (a tf32
 //    tcgen05 dispatch never costs less than ~61 cycles, so N = 128 keys per MMA1 dispatch is the efficient shape) plus,
-//    when its unit count is odd, one 64-key HALF tile that is requested first, lands first and starts the pipeline
-//    early.  1024 units over 148 CTAs is 6.92 per CTA (max 7): the 128-key split was 3.46 (max 4), i.e. the slowest CTA
+//    when its unit count is odd, one 64-key HALF tile that is requested with the first loads and processed LAST, so that
+//    the drain after the last byte is half as long.  1024 units over 148 CTAs is 6.92 per CTA (max 7): the 128-key split was 3.46 (max 4), i.e. the slowest CTA
 //    streamed 14 % more than the average.
 //  * ring 1 = two pair slots + one dedicated half-tile slot: 160 KB of a CTA's <= 224 KB are requested before anything
 //    else happens (was 128 of <= 256 KB).  Ring 2 (the MN-major copy for the second GEMM, L2 hits) has two 64-key slots.
-//  * no prep launch: the softmax warps compute pos2 / shift2 from q and kpos (warp per row, coalesced), round q to tf32
-//    on its way into TMEM, and a 12th warp turns birth[] into the per-key scale 0.99999^age / T * log2(e) tile by tile.
+//  * no prep launch: the raw q rows and their positives arrive by TMA (first in the TMA unit's queue), the softmax warps
+//    compute pos2 / shift2 from them (warp per row, transpose-reduce), round q to tf32 on its way into TMEM, and a 12th
+//    warp turns birth[] into the per-key scale 0.99999^age / T * log2(e) tile by tile.
 //  * no finalize launch: the row statistics (sum-exp, hit count: 8 bytes per row and CTA) are added into one small
 //    accumulator with red.global.add, and the last CTA to finish (device counter) turns them into losses, top-k flags,
 //    group means and the two per-row gradient coefficients -- on the four warps that are idle by then, while the
@@ -52,13 +53,15 @@ constexpr uint32_t kPairBytes = kTile * kC * 4;        // 65536
 constexpr uint32_t kPairSlab = kTile * 128;            // bytes per channel block of a pair tile
 constexpr uint32_t kUnitBytes = kUnit * kC * 4;        // 32768
 constexpr uint32_t kUnitSlab = kUnit * 128;
+constexpr uint32_t kQBytes = kRows * kC * 4;           // 65536: the Q tile (and the positives' tile)
+constexpr uint32_t kQSlab = kRows * 128;               // bytes per channel block of it
 
 // shared memory map (the dynamic segment is 1024-byte aligned: checked at kernel entry)
 constexpr uint32_t kOffPair = 0;                               // 2 x 64 KB pair slots; the [128][132] output tile at the end
 constexpr uint32_t kOffSingle = kOffPair + 2 * kPairBytes;     // 32 KB: the half tile
 constexpr uint32_t kOffW2 = kOffSingle + kUnitBytes;           // ring 2: 2 x 32 KB; the Q tile before the first ring-2 load
 constexpr uint32_t kOffBar = kOffW2 + kStages2 * kUnitBytes;
-constexpr uint32_t kNumBars = 2 + 2 + 1 + 2 * kStages2 + 1 + 2 + 2 + 1 + 1 + 1 + 2 + 2 + 1;   // (the q_load slot is now "prologue loads issued")
+constexpr uint32_t kNumBars = 2 + 2 + 1 + 2 * kStages2 + 1 + 2 + 2 + 1 + 1 + 1 + 2 + 2 + 1 + 1;   // (the q_load slot is now "prologue loads issued")
 constexpr int kStatCopies = 16;       // the row statistics are spread over this many accumulator copies (see the epilogue)
 constexpr uint32_t kOffTmemPtr = kOffBar + 8 * kNumBars;
 constexpr uint32_t kOffFlag = kOffTmemPtr + 8;
@@ -66,7 +69,7 @@ constexpr uint32_t kOffDs = kOffBar + 256;                     // [2][128] float
 constexpr uint32_t kOffRow = kOffDs + 2 * kTile * 4;           // [128] float2 (pos2, shift2); later [2][128] sum / count
 constexpr uint32_t kSmemBytes = kOffRow + kRows * 8;
 static_assert(kOffFlag + 8 <= kOffDs, "barrier block overflows");
-static_assert(kRows * 512 <= kStages2 * kUnitBytes, "the Q tile is staged through ring 2");
+static_assert(kQBytes <= kStages2 * kUnitBytes && kQBytes <= kPairBytes, "the Q tile is staged through ring 2, the positives through pair slot 1");
 static_assert(kRows * kLd * 4 <= 2 * kPairBytes, "the output tile is staged through the pair slots");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 
@@ -103,17 +106,6 @@ struct Params {
   float key_norm_bound;
 };
 
-// A coherent (not .nc) volatile load: neither the compiler nor ptxas moves it across a barrier, so it is issued where
-// it is written (the read-only path's loads are sunk to their first use, microseconds later under load).
-__device__ __forceinline__ float4 ld_now(const float4 *p) {
-  float4 r;
-  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-               : "l"(p)
-               : "memory");
-  return r;
-}
-
 // Several independent InfoNCE terms ("jobs": their own queries, queue and outputs) in ONE launch.  blockIdx.y runs over
 // the row blocks of all jobs, blockIdx.x over the key ranges of a job, so the jobs occupy disjoint sets of SMs and the
 // fixed costs of a launch -- ramp (first bytes 2-3 us after launch), drain, finalize, launch gap: ~9 of the 15 us a
@@ -124,16 +116,12 @@ struct alignas(64) JobTable {
   CUtensorMap tmap_w[kMaxJobs];     // queue [K_local][128] fp32: 128-key box, 128B swizzle (pair tiles, K-major)
   CUtensorMap tmap_wh[kMaxJobs];    // the same, 64-key box (half tile)
   CUtensorMap tmap_w2[kMaxJobs];    // 64-key box, 32-byte-atom 128B swizzle (MN-major copy)
+  CUtensorMap tmap_q[kMaxJobs];     // query rows [M][128 of ld] fp32: 128-row box, 128B swizzle (rows >= M zero-filled)
+  CUtensorMap tmap_k[kMaxJobs];     // FUSED: positives [M][128], same box
   Params p[kMaxJobs];
   int n_jobs;
   int rb_begin[kMaxJobs + 1];       // first blockIdx.y of each job (row blocks of 128 query rows)
 };
-
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
-               "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
 
 #ifdef MSCL_TC_TIMELINE
 __device__ unsigned long long g_timeline_f[148 * 2 * 32];
@@ -250,6 +238,7 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
   while (job + 1 < jt.n_jobs && (int)blockIdx.y >= jt.rb_begin[job + 1]) ++job;
   const Params &p = jt.p[job];
   const CUtensorMap &tmap_w = jt.tmap_w[job], &tmap_wh = jt.tmap_wh[job], &tmap_w2 = jt.tmap_w2[job];
+  const CUtensorMap &tmap_q = jt.tmap_q[job], &tmap_k = jt.tmap_k[job];
   const unsigned n_ctas_job = gridDim.x * (unsigned)(jt.rb_begin[job + 1] - jt.rb_begin[job]);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *gbase = smem_raw;
@@ -274,7 +263,8 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
   auto bar_dfull = [&](int b) { return bar0 + 8u * (kB + 8 + b); };
   auto bar_dfree = [&](int b) { return bar0 + 8u * (kB + 10 + b); };
   const uint32_t bar_ticket = bar0 + 8u * (kB + 12);           // this CTA's ticket (last or not) is in last_flag
-  static_assert(kB + 13 == kNumBars, "barrier count");
+  const uint32_t bar_kload = bar0 + 8u * (kB + 13);            // the positives' tile landed (TMA)
+  static_assert(kB + 14 == kNumBars, "barrier count");
   volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(gbase + kOffTmemPtr);
   volatile int *last_flag = reinterpret_cast<volatile int *>(gbase + kOffFlag);
   float *ds_smem = reinterpret_cast<float *>(gbase + kOffDs);
@@ -294,10 +284,16 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
   const int64_t key_end = u_end * kUnit < p.K_local ? u_end * kUnit : p.K_local;
   const int row0 = ((int)blockIdx.y - jt.rb_begin[job]) * kRows;
   // step i covers keys [key0(i), key0(i) + (half tile ? 64 : 128))
-  auto step_key0 = [&](int i) { return key_begin + (i == 0 ? 0 : (int64_t)i * kTile - hasH * kUnit); };
+  // processing order = key order: the pair tiles first, the half tile (when the unit count is odd) LAST -- it is requested
+  // with the first loads and waits in its own slot; as the last step it halves the drain (MMA1 -> softmax -> MMA2 of 64
+  // keys instead of 128 after the last byte has landed)
+  auto step_key0 = [&](int i) { return key_begin + (int64_t)i * kTile; };
+  auto step_is_h = [&](int i) { return hasH && i == nt - 1; };
 
   if (warp == 0 && lane == 0) {
     TLF(0);
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+    if (FUSED) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_wh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
@@ -318,9 +314,10 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
       mbar_init(bar_dfree(b), kSoftmaxWarps);
     }
     mbar_init(bar_ofull, 1);
-    mbar_init(bar_qload, kSoftmaxWarps);
+    mbar_init(bar_qload, 1);
     mbar_init(bar_qfree, kSoftmaxWarps);
     mbar_init(bar_ticket, 1);
+    mbar_init(bar_kload, 1);
     *last_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -343,31 +340,37 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
         const int s = pi & 1;
         mbar_wait(bar_empty1(s), ((uint32_t)(pi >> 1) & 1u) ^ 1u);
         mbar_arrive_expect_tx(bar_full1(s), kPairBytes);
-        tma_load_3d(sPair + s * kPairBytes, &tmap_w, bar_full1(s), 0, (int)(key_begin + hasH * kUnit + (int64_t)pi * kTile), 0);
+        tma_load_3d(sPair + s * kPairBytes, &tmap_w, bar_full1(s), 0, (int)(key_begin + (int64_t)pi * kTile), 0);
       };
-      auto load_first = [&](int n_pairs) {
+      auto load_half = [&]() {
         if (hasH) {
           mbar_arrive_expect_tx(bar_fullH, kUnitBytes);
-          tma_load_3d(sSingle, &tmap_wh, bar_fullH, 0, (int)key_begin, 0);
+          tma_load_3d(sSingle, &tmap_wh, bar_fullH, 0, (int)(key_begin + (int64_t)np * kTile), 0);
         }
-        for (int pi = 0; pi < n_pairs && pi < np; ++pi) load_pair(pi);
       };
       // kFlagEarlyPrefetch: the caller guarantees the queue was not written by the launch this grid may overlap with
       // (programmatic dependent launch), so its tiles may be requested before the dependency wait.
-      // The 96 KB of q / kpos rows every CTA needs come through the same L2 -> SM path as the queue tiles and were
-      // measured to take ~4 us when issued behind 160 KB of tile requests: the bulk of the tile requests is held back
-      // until the softmax warps have issued those loads (bar_qload).
-      if (p.flags & kFlagEarlyPrefetch) {
-        load_first(0);       // the half tile only
-        pdl_wait();
-        pdl_trigger();       // only after the wait: a dependent of THIS grid may then assume this grid's predecessors are done
-        mbar_wait(bar_qload, 0);
-        for (int pi = 0; pi < 2 && pi < np; ++pi) load_pair(pi);
-      } else {
-        pdl_wait();
-        pdl_trigger();
-        mbar_wait(bar_qload, 0);
-        load_first(2);
+      // The query rows (and, FUSED, their positives) every CTA needs come FIRST in the TMA unit's queue after the wait:
+      // per-thread loads of those 96 KB were throttled by the load/store unit's miss capacity (1.3 us just to issue
+      // them) and, behind 160 KB of tile requests, took ~4 us to arrive.  Q is staged in the ring-2 area, the positives
+      // in pair slot 1 -- whose first queue tile therefore waits until the softmax warps have consumed them (bar_qfree).
+      // Request order of the queue tiles = processing order: pair 0, the half tile's slot (processed last, but its
+      // request does not have to wait for anything), pair 1, ...
+      const bool early = (p.flags & kFlagEarlyPrefetch) != 0;
+      if (early && np > 0) load_pair(0);
+      pdl_wait();
+      pdl_trigger();         // only after the wait: a dependent of THIS grid may then assume this grid's predecessors are done
+      mbar_arrive_expect_tx(bar_qload, kQBytes);
+      tma_load_3d(sW2, &tmap_q, bar_qload, 0, row0, 0);           // MMA1 needs Q: first
+      if (!(early && np > 0) && np > 0) load_pair(0);             // ... and the first queue tile: second
+      if (FUSED) {                                                 // the positives are only needed by the first softmax
+        mbar_arrive_expect_tx(bar_kload, kQBytes);
+        tma_load_3d(sPair + kPairBytes, &tmap_k, bar_kload, 0, row0, 0);
+      }
+      load_half();
+      if (np > 1) {
+        if (FUSED) mbar_wait(bar_qfree, 0);
+        load_pair(1);
       }
       TLF(18);
       for (int pi = 2; pi < np; ++pi) load_pair(pi);
@@ -402,7 +405,7 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
       const int b = i & 1;
       mbar_wait(bar_dfree(b), ((uint32_t)(i >> 1) & 1u) ^ 1u);
       const int64_t k0 = step_key0(i) + 4 * lane;
-      const int64_t tile_end = (hasH && i == 0) ? key_begin + kUnit : step_key0(i) + kTile;
+      const int64_t tile_end = step_key0(i) + (step_is_h(i) ? kUnit : kTile);
       const int64_t lim = tile_end < key_end ? tile_end : key_end;
       int bi[4] = {0, 0, 0, 0};
       if (k0 + 3 < lim) {
@@ -434,7 +437,7 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
     if (elect_one()) {
       auto issue_mma1 = [&](int i) {
         const uint32_t d = tmem + kColS + (uint32_t)(i & 1) * kTile;
-        if (hasH && i == 0) {
+        if (step_is_h(i)) {
           mbar_wait(bar_fullH, 0);
           tc_fence_after();
 #pragma unroll
@@ -446,7 +449,7 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
           }
           tc_commit(bar_sfull(i & 1));
         } else {
-          const int pi = i - hasH;
+          const int pi = i;
           const int s = pi & 1;
           mbar_wait(bar_full1(s), (uint32_t)(pi >> 1) & 1u);
           tc_fence_after();
@@ -475,8 +478,8 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
         mbar_wait(bar_pfull(i & 1), (uint32_t)(i >> 1) & 1u);
         tc_fence_after();
         if (GRAD) {
-          const int n_un = (hasH && i == 0) ? 1 : 2;
-          const int u0 = i == 0 ? 0 : 2 * i - hasH;
+          const int n_un = step_is_h(i) ? 1 : 2;
+          const int u0 = 2 * i;
           for (int h = 0; h < n_un; ++h) {
             const int u = u0 + h;
             const int s = u % kStages2;
@@ -517,47 +520,47 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
     const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     float2 *rowinfo = reinterpret_cast<float2 *>(gbase + kOffRow);
     const float sc = p.inv_T * kLog2e;
-    // ---- Q tile: global -> shared (warp per row: rows sw, sw+8, ..., one coalesced 512-byte load each) -> TMEM (thread per
-    // row).  Staged in the ring-2 area, dense 512-byte rows whose 16-byte chunks are XOR-swizzled with the row index, so
-    // that both the row-wise writes and the thread-per-row reads are free of bank conflicts.  (A TMA load of this tile
-    // queues behind the queue tiles in the SM's TMA unit and lands microseconds late.)
-    uint8_t *qs = gbase + kOffW2;
-    const int q_ld = FUSED ? kC : kLd;
-    // Every global load of the prologue is issued NOW, before the queue tiles flood the memory system (a load issued
-    // 2 us later was measured to take ~3 us): q rows by cp.async straight into shared memory, positives into registers.
+    // ---- Q tile (TMA, 4 channel-block slabs of [128 rows][128 B], 128B-swizzled; rows >= M zero) -> tf32 -> TMEM, thread
+    // per row; FUSED: pos2 = q.k / T * log2e and shift2 = |q| * bound / T * log2e from the Q and positives tiles, warp per row
+    const uint8_t *qs = gbase + kOffW2;
+    const uint8_t *ks = gbase + kOffPair + kPairBytes;
     constexpr int kRW = kRows / kSoftmaxWarps;     // 16 rows per warp
+    mbar_wait(bar_qload, 0);
+    {   // this row of Q -> TMEM columns [kColQ + 64*half, +64): the A operand of every MMA1
 #pragma unroll
-    for (int u = 0; u < kRW; ++u) {
-      const int rl = sw + u * kSoftmaxWarps;
-      const uint32_t dst = smem_u32(qs + rl * 512 + ((lane ^ (rl & 31)) << 4));
-      if (row0 + rl < p.M) {
-        const float *src = p.q + (int64_t)(row0 + rl) * q_ld + lane * 4;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-      } else {
-        asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "f"(0.f) : "memory");
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cb = half * 2 + hh;
+        const uint8_t *rowp = qs + cb * kQSlab + r * 128;
+        uint32_t v[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 f = *reinterpret_cast<const float4 *>(rowp + ((c ^ (r & 7)) << 4));
+          if (FUSED) f = to_tf32_rn(f);
+          v[c * 4 + 0] = __float_as_uint(f.x);
+          v[c * 4 + 1] = __float_as_uint(f.y);
+          v[c * 4 + 2] = __float_as_uint(f.z);
+          v[c * 4 + 3] = __float_as_uint(f.w);
+        }
+        TC_ST32(lane_base + kColQ + cb * 32, v);
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_q);
+      if (threadIdx.x == 64) TLF(2);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    float4 rb[kRW];
     if (FUSED) {
-#pragma unroll
-      for (int u = 0; u < kRW; ++u) {
-        const int rr = row0 + sw + u * kSoftmaxWarps;
-        rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rr < p.M) rb[u] = ld_now(reinterpret_cast<const float4 *>(p.kpos + (int64_t)rr * kC) + lane);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_qload);         // this warp's prologue loads are in flight: the tile requests may follow
-    // pos2 = q.k / T * log2e and shift2 = |q| * bound / T * log2e, one warp per row
-    auto rowinfo_reduce = [&]() {
-      // vals[u] = this lane's part of q.k of row slot u, vals[16 + u] = of |q|^2
+      mbar_wait(bar_kload, 0);
+      // vals[u] = this lane's part of q.k of row slot u (row sw + 8u), vals[16 + u] = of |q|^2; lane <-> 16-byte chunk
       float vals[2 * kRW];
+      const int slab = lane >> 3, cpos = lane & 7;
 #pragma unroll
       for (int u = 0; u < kRW; ++u) {
         const int rl = sw + u * kSoftmaxWarps;
-        const float4 a = *reinterpret_cast<const float4 *>(qs + rl * 512 + ((lane ^ (rl & 31)) << 4));
-        vals[u] = a.x * rb[u].x + a.y * rb[u].y + a.z * rb[u].z + a.w * rb[u].w;
+        const int off = slab * kQSlab + rl * 128 + ((cpos ^ (rl & 7)) << 4);
+        const float4 a = *reinterpret_cast<const float4 *>(qs + off);
+        const float4 b = *reinterpret_cast<const float4 *>(ks + off);
+        vals[u] = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
         vals[kRW + u] = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
       }
       if (threadIdx.x == 64) TLF(12);
@@ -582,35 +585,10 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
         // one CTA per row block publishes the pair for the finalising CTA
         if (blockIdx.x == 0) *reinterpret_cast<float2 *>(p.rowaux + (int64_t)(row0 + rl) * 4) = ri;
       }
-    };
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
-    {   // this row of Q: smem -> tf32 -> TMEM columns [kColQ + 64*half, +64): the A operand of every MMA1
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int cb = half * 2 + hh;
-        uint32_t v[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 f = *reinterpret_cast<const float4 *>(qs + r * 512 + (((cb * 8 + c) ^ (r & 31)) << 4));
-          if (FUSED) f = to_tf32_rn(f);
-          v[c * 4 + 0] = __float_as_uint(f.x);
-          v[c * 4 + 1] = __float_as_uint(f.y);
-          v[c * 4 + 2] = __float_as_uint(f.z);
-          v[c * 4 + 3] = __float_as_uint(f.w);
-        }
-        TC_ST32(lane_base + kColQ + cb * 32, v);
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_q);
-      if (threadIdx.x == 64) TLF(2);
     }
-    if (FUSED) rowinfo_reduce();
     if (threadIdx.x == 64) TLF(13);
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_qfree);         // the staging area goes back to ring 2
+    if (lane == 0) mbar_arrive(bar_qfree);         // the staging areas go back to ring 2 / ring 1
     if (FUSED) {
       asm volatile("bar.sync 1, %0;" ::"r"(kSoftmaxWarps * 32) : "memory");
       if (row_ok) {
@@ -634,7 +612,7 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
     if (threadIdx.x == 64) TLF(14);
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
-      const bool is_h = hasH && i == 0;
+      const bool is_h = step_is_h(i);
       // a pair tile: this warp's 64 keys as two 32-key chunks; the half tile: one 32-key chunk per warp
       const int koff = is_h ? half * 32 : half * kUnit;
       const int nch = is_h ? 1 : 2;
@@ -818,6 +796,12 @@ static int launch(bool fused, bool grad, int n_jobs, const Params *ps, const flo
     if (rc) return rc;
     rc = make_map(&jt.tmap_w2[j], queues[j], p.K_local, kC, kUnit, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
+    rc = make_map(&jt.tmap_q[j], p.q, p.M, fused ? kC : kLd, kRows);
+    if (rc) return rc;
+    if (fused) {
+      rc = make_map(&jt.tmap_k[j], p.kpos, p.M, kC, kRows);
+      if (rc) return rc;
+    }
     jt.p[j] = p;
     jt.rb_begin[j + 1] = jt.rb_begin[j] + (p.M + kRows - 1) / kRows;
   }

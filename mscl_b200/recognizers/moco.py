@@ -231,6 +231,16 @@ class MoCoV2(BaseMoCoRecognizer):
         return shf.exchange(x.contiguous(), plan, fx.gather_rows), idx_unshuffle
 
     @torch.no_grad()
+    def _batch_shuffle_begin(self, x):
+        """The same shuffle with the all-to-all left in flight: returns (pending, idx_unshuffle); `pending.finish()` gives
+        the rows this rank feeds its key encoder.  Only used with more than one rank."""
+        world = dist.get_world_size()
+        n = x.shape[0]
+        idx_shuffle = shf.draw_permutation(n * world, x.device, self._shuffle_group())
+        plan = shf.ShufflePlan(idx_shuffle, n, dist.get_rank(), world)
+        return shf.exchange_begin(x.contiguous(), plan, fx.gather_rows), torch.argsort(idx_shuffle)
+
+    @torch.no_grad()
     def _batch_unshuffle_ddp(self, x, idx_unshuffle):
         """moco.py:174-191."""
         world = dist.get_world_size() if _dist_on() else 1
@@ -257,13 +267,25 @@ class MoCoV2(BaseMoCoRecognizer):
         flow recognizer is called twice): CUDA-graphed encoder paths (mscl_b200/graphed.py) keep one set of static
         activations per site."""
         graphed = getattr(self, "_graphed_paths", None)
+        pending = None
+        if _dist_on() and dist.get_world_size() > 1:
+            # More than one rank: the key encoder's momentum update and the shuffle exchange are started BEFORE the query
+            # forward instead of after it (moco.py:531-536), so the all-to-all travels while the query encoder runs.  Same
+            # results: the update reads the query parameters, which the forward does not change, and the permutation is
+            # still the next draw of the CPU generator (nothing in the query forward touches it).
+            with torch.no_grad():
+                self._momentum_update_key_encoder()
+                pending, idx_unshuffle = self._batch_shuffle_begin(im_k)
         if graphed is not None and self.training and torch.is_grad_enabled():
             q, q_mlvl, sup_loss = graphed.q(site, im_q)
         else:
             q, q_mlvl, sup_loss = self.q_path(im_q)
         with torch.no_grad():
-            self._momentum_update_key_encoder()
-            im_k, idx_unshuffle = self._batch_shuffle_ddp(im_k)
+            if pending is not None:
+                im_k = pending.finish()
+            else:
+                self._momentum_update_key_encoder()
+                im_k, idx_unshuffle = self._batch_shuffle_ddp(im_k)
             if graphed is not None and self.training and not unshuffle_mlvl:
                 k, k_mlvl = graphed.k(site, im_k)
             else:

@@ -64,6 +64,27 @@ def _upload(idx, dev):
     return idx.pin_memory().to(dev, non_blocking=True)
 
 
+class PendingExchange:
+    """An exchange whose all-to-all is in flight (async): `finish()` waits for it and orders the received rows."""
+
+    def __init__(self, work, recv, send, plan, gather_rows):
+        self.work, self.recv, self.send, self.plan, self.gather_rows = work, recv, send, plan, gather_rows
+
+    def finish(self):
+        self.work.wait()                     # the current stream now waits for the collective; the host does not
+        return self.gather_rows(self.recv, _upload(self.plan.recv_pos, self.recv.device))
+
+
+def exchange_begin(x, plan, gather_rows):
+    """First half of `exchange`: gather the rows to send and START the all-to-all (async_op).  Whatever the caller launches
+    before `finish()` overlaps with the transfer -- MoCoV2.extract_feat runs the query encoder there, so the 38 MB of clips
+    a rank trades per shuffle no longer sit exposed in front of the key encoder."""
+    send = gather_rows(x, _upload(plan.send_idx, x.device))
+    recv = torch.empty_like(x)
+    work = dist.all_to_all_single(recv, send, output_split_sizes=plan.out_splits, input_split_sizes=plan.in_splits, async_op=True)
+    return PendingExchange(work, recv, send, plan, gather_rows)
+
+
 def exchange(x, plan, gather_rows):
     """Run a ShufflePlan on device tensor x (n_local, ...) with torch.distributed all_to_all.
     `gather_rows(x, idx)` is the row-gather kernel (functional.gather_rows)."""
