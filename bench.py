@@ -453,6 +453,10 @@ def write_timeline(path, step_fn, flush, sync, rank, world, n=3):
     tot = sum(v[1] for v in agg.values()) or 1.0
     for name, (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
         lines.append(f"{t / n / 1e3:8.3f} ms {100 * t / tot:5.1f}% {cnt / n:7.1f}x  {name}")
+    lines.append("# host side: top ops by SELF CPU time per step (the step is host-issue bound: what the host spends is what the GPU waits for)")
+    cpu = sorted(prof.key_averages(), key=lambda e: -e.self_cpu_time_total)
+    for e in cpu[:30]:
+        lines.append(f"{e.self_cpu_time_total / n / 1e3:8.3f} ms self {e.cpu_time_total / n / 1e3:8.3f} ms total {e.count / n:7.1f}x  {e.key[:110]}")
     os.makedirs(os.path.dirname(os.path.abspath(path)) or ".", exist_ok=True)
     with open(path, "w") as f:
         f.write("\n".join(lines) + "\n")

@@ -62,12 +62,29 @@ class IdentityAug:
         return im_q, im_k, flow_q, flow_k, aux_info
 
 
+_DEV_CONST = {}
+
+
+def _dev_const(name, device, make):
+    """A small constant tensor, built on the host ONCE per device and cached.  Building it per call (`torch.tensor(...,
+    device=cuda)`, a pageable `.to(device)`, `torch.linalg.inv` on the device) costs a host <-> device synchronisation each
+    time: the augmentation did that six times per step, each one draining the host's run-ahead (profiles/r02_timeline_host_*)."""
+    key = (name, str(device))
+    t = _DEV_CONST.get(key)
+    if t is None:
+        t = _DEV_CONST[key] = make().to(device)
+    return t
+
+
+_YIQ = [[0.299, 0.587, 0.114], [0.596, -0.274, -0.322], [0.211, -0.523, 0.312]]
+
+
 def _hue_matrix(h):
     """(n,3,3) RGB->RGB matrices rotating hue by h (fraction of a turn, per sample) in YIQ space."""
     theta = h * 2 * math.pi
     c, s = torch.cos(theta), torch.sin(theta)
-    yiq = torch.tensor([[0.299, 0.587, 0.114], [0.596, -0.274, -0.322], [0.211, -0.523, 0.312]], device=h.device)
-    inv = torch.linalg.inv(yiq)
+    yiq = _dev_const("yiq", h.device, lambda: torch.tensor(_YIQ))
+    inv = _dev_const("yiq_inv", h.device, lambda: torch.linalg.inv(torch.tensor(_YIQ)))
     rot = torch.zeros(h.shape[0], 3, 3, device=h.device)
     rot[:, 0, 0] = 1
     rot[:, 1, 1], rot[:, 1, 2], rot[:, 2, 1], rot[:, 2, 2] = c, -s, s, c
@@ -96,7 +113,13 @@ class SyncMoCoAugmentV5:
         self.blur_radius = int(0.1 * crop_size) // 2 * 2 + 1
 
     def _normalize(self, x):
-        return (x - self.mean.to(x.device)) / self.std.to(x.device)
+        mean = _dev_const("aug_mean", x.device, lambda: self.mean)
+        std = _dev_const("aug_std", x.device, lambda: self.std)
+        return (x - mean) / std
+
+    def _norm_table(self, device):
+        """[mean3, std3] on `device` (cached: a per-call `.to(device)` of a host tensor synchronises the stream)."""
+        return _dev_const("aug_norm", device, lambda: torch.cat([self.mean.view(-1), self.std.view(-1)]))
 
     def flip(self, clips, mask):
         """Mirror the clips selected by the boolean mask along W (deterministic piece)."""
@@ -158,7 +181,7 @@ class SyncMoCoAugmentV5:
         clips, aux_info, mask = self.forward_flip(clips, aux_info, suffix, flip_clips=False)
         frames = clips.shape[2] if self.sync_level[0 if suffix == "_q" else 1] == "batch" else 1
         prm = self._color_params(clips.shape[0], clips.device, frames)
-        norm = torch.cat([self.mean.view(-1), self.std.view(-1)]).to(clips.device)
+        norm = self._norm_table(clips.device)
         out = fx.color_pipeline(clips.contiguous().float(), self._pack_params(prm, mask.repeat_interleave(frames), weak),
                                 prm["taps"].contiguous(), norm)
         if flow is not None:
@@ -212,7 +235,7 @@ class MoCoAugmentV2(SyncMoCoAugmentV5):
         prm["jit"] = (torch.rand(1, device=dev) < 0.8).expand(n * t)
         prm["blur"] = (torch.rand(1, device=dev) < 0.5).expand(n * t)
         mask = torch.rand(n * t, device=dev) < 0.5
-        norm = torch.cat([self.mean.view(-1), self.std.view(-1)]).to(dev)
+        norm = self._norm_table(dev)
         out = fx.color_pipeline(frames, self._pack_params(prm, mask, False), prm["taps"].contiguous(), norm)
         return out.view(n, t, c, h, w).permute(0, 2, 1, 3, 4).contiguous()
 
