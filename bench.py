@@ -317,7 +317,8 @@ def run_reference(args, rank):
 # algorithmic bytes (one per op instance); `aux` entry points are further launches of the SAME op instance (its backward
 # kernel, the exchange kernels of the sharded queue, ...): their time is added, their bytes are not.
 OPS = [
-    ("K1 InfoNCE (op)", "8a1-a3", ("mscl_infonce_fused", "mscl_infonce_fused_multi", "mscl_infonce_partial", "mscl_infonce_pass"),
+    ("K1 InfoNCE (op)", "8a1-a3", ("mscl_infonce_fused", "mscl_infonce_fused_multi", "mscl_infonce_fused_multi_x", "mscl_infonce_partial",
+                                  "mscl_infonce_pass"),
      ("mscl_infonce_bwd_slabs", "mscl_infonce_prep", "mscl_infonce_finalize", "mscl_infonce_bwd", "mscl_infonce_reduce",
       "mscl_infonce_reduce_scatter")),
     ("K2 LMCL pooling + loss (op)", "8a4", ("mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_hw_mean_ndhwc_fwd", "mscl_hw_mean_ndhwc_bwd",
@@ -718,6 +719,12 @@ def run_b200(args, rank, local_rank, world):
                 if r["config"] == "cfg2" and r["kernel"].startswith("K1 x2 ops in one launch + their backward"):
                     roofline["frac_standalone_pair"] = r["frac_hbm"]
                     roofline["us_standalone_pair"] = r["us"]
+                if r["config"] == "cfg2" and r["kernel"].startswith("K1 step launch + its two backward"):
+                    roofline["frac_standalone_step_launch"] = r["frac_hbm"]
+                    roofline["us_standalone_step_launch"] = r["us"]
+                if r["config"] == "cfg2" and r["kernel"].startswith("K1 step launch = "):
+                    roofline["frac_standalone_step_forward_launch"] = r["frac_hbm"]
+                    roofline["us_standalone_step_forward_launch"] = r["us"]
                 if r["config"] == "cfg2" and r["kernel"].startswith("K1 x2 ops in one launch = "):
                     roofline["frac_standalone_pair_forward_launch"] = r["frac_hbm"]
                     roofline["us_standalone_pair_forward_launch"] = r["us"]

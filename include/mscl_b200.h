@@ -59,8 +59,10 @@ int mscl_device_check(int dev);
  * written rows becomes 1 and every other age grows by one (kept implicitly as
  * n_enq - birth).  ptr <- (ptr + B_all) % K_total; n_enq <- n_enq + 1.
  * If d_saved != NULL the overwritten rows (those in this shard) are first copied
- * to d_saved[B_all, C] and their birth to d_saved_birth[B_all] (snapshot support,
- * moco.py:484-488).  If d_queue_tf32 != NULL the same rows are also written there
+ * to d_saved[B_all, C] -- from d_queue_tf32 when it is given, i.e. in the form the
+ * tensor-core pass reads, else from d_queue -- and their birth to d_saved_birth[B_all]
+ * (snapshot support, moco.py:484-488; mscl_infonce_fused_multi_x streams them for the
+ * rows that read the queue as it was before this enqueue).  If d_queue_tf32 != NULL the new rows are also written there
  * rounded to nearest tf32: the operand copy the tensor-core pass reads (the tensor
  * core itself would truncate fp32, a systematic -3.5e-4 relative bias per operand).
  */
@@ -271,6 +273,26 @@ int mscl_infonce_fused_multi(int32_t n_jobs, const float *const *d_q, const floa
                              int32_t with_grad, const int32_t *flags, float *const *d_row_loss, float *const *d_rowaux,
                              float *const *d_group_out, mscl_stream_t stream);
 int mscl_infonce_fused_parts_multi(int32_t n_jobs, const int32_t *M, const int64_t *K_local, int32_t num_sms);
+/* The same launch with an "epoch split" on ONE of its jobs (x_job; -1: none, then identical to mscl_infonce_fused_multi):
+ * rows [row_split, M) of that job read its queue as it is, rows [0, row_split) read it as it was BEFORE its last
+ * enqueue, which wrote rep_n (<= 128) keys into slots [rep_begin, rep_begin + rep_n) and saved what it overwrote:
+ * d_xkeys [rep_n, 128] / d_xbirth [rep_n] = mscl_enqueue's d_saved / d_saved_birth.  Before that enqueue every age was
+ * one lower and those slots held the saved keys (moco.py:423-440: count += 1, count[ptr:ptr+B] = 1).
+ * That is the pair of queue states MSCLWithAug reads within one step (mscl.py:228-277: the base-flow call's logits
+ * before its enqueue, the FRA call's and the cross-modal rf terms after it), so the step streams W_flow ONCE for both.
+ * How: the pre rows' q is scaled by 1/0.99999 before its tf32 rounding (a uniform age - 1) and their gradient
+ * coefficient by the same factor; in the queue's own tiles the freshly written slots are masked for them; the saved keys
+ * are one extra 128-key tile (same key indices, the age they would have now) that only the pre rows see, streamed by
+ * the CTA with the fewest queue units.  d_dup_slot / dup_age keep their meaning (rows at or after row_split whose
+ * positive is one of the keys just enqueued: global slot rep_begin + i, dup_age = 1). */
+int mscl_infonce_fused_multi_x(int32_t n_jobs, const float *const *d_q, const float *const *d_kpos, const int32_t *M,
+                               const float *const *d_queue_tf32, const int32_t *const *d_birth,
+                               const int64_t *const *d_qstate, const int64_t *K_local, const float *inv_T,
+                               const float *key_norm_bound, const int32_t *const *d_dup_slot, const int32_t *dup_age,
+                               float *const *d_ws, float *const *d_part, int32_t n_part, const int32_t *rows_per_group,
+                               int32_t with_grad, const int32_t *flags, float *const *d_row_loss, float *const *d_rowaux,
+                               float *const *d_group_out, int32_t x_job, const float *d_xkeys, const int32_t *d_xbirth,
+                               int64_t rep_begin, int32_t rep_n, int32_t row_split, mscl_stream_t stream);
 int mscl_infonce_bwd_slabs(const float *d_part, int32_t n_part, int32_t M, const float *d_kpos, const float *d_rowaux,
                            const float *d_gout, int32_t rows_per_group, float *d_dq, mscl_stream_t stream);
 /* The pass alone in the same form, for the sharded queue: d_qpack [M, 132] is the gathered table mscl_infonce_prep fills

@@ -8,7 +8,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmscl_b200.so")
+# MSCL_LIB: another build of the same library (e.g. the MSCL_TIMELINE=1 debug build kept next to the product one)
+LIB_PATH = os.environ.get("MSCL_LIB") or os.path.join(_HERE, "lib", "libmscl_b200.so")
 
 c_int = ctypes.c_int32
 c_i64 = ctypes.c_int64
@@ -44,6 +45,8 @@ PROTOTYPES = {
     "mscl_infonce_fused": [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_int, c_ptr, c_ptr, c_int, c_int,
                            c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     "mscl_infonce_fused_multi": [c_int] + [c_ptr] * 13 + [c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "mscl_infonce_fused_multi_x": [c_int] + [c_ptr] * 13 + [c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_i64,
+                                   c_int, c_int, c_ptr],
     "mscl_infonce_fused_parts_multi": [c_int, c_ptr, c_ptr, c_int],
     "mscl_infonce_bwd_slabs": [c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr],
     "mscl_infonce_pass": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_ptr, c_int, c_int, c_int, c_ptr],

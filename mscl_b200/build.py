@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libmscl_b200.so")
+LIB = os.environ.get("MSCL_LIB_OUT") or os.path.join(LIBDIR, "libmscl_b200.so")      # MSCL_LIB_OUT: debug builds kept aside
 SOURCES = ["abi.cu", "enqueue.cu", "ema.cu", "fra.cu", "lmcl.cu", "infonce.cu", "infonce_tc.cu", "infonce_fused.cu", "resample.cu", "augment.cu", "optim.cu", "retrieval.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        obj = os.path.join(LIBDIR, src.replace(".cu", ".o") if not os.environ.get("MSCL_LIB_OUT") else "dbg_" + src.replace(".cu", ".o"))
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if os.environ.get("MSCL_TIMELINE"):      # debug build: per-CTA phase timestamps in the tcgen05 kernel
             cmd.insert(1, "-DMSCL_TC_TIMELINE")

@@ -30,7 +30,10 @@ enqueue_kernel(float *__restrict__ queue, float *__restrict__ queue_tf32, int32_
     if (local < 0 || local >= K_local) continue;
     float4 *dst = reinterpret_cast<float4 *>(queue + local * (int64_t)C4 * 4) + c4;
     if (saved != nullptr) {
-      reinterpret_cast<float4 *>(saved)[v] = *dst;
+      // the overwritten row, in the form the tensor-core pass reads (the rounded operand copy when there is one): what
+      // mscl_infonce_fused_multi_x streams for the rows that still read the queue as it was before this enqueue
+      reinterpret_cast<float4 *>(saved)[v] =
+          queue_tf32 != nullptr ? reinterpret_cast<float4 *>(queue_tf32 + local * (int64_t)C4 * 4)[c4] : *dst;
       if (c4 == 0) saved_birth[i] = birth[local];
     }
     const float4 kv = __ldg(reinterpret_cast<const float4 *>(keys) + v);

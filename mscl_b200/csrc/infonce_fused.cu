@@ -104,6 +104,17 @@ struct Params {
   int flags;
   float inv_T;
   float key_norm_bound;
+  // "epoch split" (mscl_infonce_fused_multi_x): rows [0, row_split) see the queue as it was BEFORE its last enqueue --
+  // every age one lower (their q rows are scaled by pre_scale = 1 / 0.99999 on their way into TMEM), the slots
+  // [rep_begin, rep_begin + rep_n) holding the rep_n keys that enqueue overwrote (saved by mscl_enqueue together with
+  // their births), which one CTA (blockIdx.x == ex_cta) streams as one extra pair tile carrying the same key indices.
+  // row_split == 0: no such rows.
+  const int32_t *xbirth;     // [rep_n] births of the overwritten keys
+  int64_t rep_begin;
+  int rep_n;
+  int row_split;
+  int ex_cta;
+  float pre_scale;
 };
 
 // Several independent InfoNCE terms ("jobs": their own queries, queue and outputs) in ONE launch.  blockIdx.y runs over
@@ -118,8 +129,11 @@ struct alignas(64) JobTable {
   CUtensorMap tmap_w2[kMaxJobs];    // 64-key box, 32-byte-atom 128B swizzle (MN-major copy)
   CUtensorMap tmap_q[kMaxJobs];     // query rows [M][128 of ld] fp32: 128-row box, 128B swizzle (rows >= M zero-filled)
   CUtensorMap tmap_k[kMaxJobs];     // FUSED: positives [M][128], same box
+  CUtensorMap tmap_x;               // job x_job's overwritten keys [rep_n][128]: 128-key box (rows >= rep_n zero-filled)
+  CUtensorMap tmap_x2;              // the same, 64-key box, 32-byte-atom swizzle
   Params p[kMaxJobs];
   int n_jobs;
+  int x_job;                        // the one job that carries an epoch split, or -1
   int rb_begin[kMaxJobs + 1];       // first blockIdx.y of each job (row blocks of 128 query rows)
 };
 
@@ -138,8 +152,8 @@ __device__ __forceinline__ unsigned long long gtime_f() {
 // 32 keys of one tile for one query row, on registers (see infonce_tc.cu::softmax_half); the 32 per-key scales come
 // from shared memory (warp-uniform addresses: broadcast reads).
 template <bool GRAD, bool FULL>
-__device__ __forceinline__ void softmax_chunk(uint32_t (&v)[32], const float4 *ds, float shift2, float pos2, int nvalid,
-                                              int dupcol, float &sum, int &cnt) {
+__device__ __forceinline__ void softmax_chunk(uint32_t (&v)[32], const float4 *ds, float shift2, float pos2, uint32_t okmask,
+                                              float &sum, int &cnt) {
   float s4[4] = {0.f, 0.f, 0.f, 0.f};
   uint32_t c4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -153,7 +167,7 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[32], const float4 *d
       float p = ex2(fmaf(sv, dd[e], -shift2));
       uint32_t hit = __float_as_uint(fmaf(-sv, dd[e], pos2)) >> 31;    // 1 iff logit > positive logit
       if (!FULL) {
-        const bool ok = j < nvalid && j != dupcol;      // the duplicate of the positive is added exactly by the epilogue
+        const bool ok = (okmask >> j) & 1u;    // not past the end, not the positive's duplicate (added exactly by the epilogue), visible to this row
         p = ok ? p : 0.f;
         hit = ok ? hit : 0u;
       }
@@ -166,6 +180,19 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[32], const float4 *d
   cnt += (int)((c4[0] + c4[1]) + (c4[2] + c4[3]));
 }
 
+// A strong (gpu-scope, L2) load: what the last CTA reads the other CTAs' statistics with.  Their adds were performed at L2
+// before their ticket increments (fence in between) and this CTA's ticket increment came after all of those, so a load
+// that is served by L2 sees them; no second fence (MEMBAR.ALL.GPU + L1 invalidate: ~0.9 us on the kernel's critical
+// path, twice) is spent on it.
+__device__ __forceinline__ float4 ld_strong_v4(const float4 *p) {
+  float4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
+  asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
 // The last CTA, on its four idle warps (128 threads): row statistics -> per-row loss / top-k count / gradient
 // coefficients, per-group means; accumulator and counter left zero.  (formulas: infonce.cu::infonce_finalize_kernel)
 //   d loss_i / d q_i = gout * [ ((p0 - 1)/T + w_dup inv_Z ln2) k_i + inv_Z ln2 sum_slabs O_i ] / rows_per_group
@@ -176,8 +203,8 @@ __device__ __forceinline__ void finalize_stats(const Params &p, int tid, unsigne
     float4 *arow = reinterpret_cast<float4 *>(p.rowaux) + row;
     float4 st[kStatCopies];
 #pragma unroll
-    for (int c = 0; c < kStatCopies; ++c) st[c] = __ldcg(reinterpret_cast<float4 *>(p.ws) + (int64_t)c * p.M + row);
-    const float4 ra = __ldcg(arow);
+    for (int c = 0; c < kStatCopies; ++c) st[c] = ld_strong_v4(reinterpret_cast<float4 *>(p.ws) + (int64_t)c * p.M + row);
+    const float4 ra = ld_strong_v4(arow);
     const int dup = p.dup_slot != nullptr ? __ldg(p.dup_slot + row) : -1;
     float sum = 0.f, cnt = 0.f, w = 0.f;
 #pragma unroll
@@ -199,7 +226,8 @@ __device__ __forceinline__ void finalize_stats(const Params &p, int tid, unsigne
     const float p0 = e0 * inv_Z;
     const float co = inv_Z * kLn2 * inv_rows;
     const float ck = (p0 - 1.0f) * p.inv_T * inv_rows + w * co;
-    __stcg(arow, make_float4(pos2, shift2, ck, co));
+    // epoch split: a pre row's negatives were scored with q / 0.99999, so d logit_j / d q carries that factor too
+    __stcg(arow, make_float4(pos2, shift2, ck, row < p.row_split ? co * p.pre_scale : co));
     const float loss = (shift2 + log2f(Z) - pos2) * kLn2;
     p.row_loss[row] = loss;
     p.row_loss[p.M + row] = cnt;
@@ -208,6 +236,9 @@ __device__ __forceinline__ void finalize_stats(const Params &p, int tid, unsigne
       sm_rows[p.M + row] = cnt;
     }
   }
+#ifdef MSCL_TC_TIMELINE
+  if (tid == 0) TLF(24);
+#endif
   __threadfence_block();
   asm volatile("bar.sync 2, 128;" ::: "memory");
   const bool from_smem = 2 * p.M <= sm_cap;
@@ -278,17 +309,27 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
   const int64_t u_end = n_units * (blockIdx.x + 1) / gridDim.x;
   const int nu = (int)(u_end - u_begin);
   const int hasH = nu & 1;
-  const int np = nu >> 1;
+  const int npn = nu >> 1;                          // pair tiles of the queue
+  // epoch split: the one CTA (per row block) that also streams the keys the last enqueue overwrote, as one more pair tile
+  const bool job_x = FUSED && job == jt.x_job;
+  const int hasX = (job_x && (int)blockIdx.x == p.ex_cta) ? 1 : 0;
+  const int n_xu = (p.rep_n + kUnit - 1) / kUnit;   // 64-key units of it that hold keys (1 or 2)
+  const int np = npn + hasX;                        // pair steps (ring-1 pair slots)
   const int nt = np + hasH;                         // processing steps
   const int64_t key_begin = u_begin * kUnit;
   const int64_t key_end = u_end * kUnit < p.K_local ? u_end * kUnit : p.K_local;
+  const int64_t rep_end = p.rep_begin + p.rep_n;
   const int row0 = ((int)blockIdx.y - jt.rb_begin[job]) * kRows;
   // step i covers keys [key0(i), key0(i) + (half tile ? 64 : 128))
-  // processing order = key order: the pair tiles first, the half tile (when the unit count is odd) LAST -- it is requested
-  // with the first loads and waits in its own slot; as the last step it halves the drain (MMA1 -> softmax -> MMA2 of 64
-  // keys instead of 128 after the last byte has landed)
-  auto step_key0 = [&](int i) { return key_begin + (int64_t)i * kTile; };
+  // processing order = key order: the pair tiles first (the overwritten keys' tile after them), the half tile (when the unit count
+  // is odd) LAST -- it is requested with the first loads and waits in its own slot; as the last step it halves the drain
+  // (MMA1 -> softmax -> MMA2 of 64 keys instead of 128 after the last byte has landed)
   auto step_is_h = [&](int i) { return hasH && i == nt - 1; };
+  auto step_is_x = [&](int i) { return hasX && i == npn; };
+  auto step_key0 = [&](int i) {
+    return step_is_x(i) ? p.rep_begin : key_begin + (int64_t)(step_is_h(i) ? npn : i) * kTile;
+  };
+  auto step_units = [&](int i) { return step_is_h(i) ? 1 : (step_is_x(i) ? n_xu : 2); };
 
   if (warp == 0 && lane == 0) {
     TLF(0);
@@ -297,6 +338,10 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_wh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w2) : "memory");
+    if (hasX) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&jt.tmap_x) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&jt.tmap_x2) : "memory");
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_full1(s), 1);
       mbar_init(bar_empty1(s), 1);
@@ -340,12 +385,15 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
         const int s = pi & 1;
         mbar_wait(bar_empty1(s), ((uint32_t)(pi >> 1) & 1u) ^ 1u);
         mbar_arrive_expect_tx(bar_full1(s), kPairBytes);
-        tma_load_3d(sPair + s * kPairBytes, &tmap_w, bar_full1(s), 0, (int)(key_begin + (int64_t)pi * kTile), 0);
+        if (hasX && pi == npn)      // the overwritten keys (rows >= rep_n of the box are zero-filled and count as landed bytes)
+          tma_load_3d(sPair + s * kPairBytes, &jt.tmap_x, bar_full1(s), 0, 0, 0);
+        else
+          tma_load_3d(sPair + s * kPairBytes, &tmap_w, bar_full1(s), 0, (int)(key_begin + (int64_t)pi * kTile), 0);
       };
       auto load_half = [&]() {
         if (hasH) {
           mbar_arrive_expect_tx(bar_fullH, kUnitBytes);
-          tma_load_3d(sSingle, &tmap_wh, bar_fullH, 0, (int)(key_begin + (int64_t)np * kTile), 0);
+          tma_load_3d(sSingle, &tmap_wh, bar_fullH, 0, (int)(key_begin + (int64_t)npn * kTile), 0);
         }
       };
       // kFlagEarlyPrefetch: the caller guarantees the queue was not written by the launch this grid may overlap with
@@ -356,13 +404,14 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
       // in pair slot 1 -- whose first queue tile therefore waits until the softmax warps have consumed them (bar_qfree).
       // Request order of the queue tiles = processing order: pair 0, the half tile's slot (processed last, but its
       // request does not have to wait for anything), pair 1, ...
-      const bool early = (p.flags & kFlagEarlyPrefetch) != 0;
-      if (early && np > 0) load_pair(0);
+      // (never the overwritten keys' tile: the enqueue that saved them may be the launch before this one)
+      const bool early = (p.flags & kFlagEarlyPrefetch) != 0 && npn > 0;
+      if (early) load_pair(0);
       pdl_wait();
       pdl_trigger();         // only after the wait: a dependent of THIS grid may then assume this grid's predecessors are done
       mbar_arrive_expect_tx(bar_qload, kQBytes);
       tma_load_3d(sW2, &tmap_q, bar_qload, 0, row0, 0);           // MMA1 needs Q: first
-      if (!(early && np > 0) && np > 0) load_pair(0);             // ... and the first queue tile: second
+      if (!early && np > 0) load_pair(0);                         // ... and the first queue tile: second
       if (FUSED) {                                                 // the positives are only needed by the first softmax
         mbar_arrive_expect_tx(bar_kload, kQBytes);
         tma_load_3d(sPair + kPairBytes, &tmap_k, bar_kload, 0, row0, 0);
@@ -382,11 +431,20 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
     if (GRAD && elect_one()) {
       if (!(p.flags & kFlagEarlyPrefetch)) pdl_wait();
       mbar_wait(bar_qfree, 0);                      // ring 2 held the Q tile
-      for (int u = 0; u < nu; ++u) {
-        const int s = u % kStages2;
-        mbar_wait(bar_empty2(s), ((uint32_t)(u / kStages2) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar_full2(s), kUnitBytes);
-        tma_load_3d(sW2 + s * kUnitBytes, &tmap_w2, bar_full2(s), 0, (int)(key_begin + (int64_t)u * kUnit), 0);
+      int u = 0;
+      for (int i = 0; i < nt; ++i) {
+        const bool is_x = step_is_x(i);
+        const int n_un = step_units(i);
+        const int64_t k0 = step_key0(i);
+        for (int h = 0; h < n_un; ++h, ++u) {
+          const int s = u % kStages2;
+          mbar_wait(bar_empty2(s), ((uint32_t)(u / kStages2) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(bar_full2(s), kUnitBytes);
+          if (is_x)
+            tma_load_3d(sW2 + s * kUnitBytes, &jt.tmap_x2, bar_full2(s), 0, h * kUnit, 0);
+          else
+            tma_load_3d(sW2 + s * kUnitBytes, &tmap_w2, bar_full2(s), 0, (int)(k0 + (int64_t)h * kUnit), 0);
+        }
       }
     }
 #ifdef MSCL_TC_TIMELINE
@@ -404,11 +462,17 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
       mbar_wait(bar_dfree(b), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      const bool is_x = step_is_x(i);
       const int64_t k0 = step_key0(i) + 4 * lane;
       const int64_t tile_end = step_key0(i) + (step_is_h(i) ? kUnit : kTile);
-      const int64_t lim = tile_end < key_end ? tile_end : key_end;
+      const int64_t lim_q = tile_end < key_end ? tile_end : key_end;
+      const int64_t lim = is_x ? rep_end : lim_q;
       int bi[4] = {0, 0, 0, 0};
-      if (k0 + 3 < lim) {
+      if (is_x) {       // the overwritten keys: the age they would have now; the rows that see them carry the 1 / 0.99999
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (k0 + e < lim) bi[e] = __ldg(p.xbirth + (k0 + e - p.rep_begin));
+      } else if (k0 + 3 < lim) {
         const int4 t = __ldg(reinterpret_cast<const int4 *>(p.birth + k0));
         bi[0] = t.x; bi[1] = t.y; bi[2] = t.z; bi[3] = t.w;
       } else {
@@ -470,6 +534,7 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
       TLF(28);
       if (nt > 0) issue_mma1(0);
       TLF(29);
+      int u_run = 0;                     // 64-key units handed to MMA2 so far (ring-2 slot and phase)
       for (int i = 0; i < nt; ++i) {
         if (i + 1 < nt) issue_mma1(i + 1);
 #ifdef MSCL_TC_TIMELINE
@@ -478,10 +543,9 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
         mbar_wait(bar_pfull(i & 1), (uint32_t)(i >> 1) & 1u);
         tc_fence_after();
         if (GRAD) {
-          const int n_un = step_is_h(i) ? 1 : 2;
-          const int u0 = 2 * i;
-          for (int h = 0; h < n_un; ++h) {
-            const int u = u0 + h;
+          const int n_un = step_units(i);
+          for (int h = 0; h < n_un; ++h, ++u_run) {
+            const int u = u_run;
             const int s = u % kStages2;
             mbar_wait(bar_full2(s), (uint32_t)(u / kStages2) & 1u);
             tc_fence_after();
@@ -526,6 +590,8 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
     const uint8_t *ks = gbase + kOffPair + kPairBytes;
     constexpr int kRW = kRows / kSoftmaxWarps;     // 16 rows per warp
     mbar_wait(bar_qload, 0);
+    const bool is_pre = FUSED && row < p.row_split;       // sees the queue as it was one enqueue ago (epoch split)
+    const float qfac = is_pre ? p.pre_scale : 1.f;
     {   // this row of Q -> TMEM columns [kColQ + 64*half, +64): the A operand of every MMA1
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -535,7 +601,7 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4 f = *reinterpret_cast<const float4 *>(rowp + ((c ^ (r & 7)) << 4));
-          if (FUSED) f = to_tf32_rn(f);
+          if (FUSED) f = to_tf32_rn(make_float4(f.x * qfac, f.y * qfac, f.z * qfac, f.w * qfac));
           v[c * 4 + 0] = __float_as_uint(f.x);
           v[c * 4 + 1] = __float_as_uint(f.y);
           v[c * 4 + 2] = __float_as_uint(f.z);
@@ -614,9 +680,11 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
       const int b = i & 1;
       const bool is_h = step_is_h(i);
       // a pair tile: this warp's 64 keys as two 32-key chunks; the half tile: one 32-key chunk per warp
+      const bool is_x = step_is_x(i);
       const int koff = is_h ? half * 32 : half * kUnit;
       const int nch = is_h ? 1 : 2;
       const int64_t key0 = step_key0(i) + koff;
+      const int64_t lim = is_x ? rep_end : key_end;
       const bool active = warp_ok;
       mbar_wait(bar_dfull(b), (uint32_t)(i >> 1) & 1u);
       mbar_wait(bar_sfull(b), (uint32_t)(i >> 1) & 1u);
@@ -635,16 +703,32 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
         for (int ch = 0; ch < 2; ++ch) {
           if (ch >= nch) break;                    // warp-uniform
           const int64_t k0 = key0 + ch * 32;
-          const int64_t left = key_end - k0;
+          const int64_t left = lim - k0;
           const int nvalid = left < 32 ? (left < 0 ? 0 : (int)left) : 32;
           const int64_t dcol = dup_local - k0;
           const bool has_dup = dcol >= 0 && dcol < 32;
+          // epoch split: the slots the last enqueue wrote are invisible to the pre rows in the queue's own tiles; the
+          // overwritten keys' tile is visible to the pre rows only
+          const bool split_here = job_x && (is_x || (k0 < rep_end && k0 + 32 > p.rep_begin));
           uint32_t(&v)[32] = ch ? v1 : v0;
           // warp-uniform choice (tcgen05.ld/st are .sync.aligned): slow path if any row of the warp needs it
-          if (nvalid == 32 && !__any_sync(0xffffffffu, has_dup))
-            softmax_chunk<GRAD, true>(v, ds + ch * 8, shift2, pos2, 32, -1, sum, cnt);
-          else
-            softmax_chunk<GRAD, false>(v, ds + ch * 8, shift2, pos2, nvalid, has_dup ? (int)dcol : -1, sum, cnt);
+          if (nvalid == 32 && !split_here && !__any_sync(0xffffffffu, has_dup)) {
+            softmax_chunk<GRAD, true>(v, ds + ch * 8, shift2, pos2, 0xffffffffu, sum, cnt);
+          } else {
+            uint32_t ok = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+            if (has_dup) ok &= ~(1u << (int)dcol);
+            if (split_here) {
+              if (is_x) {
+                ok = is_pre ? ok : 0u;
+              } else if (is_pre) {
+                const int64_t lo = p.rep_begin - k0, hi = rep_end - k0;
+                const int l = lo < 0 ? 0 : (int)lo, h = hi > 32 ? 32 : (int)hi;      // 0 <= l < h <= 32 here
+                const uint32_t below_h = h >= 32 ? 0xffffffffu : ((1u << h) - 1u);
+                ok &= ~(below_h & ~((1u << l) - 1u));
+              }
+            }
+            softmax_chunk<GRAD, false>(v, ds + ch * 8, shift2, pos2, ok, sum, cnt);
+          }
           if (GRAD) TC_ST32(taddr + ch * 32, v);
         }
         if (GRAD) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -739,17 +823,20 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
         const int rl = lane + 32 * u;
         if (row0 + rl < p.M) {
           float *wrow = p.ws + ((int64_t)(blockIdx.x % kStatCopies) * p.M + row0 + rl) * 4;
-          atomicAdd(wrow, red[rl]);
-          atomicAdd(wrow + 1, red[kRows + rl]);
+          red_add_v2(wrow, red[rl], red[kRows + rl]);
         }
       }
     }
     asm volatile("fence.acq_rel.gpu;" ::: "memory");      // the adds above are performed before the ticket below
     __syncwarp();
     if (lane == 0) {
+      TLF(25);
       unsigned *counter = reinterpret_cast<unsigned *>(p.ws + (int64_t)kStatCopies * p.M * 4);
       const unsigned done = atomicAdd(counter, 1u);
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#ifdef MSCL_TC_TIMELINE
+      if (done != 0xffffffffu) TLF(26);
+#endif
+      // (no acquire fence here: the last CTA reads the statistics with strong L2 loads, see ld_strong_v4)
       *last_flag = (done == n_ctas_job - 1u) ? 2 : 1;
       mbar_arrive(bar_ticket);                   // release: the flag is visible to whoever completes the wait below
       TLF(7);
@@ -761,7 +848,7 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
     mbar_wait(bar_ticket, 0);
     const int f = *last_flag;
     if (f == 2) {
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      if (warp == 0 && lane == 0) TLF(27);
       const int tid = (warp < 2 ? warp : warp - kSoftmaxWarps) * 32 + lane;
       // scratch for the row losses: the half-tile slot (consumed long ago; the softmax warps stage O in the pair slots)
       finalize_stats(p, tid, reinterpret_cast<unsigned *>(p.ws + (int64_t)kStatCopies * p.M * 4),
@@ -779,12 +866,14 @@ infonce_fused_kernel(const __grid_constant__ JobTable jt) {
   if (threadIdx.x == 0) TLF(3);
 }
 
-static int launch(bool fused, bool grad, int n_jobs, const Params *ps, const float *const *queues, int n_part, cudaStream_t s) {
+static int launch(bool fused, bool grad, int n_jobs, const Params *ps, const float *const *queues, int n_part, cudaStream_t s,
+                  int x_job = -1, const float *d_xkeys = nullptr) {
   MSCL_CHECK_ARG(n_jobs >= 1 && n_jobs <= kMaxJobs, "n_jobs=%d must be in [1, %d]", n_jobs, kMaxJobs);
   MSCL_CHECK_ARG(n_part > 0, "n_part=%d must be positive", n_part);
   JobTable jt;
   memset(&jt, 0, sizeof(jt));
   jt.n_jobs = n_jobs;
+  jt.x_job = x_job;
   int64_t max_units = 0;
   for (int j = 0; j < n_jobs; ++j) {
     const Params &p = ps[j];
@@ -804,6 +893,23 @@ static int launch(bool fused, bool grad, int n_jobs, const Params *ps, const flo
     }
     jt.p[j] = p;
     jt.rb_begin[j + 1] = jt.rb_begin[j] + (p.M + kRows - 1) / kRows;
+    if (j == x_job) {
+      rc = make_map(&jt.tmap_x, d_xkeys, p.rep_n, kC, kTile);
+      if (rc) return rc;
+      rc = make_map(&jt.tmap_x2, d_xkeys, p.rep_n, kC, kUnit, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+      if (rc) return rc;
+      // the extra pair tile goes to the CTA that streams the fewest units of the queue (the first of them)
+      int best = 0;
+      int64_t best_nu = -1;
+      for (int b = 0; b < n_part; ++b) {
+        const int64_t nu = n_units * (b + 1) / n_part - n_units * b / n_part;
+        if (best_nu < 0 || nu < best_nu) {
+          best_nu = nu;
+          best = b;
+        }
+      }
+      jt.p[j].ex_cta = best;
+    }
   }
   for (int j = n_jobs; j < kMaxJobs; ++j) jt.rb_begin[j + 1] = jt.rb_begin[n_jobs];
   MSCL_CHECK_ARG(n_part <= max_units, "n_part=%d exceeds the %lld 64-key units of the largest queue", n_part, (long long)max_units);
@@ -858,6 +964,9 @@ static int fused_job(Params &p, const float *d_q, const float *d_kpos, int32_t M
   p.flags = flags;
   p.inv_T = inv_T;
   p.key_norm_bound = key_norm_bound;
+  p.row_split = 0;
+  p.ex_cta = -1;
+  p.pre_scale = 1.f;
   return MSCL_OK;
 }
 
@@ -877,15 +986,17 @@ extern "C" int mscl_infonce_fused(const float *d_q, const float *d_kpos, int32_t
   return launch(true, with_grad != 0, 1, &p, &d_queue, n_part, mscl::as_stream(stream));
 }
 
-extern "C" int mscl_infonce_fused_multi(int32_t n_jobs, const float *const *d_q, const float *const *d_kpos, const int32_t *M,
-                                        const float *const *d_queue, const int32_t *const *d_birth,
-                                        const int64_t *const *d_qstate, const int64_t *K_local, const float *inv_T,
-                                        const float *key_norm_bound, const int32_t *const *d_dup_slot, const int32_t *dup_age,
-                                        float *const *d_ws, float *const *d_part, int32_t n_part,
-                                        const int32_t *rows_per_group, int32_t with_grad, const int32_t *flags,
-                                        float *const *d_row_loss, float *const *d_rowaux, float *const *d_group_out,
-                                        mscl_stream_t stream) {
+extern "C" int mscl_infonce_fused_multi_x(int32_t n_jobs, const float *const *d_q, const float *const *d_kpos, const int32_t *M,
+                                          const float *const *d_queue, const int32_t *const *d_birth,
+                                          const int64_t *const *d_qstate, const int64_t *K_local, const float *inv_T,
+                                          const float *key_norm_bound, const int32_t *const *d_dup_slot,
+                                          const int32_t *dup_age, float *const *d_ws, float *const *d_part, int32_t n_part,
+                                          const int32_t *rows_per_group, int32_t with_grad, const int32_t *flags,
+                                          float *const *d_row_loss, float *const *d_rowaux, float *const *d_group_out,
+                                          int32_t x_job, const float *d_xkeys, const int32_t *d_xbirth, int64_t rep_begin,
+                                          int32_t rep_n, int32_t row_split, mscl_stream_t stream) {
   using namespace mscl::tcf;
+  MSCL_CHECK_ARG(x_job >= -1 && x_job < n_jobs, "x_job=%d must be -1 or a job index below %d", x_job, n_jobs);
   MSCL_CHECK_ARG(n_jobs >= 1 && n_jobs <= kMaxJobs, "n_jobs=%d must be in [1, %d]", n_jobs, kMaxJobs);
   MSCL_CHECK_ARG(d_q && d_kpos && M && d_queue && d_birth && d_qstate && K_local && inv_T && key_norm_bound && d_dup_slot &&
                      dup_age && d_ws && d_part && rows_per_group && flags && d_row_loss && d_rowaux && d_group_out,
@@ -899,7 +1010,33 @@ extern "C" int mscl_infonce_fused_multi(int32_t n_jobs, const float *const *d_q,
     for (int i = 0; i < j; ++i)
       MSCL_CHECK_ARG(d_ws[i] != d_ws[j], "jobs %d and %d share a workspace", i, j);
   }
-  return launch(true, with_grad != 0, n_jobs, ps, d_queue, n_part, mscl::as_stream(stream));
+  if (x_job >= 0) {
+    Params &p = ps[x_job];
+    MSCL_CHECK_ARG(d_xkeys && d_xbirth && ((uintptr_t)d_xkeys & 15) == 0, "d_xkeys (16-byte aligned) and d_xbirth are required");
+    MSCL_CHECK_ARG(rep_n >= 1 && rep_n <= kTile, "rep_n=%d must be in [1, %d]", rep_n, kTile);
+    MSCL_CHECK_ARG(rep_begin >= 0 && rep_begin + rep_n <= p.K_local, "replaced slots [%lld, +%d) leave the queue",
+                   (long long)rep_begin, rep_n);
+    MSCL_CHECK_ARG(row_split >= 0 && row_split <= p.M, "row_split=%d must be in [0, M=%d]", row_split, p.M);
+    p.xbirth = d_xbirth;
+    p.rep_begin = rep_begin;
+    p.rep_n = rep_n;
+    p.row_split = row_split;
+    p.pre_scale = 1.0f / 0.99999f;
+  }
+  return launch(true, with_grad != 0, n_jobs, ps, d_queue, n_part, mscl::as_stream(stream), x_job, d_xkeys);
+}
+
+extern "C" int mscl_infonce_fused_multi(int32_t n_jobs, const float *const *d_q, const float *const *d_kpos, const int32_t *M,
+                                        const float *const *d_queue, const int32_t *const *d_birth,
+                                        const int64_t *const *d_qstate, const int64_t *K_local, const float *inv_T,
+                                        const float *key_norm_bound, const int32_t *const *d_dup_slot, const int32_t *dup_age,
+                                        float *const *d_ws, float *const *d_part, int32_t n_part,
+                                        const int32_t *rows_per_group, int32_t with_grad, const int32_t *flags,
+                                        float *const *d_row_loss, float *const *d_rowaux, float *const *d_group_out,
+                                        mscl_stream_t stream) {
+  return mscl_infonce_fused_multi_x(n_jobs, d_q, d_kpos, M, d_queue, d_birth, d_qstate, K_local, inv_T, key_norm_bound,
+                                    d_dup_slot, dup_age, d_ws, d_part, n_part, rows_per_group, with_grad, flags, d_row_loss,
+                                    d_rowaux, d_group_out, -1, nullptr, nullptr, 0, 0, 0, stream);
 }
 
 extern "C" int mscl_infonce_pass(const float *d_qpack, int32_t M, const float *d_queue, const int32_t *d_birth,

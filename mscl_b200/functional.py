@@ -152,24 +152,33 @@ class NegativeQueue:
         return w
 
     @torch.no_grad()
-    def enqueue(self, keys_all):
-        """keys_all: (B_all, C) rank-major gathered keys (moco.py:423-440)."""
+    def enqueue(self, keys_all, save=False):
+        """keys_all: (B_all, C) rank-major gathered keys (moco.py:423-440).  save=True (unsharded queues): returns
+        (old_keys (B_all, C) in the tensor-core pass's operand form, old_birth int32 (B_all,), first slot) of the rows
+        this enqueue overwrote -- what `infonce_multi` needs to score rows against the queue as it was before it."""
         _chk(keys_all, name="keys")
         b = keys_all.shape[0]
         if self.K % b != 0:
             raise AssertionError(f"K={self.K} must be a multiple of the gathered batch size {b}")  # moco.py:432
         if self.ptr + b > self.K:
             raise _cabi.MsclError("queue pointer is not aligned to the batch size (batch size changed mid-cycle)")
+        saved = None
+        if save:
+            if self.world != 1:
+                raise _cabi.MsclError("enqueue(save=True) needs an unsharded queue")
+            saved = (torch.empty(b, self.C, device=self.device), torch.empty(b, dtype=torch.int32, device=self.device), self.ptr)
         _cabi.call("mscl_enqueue", self.queue.data_ptr(), self.queue_tf32.data_ptr(), self.birth.data_ptr(),
                    self.qstate.data_ptr(),
-                   keys_all.data_ptr(), b, self.C, self.K, self.shard_begin, self.K_local, None, None, _stream(),
-                   algo_bytes=2 * b * self.C * 4)
+                   keys_all.data_ptr(), b, self.C, self.K, self.shard_begin, self.K_local,
+                   saved[0].data_ptr() if save else None, saved[1].data_ptr() if save else None, _stream(),
+                   algo_bytes=(3 if save else 2) * b * self.C * 4)
         if self.world > 1:      # the whole-queue fp32 master every rank keeps for a collective-free state_dict()
             _cabi.call("mscl_enqueue", self.full_queue.data_ptr(), None, self.full_birth.data_ptr(), self.full_qstate.data_ptr(),
                        keys_all.data_ptr(), b, self.C, self.K, 0, self.K, None, None, _stream())
         self.ptr = (self.ptr + b) % self.K
         self.n_enq += 1
         self._fresh = True
+        return saved
 
 
 # ----------------------------------------------------------------------------------------
@@ -346,7 +355,7 @@ class _InfoNCEMulti(torch.autograd.Function):
     """Several independent fused InfoNCE terms in one launch (mscl_infonce_fused_multi); one backward kernel per job."""
 
     @staticmethod
-    def forward(ctx, jobs, need_grad, *qs):
+    def forward(ctx, jobs, need_grad, split, *qs):
         import ctypes
         n = len(jobs)
         dev = qs[0].device
@@ -365,13 +374,17 @@ class _InfoNCEMulti(torch.autograd.Function):
         group_out = [torch.empty(M // j["rows_per_group"], 4, device=dev) for M, j in zip(Ms, jobs)]
         nbytes = sum(infonce_algo_bytes(M, K) for M, K in zip(Ms, Ks))
         flops = sum((4 if need_grad else 2) * M * K * DIM for M, K in zip(Ms, Ks))
-        _cabi.call("mscl_infonce_fused_multi", n, arr_ptr(qs), arr_ptr([j["kpos"] for j in jobs]), arr_i32(Ms),
+        x_job, xkeys, xbirth, rep_begin, row_split = split if split is not None else (-1, None, None, 0, 0)
+        _cabi.call("mscl_infonce_fused_multi_x", n, arr_ptr(qs), arr_ptr([j["kpos"] for j in jobs]), arr_i32(Ms),
                    arr_ptr([j["nq"].queue_tf32 for j in jobs]), arr_ptr([j["nq"].birth for j in jobs]),
                    arr_ptr([j["nq"].qstate for j in jobs]), arr_i64(Ks), arr_f32([j["inv_T"] for j in jobs]),
                    arr_f32([j["nq"].max_key_norm for j in jobs]), arr_ptr([j["dup_slot"] for j in jobs]),
                    arr_i32([j["dup_age"] for j in jobs]), arr_ptr(ws), arr_ptr(parts), n_part,
                    arr_i32([j["rows_per_group"] for j in jobs]), int(need_grad), arr_i32([_prefetch_flag(j["nq"]) for j in jobs]),
-                   arr_ptr(row_loss), arr_ptr(rowaux), arr_ptr(group_out), st, algo_bytes=nbytes, algo_flops=flops)
+                   arr_ptr(row_loss), arr_ptr(rowaux), arr_ptr(group_out), x_job,
+                   xkeys.data_ptr() if xkeys is not None else None, xbirth.data_ptr() if xbirth is not None else None,
+                   rep_begin, xkeys.shape[0] if xkeys is not None else 0, row_split, st,
+                   algo_bytes=nbytes + (xkeys.numel() * 4 if xkeys is not None else 0), algo_flops=flops)
         ctx.n = n
         ctx.need_grad = need_grad
         ctx.rpg = [j["rows_per_group"] for j in jobs]
@@ -400,17 +413,33 @@ class _InfoNCEMulti(torch.autograd.Function):
             _cabi.call("mscl_infonce_bwd_slabs", parts[i].data_ptr(), n_part, M, kpos[i].data_ptr(), rowaux[i].data_ptr(),
                        gout.data_ptr(), ctx.rpg[i], dq.data_ptr(), _stream(), algo_bytes=4 * M * (n_part * DIM + 2 * DIM + 4))
             dqs.append(dq)
-        return (None, None, *dqs)
+        return (None, None, None, *dqs)
 
 
 def infonce_multi(jobs):
     """Several independent fused InfoNCE terms in ONE launch.  jobs: list (<= 4) of dicts with q, kpos (M,128), nq
     (an unsharded NegativeQueue), rows_per_group, T and optionally dup_slot / dup_age, as for `infonce`.  Returns a list
-    of (group_out, row_stats) pairs.  The jobs occupy disjoint SMs and share the launch's fixed costs."""
+    of (group_out, row_stats) pairs.  The jobs occupy disjoint SMs and share the launch's fixed costs.
+
+    ONE job may carry an "epoch split" (include/mscl_b200.h, mscl_infonce_fused_multi_x): `overwritten` = what
+    `nq.enqueue(keys, save=True)` returned for the queue's LAST enqueue, and `row_split`: rows [0, row_split) are scored
+    against the queue as it was before that enqueue (ages - 1, the B slots it wrote still holding the old keys), the rows
+    from row_split on against the queue as it is."""
     if not 1 <= len(jobs) <= 4:
         raise _cabi.MsclError("infonce_multi takes 1 to 4 jobs")
     prepared, qs = [], []
-    for j in jobs:
+    split = None
+    for ji, j in enumerate(jobs):
+        if j.get("overwritten") is not None:
+            if split is not None:
+                raise _cabi.MsclError("only one job of a launch may carry an epoch split")
+            xk, xb, begin = j["overwritten"]
+            _chk(xk, name="overwritten keys"), _chk(xb, torch.int32, "overwritten births")
+            if xk.dim() != 2 or xk.shape[1] != DIM or not 1 <= xk.shape[0] <= 128 or xb.shape != (xk.shape[0],):
+                raise _cabi.MsclError(f"overwritten keys must be (B <= 128, {DIM}) with B births; got {tuple(xk.shape)}")
+            if (int(begin) + xk.shape[0]) % j["nq"].K != j["nq"].ptr:
+                raise _cabi.MsclError("`overwritten` is not what the queue's last enqueue saved")
+            split = (ji, xk, xb, int(begin), int(j["row_split"]))
         q, kpos, nq = j["q"], j["kpos"].detach(), j["nq"]
         _chk(q, name="q"), _chk(kpos, name="kpos")
         if q.dim() != 2 or q.shape[1] != DIM or kpos.shape != q.shape or q.shape[0] % j["rows_per_group"]:
@@ -424,7 +453,7 @@ def infonce_multi(jobs):
                              dup_slot=dup, dup_age=int(j.get("dup_age", 1))))
         qs.append(q)
     need_grad = bool(torch.is_grad_enabled() and any(q.requires_grad for q in qs))
-    flat = _InfoNCEMulti.apply(prepared, need_grad, *qs)
+    flat = _InfoNCEMulti.apply(prepared, need_grad, split, *qs)
     return [(flat[2 * i], flat[2 * i + 1]) for i in range(len(jobs))]
 
 

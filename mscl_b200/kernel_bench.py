@@ -207,6 +207,75 @@ def bench_k1_pair(cfg, Ms, K, pk, dev, iters=30):
     return out
 
 
+def bench_k1_step(cfg, n, K, pk, dev, iters=30):
+    """The ONE launch MSCLWithAug.objective makes for all seven InfoNCE terms of a step (mscl_infonce_fused_multi_x):
+    job 0 = 3n rows over W_rgb; job 1 = 4n rows over W_flow with an epoch split -- n rows read it as it was before the
+    base-flow enqueue (ages - 1, the n slots it wrote still holding the keys it overwrote), 3n rows as it is (n of them
+    finding their own positive among the new keys).  The reference's three distinct negative matrices cost two queue
+    reads."""
+    import ctypes
+    Ms = [3 * n, 4 * n]
+    rot = n_rot(2 * K * 512)
+    g = torch.Generator().manual_seed(K + n)
+    rings = []
+    for s in range(rot):
+        qs = []
+        for _ in range(2):
+            nq = fx.NegativeQueue(K, 128, dev)
+            nq.load(F.normalize(torch.randn(128, K, generator=g), dim=0), torch.randint(0, 2000, (K,), generator=g), 5 * n)
+            qs.append(nq)
+        rings.append(qs)
+    q = [F.normalize(torch.randn(M, 128, generator=g), dim=1).to(dev) for M in Ms]
+    k = [F.normalize(torch.randn(M, 128, generator=g), dim=1).to(dev) for M in Ms]
+    xkeys = F.normalize(torch.randn(n, 128, generator=g), dim=1).to(dev)       # what the enqueue overwrote ...
+    xbirth = torch.randint(0, 100, (n,), generator=g, dtype=torch.int32).to(dev)      # ... and its births
+    dup = torch.full((4 * n,), -1, dtype=torch.int32)
+    dup[2 * n:3 * n] = torch.arange(n, dtype=torch.int32) + 5 * n
+    dup = dup.to(dev)
+    arr_i32 = lambda v: (ctypes.c_int32 * 2)(*v)
+    arr_i64 = lambda v: (ctypes.c_int64 * 2)(*v)
+    arr_f32 = lambda v: (ctypes.c_float * 2)(*v)
+    arr_ptr = lambda ts: (ctypes.c_void_p * 2)(*[(t.data_ptr() if t is not None else None) for t in ts])
+    n_part = _cabi.query("mscl_infonce_fused_parts_multi", 2, arr_i32(Ms), arr_i64([K] * 2), fx.sm_count(dev))
+    ws = [torch.zeros(16 * M * 4 + 4, device=dev) for M in Ms]
+    part = [torch.empty(n_part, M, fx.PACK_LD, device=dev) for M in Ms]
+    rowaux = [torch.empty(M, 4, device=dev) for M in Ms]
+    row_loss = [torch.empty(2 * M, device=dev) for M in Ms]
+    gout = [torch.empty(M // n, 4, device=dev) for M in Ms]
+    dq = [torch.empty(M, 128, device=dev) for M in Ms]
+    gone = [torch.ones(M // n, device=dev) for M in Ms]
+    tabs = [dict(queue=arr_ptr([nq.queue_tf32 for nq in qs]), birth=arr_ptr([nq.birth for nq in qs]),
+                 qstate=arr_ptr([nq.qstate for nq in qs])) for qs in rings]
+    fixed = dict(q=arr_ptr(q), k=arr_ptr(k), M=arr_i32(Ms), K=arr_i64([K] * 2), invT=arr_f32([1 / 0.07] * 2), bound=arr_f32([1.0] * 2),
+                 dup=arr_ptr([None, dup]), age=arr_i32([1, 1]), ws=arr_ptr(ws), part=arr_ptr(part), rpg=arr_i32([n, n]),
+                 flags=arr_i32([1, 1]), rl=arr_ptr(row_loss), ra=arr_ptr(rowaux), go=arr_ptr(gout))
+
+    def fwd(i):
+        t = tabs[i % rot]
+        _cabi.call("mscl_infonce_fused_multi_x", 2, fixed["q"], fixed["k"], fixed["M"], t["queue"], t["birth"], t["qstate"],
+                   fixed["K"], fixed["invT"], fixed["bound"], fixed["dup"], fixed["age"], fixed["ws"], fixed["part"], n_part,
+                   fixed["rpg"], 1, fixed["flags"], fixed["rl"], fixed["ra"], fixed["go"], 1, xkeys.data_ptr(), xbirth.data_ptr(), 5 * n, n, n,
+                   _st())
+
+    def fwd_bwd(i):
+        fwd(i)
+        for j in range(2):
+            _cabi.call("mscl_infonce_bwd_slabs", part[j].data_ptr(), n_part, Ms[j], k[j].data_ptr(), rowaux[j].data_ptr(),
+                       gone[j].data_ptr(), n, dq[j].data_ptr(), _st())
+
+    ab = sum(fx.infonce_algo_bytes(M, K) for M in Ms) + n * 512
+    fl = sum(4 * M * K * 128 for M in Ms)
+    ab3 = fx.infonce_algo_bytes(3 * n, K) * 2 + fx.infonce_algo_bytes(n, K)       # the same terms as three separate ops
+    shape = f"M={Ms[0]}+({n}|{3 * n}) K={K} x2 queues"
+    us_f, us_fb = time_train(fwd, iters), time_train(fwd_bwd, iters)
+    out = [row(cfg, "K1 step launch = infonce_fused_kernel<grad>, 2 jobs, epoch split on W_flow (all 7 terms of a step)", shape,
+               us_f, ab, fl, pk, note=f"{n_part} CTAs per job; bytes = the two queues once each; the same terms as three "
+               f"separate ops are {ab3} algorithmic bytes = {ab3 / us_f / 1e3 / pk:.3f} of the HBM roofline, {us_f / 3:.1f} us per op"),
+           row(cfg, "K1 step launch + its two backward kernels", shape, us_fb, ab, fl, pk)]
+    del rings
+    return out
+
+
 # ------------------------------------------------------------------------------------------ K2
 def bench_k2(cfg, N, t, pk, dev, iters=30):
     out = []
@@ -418,6 +487,7 @@ def run(configs=("cfg2", "cfg3", "cfg4", "cfg5"), device=0, verbose=True):
         for M in (96, 32):
             add(bench_k1("cfg2", M, 65536, pk, dev))
         add(bench_k1_pair("cfg2", (96, 32), 65536, pk, dev))
+        add(bench_k1_step("cfg2", 32, 65536, pk, dev))
         add(bench_k2("cfg2", 32, 4, pk, dev))
         add(bench_k3("cfg2", 32, 8, pk, dev))
         add(bench_k4("cfg2", "r18 RGB key side", r3d18_key_sizes(), pk, dev))

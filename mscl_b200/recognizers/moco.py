@@ -205,10 +205,11 @@ class MoCoV2(BaseMoCoRecognizer):
 
     # ------------------------------------------------------------------ K5
     @torch.no_grad()
-    def _dequeue_and_enqueue(self, keys):
+    def _dequeue_and_enqueue(self, keys, save=False):
+        """moco.py:423-440.  save=True: returns what the enqueue overwrote (functional.NegativeQueue.enqueue)."""
         keys = concat_all_gather(keys.contiguous())
         self.batch_size = keys.shape[0]
-        self.negative_queue(keys.device).enqueue(keys.contiguous())
+        return self.negative_queue(keys.device).enqueue(keys.contiguous(), save=save)
 
     # ------------------------------------------------------------------ K6
     def _shuffle_group(self):
@@ -323,18 +324,37 @@ class MoCoV2(BaseMoCoRecognizer):
         return out
 
     @staticmethod
+    def can_launch_together(recs, device):
+        """Can `contrast_many` put passes over these recognizers' queues into ONE launch?  (CUDA, distinct unsharded
+        queues, at most four.)"""
+        if torch.device(device).type != "cuda" or not 1 <= len(recs) <= 4:
+            return False
+        queues = [rec.negative_queue(device) for rec in recs]
+        return all(nq.world == 1 for nq in queues) and len({id(nq) for nq in queues}) == len(queues)
+
+    @staticmethod
     def contrast_many(calls):
         """Several `contrast` calls on DIFFERENT recognizers (queues) that do not depend on each other, as ONE launch
         when none of the queues is sharded (functional.infonce_multi: the jobs share the launch's fixed costs);
-        otherwise one after the other.  calls: list of (recognizer, terms, T).  Returns the list of their results."""
-        if len(calls) < 2 or not all(terms[0][0].is_cuda for _, terms, _ in calls):
-            return [rec.contrast(terms, T) for rec, terms, T in calls]      # (contrast refuses host tensors itself)
-        stacked = [(rec,) + rec._stack_terms(terms) + (T,) for rec, terms, T in calls]
-        queues = [rec.negative_queue(q.device) for rec, q, _, _, _, _ in stacked]
-        if len(calls) < 2 or len(calls) > 4 or any(nq.world != 1 for nq in queues) or len({id(nq) for nq in queues}) != len(queues):
-            return [rec.contrast(terms, T) for rec, terms, T in calls]
-        jobs = [dict(q=q, kpos=kp, nq=nq, rows_per_group=n, T=rec.T if T is None else T, dup_slot=dup)
-                for (rec, q, kp, dup, n, T), nq in zip(stacked, queues)]
+        otherwise one after the other.  calls: list of (recognizer, terms, T) or (recognizer, terms, T, split) with
+        split = (overwritten, n_pre): the first n_pre terms read the recognizer's queue as it was BEFORE its last enqueue
+        (`overwritten` = what that `_dequeue_and_enqueue(..., save=True)` returned), the others as it is -- one call at
+        most, and only where `can_launch_together` holds.  Returns the list of their results."""
+        calls = [tuple(c) + (None,) * (4 - len(c)) for c in calls]
+        has_split = any(sp is not None for _, _, _, sp in calls)
+        together = all(terms[0][0].is_cuda for _, terms, _, _ in calls) and \
+            MoCoV2.can_launch_together([rec for rec, _, _, _ in calls], calls[0][1][0][0].device)
+        if has_split and not together:
+            raise fx._cabi.MsclError("an epoch-split pass needs unsharded CUDA queues (check can_launch_together first)")
+        if not together or (len(calls) < 2 and not has_split):
+            return [rec.contrast(terms, T) for rec, terms, T, _ in calls]      # (contrast refuses host tensors itself)
+        jobs = []
+        for rec, terms, T, sp in calls:
+            q, kp, dup, n = rec._stack_terms(terms)
+            job = dict(q=q, kpos=kp, nq=rec.negative_queue(q.device), rows_per_group=n, T=rec.T if T is None else T, dup_slot=dup)
+            if sp is not None:
+                job.update(overwritten=sp[0], row_split=int(sp[1]) * n)
+            jobs.append(job)
         return [out for out, _ in fx.infonce_multi(jobs)]
 
     def enqueue_slots(self, n_local, device):

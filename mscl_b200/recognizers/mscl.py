@@ -17,6 +17,7 @@ pre-enqueue RGB queue exist.  Effects visible from outside (queue contents, poin
 from collections import OrderedDict
 
 import torch
+import torch.distributed as dist
 
 from ..registry import RECOGNIZERS, build_ssl_aug
 from .base_moco import TwoBranchRecognizer
@@ -136,6 +137,8 @@ class MSCLWithAug(TwoBranchRecognizer):
         self._build_cls_head(moco_mx_head, name="moco_mx_head")
         self._build_cls_head(sup_head, name="sup_head")
         self.aug_gpu = build_ssl_aug(aug)
+        # train_cfg=dict(merge_flow_epochs=False) keeps the three-pass schedule (W_flow streamed before AND after its enqueue)
+        self.merge_flow_epochs = bool((train_cfg or {}).get("merge_flow_epochs", True))
 
     def train_step(self, data_batch, optimizer, **kwargs):
         im_q = data_batch[self.im_key][0]
@@ -183,6 +186,11 @@ class MSCLWithAug(TwoBranchRecognizer):
                 by_T.setdefault(T, []).append((name, qq, kk, dup))
             return list(by_T.items())
 
+        def launch(calls, names):
+            for out, nm in zip(type(rec).contrast_many(calls), names):
+                for i, name in enumerate(nm):
+                    rows[name] = out[i]
+
         def run(*phase_owner):
             """The passes of the given (phase, recognizer) pairs; passes over different queues that do not depend on
             each other go out as ONE launch (MoCoV2.contrast_many)."""
@@ -191,15 +199,30 @@ class MSCLWithAug(TwoBranchRecognizer):
                 for T, items in passes(phase):
                     calls.append((owner, [(qq, kk, dup) for _, qq, kk, dup in items], T))
                     names.append([item[0] for item in items])
-            for out, nm in zip(type(rec).contrast_many(calls), names):
-                for i, name in enumerate(nm):
-                    rows[name] = out[i]
+            launch(calls, names)
 
-        # W_rgb before this step's enqueue and W_flow before the base-flow enqueue: two independent passes, one launch
-        run(("rgb_pre", rec), ("flow_pre", recf))
-        rec._dequeue_and_enqueue(k)                # RGB call's enqueue (deferred past its consumers)
-        recf._dequeue_and_enqueue(k_f)             # base-flow call's enqueue
-        run(("flow_post", recf))                   # W_flow containing this step's base-flow keys
+        pre_f, post_f = passes("flow_pre"), passes("flow_post")
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if (self.merge_flow_epochs and len(passes("rgb_pre")) == 1 and len(pre_f) == 1 and len(post_f) == 1 and pre_f[0][0] == post_f[0][0]
+                and k_f.shape[0] * world <= 128 and type(rec).can_launch_together([rec, recf], q.device)):
+            # W_flow before and after the base-flow enqueue differ in B slots and one unit of age: ONE pass over it serves
+            # both row sets (mscl_infonce_fused_multi_x) -- the enqueue runs first and hands over what it overwrote -- in
+            # the same launch as the W_rgb pass: the whole step's InfoNCE is one launch over two queues instead of three
+            # passes.  (The RGB enqueue still follows its consumers.)
+            overwritten = recf._dequeue_and_enqueue(k_f, save=True)      # base-flow call's enqueue
+            calls = [(rec, [(qq, kk, dup) for _, qq, kk, dup in items], T) for T, items in passes("rgb_pre")]
+            names = [[item[0] for item in items] for _, items in passes("rgb_pre")]
+            both = pre_f[0][1] + post_f[0][1]
+            calls.append((recf, [(qq, kk, dup) for _, qq, kk, dup in both], pre_f[0][0], (overwritten, len(pre_f[0][1]))))
+            names.append([item[0] for item in both])
+            launch(calls, names)
+            rec._dequeue_and_enqueue(k)                # RGB call's enqueue (deferred past its consumers)
+        else:
+            # W_rgb before this step's enqueue and W_flow before the base-flow enqueue: two independent passes, one launch
+            run(("rgb_pre", rec), ("flow_pre", recf))
+            rec._dequeue_and_enqueue(k)                # RGB call's enqueue (deferred past its consumers)
+            recf._dequeue_and_enqueue(k_f)             # base-flow call's enqueue
+            run(("flow_post", recf))                   # W_flow containing this step's base-flow keys
         if self.update_aug_flow:
             recf._dequeue_and_enqueue(k_af)
 

@@ -340,6 +340,74 @@ def test_infonce_multi_jobs_match_single_launches_and_oracle(fx):
         assert _rel(o1[:, 0], out[:, 0]) < 1e-6 and torch.equal(r1[M:], rows[M:]) and _rel(q1.grad, qd.grad) < 1e-5
 
 
+@pytest.mark.parametrize("n,K,ptr_steps,with_other_job", [(32, 65536, 5, True), (32, 65536, 2047, False), (8, 4096, 3, False),
+                                                          (64, 16384, 1, True), (24, 960, 0, False), (128, 8192, 7, True)])
+def test_infonce_epoch_split_vs_oracle(fx, n, K, ptr_steps, with_other_job):
+    """mscl_infonce_fused_multi_x: ONE pass over a queue for rows that read it as it was before its last enqueue (the
+    base-flow call's own term, moco.py:481-498) and rows that read it after (mscl.py:239-277: own_aug, rf -- whose positives
+    ARE the new keys -- and rf_aug).  Checked against the oracle evaluated on the two queue states, and against the
+    three-pass schedule (pass, enqueue, pass) on the device."""
+    from oracle import mscl_oracle as O
+    T = 0.07
+    q_all, kpos_all, queue, count = _make_case(n + K + ptr_steps, 4 * n, K, n)
+    ptr = (ptr_steps * n) % K
+    g = torch.Generator().manual_seed(n)
+    new_keys = F.normalize(torch.randn(n, 128, generator=g), dim=1)
+    kpos_all[2 * n:3 * n] = new_keys                      # the rf group's positives are the keys about to be enqueued
+    q_all[2 * n:3 * n] = F.normalize(new_keys + torch.linspace(0.05, 1.2, n).unsqueeze(1) * torch.randn(n, 128, generator=g), dim=1)
+    # oracle: pre rows on the queue as it is, post rows on the queue after the enqueue
+    ref_pre, g_pre, lg_pre = _oracle_infonce(q_all[:n], kpos_all[:n], queue, count, T, n)
+    queue2, count2 = queue.clone(), count.clone()
+    assert O.enqueue(queue2, count2, ptr, new_keys) == (ptr + n) % K
+    ref_post, g_post, lg_post = _oracle_infonce(q_all[n:], kpos_all[n:], queue2, count2, T, n)
+    ref, gref = ref_pre + ref_post, torch.cat([g_pre, g_post])
+    dup = torch.full((4 * n,), -1, dtype=torch.int32)
+    dup[2 * n:3 * n] = torch.arange(n, dtype=torch.int32) + ptr
+    nq = fx.NegativeQueue(K)
+    nq.load(queue, count, ptr)
+    overwritten = nq.enqueue(new_keys.cuda(), save=True)
+    assert overwritten[2] == ptr and torch.equal(overwritten[1].cpu().long(), int(count.max()) - count[ptr:ptr + n])
+    qd = q_all.cuda().requires_grad_(True)
+    jobs = [dict(q=qd, kpos=kpos_all.cuda(), nq=nq, rows_per_group=n, T=T, dup_slot=dup.cuda(), dup_age=1,
+                 overwritten=overwritten, row_split=n)]
+    if with_other_job:       # as in the step: an ordinary job over another queue in the same launch, listed first
+        q2, k2, queue_b, count_b = _make_case(7, 96, 65536, 32)
+        nq_b = fx.NegativeQueue(65536)
+        nq_b.load(queue_b, count_b, 0)
+        q2d = q2.cuda().requires_grad_(True)
+        jobs.insert(0, dict(q=q2d, kpos=k2.cuda(), nq=nq_b, rows_per_group=32, T=T))
+    outs = fx.infonce_multi(jobs)
+    sum(o[:, 0].sum() for o, _ in outs).backward()
+    out, rows = outs[-1]
+    for gi, (loss, _, _) in enumerate(ref):
+        assert abs(float(out[gi, 0]) - float(loss)) <= 1e-3 * abs(float(loss)), (gi, float(out[gi, 0]), float(loss))
+    logits = torch.cat([lg_pre, lg_post])
+    neg, pos = logits[:, 1:].clone(), logits[:, :1]
+    cnt_ref = (neg > pos).sum(1).float()
+    neg[torch.arange(2 * n, 3 * n), dup[2 * n:3 * n].long()] = 1e9      # ranked exactly by the epilogue, never a close call
+    close_call = ((neg - pos).abs() < 0.02).sum(1)
+    assert bool(((rows[4 * n:].cpu() - cnt_ref).abs() <= close_call).all()), (rows[4 * n:].cpu(), cnt_ref)
+    assert _rel(qd.grad.cpu(), gref) < 1e-3, _rel(qd.grad.cpu(), gref)
+    if with_other_job:
+        ref_b, g_b, _ = _oracle_infonce(q2, k2, queue_b, count_b, T, 32)
+        for gi, (loss, _, _) in enumerate(ref_b):
+            assert abs(float(outs[0][0][gi, 0]) - float(loss)) <= 1e-3 * abs(float(loss))
+        assert _rel(q2d.grad.cpu(), g_b) < 1e-3
+    # the three-pass schedule on the device: pass over the pre rows, enqueue, pass over the post rows
+    q3 = q_all.cuda().requires_grad_(True)
+    kd = kpos_all.cuda()
+    nq3 = fx.NegativeQueue(K)
+    nq3.load(queue, count, ptr)
+    o_pre, r_pre = fx.infonce(q3[:n], kd[:n], nq3, n, T)
+    nq3.enqueue(new_keys.cuda())
+    assert torch.equal(nq3.queue, nq.queue) and torch.equal(nq3.birth, nq.birth)
+    o_post, r_post = fx.infonce(q3[n:], kd[n:], nq3, n, T, dup_slot=dup[n:].cuda(), dup_age=1)
+    (o_pre[:, 0].sum() + o_post[:, 0].sum()).backward()
+    assert _rel(torch.cat([o_pre[:, 0], o_post[:, 0]]), out[:, 0]) < 2e-4
+    assert float((torch.cat([r_pre[n:], r_post[3 * n:]]) - rows[4 * n:]).abs().max()) <= 2
+    assert _rel(q3.grad, qd.grad) < 5e-4
+
+
 def test_infonce_fused_workspace_stays_zero_and_repeats(fx):
     """mscl_infonce_fused accumulates the row statistics into a zero workspace and must leave it zero (accumulator AND
     CTA counter), so back-to-back calls agree to rounding (the float adds are unordered) and never see stale sums."""
