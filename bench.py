@@ -319,7 +319,7 @@ def run_reference(args, rank):
 OPS = [
     ("K1 InfoNCE (op)", "8a1-a3", ("mscl_infonce_fused", "mscl_infonce_fused_multi", "mscl_infonce_fused_multi_x", "mscl_infonce_partial",
                                   "mscl_infonce_pass"),
-     ("mscl_infonce_bwd_slabs", "mscl_infonce_prep", "mscl_infonce_finalize", "mscl_infonce_bwd", "mscl_infonce_reduce",
+     ("mscl_infonce_bwd_slabs", "mscl_infonce_bwd_slabs_multi", "mscl_infonce_prep", "mscl_infonce_finalize", "mscl_infonce_bwd", "mscl_infonce_reduce",
       "mscl_infonce_reduce_scatter")),
     ("K2 LMCL pooling + loss (op)", "8a4", ("mscl_hw_mean_fwd", "mscl_hw_mean_bwd", "mscl_hw_mean_ndhwc_fwd", "mscl_hw_mean_ndhwc_bwd",
                                              "mscl_lmcl"), ()),
@@ -667,10 +667,12 @@ def run_b200(args, rank, local_rank, world):
         return
     kernels = summarise_kernels(rec, args.steps, pk)
     ops = summarise_ops(rec, args.steps, pk)
-    # `roofline`: the OP with the largest share of the step among the ops of the contrastive path proper (SURVEY.md
-    # section 8a: K1-K6), all its launches summed; the adjacent ones (K7-K10) are in `roofline_all` / `kernels`.
+    # `roofline`: the north star's kernel, the K1 InfoNCE op (VERDICT r01 "next" 2), all its
+    # launches summed -- since round 2 it is ONE forward launch for the step's seven terms and no longer the path op with
+    # the largest share (that is the EMA, `largest_path_op`); every op, path and adjacent, is in `roofline_all`.
     on_path = [o for o in ops if o["op"] in PATH_OPS]
-    top = on_path[0] if on_path else (ops[0] if ops else None)
+    k1 = [o for o in ops if o["op"] == "K1 InfoNCE (op)"]
+    top = k1[0] if k1 else (on_path[0] if on_path else (ops[0] if ops else None))
     roofline = None
     traffic = {}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
@@ -686,7 +688,11 @@ def run_b200(args, rank, local_rank, world):
                     "timing": "in-step: CUDA events around every launch of the op inside the timed region (each pair includes the "
                               "launch gap); frac_standalone = the same op alone, launch trains over L2-cold buffers "
                               "(kernel_rooflines)",
-                    "selection": "largest step share among the section-8a path ops (K1-K6), all launches of an op summed"}
+                    "selection": "the K1 InfoNCE op (the north star's kernel), all launches of the op summed",
+                    "largest_path_op": ({"op": on_path[0]["op"], "step_share_ms": on_path[0]["step_share_ms"],
+                                         "frac": on_path[0].get("frac_hbm")} if on_path else None),
+                    "terms_per_instance": "one instance = ONE forward launch covering all 7 InfoNCE terms of the step (three "
+                                          "negative-matrix states of the reference, two queue reads) + one backward launch"}
     clips = N * world
     line = {"metric": METRIC, "value": clips / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -719,7 +725,7 @@ def run_b200(args, rank, local_rank, world):
                 if r["config"] == "cfg2" and r["kernel"].startswith("K1 x2 ops in one launch + their backward"):
                     roofline["frac_standalone_pair"] = r["frac_hbm"]
                     roofline["us_standalone_pair"] = r["us"]
-                if r["config"] == "cfg2" and r["kernel"].startswith("K1 step launch + its two backward"):
+                if r["config"] == "cfg2" and r["kernel"].startswith("K1 step launch + its backward"):
                     roofline["frac_standalone_step_launch"] = r["frac_hbm"]
                     roofline["us_standalone_step_launch"] = r["us"]
                 if r["config"] == "cfg2" and r["kernel"].startswith("K1 step launch = "):

@@ -295,6 +295,11 @@ int mscl_infonce_fused_multi_x(int32_t n_jobs, const float *const *d_q, const fl
                                int64_t rep_begin, int32_t rep_n, int32_t row_split, mscl_stream_t stream);
 int mscl_infonce_bwd_slabs(const float *d_part, int32_t n_part, int32_t M, const float *d_kpos, const float *d_rowaux,
                            const float *d_gout, int32_t rows_per_group, float *d_dq, mscl_stream_t stream);
+/* mscl_infonce_bwd_slabs for all jobs of one mscl_infonce_fused_multi(_x) launch (same n_part) in ONE launch: host arrays
+ * of n_jobs (<= 4) entries. */
+int mscl_infonce_bwd_slabs_multi(int32_t n_jobs, const float *const *d_part, int32_t n_part, const int32_t *M,
+                                 const float *const *d_kpos, const float *const *d_rowaux, const float *const *d_gout,
+                                 const int32_t *rows_per_group, float *const *d_dq, mscl_stream_t stream);
 /* The pass alone in the same form, for the sharded queue: d_qpack [M, 132] is the gathered table mscl_infonce_prep fills
  * on every rank; d_part float [n_part, M, 132] receives the per-CTA slabs exactly as mscl_infonce_partial writes them
  * (mscl_infonce_reduce_scatter / mscl_infonce_finalize follow as before), n_part from mscl_infonce_fused_parts. */

@@ -49,6 +49,7 @@ PROTOTYPES = {
                                    c_int, c_int, c_ptr],
     "mscl_infonce_fused_parts_multi": [c_int, c_ptr, c_ptr, c_int],
     "mscl_infonce_bwd_slabs": [c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr],
+    "mscl_infonce_bwd_slabs_multi": [c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "mscl_infonce_pass": [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_ptr, c_int, c_int, c_int, c_ptr],
     "mscl_infonce_fused_parts": [c_int, c_i64, c_int],
     "mscl_gather_rows": [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr],

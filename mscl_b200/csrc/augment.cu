@@ -328,24 +328,40 @@ color_pipeline_fast_kernel(const float *__restrict__ x, const float *__restrict_
   for (int task = warp; task < 3 * SR; task += nwarps) {
     float *row = sm + task * W;                 // planes are contiguous: row `task` of the 3*SR stacked rows
     const int w0 = lane * 4;
-    float win[4 + TAPS - 1];
+    // the lane's 4 + TAPS - 1 inputs as whole 16-byte chunks around its own (conflict-free 128-bit shared loads; one scalar
+    // load per input is a 4-way bank conflict, the lanes being 4 floats apart), chunks clamped to the row and the few
+    // inputs beyond its ends (reflect border: lanes at the row's ends only) patched afterwards
+    constexpr int CH = (HALF + 3) / 4;          // chunks needed on each side of the lane's own
+    constexpr int OFF = 4 * CH - HALF;          // win[j] = buf[j + OFF]
+    float buf[4 * (2 * CH + 1)];
     if (w0 < W) {
+      const float4 *row4 = reinterpret_cast<const float4 *>(row);
 #pragma unroll
-      for (int j = 0; j < 4 + TAPS - 1; ++j) {
-        int ww = w0 - HALF + j;
-        ww = ww < 0 ? -ww : (ww >= W ? 2 * W - 2 - ww : ww);
-        win[j] = row[ww];
+      for (int c = 0; c < 2 * CH + 1; ++c) {
+        const int q = min(max(lane - CH + c, 0), W4 - 1);
+        const float4 v = row4[q];
+        buf[4 * c] = v.x, buf[4 * c + 1] = v.y, buf[4 * c + 2] = v.z, buf[4 * c + 3] = v.w;
+      }
+      if (w0 < HALF || w0 + 3 + HALF >= W) {
+#pragma unroll
+        for (int j = 0; j < 4 + TAPS - 1; ++j) {
+          const int ww = w0 - HALF + j;
+          if (ww < 0) buf[j + OFF] = row[-ww];
+          else if (ww >= W) buf[j + OFF] = row[2 * W - 2 - ww];
+        }
       }
     }
     __syncwarp();
     if (w0 < W) {
+      float o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < TAPS; ++k) acc = fmaf(tp[k], win[e + k], acc);
-        if (w0 + e < W) row[w0 + e] = acc;
+        for (int k = 0; k < TAPS; ++k) acc = fmaf(tp[k], buf[e + k + OFF], acc);
+        o[e] = acc;
       }
+      *reinterpret_cast<float4 *>(row + w0) = make_float4(o[0], o[1], o[2], o[3]);      // W % 4 == 0: w0 + 3 < W
     }
     __syncwarp();
   }

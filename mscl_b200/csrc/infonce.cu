@@ -322,9 +322,84 @@ infonce_bwd_slabs_kernel(const float *__restrict__ part, int n_part, int M, cons
   dq[(int64_t)i * kC + c] = __ldg(gout + i / rows_per_group) * fmaf(ra.z, kpos[(int64_t)i * kC + c], ra.w * o);
 }
 
+// The same for the jobs of one mscl_infonce_fused_multi(_x) launch, in ONE launch: blockIdx.x runs over the rows of all jobs.
+struct BwdJobs {
+  const float *part[4];
+  const float *kpos[4];
+  const float *rowaux[4];
+  const float *gout[4];
+  float *dq[4];
+  int M[4];
+  int rows_per_group[4];
+  int row_begin[5];
+  int n_jobs;
+  int n_part;
+};
+
+__global__ void __launch_bounds__(128 * kFinGroups)
+infonce_bwd_slabs_multi_kernel(const __grid_constant__ BwdJobs jb) {
+  int j = 0;
+  while (j + 1 < jb.n_jobs && (int)blockIdx.x >= jb.row_begin[j + 1]) ++j;
+  const int i = (int)blockIdx.x - jb.row_begin[j], c = threadIdx.x & 127, g = threadIdx.x >> 7;
+  const int M = jb.M[j], n_part = jb.n_part;
+  const int64_t slab = (int64_t)M * kLd;
+  const float *src = jb.part[j] + (int64_t)i * kLd;
+  __shared__ float s_o[kFinGroups][128];
+  float o = 0.f;
+  pdl_wait();
+  pdl_trigger();
+  for (int p0 = g; p0 < n_part; p0 += kFinGroups * kFinMaxPer) {
+    float v[kFinMaxPer];
+#pragma unroll
+    for (int u = 0; u < kFinMaxPer; ++u) {
+      const int p = p0 + u * kFinGroups;
+      v[u] = p < n_part ? __ldg(src + p * slab + c) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kFinMaxPer; ++u) o += v[u];
+  }
+  s_o[g][c] = o;
+  __syncthreads();
+  if (g != 0) return;
+  o = 0.f;
+#pragma unroll
+  for (int k = 0; k < kFinGroups; ++k) o += s_o[k][c];
+  const float4 ra = __ldg(reinterpret_cast<const float4 *>(jb.rowaux[j]) + i);
+  jb.dq[j][(int64_t)i * kC + c] =
+      __ldg(jb.gout[j] + i / jb.rows_per_group[j]) * fmaf(ra.z, jb.kpos[j][(int64_t)i * kC + c], ra.w * o);
+}
+
 }  // namespace mscl
 
 extern "C" {
+
+int mscl_infonce_bwd_slabs_multi(int32_t n_jobs, const float *const *d_part, int32_t n_part, const int32_t *M,
+                                 const float *const *d_kpos, const float *const *d_rowaux, const float *const *d_gout,
+                                 const int32_t *rows_per_group, float *const *d_dq, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(n_jobs >= 1 && n_jobs <= 4, "n_jobs=%d must be in [1, 4]", n_jobs);
+  MSCL_CHECK_ARG(d_part && M && d_kpos && d_rowaux && d_gout && rows_per_group && d_dq, "null table");
+  MSCL_CHECK_ARG(n_part > 0, "n_part=%d must be positive", n_part);
+  mscl::BwdJobs jb = {};
+  jb.n_jobs = n_jobs;
+  jb.n_part = n_part;
+  for (int j = 0; j < n_jobs; ++j) {
+    MSCL_CHECK_ARG(d_part[j] && d_kpos[j] && d_rowaux[j] && d_gout[j] && d_dq[j], "null pointer in job %d", j);
+    MSCL_CHECK_ARG(M[j] > 0 && rows_per_group[j] > 0 && M[j] % rows_per_group[j] == 0,
+                   "job %d: M=%d must be a multiple of rows_per_group=%d", j, M[j], rows_per_group[j]);
+    MSCL_CHECK_ARG(((uintptr_t)d_rowaux[j] & 15) == 0, "rowaux must be 16-byte aligned");
+    jb.part[j] = d_part[j];
+    jb.kpos[j] = d_kpos[j];
+    jb.rowaux[j] = d_rowaux[j];
+    jb.gout[j] = d_gout[j];
+    jb.dq[j] = d_dq[j];
+    jb.M[j] = M[j];
+    jb.rows_per_group[j] = rows_per_group[j];
+    jb.row_begin[j + 1] = jb.row_begin[j] + M[j];
+  }
+  MSCL_CUDA(mscl::launch_pdl(mscl::infonce_bwd_slabs_multi_kernel, dim3((unsigned)jb.row_begin[n_jobs]),
+                             dim3(128 * mscl::kFinGroups), 0, mscl::as_stream(stream), jb));
+  return MSCL_OK;
+}
 
 int mscl_infonce_bwd_slabs(const float *d_part, int32_t n_part, int32_t M, const float *d_kpos, const float *d_rowaux,
                            const float *d_gout, int32_t rows_per_group, float *d_dq, mscl_stream_t stream) {

@@ -401,18 +401,22 @@ class _InfoNCEMulti(torch.autograd.Function):
         n = ctx.n
         saved = ctx.saved_tensors
         parts, rowaux, kpos = saved[:n], saved[n:2 * n], saved[2 * n:]
-        dqs = []
-        for i in range(n):
-            g = grads[2 * i]
-            if g is None:
-                dqs.append(None)
-                continue
-            gout = g[:, 0].contiguous()
-            n_part, M = parts[i].shape[0], parts[i].shape[1]
-            dq = torch.empty(M, DIM, device=parts[i].device)
-            _cabi.call("mscl_infonce_bwd_slabs", parts[i].data_ptr(), n_part, M, kpos[i].data_ptr(), rowaux[i].data_ptr(),
-                       gout.data_ptr(), ctx.rpg[i], dq.data_ptr(), _stream(), algo_bytes=4 * M * (n_part * DIM + 2 * DIM + 4))
-            dqs.append(dq)
+        import ctypes
+        live = [i for i in range(n) if grads[2 * i] is not None]
+        dqs = [None] * n
+        if live:        # one launch for the gradients of all jobs
+            m = len(live)
+            gouts = [grads[2 * i][:, 0].contiguous() for i in live]
+            n_part = parts[live[0]].shape[0]
+            Ms = [parts[i].shape[1] for i in live]
+            for i in live:
+                dqs[i] = torch.empty(parts[i].shape[1], DIM, device=parts[i].device)
+            arr_ptr = lambda ts: (ctypes.c_void_p * m)(*[t.data_ptr() for t in ts])
+            arr_i32 = lambda v: (ctypes.c_int32 * m)(*v)
+            _cabi.call("mscl_infonce_bwd_slabs_multi", m, arr_ptr([parts[i] for i in live]), n_part, arr_i32(Ms),
+                       arr_ptr([kpos[i] for i in live]), arr_ptr([rowaux[i] for i in live]), arr_ptr(gouts),
+                       arr_i32([ctx.rpg[i] for i in live]), arr_ptr([dqs[i] for i in live]), _stream(),
+                       algo_bytes=sum(4 * M * (n_part * DIM + 2 * DIM + 4) for M in Ms))
         return (None, None, None, *dqs)
 
 

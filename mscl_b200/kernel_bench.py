@@ -191,18 +191,19 @@ def bench_k1_pair(cfg, Ms, K, pk, dev, iters=30):
                    fixed["invT"], fixed["bound"], fixed["dup"], fixed["age"], fixed["ws"], fixed["part"], n_part, fixed["rpg"], 1,
                    fixed["flags"], fixed["rl"], fixed["ra"], fixed["go"], _st())
 
+    gones = [gone] * n
+
     def fwd_bwd(i):
         fwd(i)
-        for j in range(n):
-            _cabi.call("mscl_infonce_bwd_slabs", part[j].data_ptr(), n_part, Ms[j], k[j].data_ptr(), rowaux[j].data_ptr(),
-                       gone.data_ptr(), Ms[j], dq[j].data_ptr(), _st())
+        _cabi.call("mscl_infonce_bwd_slabs_multi", n, fixed["part"], n_part, fixed["M"], fixed["k"], fixed["ra"], arr_ptr(gones),
+                   fixed["rpg"], arr_ptr(dq), _st())
 
     ab = sum(fx.infonce_algo_bytes(M, K) for M in Ms)
     fl = sum(4 * M * K * 128 for M in Ms)
     shape = "M=" + "+".join(str(M) for M in Ms) + f" K={K} x{n} queues"
     out = [row(cfg, f"K1 x{n} ops in one launch = infonce_fused_kernel<grad>, {n} jobs (what the step runs)", shape,
                time_train(fwd, iters), ab, fl, pk, note=f"{n_part} CTAs per job"),
-           row(cfg, f"K1 x{n} ops in one launch + their backward kernels", shape, time_train(fwd_bwd, iters), ab, fl, pk)]
+           row(cfg, f"K1 x{n} ops in one launch + their backward kernel", shape, time_train(fwd_bwd, iters), ab, fl, pk)]
     del rings
     return out
 
@@ -259,9 +260,8 @@ def bench_k1_step(cfg, n, K, pk, dev, iters=30):
 
     def fwd_bwd(i):
         fwd(i)
-        for j in range(2):
-            _cabi.call("mscl_infonce_bwd_slabs", part[j].data_ptr(), n_part, Ms[j], k[j].data_ptr(), rowaux[j].data_ptr(),
-                       gone[j].data_ptr(), n, dq[j].data_ptr(), _st())
+        _cabi.call("mscl_infonce_bwd_slabs_multi", 2, fixed["part"], n_part, fixed["M"], fixed["k"], fixed["ra"], arr_ptr(gone),
+                   fixed["rpg"], arr_ptr(dq), _st())
 
     ab = sum(fx.infonce_algo_bytes(M, K) for M in Ms) + n * 512
     fl = sum(4 * M * K * 128 for M in Ms)
@@ -271,7 +271,7 @@ def bench_k1_step(cfg, n, K, pk, dev, iters=30):
     out = [row(cfg, "K1 step launch = infonce_fused_kernel<grad>, 2 jobs, epoch split on W_flow (all 7 terms of a step)", shape,
                us_f, ab, fl, pk, note=f"{n_part} CTAs per job; bytes = the two queues once each; the same terms as three "
                f"separate ops are {ab3} algorithmic bytes = {ab3 / us_f / 1e3 / pk:.3f} of the HBM roofline, {us_f / 3:.1f} us per op"),
-           row(cfg, "K1 step launch + its two backward kernels", shape, us_fb, ab, fl, pk)]
+           row(cfg, "K1 step launch + its backward kernel", shape, us_fb, ab, fl, pk)]
     del rings
     return out
 

@@ -21,7 +21,7 @@ GP = os.path.join(ROOT, "gpurun_out")
 OURS = ("infonce", "ema_multi", "fra_", "hw_mean", "enqueue_kernel", "lmcl_kernel", "queue_transpose", "gather_rows",
         "clip_sgd_multi", "grad_sqnorm_multi", "grad_norm_finish", "color_pipeline", "clip_gray_sum", "flow_visualize",
         "upsample_trilinear")
-ENTRY = {"infonce_fused_kernel": "mscl_infonce_fused", "infonce_bwd_slabs_kernel": "mscl_infonce_bwd_slabs",
+ENTRY = {"infonce_fused_kernel": "mscl_infonce_fused", "infonce_bwd_slabs_kernel": "mscl_infonce_bwd_slabs", "infonce_bwd_slabs_multi_kernel": "mscl_infonce_bwd_slabs",
          "infonce_tc_kernel": "mscl_infonce_partial", "ema_multi_kernel": "mscl_ema_multi", "fra_maxrad_kernel": "mscl_fra_maxrad",
          "fra_apply_kernel": "mscl_fra_apply", "fra_fused_kernel": "mscl_fra_fused", "hw_mean_fwd_kernel": "mscl_hw_mean_fwd",
          "hw_mean_bwd_kernel": "mscl_hw_mean_bwd", "hw_mean_fwd_small_kernel": "mscl_hw_mean_fwd",

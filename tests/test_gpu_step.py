@@ -23,7 +23,7 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def head_level_cfg(K, t, same_kn=True, update_aug_flow=False, weight_aug_flow=(1.0, 1.0)):
+def head_level_cfg(K, t, same_kn=True, update_aug_flow=False, weight_aug_flow=(1.0, 1.0), merge_flow_epochs=True):
     """MSCLWithAug with the slim flow encoder on both branches (encoders are not run): the same model dict
     oracle/make_golden.py hands to the reference."""
     ce = dict(type="CrossEntropyLoss_torch", ignore_index=-1)
@@ -41,7 +41,8 @@ def head_level_cfg(K, t, same_kn=True, update_aug_flow=False, weight_aug_flow=(1
                                                    base_flow_features=dict(q_mlvl="q_flow_mlvl"),
                                                    aug_flow_features=dict(q_mlvl="q_aug_flow_mlvl"))),
                im_key="imgs", flow_key="flow_imgs", aux_info=[], update_aug_flow=update_aug_flow,
-               weight_aug_flow=weight_aug_flow, aug=dict(type="IdentityAug"), same_kn=same_kn)
+               weight_aug_flow=weight_aug_flow, aug=dict(type="IdentityAug"), same_kn=same_kn,
+               train_cfg=dict(merge_flow_epochs=merge_flow_epochs))
 
 
 def head_level_model(K, t, **switches):
@@ -49,9 +50,9 @@ def head_level_model(K, t, **switches):
     return mscl_b200.build_model(head_level_cfg(K, t, **switches)).cuda()
 
 
-def run_product_objective(inp, t):
+def run_product_objective(inp, t, **switches):
     K = inp["queue_rgb"].shape[1]
-    model = head_level_model(K, t)
+    model = head_level_model(K, t, **switches)
     model.train()
     ptr = torch.tensor([inp["ptr"]])
     missing = model.load_state_dict({
@@ -80,11 +81,11 @@ def _run_oracle_objective(inp, t):
     return log_vars, leaves, rgb, flow
 
 
-def check_objective(inp, t, golden=None):
+def check_objective(inp, t, golden=None, **switches):
     """Product vs oracle (and vs the reference's golden numbers when given) for one objective call."""
     from oracle import inputs
     ref_vars, ref_leaves, rgb, flow = _run_oracle_objective(inp, t)
-    model, log_vars, leaves = run_product_objective(inp, t)
+    model, log_vars, leaves = run_product_objective(inp, t, **switches)
     assert list(log_vars.keys()) == list(ref_vars.keys())         # the 23 keys, in the reference's order
     for k, v in log_vars.items():
         refs = [ref_vars[k]] + ([float(golden[f"logvar/{k}"])] if golden is not None else [])
@@ -138,6 +139,25 @@ def test_objective_full_size_vs_oracle(N, K, t):
     from oracle import inputs
     inp = inputs.head_inputs(seed=5, N=N, K=K, t=t, hw_rgb=14, hw_flow=7, b_all=N)
     check_objective(inp, t)
+
+
+def test_objective_three_pass_schedule_and_launch_counts(golden_dir):
+    """train_cfg=dict(merge_flow_epochs=False): W_flow streamed before AND after the base-flow enqueue (three passes, two
+    launches) instead of once for both queue states -- same numbers against the oracle and the reference's golden; and the
+    default schedule really is ONE InfoNCE launch per step."""
+    from oracle import inputs
+    from mscl_b200 import _cabi
+    g = np.load(os.path.join(golden_dir, "head_small.npz"), allow_pickle=False)
+    inp = {k[3:]: (torch.from_numpy(g[k]) if g[k].ndim else int(g[k])) for k in g.files if k.startswith("in/")}
+    check_objective(inp, 4, g, merge_flow_epochs=False)
+    inp = inputs.head_inputs(seed=5, N=32, K=65536, t=4, hw_rgb=14, hw_flow=7, b_all=32)
+    check_objective(inp, 4, merge_flow_epochs=False)
+    names = ["mscl_infonce_fused", "mscl_infonce_fused_multi_x", "mscl_infonce_bwd_slabs", "mscl_infonce_bwd_slabs_multi", "mscl_enqueue"]
+    for merge, want in ((True, [0, 1, 0, 1, 2]), (False, [1, 1, 1, 1, 2])):      # (functional.infonce_multi enters through ..._multi_x)
+        _cabi.start_timing(names)
+        run_product_objective(inp, 4, merge_flow_epochs=merge)
+        rec = _cabi.stop_timing()
+        assert [len(rec[n]) for n in names] == want, (merge, {n: len(rec[n]) for n in names})
 
 
 @pytest.mark.parametrize("vname", ["cross_kn", "aug_enqueue"])
