@@ -52,7 +52,7 @@ def _need(world):
 WORLDS = [2, 4, 8]
 
 
-def _objective_job(rank, world, N=8, K=4096):
+def _objective_job(rank, world, N=8, K=4096, shard=True):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from test_gpu_step import head_level_model
@@ -64,7 +64,7 @@ def _objective_job(rank, world, N=8, K=4096):
     import mscl_b200
     model = head_level_model(K, t)
     for rec in (model.recognizer, model.recognizer_flow):
-        rec.shard_queue = True
+        rec.shard_queue = shard
     model.train()
     ptr = torch.tensor([inp["ptr"]])
     model.load_state_dict({"recognizer.queue": inp["queue_rgb"], "recognizer.count": inp["count"], "recognizer.queue_ptr": ptr,
@@ -76,7 +76,8 @@ def _objective_job(rank, world, N=8, K=4096):
                  k_af=inp["k_af"][sl].cuda(), q_mlvl=[leaves["q_map"]], q_flow_mlvl=[leaves["qf_map"]],
                  q_aug_flow_mlvl=[leaves["qaf_map"]])
     losses = model.objective(feats)
-    assert model.recognizer.negative_queue().world == world and model.recognizer.negative_queue().K_local == K // world
+    nq = model.recognizer.negative_queue()
+    assert (nq.world == world and nq.K_local == K // world) if shard else (nq.world == 1 and nq.K_local == K)
     loss = sum(v.mean() for k, v in losses.items() if "loss" in k)
     loss.backward()
     local = {k: float(v.detach().mean()) for k, v in losses.items()}
@@ -146,6 +147,19 @@ def test_sharded_objective_at_the_config_size(world):
     """The north star's configuration: 32 clips per GPU, K = 65536 negatives sharded K/G (8192 keys per GPU at G = 8),
     every rank's 23 log variables, gradients and the gathered queue state against the replicated-queue oracle."""
     _check_objective(_run(_objective_job_cfg2, _need(world)))
+
+
+def _objective_job_cfg2_replicated(rank, world):
+    return _objective_job(rank, world, N=32, K=65536, shard=False)
+
+
+@pytest.mark.parametrize("world", WORLDS)
+def test_replicated_objective_at_the_config_size(world):
+    """The same with every rank keeping the whole queue (train_cfg shard_queue=False): the gathered keys of all ranks are
+    enqueued everywhere, and up to 128 gathered keys (world <= 4 at 32 clips per GPU) the step's InfoNCE is the ONE launch
+    with the epoch split on W_flow (mscl_infonce_fused_multi_x; the overwritten block is 32 x world keys wide, the rows'
+    own positives sit at this rank's offset inside it), beyond that the three-pass schedule."""
+    _check_objective(_run(_objective_job_cfg2_replicated, _need(world)))
 
 
 def _shuffle_job(rank, world):
