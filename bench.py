@@ -454,6 +454,26 @@ def write_timeline(path, step_fn, flush, sync, rank, world, n=3):
     tot = sum(v[1] for v in agg.values()) or 1.0
     for name, (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
         lines.append(f"{t / n / 1e3:8.3f} ms {100 * t / tot:5.1f}% {cnt / n:7.1f}x  {name}")
+    # where the GPU waits: idle gaps between consecutive device kernels (any kind), largest first, and summed by the kernel
+    # that FOLLOWS the gap (the launch the host was late with)
+    allk = sorted(((e.time_range.start, e.time_range.end, e.name) for e in kern), key=lambda x: x[0])
+    gaps, end, prev = [], None, None
+    for a, b, name in allk:
+        if end is not None and a > end:
+            gaps.append((a - end, prev, name, a - t0))
+        if end is None or b > end:
+            end, prev = b, name
+    lines.append(f"# idle gaps: {len(gaps) / n:.0f} per step, {sum(g[0] for g in gaps) / n / 1e3:.3f} ms per step; by the kernel that follows the gap")
+    byk = {}
+    for g, pv, nx, _ in gaps:
+        d = byk.setdefault(nx[:90], [0, 0.0])
+        d[0] += 1
+        d[1] += g
+    for name, (cnt, t) in sorted(byk.items(), key=lambda kv: -kv[1][1])[:25]:
+        lines.append(f"{t / n / 1e3:8.3f} ms {cnt / n:7.1f}x  before {name}")
+    lines.append("# the 25 largest single gaps: us, position in the profiled span (ms), after -> before")
+    for g, pv, nx, at in sorted(gaps, key=lambda x: -x[0])[:25]:
+        lines.append(f"{g:8.1f} us at {at / 1e3:8.2f} ms  {pv[:60]} -> {nx[:60]}")
     lines.append("# host side: top ops by SELF CPU time per step (the step is host-issue bound: what the host spends is what the GPU waits for)")
     cpu = sorted(prof.key_averages(), key=lambda e: -e.self_cpu_time_total)
     for e in cpu[:30]:
@@ -693,6 +713,13 @@ def run_b200(args, rank, local_rank, world):
                                          "frac": on_path[0].get("frac_hbm")} if on_path else None),
                     "terms_per_instance": "one instance = ONE forward launch covering all 7 InfoNCE terms of the step (three "
                                           "negative-matrix states of the reference, two queue reads) + one backward launch"}
+    if roofline is not None and roofline["op"] == "K1 InfoNCE (op)" and top["instances_per_step"] == 1.0 and not shard:
+        # the same seven terms as the three ops (three negative-matrix states) the reference's schedule and round 1 made of
+        # them: 3N rows on W_rgb, N on W_flow before its enqueue, 3N after -- three queue reads instead of two
+        from mscl_b200.functional import infonce_algo_bytes
+        ref_bytes = 2 * infonce_algo_bytes(3 * N, args.K) + infonce_algo_bytes(N, args.K)
+        roofline["as_three_reference_ops"] = {"algo_bytes_per_step": ref_bytes, "us_per_op": top["us_per_instance"] / 3,
+                                              "frac": ref_bytes / (top["step_share_ms"] * 1e-3) / 1e9 / pk["hbm"]}
     clips = N * world
     line = {"metric": METRIC, "value": clips / sec, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

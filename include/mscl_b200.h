@@ -51,6 +51,13 @@ const char *mscl_last_error(void);
 /* 0 if device `dev` can run this library (compute capability 10.x). */
 int mscl_device_check(int dev);
 
+/* Small host -> device transfer WITHOUT the copy engine: one CTA reads nbytes (a multiple of 16, <= 1 MiB) from page-locked
+ * host memory that is mapped into the device (cudaHostAlloc / cudaHostRegister under unified addressing) and stores them to
+ * d_dst.  For the few hundred per-step parameters the host draws (the augmentation's decisions, ssl_aug_v2.py:31-48): as a
+ * cudaMemcpyAsync they queue in the H2D engine behind the data loader's next batch (128 MB per step here) and stall the
+ * compute stream for the whole of it.  The host buffer must stay untouched until the kernel has run. */
+int mscl_fetch_host(void *d_dst, const void *h_src_pinned, int64_t nbytes, mscl_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * K5  ring-buffer enqueue.   replaces MoCoV2._dequeue_and_enqueue
  *     (mmaction/models/recognizers/moco.py:423-440) minus the all_gather.

@@ -19,6 +19,7 @@ c_ptr = ctypes.c_void_p
 # name -> argtypes; every entry point returns int (0 = ok).  Mirrors include/mscl_b200.h.
 PROTOTYPES = {
     "mscl_device_check": [c_int],
+    "mscl_fetch_host": [c_ptr, c_ptr, c_i64, c_ptr],
     "mscl_enqueue": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr],
     "mscl_queue_export": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr],
     "mscl_queue_import": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_ptr],

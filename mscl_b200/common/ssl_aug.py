@@ -3,7 +3,9 @@
 Adjacent to the hot path: it has to exist for the config to build
 and for (N,2,2T,H,W) flow input to become the 3-channel images the flow encoder eats.
 Two kernels do the pixel work (K8 flow_visualize, K9 color_pipeline); this file only draws the
-random decisions on the device and packs them.  The deterministic pieces (flow colour-wheel
+random decisions -- on the HOST (a few hundred numbers per step: drawing and packing them with device ops was ~100 tiny
+launches and 1.4 ms of an idle GPU per step, profiles/r02_timeline_host_g1.txt) -- packs them and uploads them in one
+asynchronous copy per view.  The deterministic pieces (flow colour-wheel
 visualisation, flip given a mask, normalisation) follow common/ssl_aug.py:87-136 and
 common/ssl_aug_v2.py:50-133 exactly, the random colour pipeline reproduces the
 reference's distribution (ColorJitter(0.4,0.4,0.4,0.1) p=.8, grayscale p=.2, Gaussian blur
@@ -14,7 +16,9 @@ lives in oracle/aug_oracle.py (test / CPU-baseline infrastructure).
 """
 import math
 
+import numpy as np
 import torch
+import torch.distributed as dist
 from .._cabi import MsclError
 from ..registry import SSL_AUGS
 
@@ -126,11 +130,22 @@ class SyncMoCoAugmentV5:
         # torch.where keeps shapes static and needs no host synchronisation (a boolean-index copy does)
         return torch.where(mask.view(-1, 1, 1, 1, 1), torch.flip(clips, [-1]), clips)
 
-    def forward_flip(self, clips, aux_info, suffix="_q", flip_clips=True):
+    def _rng(self):
+        """The host generator of this object's random decisions: seeded from torch's seed (`torch.manual_seed` makes the
+        augmentation reproducible) and the rank, advanced by nothing else (the CPU default generator, which draws the
+        shuffle permutations exactly as the reference does, is left alone)."""
+        if getattr(self, "_np_rng", None) is None:
+            rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+            self._np_rng = np.random.default_rng([int(torch.initial_seed()) % (1 << 32), rank])
+        return self._np_rng
+
+    def forward_flip(self, clips, aux_info, suffix="_q", flip_clips=True, mask=None):
+        """mask: the flip decisions (bool or uint8 (N,) on the device) when the caller has drawn them already."""
         n = clips.shape[0]
-        mask = torch.rand(n, device=clips.device) < self.flip_p
+        if mask is None:
+            mask = torch.from_numpy(self._rng().random(n) < self.flip_p).to(clips.device)
         if flip_clips:
-            clips = self.flip(clips, mask)
+            clips = self.flip(clips, mask.bool())
         if self.flow_suffix:
             full = self.flow_suffix + suffix
             for k in aux_info:
@@ -139,7 +154,7 @@ class SyncMoCoAugmentV5:
                     if isinstance(self.visualizer, FlowVisualizer):
                         img = self.visualizer(aux_info[k], mask)
                     else:
-                        img = self.flip(self.visualizer(aux_info[k]), mask)
+                        img = self.flip(self.visualizer(aux_info[k]), mask.bool())
                     if self.normalize_flow:
                         img = self._normalize(img)
                     aux_info[k] = img
@@ -150,17 +165,39 @@ class SyncMoCoAugmentV5:
         grayscale p=.2, blur p=.5, one sigma per call.  The apply decisions are per clip.  frames = 1: one set of jitter
         factors per clip ('params' sync level); frames = T: one set per frame ('batch' sync level), every tensor then
         has n*T entries in (clip, frame) order, the decisions repeated over the frames of a clip."""
+        d = self._draw_host(n, frames)
+        return {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+
+    def _draw_host(self, n, frames=1):
+        """`_color_params` as NumPy arrays on the host."""
+        g = self._rng()
         nf = n * frames
-        rnd = lambda lo, hi: torch.empty(nf, device=dev).uniform_(lo, hi)
-        dec = lambda p: (torch.rand(n, device=dev) < p).repeat_interleave(frames)
-        prm = dict(jit=dec(0.8), brightness=rnd(0.6, 1.4), contrast=rnd(0.6, 1.4),
-                   saturation=rnd(0.6, 1.4), hue=rnd(-0.1, 0.1), gray=dec(0.2),
-                   blur=dec(0.5), sigma=float(torch.empty(1).uniform_(0.1, 2.0)))
+        rnd = lambda lo, hi: g.uniform(lo, hi, nf).astype(np.float32)
+        dec = lambda p: np.repeat(g.random(n) < p, frames)
+        d = dict(jit=dec(0.8), brightness=rnd(0.6, 1.4), contrast=rnd(0.6, 1.4), saturation=rnd(0.6, 1.4),
+                 hue=rnd(-0.1, 0.1), gray=dec(0.2), blur=dec(0.5), sigma=float(g.uniform(0.1, 2.0)))
         r = self.blur_radius
-        ax = torch.arange(r, device=dev, dtype=torch.float32) - r // 2
-        k1 = torch.exp(-ax ** 2 / (2 * prm["sigma"] ** 2))
-        prm["taps"] = k1 / k1.sum()
-        return prm
+        ax = np.arange(r, dtype=np.float32) - r // 2
+        k1 = np.exp(-ax ** 2 / np.float32(2 * d["sigma"] ** 2))
+        d["taps"] = (k1 / k1.sum()).astype(np.float32)
+        return d
+
+    def _pack_host(self, d, flip, weak):
+        """`_pack_params` on the host: d from `_draw_host`, flip a bool array with one entry per row."""
+        n = flip.shape[0]
+        out = np.zeros((n, 16), dtype=np.float32)
+        out[:, 0] = flip
+        if weak:
+            return out
+        out[:, 1], out[:, 2], out[:, 3], out[:, 4] = d["jit"], d["brightness"], d["contrast"], d["saturation"]
+        theta = d["hue"].astype(np.float64) * 2 * math.pi
+        rot = np.zeros((n, 3, 3))
+        rot[:, 0, 0] = 1
+        rot[:, 1, 1], rot[:, 1, 2], rot[:, 2, 1], rot[:, 2, 2] = np.cos(theta), -np.sin(theta), np.sin(theta), np.cos(theta)
+        yiq = np.array(_YIQ, dtype=np.float32).astype(np.float64)
+        out[:, 5:14] = (np.linalg.inv(yiq)[None] @ rot @ yiq[None]).reshape(n, 9)
+        out[:, 14], out[:, 15] = d["gray"], d["blur"]
+        return out
 
     def _pack_params(self, prm, flip, weak):
         """(n,16) float rows for the fused kernel (include/mscl_b200.h, K9)."""
@@ -178,14 +215,19 @@ class SyncMoCoAugmentV5:
         if not clips.is_cuda:
             raise MsclError(f"{type(self).__name__} runs on CUDA tensors only (no CPU fallback)")
         from .. import functional as fx      # K9: flip + colour + blur + normalise in one pass over the clip
-        clips, aux_info, mask = self.forward_flip(clips, aux_info, suffix, flip_clips=False)
+        n = clips.shape[0]
         frames = clips.shape[2] if self.sync_level[0 if suffix == "_q" else 1] == "batch" else 1
-        prm = self._color_params(clips.shape[0], clips.device, frames)
-        norm = self._norm_table(clips.device)
-        out = fx.color_pipeline(clips.contiguous().float(), self._pack_params(prm, mask.repeat_interleave(frames), weak),
-                                prm["taps"].contiguous(), norm)
+        # every decision and parameter of the view drawn and packed on the host and fetched by ONE small kernel from pinned
+        # memory (functional.HostStage: not through the copy engine, where it would wait behind the loader's next batch):
+        # [n*frames, 16] K9 rows | the blur taps | the n flip decisions
+        flip = self._rng().random(n) < self.flip_p
+        d = self._draw_host(n, frames)
+        rows = self._pack_host(d, np.repeat(flip, frames), weak)
+        table, taps, mask = fx.host_stage(clips.device).upload([rows, d["taps"], flip.astype(np.uint8)], clips.device)
+        clips, aux_info, _ = self.forward_flip(clips, aux_info, suffix, flip_clips=False, mask=mask)
+        out = fx.color_pipeline(clips.contiguous().float(), table.view(n * frames, 16), taps, self._norm_table(clips.device))
         if flow is not None:
-            flow = self.flip(flow, mask)
+            flow = self.flip(flow, mask.bool())
         return out, aux_info, flow
 
     def __call__(self, im_q, im_k, aux_info):

@@ -38,9 +38,33 @@ cudaError_t ensure_dyn_smem_impl(const void *func, size_t bytes) {
   return e;
 }
 
+// One CTA copies a few KB from mapped pinned host memory into device memory (see mscl_fetch_host).
+__global__ void __launch_bounds__(256)
+fetch_host_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, int n4) {
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
+}
+
 }  // namespace mscl
 
 extern "C" {
+
+int mscl_fetch_host(void *d_dst, const void *h_src_pinned, int64_t nbytes, mscl_stream_t stream) {
+  MSCL_CHECK_ARG(d_dst && h_src_pinned, "null pointer");
+  MSCL_CHECK_ARG(nbytes > 0 && nbytes % 16 == 0 && nbytes <= (1 << 20), "nbytes=%lld must be a multiple of 16 up to 1 MiB",
+                 (long long)nbytes);
+  MSCL_CHECK_ARG((((uintptr_t)d_dst | (uintptr_t)h_src_pinned) & 15) == 0, "pointers must be 16-byte aligned");
+  void *src_dev = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer(&src_dev, const_cast<void *>(h_src_pinned), 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return mscl::set_err(MSCL_EINVAL, "h_src_pinned is not page-locked host memory mapped into the device: %s",
+                         cudaGetErrorString(e));
+  }
+  mscl::fetch_host_kernel<<<1, 256, 0, mscl::as_stream(stream)>>>(reinterpret_cast<const float4 *>(src_dev),
+                                                                   reinterpret_cast<float4 *>(d_dst), (int)(nbytes / 16));
+  MSCL_LAUNCH_CHECK();
+  return MSCL_OK;
+}
 
 int mscl_abi_version(void) { return MSCL_ABI_VERSION; }
 

@@ -200,8 +200,34 @@ static EncodeTiledFn get_encode_fn() {
 
 // rows x 128 fp32 matrix with row pitch ld floats, viewed as {32, rows, 4} so that one box lands
 // in shared memory as 4 channel-block slabs of [box_rows][128 B], 128-byte swizzled.
+// A tensor map is a pure function of (pointer, rows, pitch, box, swizzle); the queues' maps never change and PyTorch's
+// caching allocator hands the same q / positives blocks back step after step, so the ~14 driver encodes of a step launch
+// (host time the GPU spends idle: the objective is launch-latency bound) are served from a small per-thread table.
+struct MapKey {
+  const void *ptr;
+  int64_t rows;
+  int ld, box_rows, swizzle;
+  bool operator==(const MapKey &o) const {
+    return ptr == o.ptr && rows == o.rows && ld == o.ld && box_rows == o.box_rows && swizzle == o.swizzle;
+  }
+};
+struct MapCache {
+  static constexpr int kSlots = 64;
+  MapKey key[kSlots];
+  CUtensorMap map[kSlots];
+  bool used[kSlots];
+  int next;
+};
+
 static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int ld, int box_rows,
                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  static thread_local MapCache cache = {};
+  const MapKey k = {ptr, rows, ld, box_rows, (int)swizzle};
+  for (int i = 0; i < MapCache::kSlots; ++i)
+    if (cache.used[i] && cache.key[i] == k) {
+      *map = cache.map[i];
+      return MSCL_OK;
+    }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_err(MSCL_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {32, (cuuint64_t)rows, 4};
@@ -214,6 +240,10 @@ static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int ld, in
   if (r != CUDA_SUCCESS)
     return set_err(MSCL_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld ld=%d)",
                    (int)r, (long long)rows, ld);
+  cache.key[cache.next] = k;
+  cache.map[cache.next] = *map;
+  cache.used[cache.next] = true;
+  cache.next = (cache.next + 1) % MapCache::kSlots;
   return MSCL_OK;
 }
 

@@ -60,6 +60,56 @@ def sm_count(device):
     return _SM_COUNT[idx]
 
 
+class HostStage:
+    """A ring of small pinned host buffers whose contents reach the device through `mscl_fetch_host` (a kernel reading the
+    mapped buffer), not through the copy engine: per-step parameters and index tables produced on the host arrive in stream
+    order without queueing behind a data loader's bulk H2D copies.  A slot is reused only after the fetch that read it has
+    run."""
+
+    def __init__(self, slots=64):      # several steps of uploads: reusing a slot must never wait for the step in flight
+        self.slots = [None] * slots
+        self.events = [None] * slots
+        self.i = 0
+
+    def upload(self, arrays, device):
+        """arrays: list of NumPy arrays (any fixed-size dtype) -> list of flat device tensors of the same dtypes (views of
+        one device buffer, each starting on a 16-byte boundary), in ONE launch."""
+        arrays = [np.ascontiguousarray(a) for a in arrays]
+        offs, total = [], 0
+        for a in arrays:
+            offs.append(total)
+            total += (a.nbytes + 15) // 16 * 16
+        total = max(total, 16)
+        s = self.i
+        self.i = (s + 1) % len(self.slots)
+        if self.events[s] is not None:
+            self.events[s].synchronize()            # the fetch that last read this slot has run (long ago, normally)
+        if self.slots[s] is None or self.slots[s].numel() < total:
+            self.slots[s] = torch.zeros(max(total, 4096), dtype=torch.uint8, pin_memory=True)
+        host = self.slots[s].numpy()
+        for a, o in zip(arrays, offs):
+            host[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+        dev = torch.empty(total, dtype=torch.uint8, device=device)
+        _cabi.call("mscl_fetch_host", dev.data_ptr(), self.slots[s].data_ptr(), total, _stream())
+        if self.events[s] is None:
+            self.events[s] = torch.cuda.Event()
+        self.events[s].record()
+        return [dev[o:o + a.nbytes].view(torch.from_numpy(a[:0]).dtype) for a, o in zip(arrays, offs)]
+
+
+_STAGES = {}
+
+
+def host_stage(device):
+    """The calling thread's HostStage of `device`."""
+    import threading
+    key = (threading.get_ident(), str(device))
+    st = _STAGES.get(key)
+    if st is None:
+        st = _STAGES[key] = HostStage()
+    return st
+
+
 # ----------------------------------------------------------------------------------------
 # K5: the negative queue
 # ----------------------------------------------------------------------------------------

@@ -18,14 +18,29 @@ from ..backbones import ResNetFlow, torchvision_multilevel
 
 
 class DeferredLogVars:
-    """The step's log variables, still on the device as one stacked tensor; `.get()` copies them to the host once."""
+    """The step's log variables as one stacked tensor.  Their copy to pinned host memory is enqueued at once, followed by an
+    event; `.get()` waits for THAT event only.  (`stacked.tolist()` at `.get()` time would be a copy ordered behind
+    everything enqueued since -- a caller that reads them one step late, to keep the host a step ahead of the device, would
+    wait for the whole next step instead: the GPU then idled through the eager start of every step,
+    profiles/r02_timeline_host_g1.txt.)"""
 
     def __init__(self, keys, stacked):
         self.keys, self.stacked, self._values = keys, stacked, None
+        self._host = self._event = None
+        if stacked.is_cuda:
+            self._host = torch.empty(stacked.shape, dtype=stacked.dtype, pin_memory=True)
+            self._host.copy_(stacked, non_blocking=True)
+            self._event = torch.cuda.Event()
+            self._event.record()
 
     def get(self):
         if self._values is None:
-            self._values = OrderedDict(zip(self.keys, self.stacked.tolist()))
+            if self._event is not None:
+                self._event.synchronize()
+                values = self._host.tolist()
+            else:
+                values = self.stacked.tolist()
+            self._values = OrderedDict(zip(self.keys, values))
         return self._values
 
 

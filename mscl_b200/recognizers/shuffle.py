@@ -61,7 +61,9 @@ def _upload(idx, dev):
     which would stop the CPU from running ahead of the GPU six times per step."""
     if dev.type != "cuda":
         return idx.to(dev)
-    return idx.pin_memory().to(dev, non_blocking=True)
+    # ... and not through the copy engine either, where the few hundred bytes would wait behind the loader's next batch
+    from .. import functional as fx
+    return fx.host_stage(dev).upload([idx.contiguous().numpy()], dev)[0].view(idx.shape)
 
 
 class PendingExchange:

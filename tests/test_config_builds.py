@@ -107,3 +107,44 @@ def test_augmentations_refuse_host_tensors():
         aug = mscl_b200.build_ssl_aug(cfg)
         with pytest.raises(_cabi.MsclError):
             aug(x, x, {})
+
+
+def test_augmentation_host_draw_and_pack():
+    """SyncMoCoAugmentV5 draws its decisions on the host and uploads one packed table per view: the host packing
+    (`_pack_host`) equals the device-op packing the kernel tests use (`_pack_params`), the draws respect the reference's
+    ranges and sharing rules (ssl_aug_v2.py:31-48: ColorJitter(0.4,0.4,0.4,0.1) p=.8, grayscale p=.2, blur p=.5; 'batch'
+    level: decisions shared by the frames of a clip, factors per frame), and `torch.manual_seed` makes them repeatable
+    without touching the CPU default generator (which draws the shuffle permutations)."""
+    import numpy as np
+    from mscl_b200.common.ssl_aug import SyncMoCoAugmentV5
+    n, t = 64, 8
+    draws = []
+    for _ in range(2):
+        torch.manual_seed(7)
+        aug = SyncMoCoAugmentV5(crop_size=112, sync_level=("batch", "params"), t=(8, 8), flow_suffix="flow_imgs")
+        before = torch.get_rng_state()
+        d = aug._draw_host(n, t)
+        assert torch.equal(before, torch.get_rng_state())
+        draws.append(d)
+    for k in draws[0]:
+        assert np.array_equal(np.asarray(draws[0][k]), np.asarray(draws[1][k])), k
+    d = draws[0]
+    for k in ("brightness", "contrast", "saturation"):
+        assert d[k].shape == (n * t,) and d[k].min() >= 0.6 and d[k].max() <= 1.4
+        assert d[k].reshape(n, t).std(axis=1).min() > 0                       # per frame in the 'batch' level
+    assert np.abs(d["hue"]).max() <= 0.1 and 0.1 <= d["sigma"] <= 2.0
+    for k, p in (("jit", 0.8), ("gray", 0.2), ("blur", 0.5)):
+        per_clip = d[k].reshape(n, t)
+        assert (per_clip == per_clip[:, :1]).all()                            # decisions shared by the frames of a clip
+        assert abs(per_clip[:, 0].mean() - p) < 0.2
+    assert d["taps"].shape == (11,) and abs(float(d["taps"].sum()) - 1) < 1e-6 and np.allclose(d["taps"], d["taps"][::-1])
+    assert aug._draw_host(n, 1)["brightness"].shape == (n,)                   # 'params' level: one set per clip
+    flip = np.repeat(np.arange(n) % 3 == 0, t)
+    rows = aug._pack_host(d, flip, False)
+    prm = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+    ref = aug._pack_params(prm, torch.from_numpy(flip), False).numpy()
+    np.testing.assert_allclose(rows, ref, rtol=0, atol=1e-6)
+    weak = aug._pack_host(d, flip, True)
+    assert np.array_equal(weak[:, 0], flip.astype(np.float32)) and not weak[:, 1:].any()
+    prm2 = aug._color_params(4, torch.device("cpu"), 8)
+    assert prm2["jit"].dtype == torch.bool and prm2["brightness"].shape == (32,) and prm2["taps"].shape == (11,)
