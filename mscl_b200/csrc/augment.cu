@@ -342,12 +342,18 @@ color_pipeline_fast_kernel(const float *__restrict__ x, const float *__restrict_
         const float4 v = row4[q];
         buf[4 * c] = v.x, buf[4 * c + 1] = v.y, buf[4 * c + 2] = v.z, buf[4 * c + 3] = v.w;
       }
-      if (w0 < HALF || w0 + 3 + HALF >= W) {
+      if (w0 < HALF) {            // only the first HALF inputs of a lane can lie left of the row ...
 #pragma unroll
-        for (int j = 0; j < 4 + TAPS - 1; ++j) {
+        for (int j = 0; j < HALF; ++j) {
           const int ww = w0 - HALF + j;
           if (ww < 0) buf[j + OFF] = row[-ww];
-          else if (ww >= W) buf[j + OFF] = row[2 * W - 2 - ww];
+        }
+      }
+      if (w0 + 3 + HALF >= W) {   // ... and only the last HALF right of it
+#pragma unroll
+        for (int j = 4 + TAPS - 1 - HALF; j < 4 + TAPS - 1; ++j) {
+          const int ww = w0 - HALF + j;
+          if (ww >= W) buf[j + OFF] = row[2 * W - 2 - ww];
         }
       }
     }
@@ -367,30 +373,42 @@ color_pipeline_fast_kernel(const float *__restrict__ x, const float *__restrict_
   }
   __syncthreads();
   // ---- phase 3: vertical pass, 8 output rows per thread, shared -> global, normalised (frame-border rows reflect)
+  // thread <-> column (W <= 128: the first 128 threads' lane index), the 4 groups of 128 threads take the
+  // (plane, row chunk) tasks in turn: no per-task division by W, and a chunk whose window needs neither the frame's
+  // reflect border nor the clamp of a ragged end walks its column with one pointer increment per row
   constexpr int RC = 8;
   const int hchunks = (r1 - r0 + RC - 1) / RC;
-  for (int task = threadIdx.x; task < 3 * hchunks * W; task += nthr) {
-    const int w = task % W;
-    const int rest = task / W;
-    const int hc = rest % hchunks, ch = rest / hchunks;
-    const float *plane = sm + ch * SP;
-    const int h0 = r0 + hc * RC;
-    float win[RC + TAPS - 1];
+  const int w = threadIdx.x & 127, part = threadIdx.x >> 7, nparts = nthr >> 7;
+  if (w < W) {
+    const int wo = flip ? (W - 1 - w) : w;
+    for (int task = part; task < 3 * hchunks; task += nparts) {
+      const int ch = task / hchunks, hc = task - ch * hchunks;
+      const float *plane = sm + ch * SP;
+      const int h0 = r0 + hc * RC;
+      float win[RC + TAPS - 1];
+      if (h0 - HALF >= s0 && h0 + RC - 1 + HALF < s1) {      // interior: rows h0 - HALF .. h0 + RC - 1 + HALF are all staged
+        const float *pc = plane + (h0 - HALF - s0) * W + w;
 #pragma unroll
-    for (int j = 0; j < RC + TAPS - 1; ++j) {
-      int hh = h0 - HALF + j;
-      hh = hh < 0 ? -hh : (hh >= H ? 2 * H - 2 - hh : hh);
-      hh = min(max(hh, s0), s1 - 1);            // only rows of a ragged last chunk (never stored) get clamped
-      win[j] = plane[(hh - s0) * W + w];
-    }
-    const float mean = ch == 0 ? n0 : (ch == 1 ? n1 : n2);
-    const float rs = ch == 0 ? rs0 : (ch == 1 ? rs1 : rs2);
+        for (int j = 0; j < RC + TAPS - 1; ++j, pc += W) win[j] = *pc;
+      } else {
 #pragma unroll
-    for (int e = 0; e < RC; ++e) {
-      float acc = 0.f;
+        for (int j = 0; j < RC + TAPS - 1; ++j) {
+          int hh = h0 - HALF + j;
+          hh = hh < 0 ? -hh : (hh >= H ? 2 * H - 2 - hh : hh);
+          hh = min(max(hh, s0), s1 - 1);          // only rows of a ragged last chunk (never stored) get clamped
+          win[j] = plane[(hh - s0) * W + w];
+        }
+      }
+      const float mean = ch == 0 ? n0 : (ch == 1 ? n1 : n2);
+      const float rs = ch == 0 ? rs0 : (ch == 1 ? rs1 : rs2);
+      float *dst = po + ch * THW + (int64_t)h0 * W + wo;
 #pragma unroll
-      for (int k = 0; k < TAPS; ++k) acc = fmaf(tp[k], win[e + k], acc);
-      if (h0 + e < r1) po[ch * THW + (h0 + e) * W + (flip ? (W - 1 - w) : w)] = (acc - mean) * rs;
+      for (int e = 0; e < RC; ++e) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) acc = fmaf(tp[k], win[e + k], acc);
+        if (h0 + e < r1) dst[e * W] = (acc - mean) * rs;
+      }
     }
   }
 }
