@@ -10,7 +10,7 @@ timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --profile
 echo "launchlist rc=$?"; tail -3 gpurun_out/bench_under_ncu.log
 # full capture of our kernels (regex on kernel names), a few launches each
 timeout 1200 ncu --set full --clock-control none \
-    -k regex:"infonce_fused_kernel|infonce_bwd_slabs|infonce_tc_kernel|ema_multi_kernel|fra_|hw_mean|enqueue_kernel|lmcl_kernel|clip_sgd_multi|grad_sqnorm_multi|color_pipeline|flow_visualize|upsample_trilinear" -c 60 --profile-from-start off \
+    -k regex:"infonce_fused_kernel|infonce_bwd_slabs|infonce_tc_kernel|ema_multi_kernel|fra_|hw_mean|enqueue_kernel|lmcl_kernel|clip_sgd_multi|grad_sqnorm_multi|color_pipeline|clip_gray_sum|flow_visualize|upsample_trilinear|linear_axis_bwd|fetch_host" -c 60 --profile-from-start off \
     -o gpurun_out/prof_kernels -f python bench.py --steps 2 --warmup 3 --no-graphs --no-cpu-baseline --no-kernel-rooflines --profile-range > gpurun_out/prof_kernels.log 2>&1
 echo "full rc=$?"
 ncu -i gpurun_out/prof_kernels.ncu-rep --page raw --csv > gpurun_out/prof_kernels_raw.csv 2>/dev/null

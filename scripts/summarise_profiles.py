@@ -20,7 +20,7 @@ OUT = os.path.join(ROOT, "profiles")
 GP = os.path.join(ROOT, "gpurun_out")
 OURS = ("infonce", "ema_multi", "fra_", "hw_mean", "enqueue_kernel", "lmcl_kernel", "queue_transpose", "gather_rows",
         "clip_sgd_multi", "grad_sqnorm_multi", "grad_norm_finish", "color_pipeline", "clip_gray_sum", "flow_visualize",
-        "upsample_trilinear")
+        "upsample_trilinear", "linear_axis_bwd", "fetch_host")
 ENTRY = {"infonce_fused_kernel": "mscl_infonce_fused", "infonce_bwd_slabs_kernel": "mscl_infonce_bwd_slabs", "infonce_bwd_slabs_multi_kernel": "mscl_infonce_bwd_slabs",
          "infonce_tc_kernel": "mscl_infonce_partial", "ema_multi_kernel": "mscl_ema_multi", "fra_maxrad_kernel": "mscl_fra_maxrad",
          "fra_apply_kernel": "mscl_fra_apply", "fra_fused_kernel": "mscl_fra_fused", "hw_mean_fwd_kernel": "mscl_hw_mean_fwd",
