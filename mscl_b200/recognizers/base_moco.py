@@ -24,18 +24,31 @@ class DeferredLogVars:
     wait for the whole next step instead: the GPU then idled through the eager start of every step,
     profiles/r02_timeline_host_g1.txt.)"""
 
+    _ring, _ring_pos = [], 0          # pinned landing buffers + the event of the copy that last wrote each (16 slots)
+
     def __init__(self, keys, stacked):
         self.keys, self.stacked, self._values = keys, stacked, None
         self._host = self._event = None
         if stacked.is_cuda:
-            self._host = torch.empty(stacked.shape, dtype=stacked.dtype, pin_memory=True)
+            cls = DeferredLogVars
+            if not cls._ring:
+                cls._ring = [[torch.empty(256, dtype=torch.float32, pin_memory=True), None, 0] for _ in range(16)]
+            slot = cls._ring[cls._ring_pos]
+            cls._ring_pos = (cls._ring_pos + 1) % len(cls._ring)
+            if stacked.numel() > slot[0].numel() or stacked.dtype != torch.float32:
+                slot = [torch.empty(stacked.shape, dtype=stacked.dtype, pin_memory=True), None, 0]   # unusual: own buffer
+            elif slot[1] is not None:
+                slot[1].synchronize()          # 16 steps old: long done
+            slot[2] += 1                       # whoever still holds the slot's previous contents falls back to `stacked`
+            self._slot, self._gen = slot, slot[2]
+            self._host = slot[0][:stacked.numel()].view(stacked.shape)
             self._host.copy_(stacked, non_blocking=True)
-            self._event = torch.cuda.Event()
+            self._event = slot[1] = torch.cuda.Event()
             self._event.record()
 
     def get(self):
         if self._values is None:
-            if self._event is not None:
+            if self._event is not None and self._slot[2] == self._gen:
                 self._event.synchronize()
                 values = self._host.tolist()
             else:
