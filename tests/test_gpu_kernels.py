@@ -614,6 +614,32 @@ def test_augmentation_module_on_device(fx):
     assert torch.isfinite(a).all() and a.min() >= (0 - 0.485) / 0.229 - 1e-4 and a.max() <= (1 - 0.406) / 0.225 + 1e-4
 
 
+def test_fetch_host_stage(fx):
+    """functional.HostStage / mscl_fetch_host: small host tables reach the device through a kernel reading mapped pinned
+    memory (not the copy engine) -- mixed dtypes in one launch, every slot of the ring reused several times."""
+    from mscl_b200 import _cabi
+    stage = fx.HostStage(slots=4)
+    rng = np.random.default_rng(0)
+    dev = torch.device("cuda")
+    kept = []
+    for it in range(13):
+        a = rng.standard_normal((5 + it, 16)).astype(np.float32)
+        b = rng.integers(-2 ** 40, 2 ** 40, size=7 + it)
+        c = (rng.random(3 + it) < 0.5).astype(np.uint8)
+        da, db, dc = stage.upload([a, b, c], dev)
+        assert da.dtype == torch.float32 and db.dtype == torch.int64 and dc.dtype == torch.uint8
+        assert da.data_ptr() % 16 == 0 and db.data_ptr() % 16 == 0 and dc.data_ptr() % 16 == 0
+        kept.append((a, b, c, da, db, dc))
+    for a, b, c, da, db, dc in kept:          # earlier uploads survive the reuse of their host slots
+        np.testing.assert_array_equal(da.cpu().numpy().reshape(a.shape), a)
+        np.testing.assert_array_equal(db.cpu().numpy(), b)
+        np.testing.assert_array_equal(dc.cpu().numpy(), c)
+    out = torch.empty(64, device=dev)
+    pinned = torch.zeros(64, pin_memory=True)
+    with pytest.raises(_cabi.MsclError):      # size not a multiple of 16 bytes
+        _cabi.call("mscl_fetch_host", out.data_ptr(), pinned.data_ptr(), 250, torch.cuda.current_stream().cuda_stream)
+
+
 # ------------------------------------------------------------------ K10 clip + SGD
 def test_fused_clip_sgd_matches_torch(fx):
     """FusedClipSGD against torch.nn.utils.clip_grad_norm_(40) + torch.optim.SGD(lr=.02, momentum=.9, wd=1e-4)
