@@ -11,7 +11,11 @@
 //                      caller.  clip_gray_sum (the contrast step needs the clip's mean luminance) + one CTA per
 //                      frame that keeps the frame in shared memory through both blur passes: 12 B read (x2 for the
 //                      mean) and 12 B written per pixel instead of ~25 element-wise passes and two convolutions.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mscl {
 
@@ -230,7 +234,11 @@ color_pipeline_kernel(const float *__restrict__ x, const float *__restrict__ par
 // global.  Bands keep the footprint at ~65 KB, so three CTAs share an SM and one band's loads overlap another's
 // arithmetic and stores.  ~180 instructions per pixel instead of ~870 in the generic kernel.
 // The mirror of a flipped clip is applied when storing (the blur is symmetric, so flipping commutes with it).
-template <int TAPS>
+// CLUSTER_MEAN (per-frame parameters): the bands of a frame form a thread-block cluster; each CTA sums the luminance of its own
+// rows out of the staged (raw) planes and reads its peers' sums through distributed shared memory, so the frame's mean
+// luminance -- what the contrast step is taken about -- needs no pass over the clip before this kernel (clip_gray_sum read
+// the 38 MB input a second time: 11 of K9's 47 us per view).
+template <int TAPS, bool CLUSTER_MEAN>
 __global__ void __launch_bounds__(512)
 color_pipeline_fast_kernel(const float *__restrict__ x, const float *__restrict__ params, const float *__restrict__ gray_partial,
                            int n_chunks, const float *__restrict__ taps, const float *__restrict__ norm,
@@ -242,7 +250,7 @@ color_pipeline_fast_kernel(const float *__restrict__ x, const float *__restrict_
   const int n = frame / T, t = frame - n * T;
   const int unit = per_frame ? frame : n;
   const int r0 = blockIdx.y * band_rows, r1 = min(r0 + band_rows, H);        // output rows of this band
-  if (r0 >= H) return;
+  if (!CLUSTER_MEAN && r0 >= H) return;      // (the cluster form is only launched when every band has rows)
   const float *p = params + unit * kColorParams;
   const bool flip = p[0] != 0.f, jit = p[1] != 0.f, to_gray = p[14] != 0.f, blur = p[15] != 0.f;
   const int s0 = blur ? max(r0 - HALF, 0) : r0, s1 = blur ? min(r1 + HALF, H) : r1;   // staged rows
@@ -256,8 +264,9 @@ color_pipeline_fast_kernel(const float *__restrict__ x, const float *__restrict_
   for (int k = 0; k < TAPS; ++k) tp[k] = __ldg(taps + k);
   const int64_t THW = (int64_t)T * HW;
   float gsum = 0.f;
-  for (int c = 0; c < n_chunks; ++c) gsum += __ldg(gray_partial + unit * n_chunks + c);
-  const float m = br * (gsum / (per_frame ? (float)HW : (float)THW));
+  if (!CLUSTER_MEAN)
+    for (int c = 0; c < n_chunks; ++c) gsum += __ldg(gray_partial + unit * n_chunks + c);
+  float m = br * (gsum / (per_frame ? (float)HW : (float)THW));
   const float *pr = x + (int64_t)n * 3 * THW + (int64_t)t * HW;
   float *po = out + (int64_t)n * 3 * THW + (int64_t)t * HW;
   const float n0 = norm[0], n1 = norm[1], n2 = norm[2];
@@ -282,6 +291,31 @@ color_pipeline_fast_kernel(const float *__restrict__ x, const float *__restrict_
     while (!ok)
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                    : "=r"(ok) : "r"(bar_a) : "memory");
+  }
+  if (CLUSTER_MEAN && jit) {      // `jit` is a property of the frame: the whole cluster takes this branch or none of it does
+    __shared__ float cl_part[16];
+    __shared__ float cl_sum;
+    const float4 *q4 = reinterpret_cast<const float4 *>(sm + (r0 - s0) * W);      // this band's own rows, plane 0
+    const int own4 = (r1 - r0) * W >> 2, plane4 = SP >> 2;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < own4; i += nthr) {
+      const float4 r = q4[i], g = q4[plane4 + i], b = q4[2 * plane4 + i];
+      acc += (gray_of(r.x, g.x, b.x) + gray_of(r.y, g.y, b.y)) + (gray_of(r.z, g.z, b.z) + gray_of(r.w, g.w, b.w));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) cl_part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < nwarps; ++i) t += cl_part[i];
+      cl_sum = t;
+    }
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    float total = 0.f;
+    for (int rk = 0; rk < (int)cluster.num_blocks(); ++rk) total += *cluster.map_shared_rank(&cl_sum, rk);
+    m = br * (total / (float)HW);
+    cluster.sync();                 // nobody leaves (or moves on to overwrite anything) while a peer may still read its sum
   }
   // ---- phase 1: shade every staged pixel once, in place, four pixels per thread (W % 4 == 0 -> SP % 4 == 0)
   auto shade1 = [&](float &r, float &g, float &bl) {
@@ -466,24 +500,43 @@ int mscl_color_pipeline(const float *d_x, const float *d_params, const float *d_
   cudaStream_t s = mscl::as_stream(stream);
   MSCL_CHECK_ARG(!per_frame || ((int64_t)H * W) % 4 == 0, "H*W must be a multiple of 4 for per-frame parameters");
   MSCL_CHECK_ARG((int64_t)N * (per_frame ? T : 1) <= 65535, "too many clips / frames for one launch");
+  const bool fast = n_taps == 11 && W <= 128 && W > 10 && H > 10 && W % 4 == 0;     // the config's case: 11 taps, 112x112 crops
+  // bands of rows sized for ~3 CTAs per SM (<= 72 KB of staged rows incl. the 5 + 5 halo rows)
+  int bands = 1;
+  while (bands < H && (size_t)3 * ((H + bands - 1) / bands + 10) * W * 4 > 72 * 1024) ++bands;
+  const int band_rows = (H + bands - 1) / bands;
+  const size_t smem_fast = (size_t)3 * (band_rows + 10) * W * sizeof(float);
+  const bool fast_ok = fast && band_rows >= 6 && smem_fast <= 200 * 1024;
+  // per-frame parameters: the frame's mean luminance is formed inside the kernel by the cluster of its bands (no pre-pass)
+  if (fast_ok && per_frame && bands <= 8 && (bands - 1) * band_rows < H) {
+    MSCL_CUDA(mscl::ensure_dyn_smem(mscl::color_pipeline_fast_kernel<11, true>, smem_fast));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(N * T, bands);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem_fast;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = bands;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MSCL_CUDA(cudaLaunchKernelEx(&cfg, mscl::color_pipeline_fast_kernel<11, true>, d_x, d_params, (const float *)d_gray_partial,
+                                 (int)n_chunks, d_taps, d_norm, d_out, (int)T, (int)H, (int)W, band_rows, (int)per_frame));
+    return MSCL_OK;
+  }
   if (per_frame)
     mscl::clip_gray_sum_kernel<<<dim3(n_chunks, N * T), 256, 0, s>>>(d_x, d_gray_partial, THW, (int64_t)H * W, T);
   else
     mscl::clip_gray_sum_kernel<<<dim3(n_chunks, N), 256, 0, s>>>(d_x, d_gray_partial, THW, THW, 1);
   MSCL_LAUNCH_CHECK();
-  if (n_taps == 11 && W <= 128 && W > 10 && H > 10 && W % 4 == 0) {     // the config's case: 11 taps, 112x112 crops
-    // bands of rows sized for ~3 CTAs per SM (<= 72 KB of staged rows incl. the 5 + 5 halo rows)
-    int bands = 1;
-    while (bands < H && (size_t)3 * ((H + bands - 1) / bands + 10) * W * 4 > 72 * 1024) ++bands;
-    const int band_rows = (H + bands - 1) / bands;
-    const size_t smem_fast = (size_t)3 * (band_rows + 10) * W * sizeof(float);
-    if (band_rows >= 6 && smem_fast <= 200 * 1024) {
-      MSCL_CUDA(mscl::ensure_dyn_smem(mscl::color_pipeline_fast_kernel<11>, smem_fast));
-      mscl::color_pipeline_fast_kernel<11><<<dim3(N * T, bands), 512, smem_fast, s>>>(d_x, d_params, d_gray_partial, n_chunks,
-                                                                                      d_taps, d_norm, d_out, T, H, W, band_rows, per_frame);
-      MSCL_LAUNCH_CHECK();
-      return MSCL_OK;
-    }
+  if (fast_ok) {
+    MSCL_CUDA(mscl::ensure_dyn_smem(mscl::color_pipeline_fast_kernel<11, false>, smem_fast));
+    mscl::color_pipeline_fast_kernel<11, false><<<dim3(N * T, bands), 512, smem_fast, s>>>(d_x, d_params, d_gray_partial, n_chunks,
+                                                                                           d_taps, d_norm, d_out, T, H, W, band_rows, per_frame);
+    MSCL_LAUNCH_CHECK();
+    return MSCL_OK;
   }
   MSCL_CUDA(mscl::ensure_dyn_smem(mscl::color_pipeline_kernel, smem));
   mscl::color_pipeline_kernel<<<N * T, 512, smem, s>>>(d_x, d_params, d_gray_partial, n_chunks, d_taps, n_taps, d_norm, d_out,

@@ -452,18 +452,24 @@ def bench_k789(cfg, N, pk, dev, iters=20):
     xs = [torch.rand(N, 3, T, 112, 112, device=dev) for _ in range(rot)]
     ys = [torch.empty(N, 3, T, 112, 112, device=dev) for _ in range(rot)]
     torch.manual_seed(0)
-    prm = aug._color_params(N, dev)
     norm = torch.cat([aug.mean.view(-1), aug.std.view(-1)]).to(dev)
-    scratch = torch.empty(N, fx._GRAY_CHUNKS, device=dev)
-    for name, blur in (("drawn decisions (p_blur=.5)", None), ("all clips blurred", True), ("no clip blurred", False)):
-        if blur is not None:
-            prm["blur"] = torch.full((N,), blur, device=dev)
-        params = aug._pack_params(prm, flip.bool(), False)
-        taps = prm["taps"].contiguous()
-        us = time_train(lambda i: _cabi.call("mscl_color_pipeline", xs[i % rot].data_ptr(), params.data_ptr(), taps.data_ptr(),
-                                             taps.numel(), norm.data_ptr(), scratch.data_ptr(), fx._GRAY_CHUNKS,
-                                             ys[i % rot].data_ptr(), N, T, 112, 112, 0, _st()), iters)
-        out.append(row(cfg, "clip_gray_sum + color_pipeline", f"({N},3,{T},112,112) {name}", us, 36 * N * T * HW, 0, pk))
+    # per-frame jitter factors (the config's 'batch' sync level: what the step runs; the frame's mean luminance is formed in
+    # the kernel by the cluster of its bands) and per-clip ones ('params' level: clip_gray_sum pre-pass + the pipeline)
+    for frames, label in ((T, "per-frame factors: color_pipeline (cluster mean)"), (1, "per-clip factors: clip_gray_sum + color_pipeline")):
+        prm = aug._color_params(N, dev, frames)
+        chunks = 1 if frames > 1 else fx._GRAY_CHUNKS
+        scratch = torch.empty(N * frames, chunks, device=dev)
+        cases = (("drawn decisions (p_blur=.5)", None), ("all clips blurred", True), ("no clip blurred", False)) if frames > 1 else \
+            (("drawn decisions (p_blur=.5)", None),)
+        for name, blur in cases:
+            if blur is not None:
+                prm["blur"] = torch.full((N * frames,), blur, device=dev)
+            params = aug._pack_params(prm, flip.bool().repeat_interleave(frames), False)
+            taps = prm["taps"].contiguous()
+            us = time_train(lambda i: _cabi.call("mscl_color_pipeline", xs[i % rot].data_ptr(), params.data_ptr(), taps.data_ptr(),
+                                                 taps.numel(), norm.data_ptr(), scratch.data_ptr(), chunks,
+                                                 ys[i % rot].data_ptr(), N, T, 112, 112, int(frames > 1), _st()), iters)
+            out.append(row(cfg, label, f"({N},3,{T},112,112) {name}", us, 36 * N * T * HW, 0, pk))
     return out
 
 

@@ -10,5 +10,5 @@ dev = torch.device("cuda", 0)
 pk, _ = kb.hbm_peak()
 for r in kb.bench_k789("cfg2", 32, pk, dev):
     if "color" in r["kernel"] or "flow_vis" in r["kernel"]:
-        print(f"{r['kernel'][:60]:<60} {r['shape']:<60} {r['us']:7.1f} us {100*r['frac_hbm']:5.1f}%")
+        print(f"{r['kernel'][:66]:<66} {r['shape']:<52} {r['us']:7.1f} us {100*r['frac_hbm']:5.1f}%")
 PY
