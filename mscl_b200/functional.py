@@ -872,5 +872,6 @@ def color_pipeline(x, params, taps, norm):
     chunks = 1 if per_frame else _GRAY_CHUNKS
     scratch = torch.empty(params.shape[0], chunks, device=x.device)
     _cabi.call("mscl_color_pipeline", x.data_ptr(), params.data_ptr(), taps.data_ptr(), taps.numel(), norm.data_ptr(),
-               scratch.data_ptr(), chunks, out.data_ptr(), N, T, H, W, per_frame, _stream(), algo_bytes=36 * N * T * H * W)
+               scratch.data_ptr(), chunks, out.data_ptr(), N, T, H, W, per_frame, _stream(),
+               algo_bytes=(24 if per_frame else 36) * N * T * H * W)      # per-clip factors: the luminance pre-pass reads x again
     return out

@@ -469,7 +469,7 @@ def bench_k789(cfg, N, pk, dev, iters=20):
             us = time_train(lambda i: _cabi.call("mscl_color_pipeline", xs[i % rot].data_ptr(), params.data_ptr(), taps.data_ptr(),
                                                  taps.numel(), norm.data_ptr(), scratch.data_ptr(), chunks,
                                                  ys[i % rot].data_ptr(), N, T, 112, 112, int(frames > 1), _st()), iters)
-            out.append(row(cfg, label, f"({N},3,{T},112,112) {name}", us, 36 * N * T * HW, 0, pk))
+            out.append(row(cfg, label, f"({N},3,{T},112,112) {name}", us, (24 if frames > 1 else 36) * N * T * HW, 0, pk))
     return out
 
 
