@@ -625,11 +625,11 @@ def run_b200(args, rank, local_rank, world):
         return float(ms[0]) / 1e3 / steps, float(ms[1]) / 1e3 / steps      # seconds per step (device, wall)
 
     # ---- device-resident inputs: `value` ----
-    # W untimed steps as asked -- and never fewer than 8 in all: the steps right after construction are not the steady state
+    # W untimed steps as asked -- and never fewer than 8 in all (15 with several ranks): the steps right after construction are not the steady state
     # (the caching allocators grow to the footprint of a host that runs a step ahead, each cudaMalloc a synchronisation; DDP
     # rebuilds its buckets; NCCL sets its channels up at the first collective of each kind).  Measured at two GPUs with
     # W = 3: 34.8 ms per step over the next 10 steps against 32.4 ms after 15 untimed ones.
-    untimed = max(args.warmup, 8)
+    untimed = max(args.warmup, 8 if world == 1 else 15)      # (N = 2, W = 3: 33.0 ms with 8 untimed steps, 32.4 ms with 15)
     for i in range(untimed):
         train_step(resident[i % 2])
     sampler = ClockSampler(local_rank)
