@@ -232,16 +232,61 @@ def test_r50_config_whole_step_host_logic(cpu_kernels, monkeypatch):
         assert rec._cpu_state.ptr == ob.state.ptr and rec.iters == ob.state.iters
 
 
+def _fake_enqueue_save(self, keys, save=False):
+    """`_fake_enqueue` that can also hand back what it overwrote: (old keys (B,C), old counts (B,), first slot)."""
+    st = self._cpu_state
+    b, ptr = keys.shape[0], st.ptr
+    saved = (st.queue[:, ptr:ptr + b].t().clone(), st.count[ptr:ptr + b].clone(), ptr) if save else None
+    _fake_enqueue(self, keys)
+    return saved
+
+
+def _fake_contrast_many(calls):
+    """`MoCoV2.contrast_many` with oracle arithmetic: a call that carries an epoch split (overwritten, n_pre) evaluates its
+    first n_pre terms on the queue state BEFORE the recognizer's last enqueue -- rebuilt from what that enqueue saved
+    (moco.py:423-440 backwards: the slots get their old keys and counts back, every other count loses one) -- and the
+    others on the state as it is."""
+    outs = []
+    for call in calls:
+        rec, terms, T = call[:3]
+        split = call[3] if len(call) > 3 else None
+        if split is None:
+            outs.append(_fake_contrast(rec, terms, T))
+            continue
+        (old_keys, old_count, ptr), n_pre = split
+        st = rec._cpu_state
+        b = old_keys.shape[0]
+        assert (ptr + b) % st.queue.shape[1] == st.ptr          # `overwritten` belongs to the LAST enqueue of this queue
+        pre = O.QueueState(st.queue.clone(), st.count - 1, ptr)
+        pre.queue[:, ptr:ptr + b] = old_keys.t()
+        pre.count[ptr:ptr + b] = old_count
+        rec._cpu_state = pre
+        a = _fake_contrast(rec, terms[:n_pre], T)
+        rec._cpu_state = st
+        outs.append(torch.cat([a, _fake_contrast(rec, terms[n_pre:], T)]))
+    return outs
+
+
+@pytest.mark.parametrize("merged", [False, True])
 @pytest.mark.parametrize("vname", ["cross_kn", "aug_enqueue"])
-def test_mscl_with_aug_switches_host_logic(cpu_kernels, vname, golden_dir):
+def test_mscl_with_aug_switches_host_logic(cpu_kernels, monkeypatch, vname, merged, golden_dir):
     """MSCLWithAug.objective with `same_kn=False` / `update_aug_flow=True, weight_aug_flow=(0.5, 0)`: which queue state
-    each stacked term reads, the extra enqueue, the halved / dropped loss terms -- against the reference's numbers."""
+    each stacked term reads, the extra enqueue, the halved / dropped loss terms -- against the reference's numbers; in the
+    three-pass schedule (what runs without a CUDA device) and in the one-launch schedule of the device path (`merged`: the
+    base-flow enqueue first, its overwritten block handed to ONE stacked pass over W_flow, the RGB enqueue last)."""
     from test_gpu_step import head_level_cfg
     from test_oracle_golden import MSCL_VARIANTS, check_mscl_variant_step
     g = np.load(os.path.join(golden_dir, "mscl_variants.npz"), allow_pickle=False)
     kw = eval(str(g["kwargs"]))
     inp = inputs.head_inputs(**kw)
     model = mscl_b200.build_model(head_level_cfg(kw["K"], kw["t"], **MSCL_VARIANTS[vname])).train()
+    launches = []
+    if merged:
+        monkeypatch.setattr(MoCoV2, "can_launch_together", staticmethod(lambda recs, device: True))
+        monkeypatch.setattr(MoCoV2, "_dequeue_and_enqueue", _fake_enqueue_save)
+        monkeypatch.setattr(MoCoV2, "contrast_many",
+                            staticmethod(lambda calls: (launches.append([len(c) > 3 and c[3] is not None for c in calls]),
+                                                        _fake_contrast_many(calls))[1]))
     model.recognizer._cpu_state = O.QueueState(inp["queue_rgb"], inp["count"], inp["ptr"])
     model.recognizer_flow._cpu_state = O.QueueState(inp["queue_flow"], inp["count"], inp["ptr"])
     N = kw["N"]
@@ -260,6 +305,8 @@ def test_mscl_with_aug_switches_host_logic(cpu_kernels, vname, golden_dir):
                   for br, rec in (("rgb", model.recognizer), ("flow", model.recognizer_flow))}
         check_mscl_variant_step(g, f"{vname}/step{step}", log_vars, {n: l.grad for n, l in leaves.items()}, states,
                                 rel=2e-6, rel_grad=2e-5, rel_map=1e-4)
+    if merged:      # per step ONE stacked launch: the W_rgb job plain, the W_flow job with the epoch split
+        assert launches == [[False, True], [False, True]], launches
 
 
 def test_eval_mode_step_host_logic(cpu_kernels, monkeypatch):
